@@ -1,0 +1,158 @@
+"""The oracle (oracle/*.py) against the golden vectors produced by the unmodified
+reference (oracle/gen_golden.py -> tests/golden/).  CPU only."""
+import numpy as np
+import PIL.Image as Image
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden
+from oracle import model_oracle as MO
+from oracle import outil_oracle as OO
+from oracle import pair_oracle as PO
+from oracle import synth
+from oracle import warp_oracle as WO
+
+RANSAC_CASES = ["ransac_m120", "ransac_m636", "ransac_grid", "ransac_remainder_only", "ransac_none", "ransac_lowinlier"]
+
+
+def test_wh_tensor_bit_exact():
+    g = golden("wh_tensor")
+    W, H = OO.getWHTensor(int(g["h"]), int(g["w"]))
+    assert np.array_equal(W, g["W"]) and np.array_equal(H, g["H"])
+    Wi, Hi = OO.getWHTensor_Int(int(g["h"]), int(g["w"]))
+    assert np.array_equal(Wi, g["Wi"]) and np.array_equal(Hi, g["Hi"])
+
+
+def test_mutual_matching_identical_pairs():
+    g = golden("mutual_matching")
+    i1, i2 = OO.mutualMatching(g["featA"], g["featB"])
+    assert np.array_equal(i1, g["index1"]) and np.array_equal(i2, g["index2"])
+    assert 11 not in i2                      # the all-zero target column never matches
+
+
+@pytest.mark.parametrize("name", RANSAC_CASES)
+def test_homography_prediction_score(name):
+    g = golden(name)
+    us = OO.unique_samples(g["samples"])[: len(g["chunk0_H"])]
+    H = OO.Homography(g["match1"][us], g["match2"][us])
+    assert np.array_equal(H, g["chunk0_H"])                       # same LAPACK -> same bits
+    err = OO.Prediction(g["match1"], g["match2"], H[:8])
+    np.testing.assert_allclose(err, g["chunk0_err8"], rtol=2e-4, atol=5e-6)   # x/z is ill-conditioned near z=0; exact fits are pure rounding noise
+    dets = OO.det3(H)
+    np.testing.assert_allclose(dets, g["chunk0_dets"], rtol=1e-4, atol=1e-7)
+    _, counts = OO.ScoreRANSAC(g["match1"], g["match2"], float(g["tol"]), us)
+    assert np.array_equal(counts, g["chunk0_counts"])
+
+
+@pytest.mark.parametrize("name", RANSAC_CASES)
+def test_ransac_bit_exact(name):
+    g = golden(name)
+    H, nb, inl, m2 = OO.RANSAC_from_samples(g["match1"], g["match2"], g["samples"], float(g["tol"]))
+    if bool(g["is_none"]):
+        assert H is None and nb == 0 and inl == [] and m2 == []
+        return
+    assert np.array_equal(H, g["H"])
+    assert int(nb) == int(g["nbInlier"])
+    assert np.array_equal(inl, g["isInlier"])
+
+
+def test_ransac_typeerror_when_no_model():
+    m1, m2, _ = synth.make_matches(3, 40, 0.0)
+    s = synth.draw_samples(3, 40, 50)
+    with pytest.raises(TypeError):
+        OO.RANSAC_from_samples(m1, m2, s, 0.0)
+
+
+def test_householder_null_vector_matches_lapack_sign():
+    m1, m2, _ = synth.make_matches(21, 200, 0.6)
+    s = OO.unique_samples(synth.draw_samples(21, 200, 300))
+    A = OO.dlt_matrix(m1[s], m2[s])
+    _, _, vh = np.linalg.svd(A)
+    for n in range(len(A)):
+        h = OO.householder_null_vector(A[n])
+        assert np.max(np.abs(h - vh[n, 8])) < 1e-9
+
+
+def test_feature_extractor():
+    g = golden("feature_extractor")
+    y = MO.feature_extractor(torch.from_numpy(g["x"]), synth.feature_extractor_state(int(g["seed"])))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-4, atol=1e-4)
+
+
+def test_fine_heads():
+    g = golden("fine_heads")
+    corr = MO.corr_neigh(torch.from_numpy(g["a"]), torch.from_numpy(g["b"]))
+    np.testing.assert_allclose(corr.numpy(), g["corr"], rtol=1e-5, atol=1e-6)
+    flow = MO.net_flow_coarse(torch.from_numpy(g["corr"]), synth.net_flow_coarse_state(1))
+    np.testing.assert_allclose(flow.numpy(), g["flow"], rtol=1e-4, atol=1e-6)
+    match = MO.net_matchability(torch.from_numpy(g["corr"]), synth.net_matchability_state(2))
+    np.testing.assert_allclose(match.numpy(), g["match"], rtol=1e-4, atol=1e-6)
+
+
+def test_resnet50_conv4():
+    g = golden("resnet50_conv4")
+    y = MO.resnet50_conv4(torch.from_numpy(g["x"]), synth.resnet50_conv4_state(int(g["seed"])))
+    scale = np.abs(g["y"]).max()
+    assert np.abs(y.numpy() - g["y"]).max() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("tag,m21", [("hpatch", False), ("corr", True)])
+def test_pred_flow_mask(tag, m21):
+    g = golden("pred_flow_mask_" + tag)
+    net = {"netFeatCoarse": synth.feature_extractor_state(0), "netFlowCoarse": synth.net_flow_coarse_state(1),
+           "netMatch": synth.net_matchability_state(2)}
+    Is, It = torch.from_numpy(g["Is"]), torch.from_numpy(g["It"])
+    featt = F.normalize(MO.feature_extractor(It, net["netFeatCoarse"]))
+    grid = WO.base_grid(48, 64)
+    flowCoarse = WO.warp_grid(g["H"], 48, 64)
+    flow12, match, f8, m8 = PO.pred_flow_mask(Is, featt, flowCoarse, grid, net, with_match21=m21)
+    np.testing.assert_allclose(f8, g["flowDown8"], atol=1e-6)
+    np.testing.assert_allclose(m8, g["matchDown8"], atol=1e-6)
+    np.testing.assert_allclose(flow12.numpy(), g["flow12"], atol=1e-5)
+    np.testing.assert_allclose(match, g["match"], atol=1e-5)
+
+
+def test_get_flow_all():
+    g = golden("get_flow_all")
+    fg, _ = WO.get_flow_all(g["flow"], g["H"], g["mask"], 40, 56, th=float(g["th"]), multiH=True)
+    np.testing.assert_allclose(fg.numpy(), g["flowGlobal"], atol=1e-6)
+
+
+def test_coarse_align_variant_C():
+    g = golden("coarse_align_C")
+    c = PO.CoarseAlignOracle(synth.resnet50_conv4_state(0), nbScale=3, nbIter=500, tolerance=0.05, minSize=128,
+                             scaleR=1.5, variant="C")
+    c.setSource(Image.fromarray(g["src"]))
+    c.setTarget(Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.Is), g["Is"]) and np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale, g["WMulti"]) and np.array_equal(c.HMultiScale, g["HMulti"])
+    np.testing.assert_allclose(c.featt.numpy(), g["featt"], atol=2e-5)
+    real = torch.randint
+    torch.randint = lambda high, size, **k: torch.from_numpy(g["samples"]).clone()
+    try:
+        H, mask = c.getCoarse(np.zeros((c.It.size[1], c.It.size[0])))
+    finally:
+        torch.randint = real
+    assert len(c.match1) == int(g["nbMatch"])
+    np.testing.assert_allclose(H, g["H"], atol=1e-5)
+    assert np.array_equal(mask, g["inlierMask"])
+
+
+def test_coarse_align_variant_A():
+    g = golden("coarse_align_A")
+    c = PO.CoarseAlignOracle(synth.resnet50_conv4_state(0), nbScale=3, nbIter=500, tolerance=0.05, minSize=96,
+                             scaleR=1.5, variant="A")
+    c.setPair(Image.fromarray(g["src"]), Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale[c.index1], g["W1"]) and np.array_equal(c.Wt[c.index2], g["W2"])
+    assert np.array_equal(c.WtInt[c.index2], g["W2i"]) and np.array_equal(c.HtInt[c.index2], g["H2i"])
+    real = torch.randint
+    for key_s, key_h, Mt in (("samples0", "H0", np.zeros_like(g["Mt"])), ("samples1", "H1", g["Mt"])):
+        torch.randint = lambda high, size, **k: torch.from_numpy(g[key_s]).clone()
+        try:
+            H = c.getCoarse(Mt)
+        finally:
+            torch.randint = real
+        np.testing.assert_allclose(H, g[key_h], atol=1e-5)
+    assert len(c.match1) == int(g["nbMatch1"])
