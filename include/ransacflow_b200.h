@@ -1,0 +1,140 @@
+/*
+ * ransacflow_b200 - C ABI of the B200 (sm_100a) implementation of RANSAC-Flow's
+ * per-pair inference hot path.
+ *
+ * The reference (XiSHEN0220/RANSAC-Flow) is pure Python on PyTorch: it has no
+ * FFI.  Its drop-in boundary is a set of Python modules (`outil`, `model`,
+ * `coarseAlignFeatMatch`, `kornia.geometry`).  The Python
+ * mirror of those modules (package `ransac-flow_b200/`) is a thin layer over
+ * THIS library; every entry point below names the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers
+ *     unless the parameter name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *     every call is asynchronous on that stream unless stated otherwise;
+ *   - return value 0 = OK, non-zero = error (message: rf_last_error_string());
+ *   - no allocation inside: scratch memory comes from the caller (`ws`), sized
+ *     by the matching `*_workspace()` query;
+ *   - activations are NHWC fp32, "ragged batch": `nimg` images of different
+ *     (H, W) packed back to back in one buffer (`hw_host[2*i] = H_i`,
+ *     `hw_host[2*i+1] = W_i`); outputs are packed the same way;
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef RANSACFLOW_B200_H
+#define RANSACFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RF_MAX_IMGS 16
+
+/* status written by rf_ransac_homography to *status_out (device int) */
+#define RF_RANSAC_OK 0          /* H_out / nbInlier_out / mask_out valid                          */
+#define RF_RANSAC_NONE 1        /* reference returns (None, 0, [], []): utils/outil.py:145-146      */
+#define RF_RANSAC_NO_MODEL 2    /* reference raises TypeError at utils/outil.py:162 (bestParams None) */
+#define RF_RANSAC_TOO_FEW 3     /* fewer than 4 matches (callers return None before calling)      */
+
+int rf_version(void);
+const char* rf_last_error_string(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+uint64_t rf_launch_count(void);
+
+/* ---------------------------------------------------------------- matching --
+ * utils/outil.py:32-45 mutualMatching, fused: the NA x NB score matrix is never
+ * written.  featA [NA][C], featB [NB][C] (K-major rows = one feature vector).
+ * Outputs: idx1/idx2 (int64, capacity >= min(NA,NB)) sorted by idx1, *count.
+ * precision: 0 = exact fp32 FMA (SIMT), 1 = 3xTF32 on tcgen05 tensor cores. */
+size_t rf_corr_mutual_nn_workspace(int NA, int NB);
+int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
+                      int64_t* idx1_out, int64_t* idx2_out, int* count_out,
+                      void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ------------------------------------------------------------------ RANSAC --
+ * utils/outil.py:117-164 RANSAC + :102-113 ScoreRANSAC + :68-87 Homography +
+ * :97-100 Prediction as ONE persistent kernel.  `samples` is the (nbIter,4)
+ * int64 tensor `torch.randint` returned at utils/outil.py:120 (the draw stays
+ * on the host side so the generator stream is the reference's).
+ * match1/match2 [M][3] fp32 (x, y, 1).  `M_dev` (nullable) overrides M with a
+ * device-side count (<= M) so no host sync is needed after matching.
+ * Outputs: H_out[9] fp32, nbInlier_out int64, mask_out[M] u8, status_out int. */
+size_t rf_ransac_workspace(int nbIter);
+int rf_ransac_homography(const float* match1, const float* match2, int M, const int* M_dev,
+                         const int64_t* samples, int nbIter, float tolerance, int chunk,
+                         float* H_out, int64_t* nbInlier_out, uint8_t* mask_out, int* status_out,
+                         void* ws, size_t ws_bytes, void* stream);
+/* utils/outil.py:68-87 Homography alone: X,Y [N][4][3] -> H [N][9] (for tests). */
+int rf_homography_dlt(const float* X, const float* Y, int N, float* H_out, void* stream);
+/* utils/outil.py:97-100 Prediction: err [N][M]. */
+int rf_prediction(const float* match1, const float* match2, int M, const float* H, int N, float* err_out, void* stream);
+/* coarseAlignFeatMatch.py (variant A :158-168, variant C :146-155): gather the
+ * matched cell-centre coordinates into match1/match2 [M][3] = (x=H, y=W, 1).
+ * valid16 (nullable, u8 [NB]) drops matches whose target cell is masked; the
+ * surviving count goes to *count_out, order preserved. */
+int rf_build_matches(const int64_t* idx1, const int64_t* idx2, const int* count_in,
+                     const float* W1, const float* H1, const float* W2, const float* H2,
+                     const uint8_t* valid16, float* match1_out, float* match2_out,
+                     int64_t* idx2_kept_out, int* count_out, int capacity, void* stream);
+
+/* ---------------------------------------------------------------- networks --
+ * conv + folded BatchNorm (eval) + optional residual add + optional ReLU:
+ * model/model.py:27-56,59-125,167-322; torchvision ResNet-50 bottlenecks.
+ * x: ragged NHWC [sum HW][Cin]; w: [R*S*Cin][Cout] (tap-major, Cout contiguous);
+ * bias [Cout] (nullable); residual: packed like y (nullable).
+ * engine: 0 = fp32 SIMT implicit GEMM, 1 = TF32 tcgen05 implicit GEMM
+ * (w_tc = same weights as [Cout][R*S*Cin], required for engine 1). */
+int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
+                   const float* w, const float* w_tc, const float* bias, const float* residual,
+                   int Cout, int R, int S, int stride, int pad, int relu, int engine,
+                   float* y, void* stream);
+/* max pooling k x k / stride / zero-free padding: nn.MaxPool2d (model/model.py:71; torchvision resnet maxpool) */
+int rf_maxpool2d_nhwc(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad,
+                      float* y, void* stream);
+/* model/downsample.py:12-46: reflect-pad 1 + depthwise [1 2 1]x[1 2 1]/16, stride */
+int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C, int stride, float* y, void* stream);
+/* F.normalize(x, dim=1): y = x / max(||x||_2, 1e-12) per pixel over C (P = total pixels).
+ * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
+int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
+/* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][k*k] */
+int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, float* out, void* stream);
+/* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */
+int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream);
+/* model/model.py:306: sigmoid, NHWC [P][1] -> [P] */
+int rf_sigmoid(const float* x, long long n, float* y, void* stream);
+/* ToTensor (+ Normalize): u8 HWC -> fp32 NHWC, (v/255 - mean)/std, exact torchvision op order.
+ * normalize = 0 gives plain ToTensor.  (coarseAlignFeatMatch.py:63-66,106) */
+int rf_preproc_u8(const uint8_t* img, long long npix, int normalize, float* out_nhwc, void* stream);
+/* PIL ImagingResample (LANCZOS, 8bpc fixed point) on device: one pass.
+ * coefficients come from rf_lanczos_coeffs_host (exact PIL arithmetic). */
+int rf_resample_u8(const uint8_t* in, int in_h, int in_w, int channels, int horizontal,
+                   const int* bounds, const int* kk, int ksize, int out_size, uint8_t* out, void* stream);
+int rf_lanczos_coeffs_host(int in_size, int out_size, int* bounds_host, int* kk_host, int kk_capacity, int* ksize_out);
+
+/* -------------------------------------------------------------------- warp --
+ * kornia 0.1.4 HomographyWarper.warp_grid: H [N][9] -> grid [N][h][w][2] */
+int rf_warp_grid(const float* H, int N, int h, int w, float* grid_out, void* stream);
+/* F.grid_sample(bilinear, zeros).  Generic element strides so NCHW and NHWC both work.
+ * in: (N,C,Hin,Win) with strides in_s[4] (N,C,H,W); grid [N][Hout][Wout][2]; out strides out_s[4]. */
+int rf_grid_sample(const float* in, int N, int C, int Hin, int Win, const long long* in_s_host,
+                   const float* grid, int Hout, int Wout, int align_corners,
+                   float* out, const long long* out_s_host, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False): NCHW [NC][h][w] -> [NC][H][W] */
+int rf_upsample_bilinear(const float* in, int NC, int h, int w, int H, int W, float* out, void* stream);
+/* PredFlowMask tail, evaluation/evalHpatch/evaluation.py:37-51 fused:
+ * flowUp = clamp(interp(flowDown8) + grid); flow12 = grid_sample(coarse, flowUp);
+ * match = interp(match12) [* grid_sample(interp(match21), flowUp)] * inside(flow12).
+ * flowDown8 NCHW [2][h8][w8]; match12/match21 [h8][w8] (match21 nullable);
+ * coarse [H][W][2]; outputs flow12 [H][W][2], match [H][W] (nullable), flowUp [H][W][2] (nullable). */
+int rf_compose_fine(const float* flowDown8, const float* match12, const float* match21, int h8, int w8,
+                    const float* coarse, int H, int W, int clamp, int align_corners,
+                    float* flow12_out, float* match_out, float* flowUp_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,503 @@
+// HBM-bound kernels of the hot path: pooling, anti-aliased downsampling, L2
+// normalisation, local correlation, flow/matchability heads' epilogues, image
+// pre-processing, homography grids, bilinear sampling and the fused
+// fine-flow composition.  All NHWC fp32, coalesced along channels, vectorised
+// (float4) where the channel count allows.
+#include "common.cuh"
+
+namespace rf {
+
+// ---------------------------------------------------------------------------
+// nn.MaxPool2d(k, stride, pad) on a ragged NHWC batch (model/model.py:71: k=2,s=1;
+// torchvision resnet: k=3,s=2,p=1).  One thread per (output pixel, channel quad).
+// ---------------------------------------------------------------------------
+__global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y,
+                               int C, int k, int stride, int pad) {
+    const int c4n = C >> 2;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * c4n;
+    if (t >= total) return;
+    long long pm = t / c4n;
+    int c4 = (int)(t - pm * c4n);
+    int im = find_img(set, pm);
+    int local = (int)(pm - set.out_pix[im]);
+    int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+    const int H = set.H[im], W = set.W[im];
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < k; ++r) {
+        int iy = oy * stride - pad + r;
+        if (iy < 0 || iy >= H) continue;
+        for (int s = 0; s < k; ++s) {
+            int ix = ox * stride - pad + s;
+            if (ix < 0 || ix >= W) continue;
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + (set.in_pix[im] + (long long)iy * W + ix) * C) + c4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    reinterpret_cast<float4*>(y + pm * C)[c4] = m;
+}
+
+// ---------------------------------------------------------------------------
+// model/downsample.py:12-46: ReflectionPad2d(1) + depthwise [1 2 1]x[1 2 1]/16, stride s
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int stride) {
+    const int c4n = C >> 2;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * c4n;
+    if (t >= total) return;
+    long long pm = t / c4n;
+    int c4 = (int)(t - pm * c4n);
+    int im = find_img(set, pm);
+    int local = (int)(pm - set.out_pix[im]);
+    int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+    const int H = set.H[im], W = set.W[im];
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        int iy = reflect1(oy * stride - 1 + r, H);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            int ix = reflect1(ox * stride - 1 + s, W);
+            float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + (set.in_pix[im] + (long long)iy * W + ix) * C) + c4);
+            acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y); acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+        }
+    }
+    reinterpret_cast<float4*>(y + pm * C)[c4] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// F.normalize(dim=1): one warp per pixel (coarseAlignFeatMatch.py:106,124; evaluation.py:26,184)
+// ---------------------------------------------------------------------------
+__global__ void l2norm_kernel(const float* __restrict__ x, long long P, int C, const unsigned char* __restrict__ mask, float* __restrict__ y) {
+    long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (pix >= P) return;
+    const float4* src = reinterpret_cast<const float4*>(x + pix * C);
+    float4* dst = reinterpret_cast<float4*>(y + pix * C);
+    const int c4n = C >> 2;
+    if (mask != nullptr && mask[pix] == 0) {
+        for (int c = lane; c < c4n; c += 32) dst[c] = make_float4(0, 0, 0, 0);
+        return;
+    }
+    float ss = 0.f;
+    for (int c = lane; c < c4n; c += 32) {
+        float4 v = __ldg(src + c);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < c4n; c += 32) {
+        float4 v = __ldg(src + c);
+        dst[c] = make_float4(__fdiv_rn(v.x, denom), __fdiv_rn(v.y, denom), __fdiv_rn(v.z, denom), __fdiv_rn(v.w, denom));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// model/model.py:129-160 CorrNeigh: out[n,r,c,i*k+j] = sum_ch x[n,r,c,ch] * y[n,r+i-k/2,c+j-k/2,ch]
+// one warp per output pixel, lanes over channels, k*k shuffled reductions
+// ---------------------------------------------------------------------------
+__global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k,
+                                  float* __restrict__ out) {
+    long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    long long P = (long long)N * h * w;
+    if (pix >= P) return;
+    int n = (int)(pix / ((long long)h * w));
+    int rem = (int)(pix - (long long)n * h * w);
+    int r = rem / w, c = rem - r * w;
+    const int pad = k / 2, c4n = C >> 2;
+    const float4* xs = reinterpret_cast<const float4*>(x + pix * C);
+    // C <= 1024: up to 8 float4 per lane kept in registers
+    float4 xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xv[q] = (lane + 32 * q < c4n) ? __ldg(xs + lane + 32 * q) : make_float4(0, 0, 0, 0);
+    for (int i = 0; i < k; ++i) {
+        int yr = r + i - pad;
+        for (int j = 0; j < k; ++j) {
+            int yc = c + j - pad;
+            float acc = 0.f;
+            if (yr >= 0 && yr < h && yc >= 0 && yc < w) {
+                const float4* ys = reinterpret_cast<const float4*>(y + (((long long)n * h + yr) * w + yc) * C);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (lane + 32 * q < c4n) {
+                        float4 v = __ldg(ys + lane + 32 * q);
+                        acc = fmaf(xv[q].x, v.x, acc); acc = fmaf(xv[q].y, v.y, acc);
+                        acc = fmaf(xv[q].z, v.z, acc); acc = fmaf(xv[q].w, v.w, acc);
+                    }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) out[pix * (k * k) + i * k + j] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// model/model.py:226-233: softmax over k*k channels + expected offset.  logits NHWC [P][k*k]
+// ---------------------------------------------------------------------------
+__global__ void softmax_flow_kernel(const float* __restrict__ logits, int N, int h, int w, int k, float* __restrict__ flow) {
+    long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long hw = (long long)h * w;
+    if (pix >= N * hw) return;
+    const int kk = k * k, pad = k / 2;
+    const float* l = logits + pix * kk;
+    float m = -INFINITY;
+    for (int q = 0; q < kk; ++q) m = fmaxf(m, __ldg(l + q));
+    float sum = 0.f, sx = 0.f, sy = 0.f;
+    for (int q = 0; q < kk; ++q) {
+        float e = expf(__ldg(l + q) - m);
+        sum += e;
+        sx = fmaf(e, (float)(q % k - pad), sx);
+        sy = fmaf(e, (float)(q / k - pad), sy);
+    }
+    int n = (int)(pix / hw);
+    long long rem = pix - n * hw;
+    // flowX = sum p*gridX / size(3) * 2 ; flowY = sum p*gridY / size(2) * 2
+    flow[(n * 2 + 0) * hw + rem] = (sx / sum) / (float)w * 2.f;
+    flow[(n * 2 + 1) * hw + rem] = (sy / sum) / (float)h * 2.f;
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 1.f / (1.f + expf(-x[i]));
+}
+
+// ---------------------------------------------------------------------------
+// torchvision ToTensor (+ Normalize): exact op order div(255), sub(mean), div(std)
+// ---------------------------------------------------------------------------
+__global__ void preproc_kernel(const unsigned char* __restrict__ img, long long n, int normalize, float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = (int)(i % 3);
+    float v = __fdiv_rn((float)img[i], 255.f);
+    if (normalize) {
+        const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float sd = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        v = __fdiv_rn(__fsub_rn(v, mean), sd);
+    }
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// PIL ImagingResample (8 bits per channel, fixed point, one pass)
+// ---------------------------------------------------------------------------
+#define RF_PRECISION_BITS 22
+__global__ void resample_u8_kernel(const unsigned char* __restrict__ in, int in_h, int in_w, int ch, int horizontal,
+                                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int out_size,
+                                   unsigned char* __restrict__ out) {
+    const int out_h = horizontal ? in_h : out_size, out_w = horizontal ? out_size : in_w;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)out_h * out_w * ch;
+    if (t >= total) return;
+    int c = (int)(t % ch);
+    long long pq = t / ch;
+    int ox = (int)(pq % out_w), oy = (int)(pq / out_w);
+    int o = horizontal ? ox : oy;
+    int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const int* k = kk + (long long)o * ksize;
+    int ss = 1 << (RF_PRECISION_BITS - 1);
+    if (horizontal) {
+        const unsigned char* row = in + ((long long)oy * in_w) * ch + c;
+        for (int x = 0; x < cnt; ++x) ss += (int)row[(long long)(x + lo) * ch] * k[x];
+    } else {
+        const unsigned char* col = in + (long long)ox * ch + c;
+        for (int y = 0; y < cnt; ++y) ss += (int)col[(long long)(y + lo) * in_w * ch] * k[y];
+    }
+    int v = ss >> RF_PRECISION_BITS;
+    out[t] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// ---------------------------------------------------------------------------
+// homography grid, bilinear sampling, bilinear upsampling, fused composition
+// ---------------------------------------------------------------------------
+// torch.linspace(-1, 1, n)[i] as the CUDA kernel computes it
+__device__ __forceinline__ float lin11(int i, int n) {
+    if (n == 1) return -1.f;
+    float step = 2.f / (float)(n - 1);
+    return (i < n / 2) ? (-1.f + step * (float)i) : (1.f - step * (float)(n - 1 - i));
+}
+
+__global__ void warp_grid_kernel(const float* __restrict__ Hm, int N, int h, int w, float* __restrict__ grid) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long hw = (long long)h * w;
+    if (t >= N * hw) return;
+    int n = (int)(t / hw);
+    int rem = (int)(t - n * hw);
+    int r = rem / w, c = rem - r * w;
+    const float* H = Hm + n * 9;
+    float x = lin11(c, w), y = lin11(r, h);
+    float px = __fadd_rn(__fadd_rn(__fmul_rn(H[0], x), __fmul_rn(H[1], y)), H[2]);
+    float py = __fadd_rn(__fadd_rn(__fmul_rn(H[3], x), __fmul_rn(H[4], y)), H[5]);
+    float pz = __fadd_rn(__fadd_rn(__fmul_rn(H[6], x), __fmul_rn(H[7], y)), H[8]);
+    reinterpret_cast<float2*>(grid)[t] = make_float2(__fdiv_rn(px, pz), __fdiv_rn(py, pz));
+}
+
+__device__ __forceinline__ float unnormalize(float coord, int size, int align_corners) {
+    return align_corners ? ((coord + 1.f) / 2.f) * (float)(size - 1) : ((coord + 1.f) * (float)size - 1.f) / 2.f;
+}
+
+struct Strides4 { long long n, c, h, w; };
+
+__global__ void grid_sample_kernel(const float* __restrict__ in, int N, int C, int Hin, int Win, Strides4 is,
+                                   const float* __restrict__ grid, int Hout, int Wout, int align_corners,
+                                   float* __restrict__ out, Strides4 os) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long hw = (long long)Hout * Wout;
+    if (t >= N * hw) return;
+    int n = (int)(t / hw);
+    int rem = (int)(t - n * hw);
+    int r = rem / Wout, c = rem - r * Wout;
+    float2 g = __ldg(reinterpret_cast<const float2*>(grid) + t);
+    float ix = unnormalize(g.x, Win, align_corners), iy = unnormalize(g.y, Hin, align_corners);
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    float nw = (fx + 1.f - ix) * (fy + 1.f - iy), ne = (ix - fx) * (fy + 1.f - iy);
+    float sw = (fx + 1.f - ix) * (iy - fy), se = (ix - fx) * (iy - fy);
+    bool vx0 = x0 >= 0 && x0 < Win, vx1 = x1 >= 0 && x1 < Win, vy0 = y0 >= 0 && y0 < Hin, vy1 = y1 >= 0 && y1 < Hin;
+    const float* base = in + n * is.n;
+    float* ob = out + n * os.n + r * os.h + c * os.w;
+    for (int ch = 0; ch < C; ++ch) {
+        const float* p = base + ch * is.c;
+        float acc = 0.f;
+        if (vy0 && vx0) acc += __ldg(p + y0 * is.h + x0 * is.w) * nw;
+        if (vy0 && vx1) acc += __ldg(p + y0 * is.h + x1 * is.w) * ne;
+        if (vy1 && vx0) acc += __ldg(p + y1 * is.h + x0 * is.w) * sw;
+        if (vy1 && vx1) acc += __ldg(p + y1 * is.h + x1 * is.w) * se;
+        ob[ch * os.c] = acc;
+    }
+}
+
+// F.interpolate(bilinear, align_corners=False) source index / weights
+__device__ __forceinline__ void up_coord(int dst, int in_size, int out_size, int& i0, int& i1, float& l0, float& l1) {
+    float scale = (float)in_size / (float)out_size;
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+__device__ __forceinline__ float up_sample(const float* __restrict__ p, int h, int w, int H, int W, int Y, int X) {
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    up_coord(Y, h, H, y0, y1, ly0, ly1);
+    up_coord(X, w, W, x0, x1, lx0, lx1);
+    return ly0 * (lx0 * __ldg(p + y0 * w + x0) + lx1 * __ldg(p + y0 * w + x1)) +
+           ly1 * (lx0 * __ldg(p + y1 * w + x0) + lx1 * __ldg(p + y1 * w + x1));
+}
+
+__global__ void upsample_kernel(const float* __restrict__ in, int NC, int h, int w, int H, int W, float* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long HW = (long long)H * W;
+    if (t >= NC * HW) return;
+    int nc = (int)(t / HW);
+    int rem = (int)(t - nc * HW);
+    int Y = rem / W, X = rem - Y * W;
+    out[t] = up_sample(in + (long long)nc * h * w, h, w, H, W, Y, X);
+}
+
+// evaluation/evalHpatch/evaluation.py:37-51 (and evalCorr :50-55) in one pass over the full-res grid
+__global__ void compose_fine_kernel(const float* __restrict__ flow8, const float* __restrict__ m12, const float* __restrict__ m21,
+                                    int h8, int w8, const float* __restrict__ coarse, int H, int W, int clamp, int align_corners,
+                                    float* __restrict__ flow12, float* __restrict__ match, float* __restrict__ flowUp_out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)H * W) return;
+    int Y = (int)(t / W), X = (int)(t - (long long)Y * W);
+    float fx = up_sample(flow8, h8, w8, H, W, Y, X) + lin11(X, W);
+    float fy = up_sample(flow8 + h8 * w8, h8, w8, H, W, Y, X) + lin11(Y, H);
+    if (clamp) {
+        fx = fminf(fmaxf(fx, -1.f), 1.f);
+        fy = fminf(fmaxf(fy, -1.f), 1.f);
+    }
+    if (flowUp_out) reinterpret_cast<float2*>(flowUp_out)[t] = make_float2(fx, fy);
+    float ix = unnormalize(fx, W, align_corners), iy = unnormalize(fy, H, align_corners);
+    float flx = floorf(ix), fly = floorf(iy);
+    int x0 = (int)flx, y0 = (int)fly, x1 = x0 + 1, y1 = y0 + 1;
+    float nw = (flx + 1.f - ix) * (fly + 1.f - iy), ne = (ix - flx) * (fly + 1.f - iy);
+    float sw = (flx + 1.f - ix) * (iy - fly), se = (ix - flx) * (iy - fly);
+    bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+    const float2* cg = reinterpret_cast<const float2*>(coarse);
+    float ox = 0.f, oy = 0.f, mm = 0.f;
+    if (vy0 && vx0) { float2 v = __ldg(cg + (long long)y0 * W + x0); ox += v.x * nw; oy += v.y * nw; if (m21) mm += up_sample(m21, h8, w8, H, W, y0, x0) * nw; }
+    if (vy0 && vx1) { float2 v = __ldg(cg + (long long)y0 * W + x1); ox += v.x * ne; oy += v.y * ne; if (m21) mm += up_sample(m21, h8, w8, H, W, y0, x1) * ne; }
+    if (vy1 && vx0) { float2 v = __ldg(cg + (long long)y1 * W + x0); ox += v.x * sw; oy += v.y * sw; if (m21) mm += up_sample(m21, h8, w8, H, W, y1, x0) * sw; }
+    if (vy1 && vx1) { float2 v = __ldg(cg + (long long)y1 * W + x1); ox += v.x * se; oy += v.y * se; if (m21) mm += up_sample(m21, h8, w8, H, W, y1, x1) * se; }
+    reinterpret_cast<float2*>(flow12)[t] = make_float2(ox, oy);
+    if (match) {
+        float m = up_sample(m12, h8, w8, H, W, Y, X);
+        if (m21) m *= mm;
+        float inside = ((ox >= -1.f && ox <= 1.f) ? 1.f : 0.f) * ((oy >= -1.f && oy <= 1.f) ? 1.f : 0.f);
+        match[t] = m * inside;
+    }
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+extern "C" int rf_maxpool2d_nhwc(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, float* y, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && k >= 1 && stride >= 1, "rf_maxpool2d_nhwc: C must be a multiple of 4");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_maxpool2d_nhwc: bad image set");
+    long long total = set.out_pix[nimg] * (C / 4);
+    maxpool_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C, int stride, float* y, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && stride >= 1, "rf_blur_downsample_nhwc: C must be a multiple of 4");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 3, stride, 1) == 0, "rf_blur_downsample_nhwc: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur_downsample_nhwc: reflect padding needs H, W >= 2");
+    long long total = set.out_pix[nimg] * (C / 4);
+    blur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && P >= 0, "rf_l2norm_nhwc: C must be a multiple of 4");
+    if (P == 0) return 0;
+    l2norm_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, P, C, mask, y);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, float* out, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k");
+    long long P = (long long)N * h * w;
+    if (P == 0) return 0;
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream) {
+    long long P = (long long)N * h * w;
+    if (P == 0) return 0;
+    softmax_flow_kernel<<<blocks_for(P, 128), 128, 0, as_stream(stream)>>>(logits, N, h, w, k, flow_nchw);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_sigmoid(const float* x, long long n, float* y, void* stream) {
+    if (n <= 0) return 0;
+    sigmoid_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, y);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_preproc_u8(const uint8_t* img, long long npix, int normalize, float* out_nhwc, void* stream) {
+    if (npix <= 0) return 0;
+    preproc_kernel<<<blocks_for(npix * 3, 256), 256, 0, as_stream(stream)>>>(img, npix * 3, normalize, out_nhwc);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_resample_u8(const uint8_t* in, int in_h, int in_w, int channels, int horizontal,
+                              const int* bounds, const int* kk, int ksize, int out_size, uint8_t* out, void* stream) {
+    long long total = (long long)(horizontal ? in_h : out_size) * (horizontal ? out_size : in_w) * channels;
+    if (total <= 0) return 0;
+    resample_u8_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(in, in_h, in_w, channels, horizontal, bounds, kk, ksize, out_size, out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// Pillow src/libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc for the
+// LANCZOS filter (support 3), box = whole image.  Host-side, exact double arithmetic.
+static double rf_sinc(double x) {
+    if (x == 0.0) return 1.0;
+    x = x * 3.14159265358979323846;
+    return sin(x) / x;
+}
+static double rf_lanczos(double x) {
+    if (-3.0 <= x && x < 3.0) return rf_sinc(x) * rf_sinc(x / 3);
+    return 0.0;
+}
+extern "C" int rf_lanczos_coeffs_host(int in_size, int out_size, int* bounds_host, int* kk_host, int kk_capacity, int* ksize_out) {
+    RF_REQUIRE(in_size > 0 && out_size > 0, "rf_lanczos_coeffs_host: bad sizes");
+    double scale, filterscale;
+    filterscale = scale = (double)in_size / out_size;
+    if (filterscale < 1.0) filterscale = 1.0;
+    double support = 3.0 * filterscale;
+    int ksize = (int)ceil(support) * 2 + 1;
+    *ksize_out = ksize;
+    if (kk_host == nullptr) return 0;                      // size query
+    RF_REQUIRE((long long)ksize * out_size <= kk_capacity, "rf_lanczos_coeffs_host: kk buffer too small");
+    double* k = new double[ksize];
+    for (int xx = 0; xx < out_size; xx++) {
+        double center = 0 + (xx + 0.5) * scale;
+        double ww = 0.0;
+        double ss = 1.0 / filterscale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        int x;
+        for (x = 0; x < xmax; x++) {
+            double w = rf_lanczos((x + xmin - center + 0.5) * ss);
+            k[x] = w;
+            ww += w;
+        }
+        for (x = 0; x < xmax; x++)
+            if (ww != 0.0) k[x] /= ww;
+        for (; x < ksize; x++) k[x] = 0;
+        bounds_host[xx * 2 + 0] = xmin;
+        bounds_host[xx * 2 + 1] = xmax;
+        for (x = 0; x < ksize; x++) {
+            if (k[x] < 0) kk_host[xx * ksize + x] = (int)(-0.5 + k[x] * (1 << RF_PRECISION_BITS));
+            else kk_host[xx * ksize + x] = (int)(0.5 + k[x] * (1 << RF_PRECISION_BITS));
+        }
+    }
+    delete[] k;
+    return 0;
+}
+
+extern "C" int rf_warp_grid(const float* H, int N, int h, int w, float* grid_out, void* stream) {
+    long long total = (long long)N * h * w;
+    if (total <= 0) return 0;
+    warp_grid_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(H, N, h, w, grid_out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_grid_sample(const float* in, int N, int C, int Hin, int Win, const long long* in_s_host,
+                              const float* grid, int Hout, int Wout, int align_corners,
+                              float* out, const long long* out_s_host, void* stream) {
+    long long total = (long long)N * Hout * Wout;
+    if (total <= 0) return 0;
+    Strides4 is{in_s_host[0], in_s_host[1], in_s_host[2], in_s_host[3]};
+    Strides4 os{out_s_host[0], out_s_host[1], out_s_host[2], out_s_host[3]};
+    grid_sample_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(in, N, C, Hin, Win, is, grid, Hout, Wout, align_corners, out, os);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_upsample_bilinear(const float* in, int NC, int h, int w, int H, int W, float* out, void* stream) {
+    long long total = (long long)NC * H * W;
+    if (total <= 0) return 0;
+    upsample_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(in, NC, h, w, H, W, out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_compose_fine(const float* flowDown8, const float* match12, const float* match21, int h8, int w8,
+                               const float* coarse, int H, int W, int clamp, int align_corners,
+                               float* flow12_out, float* match_out, float* flowUp_out, void* stream) {
+    long long total = (long long)H * W;
+    if (total <= 0) return 0;
+    RF_REQUIRE(match_out == nullptr || match12 != nullptr, "rf_compose_fine: match_out needs match12");
+    compose_fine_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(flowDown8, match12, match21, h8, w8, coarse, H, W, clamp,
+                                                                              align_corners, flow12_out, match_out, flowUp_out);
+    RF_LAUNCHED();
+    return 0;
+}

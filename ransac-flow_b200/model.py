@@ -1,0 +1,283 @@
+"""Drop-in for the reference's ``model`` module (model/model.py): same class names,
+constructor arguments, ``state_dict`` keys and call signatures; ``forward`` runs the
+library's CUDA kernels (inference only - the training path is out of scope).
+
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` children are parameter containers only, so
+``load_state_dict(torch.load(resumePth)[key])`` works unchanged
+(quick_start/align2images.py:47-50).  BatchNorm (eval, eps 1e-5) is folded into the
+preceding bias-free convolution when the weights are first used.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import Ragged
+
+_engine = ops.ENGINE_FP32
+
+
+def set_engine(engine):
+    """'fp32' (exact FMA, SIMT) or 'tf32' (tcgen05 tensor cores)."""
+    global _engine
+    _engine = {"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32}[engine] if isinstance(engine, str) else int(engine)
+
+
+def get_engine():
+    return _engine
+
+
+def conv3x3(in_planes, out_planes, stride=1):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=3, stride=stride, padding=1, bias=False)
+
+
+def conv1x1(in_planes, out_planes, stride=1):
+    return nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=stride, bias=False)
+
+
+def _init_like_reference(module):
+    # model/model.py:75-84
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.constant_(m.weight, 1)
+            nn.init.constant_(m.bias, 0)
+
+
+class FoldedConv:
+    """conv weight (+ following eval-mode BatchNorm) packed for the kernels."""
+
+    def __init__(self, weight, bn=None, stride=1, pad=None, eps=None):
+        w = weight.detach().float()
+        cout, cin, k, _ = w.shape
+        if bn is not None:
+            e = bn.eps if eps is None else eps
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + e)
+            self.bias = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+            w = w * scale.view(-1, 1, 1, 1)
+        else:
+            self.bias = None
+        self.w = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous()      # [R*S*Cin][Cout]
+        self.w_tc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()   # [Cout][R*S*Cin]
+        self.cout, self.cin, self.k, self.stride = cout, cin, k, stride
+        self.pad = (k // 2) if pad is None else pad
+
+    def __call__(self, x, relu, residual=None, engine=None):
+        eng = _engine if engine is None else engine
+        if eng == ops.ENGINE_TF32 and (self.cin % 8 != 0):
+            eng = ops.ENGINE_FP32                      # 3-channel stems / 49-channel heads stay on the FMA engine
+        return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_tc)
+
+
+class _Engine(nn.Module):
+    """Caches folded weights; rebuilt whenever parameters change or move."""
+
+    def _folded(self):
+        ver = tuple((p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_fold_ver", None) != ver:
+            with torch.no_grad():
+                self._fold = self._fold_build()
+            self._fold_ver = ver
+        return self._fold
+
+    def _check(self, *xs):
+        if self.training:
+            raise RuntimeError("ransac_flow_b200.model is inference-only: call .eval() first (training is out of scope)")
+        for x in xs:
+            ops.need_cuda(x)
+
+
+class Downsample(nn.Module):
+    """model/downsample.py:12-46 as a parameter container (buffer ``filt``)."""
+
+    def __init__(self, pad_type="reflect", filt_size=3, stride=2, channels=None, pad_off=0):
+        super().__init__()
+        assert filt_size == 3 and pad_type in ("refl", "reflect") and pad_off == 0, "only the configuration the hot path uses"
+        self.stride, self.channels = stride, channels
+        a = torch.tensor([1.0, 2.0, 1.0])
+        filt = a[:, None] * a[None, :]
+        self.register_buffer("filt", (filt / filt.sum())[None, None].repeat(channels, 1, 1, 1))
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = nn.BatchNorm2d(planes, eps=1e-05)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = nn.BatchNorm2d(planes, eps=1e-05)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class FeatureExtractor(_Engine):
+    """model/model.py:59-125.  (N,3,H,W) -> (N,256,H/8,W/8)."""
+
+    def __init__(self):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(64, eps=1e-05)
+        self.maxpool = nn.Sequential(nn.MaxPool2d(kernel_size=2, stride=1), Downsample(filt_size=3, stride=2, channels=64))
+        self.layer1 = self._make_layer(BasicBlock, 64, 2)
+        self.layer2 = self._make_layer(BasicBlock, 128, 2, stride=2)
+        self.layer3 = self._make_layer(BasicBlock, 256, 2, stride=2)
+        _init_like_reference(self)
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = [Downsample(filt_size=3, stride=stride, channels=self.inplanes)] if stride != 1 else []
+            downsample += [conv1x1(self.inplanes, planes * block.expansion, 1), nn.BatchNorm2d(planes * block.expansion)]
+            downsample = nn.Sequential(*downsample)
+        layers = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, 1, None))
+        return nn.Sequential(*layers)
+
+    def _fold_build(self):
+        f = {"stem": FoldedConv(self.conv1.weight, self.bn1, 1), "blocks": []}
+        for layer in (self.layer1, self.layer2, self.layer3):
+            for b in layer:
+                e = {"c1": FoldedConv(b.conv1.weight, b.bn1, b.stride), "c2": FoldedConv(b.conv2.weight, b.bn2, 1), "down": None}
+                if b.downsample is not None:
+                    mods = list(b.downsample)
+                    e["down"] = (mods[0].stride if isinstance(mods[0], Downsample) else None,
+                                 FoldedConv(mods[-2].weight, mods[-1], 1, pad=0))
+                f["blocks"].append(e)
+        return f
+
+    def forward_ragged(self, x):
+        f = self._folded()
+        x = f["stem"](x, relu=True)                       # conv1 + bn1 + relu
+        x = ops.maxpool2d(x, 2, 1, 0)                     # MaxPool2d(2, stride 1)
+        x = ops.blur_downsample(x, 2)                     # anti-aliased stride 2
+        for e in f["blocks"]:
+            out = e["c1"](x, relu=True)
+            if e["down"] is not None:
+                bs, conv = e["down"]
+                r = ops.blur_downsample(x, bs) if bs is not None else x
+                r = conv(r, relu=False)
+            else:
+                r = x
+            x = e["c2"](out, relu=True, residual=r)       # conv2 + bn2 + residual + relu
+        return x
+
+    def forward(self, x):
+        self._check(x)
+        with torch.no_grad():
+            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw()
+
+
+class CorrNeigh(nn.Module):
+    """model/model.py:129-160."""
+
+    def __init__(self, kernelSize):
+        super().__init__()
+        assert kernelSize % 2 == 1
+        self.kernelSize = kernelSize
+        self.paddingSize = kernelSize // 2
+
+    def forward(self, x, y):
+        ops.need_cuda(x, y)
+        with torch.no_grad():
+            return ops.corr_neigh(Ragged.from_nchw(x), Ragged.from_nchw(y), self.kernelSize).to_nchw()
+
+
+class _Head(_Engine):
+    def __init__(self, kernelSize, cout):
+        super().__init__()
+        assert kernelSize % 2 == 1
+        self.conv1 = conv3x3(kernelSize * kernelSize, 512)
+        self.bn1 = nn.BatchNorm2d(512, eps=1e-05)
+        self.conv2 = conv3x3(512, 256)
+        self.bn2 = nn.BatchNorm2d(256, eps=1e-05)
+        self.conv3 = conv3x3(256, 128)
+        self.bn3 = nn.BatchNorm2d(128, eps=1e-05)
+        self.conv4 = conv3x3(128, cout)
+        self.kernelSize = kernelSize
+        self.paddingSize = kernelSize // 2
+        _init_like_reference(self)
+
+    def _fold_build(self):
+        return [FoldedConv(self.conv1.weight, self.bn1), FoldedConv(self.conv2.weight, self.bn2),
+                FoldedConv(self.conv3.weight, self.bn3), FoldedConv(self.conv4.weight, None)]
+
+    def trunk(self, corr):
+        f = self._folded()
+        x = f[0](corr, relu=True)
+        x = f[1](x, relu=True)
+        x = f[2](x, relu=True)
+        return f[3](x, relu=False)
+
+
+class NetFlowCoarse(_Head):
+    """model/model.py:167-249."""
+
+    def __init__(self, kernelSize):
+        super().__init__(kernelSize, kernelSize * kernelSize)
+        r = self.paddingSize
+        self.gridY = torch.arange(-r, r + 1).view(1, 1, -1, 1).expand(1, 1, kernelSize, kernelSize).contiguous().view(1, -1, 1, 1).float()
+        self.gridX = torch.arange(-r, r + 1).view(1, 1, 1, -1).expand(1, 1, kernelSize, kernelSize).contiguous().view(1, -1, 1, 1).float()
+
+    def cuda(self, device=None):
+        super().cuda(device)
+        self.gridX, self.gridY = self.gridX.cuda(), self.gridY.cuda()
+        return self     # the reference returns None here (model/model.py:205-207); callers ignore the value
+
+    def forward_ragged(self, corr):
+        return ops.softmax_flow(self.trunk(corr), self.kernelSize)
+
+    def forward(self, coef, up8X=True):
+        self._check(coef)
+        with torch.no_grad():
+            flow = self.forward_ragged(Ragged.from_nchw(coef))
+            if up8X:                                   # F.upsample_bilinear == align_corners=True; not used at inference
+                flow = torch.nn.functional.interpolate(flow, scale_factor=8, mode="bilinear", align_corners=True)
+            return flow
+
+
+class NetMatchability(_Head):
+    """model/model.py:254-322."""
+
+    def __init__(self, kernelSize):
+        super().__init__(kernelSize, 1)
+        nn.init.normal_(self.conv4.weight, mean=0.0, std=0.0001)
+
+    def forward_ragged(self, corr):
+        x = self.trunk(corr)                                # [P, 1]
+        h, w = corr.hw[0]
+        return ops.sigmoid(x.data).view(corr.n, 1, h, w)
+
+    def forward(self, feat, up8X=True):
+        self._check(feat)
+        with torch.no_grad():
+            m = self.forward_ragged(Ragged.from_nchw(feat))
+            if up8X:
+                m = torch.nn.functional.interpolate(m, scale_factor=8, mode="bilinear", align_corners=True)
+            return m
+
+
+def predFlowCoarse(corrKernel21, NetFlowCoarse, grid, up8X=True):
+    """model/model.py:331-340."""
+    flowCoarse = NetFlowCoarse(corrKernel21, up8X)
+    b, _, w, h = flowCoarse.size()
+    flowGrad = flowCoarse.narrow(2, 1, w - 1).narrow(3, 1, h - 1) - flowCoarse.narrow(2, 0, w - 1).narrow(3, 0, h - 1)
+    flowGrad = torch.norm(flowGrad, dim=1, keepdim=True)
+    flowCoarse = flowCoarse.permute(0, 2, 3, 1)
+    flowCoarse = torch.clamp(flowCoarse + grid, min=-1, max=1)
+    return flowGrad, flowCoarse
+
+
+def predFlowCoarseNoGrad(corrKernel21, NetFlowCoarse, grid, up8X=True):
+    """model/model.py:342-350."""
+    flowCoarse = NetFlowCoarse(corrKernel21, up8X).permute(0, 2, 3, 1)
+    return torch.clamp(flowCoarse + grid, min=-1, max=1)
+
+
+def predMatchability(corrKernel21, NetMatchability, up8X=True):
+    """model/model.py:353-357."""
+    return NetMatchability(corrKernel21, up8X)

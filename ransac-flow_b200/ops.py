@@ -1,0 +1,279 @@
+"""Functional wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is plumbing here (device memory, streams); every operation below is one
+or two launches of the library's own kernels.  Activations are NHWC fp32
+"ragged batches" (`Ragged`): several images of different sizes packed back to
+back so that one launch covers the whole 7-scale pyramid + target.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, need_cuda, ptr, stream
+
+ENGINE_FP32 = 0      # exact fp32 FMA (SIMT)
+ENGINE_TF32 = 1      # tcgen05 tensor cores, TF32 operands, fp32 accumulate
+
+
+class Ragged:
+    """`data` [sum(H*W), C] fp32 CUDA + list of (H, W)."""
+
+    def __init__(self, data, hw):
+        self.data = data
+        self.hw = [(int(h), int(w)) for h, w in hw]
+        self._c = (C.c_int * (2 * len(self.hw)))(*[v for p in self.hw for v in p])
+
+    @property
+    def C(self):
+        return self.data.shape[1]
+
+    @property
+    def n(self):
+        return len(self.hw)
+
+    def offsets(self):
+        o = [0]
+        for h, w in self.hw:
+            o.append(o[-1] + h * w)
+        return o
+
+    def image(self, i):
+        """(1, C, H, W) view (channels_last memory) of image i - no copy."""
+        o = self.offsets()
+        h, w = self.hw[i]
+        return self.data[o[i]:o[i + 1]].view(1, h, w, self.C).permute(0, 3, 1, 2)
+
+    def to_nchw(self):
+        """(N, C, H, W) view when all images share one size."""
+        h, w = self.hw[0]
+        assert all(p == (h, w) for p in self.hw)
+        return self.data.view(self.n, h, w, self.C).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def from_nchw(x):
+        need_cuda(x)
+        n, c, h, w = x.shape
+        d = x.float().permute(0, 2, 3, 1).contiguous().view(n * h * w, c)
+        return Ragged(d, [(h, w)] * n)
+
+
+def _out_hw(hw, k, stride, pad):
+    return [((h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1) for h, w in hw]
+
+
+def conv2d(x, w_packed, bias, Cout, k, stride, pad, relu, residual=None, engine=ENGINE_FP32, w_tc=None):
+    """conv + folded-BN bias (+ residual) (+ ReLU) on a ragged NHWC batch."""
+    need_cuda(x.data, w_packed, bias, residual.data if residual is not None else None)
+    ohw = _out_hw(x.hw, k, stride, pad)
+    y = torch.empty((sum(h * w for h, w in ohw), Cout), device=x.data.device, dtype=torch.float32)
+    check(lib.rf_conv2d_nhwc(ptr(x.data), x.n, x._c, x.C, ptr(w_packed), ptr(w_tc), ptr(bias),
+                             ptr(residual.data) if residual is not None else None,
+                             Cout, k, k, stride, pad, int(relu), int(engine), ptr(y), stream()))
+    return Ragged(y, ohw)
+
+
+def maxpool2d(x, k, stride, pad):
+    need_cuda(x.data)
+    ohw = _out_hw(x.hw, k, stride, pad)
+    y = torch.empty((sum(h * w for h, w in ohw), x.C), device=x.data.device, dtype=torch.float32)
+    check(lib.rf_maxpool2d_nhwc(ptr(x.data), x.n, x._c, x.C, k, stride, pad, ptr(y), stream()))
+    return Ragged(y, ohw)
+
+
+def blur_downsample(x, stride):
+    need_cuda(x.data)
+    ohw = _out_hw(x.hw, 3, stride, 1)
+    y = torch.empty((sum(h * w for h, w in ohw), x.C), device=x.data.device, dtype=torch.float32)
+    check(lib.rf_blur_downsample_nhwc(ptr(x.data), x.n, x._c, x.C, stride, ptr(y), stream()))
+    return Ragged(y, ohw)
+
+
+def l2norm(x2d, mask=None):
+    """x2d [P, C] -> x / max(||x||, 1e-12) per row; rows with mask == 0 become zeros."""
+    need_cuda(x2d, mask)
+    y = torch.empty_like(x2d)
+    check(lib.rf_l2norm_nhwc(ptr(x2d), x2d.shape[0], x2d.shape[1], ptr(mask), ptr(y), stream()))
+    return y
+
+
+def corr_neigh(x, y, k):
+    """x, y: Ragged with identical (h, w) per image -> Ragged with k*k channels."""
+    need_cuda(x.data, y.data)
+    h, w = x.hw[0]
+    out = torch.empty((x.data.shape[0], k * k), device=x.data.device, dtype=torch.float32)
+    check(lib.rf_corr_neigh_nhwc(ptr(x.data), ptr(y.data), x.n, h, w, x.C, k, ptr(out), stream()))
+    return Ragged(out, x.hw)
+
+
+def softmax_flow(logits, k):
+    need_cuda(logits.data)
+    h, w = logits.hw[0]
+    out = torch.empty((logits.n, 2, h, w), device=logits.data.device, dtype=torch.float32)
+    check(lib.rf_softmax_flow(ptr(logits.data), logits.n, h, w, k, ptr(out), stream()))
+    return out
+
+
+def sigmoid(x):
+    need_cuda(x)
+    y = torch.empty_like(x)
+    check(lib.rf_sigmoid(ptr(x), x.numel(), ptr(y), stream()))
+    return y
+
+
+def preproc_u8(img_u8, normalize):
+    """uint8 [P, 3] CUDA -> fp32 [P, 3] (ToTensor [+ Normalize])."""
+    need_cuda(img_u8)
+    out = torch.empty(img_u8.shape, device=img_u8.device, dtype=torch.float32)
+    check(lib.rf_preproc_u8(ptr(img_u8), img_u8.shape[0], int(normalize), ptr(out), stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- matching / RANSAC
+def corr_mutual_nn(featA, featB, precision=0):
+    """featA [NA, C], featB [NB, C] (rows = feature vectors) -> idx1, idx2 (int64 CUDA, capacity min(NA,NB)), count (int32 CUDA)."""
+    need_cuda(featA, featB)
+    NA, Cc = featA.shape
+    NB = featB.shape[0]
+    cap = max(1, min(NA, NB))
+    dev = featA.device
+    idx1 = torch.empty(cap, device=dev, dtype=torch.int64)
+    idx2 = torch.empty(cap, device=dev, dtype=torch.int64)
+    count = torch.zeros(1, device=dev, dtype=torch.int32)
+    wsz = lib.rf_corr_mutual_nn_workspace(NA, NB)
+    ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    check(lib.rf_corr_mutual_nn(ptr(featA), NA, ptr(featB), NB, Cc, ptr(idx1), ptr(idx2), ptr(count),
+                                ptr(ws), wsz, int(precision), stream()))
+    return idx1, idx2, count
+
+
+def ransac_homography(match1, match2, samples, tolerance, chunk=100, M_dev=None):
+    """Returns device tensors (H [9] f32, nbInlier [1] i64, mask [M] u8, status [1] i32)."""
+    need_cuda(match1, match2, samples, M_dev)
+    M = match1.shape[0]
+    nbIter = samples.shape[0]
+    dev = match1.device
+    H = torch.empty(9, device=dev, dtype=torch.float32)
+    nb = torch.empty(1, device=dev, dtype=torch.int64)
+    mask = torch.empty(max(M, 1), device=dev, dtype=torch.uint8)
+    status = torch.empty(1, device=dev, dtype=torch.int32)
+    wsz = lib.rf_ransac_workspace(nbIter)
+    ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    check(lib.rf_ransac_homography(ptr(match1), ptr(match2), M, ptr(M_dev), ptr(samples), nbIter, float(tolerance), int(chunk),
+                                   ptr(H), ptr(nb), ptr(mask), ptr(status), ptr(ws), wsz, stream()))
+    return H, nb, mask[:M], status
+
+
+def homography_dlt(X, Y):
+    need_cuda(X, Y)
+    N = X.shape[0]
+    H = torch.empty((N, 3, 3), device=X.device, dtype=torch.float32)
+    check(lib.rf_homography_dlt(ptr(X), ptr(Y), N, ptr(H), stream()))
+    return H
+
+
+def prediction(match1, match2, H):
+    need_cuda(match1, match2, H)
+    N, M = H.shape[0], match1.shape[0]
+    err = torch.empty((N, M), device=H.device, dtype=torch.float32)
+    check(lib.rf_prediction(ptr(match1), ptr(match2), M, ptr(H), N, ptr(err), stream()))
+    return err
+
+
+def build_matches(idx1, idx2, count, W1, H1, W2, H2, valid16=None):
+    need_cuda(idx1, idx2, count, W1, H1, W2, H2, valid16)
+    cap = idx1.shape[0]
+    dev = idx1.device
+    m1 = torch.empty((cap, 3), device=dev, dtype=torch.float32)
+    m2 = torch.empty((cap, 3), device=dev, dtype=torch.float32)
+    kept = torch.empty(cap, device=dev, dtype=torch.int64)
+    cnt = torch.zeros(1, device=dev, dtype=torch.int32)
+    check(lib.rf_build_matches(ptr(idx1), ptr(idx2), ptr(count), ptr(W1), ptr(H1), ptr(W2), ptr(H2), ptr(valid16),
+                               ptr(m1), ptr(m2), ptr(kept), ptr(cnt), cap, stream()))
+    return m1, m2, kept, cnt
+
+
+# --------------------------------------------------------------------------- warp
+def warp_grid(H, h, w):
+    need_cuda(H)
+    H = H.reshape(-1, 9).contiguous().float()
+    out = torch.empty((H.shape[0], h, w, 2), device=H.device, dtype=torch.float32)
+    check(lib.rf_warp_grid(ptr(H), H.shape[0], h, w, ptr(out), stream()))
+    return out
+
+
+def grid_sample(inp, grid, align_corners=False):
+    """F.grid_sample(inp, grid) bilinear / zeros.  Output has the memory format of the input."""
+    need_cuda(inp, grid)
+    inp = inp if inp.dtype == torch.float32 else inp.float()
+    grid = grid.contiguous().float()
+    N, Cc, Hin, Win = inp.shape
+    Hout, Wout = grid.shape[1], grid.shape[2]
+    if inp.stride(1) == 1 and Cc > 1:
+        out = torch.empty((N, Hout, Wout, Cc), device=inp.device, dtype=torch.float32).permute(0, 3, 1, 2)
+    else:
+        out = torch.empty((N, Cc, Hout, Wout), device=inp.device, dtype=torch.float32)
+    is_ = (C.c_longlong * 4)(*inp.stride())
+    os_ = (C.c_longlong * 4)(*out.stride())
+    check(lib.rf_grid_sample(ptr(inp), N, Cc, Hin, Win, is_, ptr(grid), Hout, Wout, int(align_corners), ptr(out), os_, stream()))
+    return out
+
+
+def upsample_bilinear(x, size):
+    need_cuda(x)
+    x = x.contiguous().float()
+    N, Cc, h, w = x.shape
+    out = torch.empty((N, Cc, size[0], size[1]), device=x.device, dtype=torch.float32)
+    check(lib.rf_upsample_bilinear(ptr(x), N * Cc, h, w, size[0], size[1], ptr(out), stream()))
+    return out
+
+
+def compose_fine(flowDown8, match12, match21, coarse, clamp=True, align_corners=False, want_match=True, want_flowUp=False):
+    """Fused tail of PredFlowMask.  flowDown8 (1,2,h8,w8); match12/match21 (1,1,h8,w8) or None; coarse (1,H,W,2)."""
+    need_cuda(flowDown8, match12, match21, coarse)
+    _, _, h8, w8 = flowDown8.shape
+    _, H, W, _ = coarse.shape
+    dev = coarse.device
+    flow12 = torch.empty((1, H, W, 2), device=dev, dtype=torch.float32)
+    match = torch.empty((1, 1, H, W), device=dev, dtype=torch.float32) if (want_match and match12 is not None) else None
+    flowUp = torch.empty((1, H, W, 2), device=dev, dtype=torch.float32) if want_flowUp else None
+    check(lib.rf_compose_fine(ptr(flowDown8.contiguous()), ptr(match12.contiguous()) if match12 is not None else None,
+                              ptr(match21.contiguous()) if match21 is not None else None, h8, w8, ptr(coarse.contiguous()),
+                              H, W, int(clamp), int(align_corners), ptr(flow12), ptr(match), ptr(flowUp), stream()))
+    return flow12, match, flowUp
+
+
+# --------------------------------------------------------------------------- PIL LANCZOS on device
+_coeff_cache = {}
+
+
+def lanczos_coeffs(in_size, out_size, device):
+    key = (in_size, out_size, str(device))
+    if key not in _coeff_cache:
+        ks = C.c_int(0)
+        check(lib.rf_lanczos_coeffs_host(in_size, out_size, None, None, 0, C.byref(ks)))
+        bounds = np.zeros(2 * out_size, dtype=np.int32)
+        kk = np.zeros(ks.value * out_size, dtype=np.int32)
+        check(lib.rf_lanczos_coeffs_host(in_size, out_size, bounds.ctypes.data_as(C.c_void_p), kk.ctypes.data_as(C.c_void_p),
+                                         kk.size, C.byref(ks)))
+        _coeff_cache[key] = (torch.from_numpy(bounds).to(device), torch.from_numpy(kk).to(device), ks.value)
+    return _coeff_cache[key]
+
+
+def resize_lanczos_u8(img, out_w, out_h):
+    """PIL ``Image.resize((out_w, out_h), LANCZOS)`` on a uint8 [H, W, 3] CUDA tensor (bit-exact)."""
+    need_cuda(img)
+    H, W, ch = img.shape
+    cur = img.contiguous()
+    if out_w != W:
+        b, k, ks = lanczos_coeffs(W, out_w, img.device)
+        nxt = torch.empty((H, out_w, ch), device=img.device, dtype=torch.uint8)
+        check(lib.rf_resample_u8(ptr(cur), H, W, ch, 1, ptr(b), ptr(k), ks, out_w, ptr(nxt), stream()))
+        cur, W = nxt, out_w
+    if out_h != H:
+        b, k, ks = lanczos_coeffs(H, out_h, img.device)
+        nxt = torch.empty((out_h, W, ch), device=img.device, dtype=torch.uint8)
+        check(lib.rf_resample_u8(ptr(cur), H, W, ch, 0, ptr(b), ptr(k), ks, out_h, ptr(nxt), stream()))
+        cur = nxt
+    return cur

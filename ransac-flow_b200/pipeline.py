@@ -1,0 +1,114 @@
+"""The per-pair path above the modules: ``PredFlowMask`` and the multi-hypothesis driver
+loop of the evaluation scripts, and ``getFlow_all`` / ``getFlow`` of the getResults scripts,
+restated on the library's kernels (no file IO, no metrics: those stay in the drivers).
+
+  PredFlowMask : evaluation/evalHpatch/evaluation.py:23-55, evaluation/evalCorr/evaluation.py:29-59
+  align_pair   : evaluation/evalHpatch/evaluation.py:172-243
+  getFlow_all  : evaluation/evalHpatch/getResults.py:16-63 (after the np.load calls)
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .kornia_geometry import HomographyWarper
+from .ops import Ragged
+
+
+def base_grid(h, w, device="cuda"):
+    """evaluation/evalHpatch/evaluation.py:187-189."""
+    gy = torch.linspace(-1, 1, steps=h, device=device).view(1, -1, 1, 1).expand(1, h, w, 1)
+    gx = torch.linspace(-1, 1, steps=w, device=device).view(1, 1, -1, 1).expand(1, h, w, 1)
+    return torch.cat((gx, gy), dim=3).contiguous()
+
+
+def fine_features(netFeatCoarse, img):
+    """F.normalize(netFeatCoarse(img)) as a Ragged (rows = pixels)."""
+    f = netFeatCoarse.forward_ragged(Ragged.from_nchw(img))
+    return Ragged(ops.l2norm(f.data), f.hw)
+
+
+def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False, align_corners=False):
+    """Same inputs/outputs as the reference function.  ``featt`` may be the (1,256,h8,w8) tensor the
+    reference passes or a Ragged from ``fine_features``.  ``grid`` is only used for its size (the
+    base grid is regenerated inside the fused composition kernel)."""
+    with torch.no_grad():
+        H, W = grid.size()[1], grid.size()[2]
+        IsSample = ops.grid_sample(IsTensor, flowCoarse, align_corners)
+        fs = fine_features(network["netFeatCoarse"], IsSample)
+        ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
+        k = network["netCorr"].kernelSize
+        corr12 = ops.corr_neigh(ft, fs, k)
+        corr21 = ops.corr_neigh(fs, ft, k)
+        flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
+        both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
+        mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch
+        match12Down8, match21Down8 = mboth[0:1], mboth[1:2]
+        flow12, match, _ = ops.compose_fine(flowDown8, match12Down8, match21Down8 if with_match21 else None, flowCoarse,
+                                            clamp=True, align_corners=align_corners)
+        out = torch.cat([match.reshape(-1), flowDown8.reshape(-1), mboth.reshape(-1)]).cpu().numpy()   # one D2H
+        n0, n1 = H * W, flowDown8.numel()
+        return (flow12, out[:n0].reshape(H, W), out[n0:n0 + n1].reshape(tuple(flowDown8.shape)),
+                out[n0 + n1:].reshape(1, 2, flowDown8.shape[2], flowDown8.shape[3]))
+
+
+def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):
+    """One pair through the evaluation loop (evaluation/evalHpatch/evaluation.py:172-243).
+    Returns dict(H (nH,3,3), flowDown8 (nH,2,h8,w8), matchDown8 (nH,2,h8,w8), flow12 [..], match [..])."""
+    coarseModel.setPair(Is, It)
+    Itw, Ith = coarseModel.It.size
+    if It_bg is None:
+        It_bg = np.ones((Ith, Itw), dtype=np.float32)
+    featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+    grid = torch.empty((1, Ith, Itw, 2), device="meta")                    # size carrier only
+    warper = HomographyWarper(Ith, Itw)
+    Mask = np.zeros((Ith, Itw), dtype=np.float32)
+    Hs, flows8, matches8, flows, matches = [], [], [], [], []
+    nbCoarse = 0
+    while nbCoarse <= maxCoarse:
+        fgMask = ((Mask + (1 - It_bg)) > 0.5).astype(np.float32)
+        bestPara = coarseModel.getCoarse(fgMask)
+        if bestPara is None:
+            break
+        bestParaT = torch.from_numpy(bestPara).unsqueeze(0).cuda()
+        flowCoarse = warper.warp_grid(bestParaT)
+        flowFine, matchFine, f8, m8 = PredFlowMask(coarseModel.IsTensor, featt, flowCoarse, grid, network, with_match21)
+        if (matchFine * (1 - fgMask)).mean() > maskRegionTh or nbCoarse == 0:
+            Hs.append(bestPara[None])
+            flows8.append(f8)
+            matches8.append(m8)
+            flows.append(flowFine)
+            matches.append(matchFine)
+            nbCoarse += 1
+            matchFine = matchFine if len(matches8) == 0 else matchFine * (1 - fgMask)
+            Mask = ((Mask + matchFine) >= 1.0).astype(np.float32)
+        else:
+            break
+    cat = lambda l: np.concatenate(l, axis=0) if l else np.zeros((0,))
+    return dict(H=cat(Hs), flowDown8=cat(flows8), matchDown8=cat(matches8), flow12=flows, match=matches)
+
+
+def getFlow_all(flow, param, match, outH, outW, th=0.95, multiH=True, with_match21=False):
+    """evaluation/evalHpatch/getResults.py:16-63 on device tensors: flow (nH,2,h8,w8), param (nH,3,3),
+    match (nH,2,h8,w8) -> flowGlobal (1,outH,outW,2).  The reference runs this on CPU tensors; the
+    composition here is the fused kernel, the first-hypothesis-wins merge is elementwise torch."""
+    flow = torch.as_tensor(flow, dtype=torch.float32).cuda()
+    param = torch.as_tensor(param, dtype=torch.float32).cuda()
+    match = torch.as_tensor(match, dtype=torch.float32).cuda()
+    coarse = ops.warp_grid(param, outH, outW)
+    fl, ms = [], []
+    for i in range(flow.shape[0]):
+        f12, m, _ = ops.compose_fine(flow[i:i + 1], match[i:i + 1, 0:1], match[i:i + 1, 1:2] if with_match21 else None,
+                                     coarse[i:i + 1], clamp=True)
+        fl.append(f12)
+        ms.append(m)
+    f = torch.clamp(torch.cat(fl, dim=0), min=-1, max=1)
+    m = torch.cat(ms, dim=0).permute(0, 2, 3, 1)
+    flowGlobal = f[:1].clone()
+    if multiH:
+        mb = m[:1] >= th
+        for i in range(1, len(m)):
+            tmp = (m.narrow(0, i, 1) >= th) * (~mb)
+            mb = mb + tmp
+            tmp = tmp.expand_as(flowGlobal)
+            flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    return flowGlobal

@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ransacflow_b200.h
+declares, the host-side mirrors keep the reference's API surface, and compute calls fail loudly
+without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import pair_oracle as PO
+from oracle import synth
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ransacflow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(rf):
+    lib = ctypes.CDLL(rf._lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 24
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert set(syms) == set(rf._lib.SIGNATURES), "ctypes table and header disagree"
+    assert rf._lib.lib.rf_version() >= 100
+
+
+def test_workspace_queries_are_host_only(rf):
+    assert rf._lib.lib.rf_ransac_workspace(1000) >= 1000 * (4 + 36)
+    assert rf._lib.lib.rf_corr_mutual_nn_workspace(13065, 1200) >= (13065 + 1200) * 8
+
+
+def test_lanczos_coefficients_match_pil(rf):
+    """rf_lanczos_coeffs_host is host arithmetic: check it through a numpy emulation of the 8bpc
+    resampler against PIL itself (bit exact)."""
+    import PIL.Image as Image
+    rs = np.random.RandomState(0)
+    img = rs.randint(0, 256, (37, 53, 3)).astype(np.uint8)
+    for (ow, oh) in [(96, 64), (20, 11), (53, 80)]:
+        cur = img
+        for axis, (insz, outsz) in ((1, (img.shape[1], ow)), (0, (img.shape[0], oh))):
+            if insz == outsz:
+                continue
+            ks = ctypes.c_int(0)
+            assert rf._lib.lib.rf_lanczos_coeffs_host(insz, outsz, None, None, 0, ctypes.byref(ks)) == 0
+            b = np.zeros(2 * outsz, np.int32)
+            kk = np.zeros(ks.value * outsz, np.int32)
+            assert rf._lib.lib.rf_lanczos_coeffs_host(insz, outsz, b.ctypes.data_as(ctypes.c_void_p),
+                                                      kk.ctypes.data_as(ctypes.c_void_p), kk.size, ctypes.byref(ks)) == 0
+            kk = kk.reshape(outsz, ks.value)
+            src = np.moveaxis(cur, axis, 0).astype(np.int64)
+            out = np.zeros((outsz,) + src.shape[1:], np.int64)
+            for o in range(outsz):
+                lo, n = b[2 * o], b[2 * o + 1]
+                acc = (1 << 21) + np.tensordot(kk[o, :n].astype(np.int64), src[lo:lo + n], axes=(0, 0))
+                out[o] = np.clip(acc >> 22, 0, 255)
+            cur = np.moveaxis(out.astype(np.uint8), 0, axis)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.LANCZOS))
+        assert np.array_equal(cur, ref)
+
+
+def test_state_dict_keys_match_reference_layout(rf):
+    fe = rf.model.FeatureExtractor()
+    assert set(fe.state_dict().keys()) == set(synth.feature_extractor_state(0).keys())
+    fe.load_state_dict(synth.feature_extractor_state(0))            # strict
+    nf, nm, nc = rf.model.NetFlowCoarse(7), rf.model.NetMatchability(7), rf.model.CorrNeigh(7)
+    assert set(nf.state_dict().keys()) == set(synth.net_flow_coarse_state(1).keys())
+    assert set(nm.state_dict().keys()) == set(synth.net_matchability_state(2).keys())
+    assert len(nc.state_dict()) == 0
+    nf.load_state_dict(synth.net_flow_coarse_state(1))
+    nm.load_state_dict(synth.net_matchability_state(2))
+
+
+def test_scale_list_and_sizes_match_oracle(rf):
+    from importlib import import_module
+    ca = import_module("ransac_flow_b200.coarseAlignFeatMatch")
+    for n, r in [(7, 2), (3, 1.2), (5, 1.5), (1, 2)]:
+        assert ca.scale_list(n, r) == PO.scale_list(n, r)
+    a = ca.CoarseAlignA.__new__(ca.CoarseAlignA)
+    a.strideNet = 16
+    c = ca.CoarseAlignC.__new__(ca.CoarseAlignC)
+    c.strideNet = 16
+    for (w, h, ms) in [(640, 480, 480), (1241, 376, 800), (447, 315, 400), (720, 480, 960)]:
+        assert a._target_size(w, h, ms) == PO.resized_size(w, h, ms, 16, "min")
+        assert c._target_size(w, h, ms) == PO.resized_size(w, h, ms, 16, "max")
+    # 480x640, scaleR 2 -> NA = 13065
+    sizes = [a._target_size(640, 480, int(480 * s)) for s in ca.scale_list(7, 2)]
+    assert sum((w // 16) * (h // 16) for w, h in sizes) == 13065
+
+
+def test_no_cpu_fallback(rf):
+    x = torch.zeros(4, 8)
+    with pytest.raises(rf._lib.RFError):
+        rf.ops.l2norm(x)
+    with pytest.raises(rf._lib.RFError):
+        rf.outil.mutualMatching(torch.zeros(8, 4), torch.zeros(8, 4))
+    with pytest.raises(rf._lib.RFError):
+        rf.model.FeatureExtractor().eval()(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(rf._lib.RFError):
+        rf.kornia_geometry.HomographyWarper(4, 4).warp_grid(torch.eye(3)[None])
+    if not torch.cuda.is_available():
+        with pytest.raises(rf._lib.RFError):
+            rf.CoarseAlignA(7, 1000, 0.05, "Homography", 480, segNet=False, resnet_state_dict={})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ransac-flow_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
