@@ -164,7 +164,23 @@ class _CoarseAlignBase:
 
     @staticmethod
     def _as_pil(I):
-        return Image.fromarray(I.cpu().numpy()) if torch.is_tensor(I) else I
+        return I                              # kept as is; the ``Is`` / ``It`` properties convert lazily
+
+    def _get_img(self, name):
+        v = self.__dict__.get(name)
+        if torch.is_tensor(v):                # device-resident resized image: materialise the PIL view on first use
+            v = Image.fromarray(v.cpu().numpy())
+            self.__dict__[name] = v
+        return v
+
+    Is = property(lambda self: self._get_img("_Is"), lambda self, v: self.__dict__.__setitem__("_Is", v))
+    It = property(lambda self: self._get_img("_It"), lambda self, v: self.__dict__.__setitem__("_It", v))
+
+    @property
+    def target_size(self):
+        """(w, h) of the resized target without forcing a device->host copy."""
+        v = self.__dict__.get("_It")
+        return (int(v.shape[1]), int(v.shape[0])) if torch.is_tensor(v) else v.size
 
     def _to_tensor01(self, u8):
         h, w = int(u8.shape[0]), int(u8.shape[1])

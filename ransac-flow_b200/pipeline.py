@@ -55,7 +55,7 @@ def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, wit
     """One pair through the evaluation loop (evaluation/evalHpatch/evaluation.py:172-243).
     Returns dict(H (nH,3,3), flowDown8 (nH,2,h8,w8), matchDown8 (nH,2,h8,w8), flow12 [..], match [..])."""
     coarseModel.setPair(Is, It)
-    Itw, Ith = coarseModel.It.size
+    Itw, Ith = coarseModel.target_size
     if It_bg is None:
         It_bg = np.ones((Ith, Itw), dtype=np.float32)
     featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)

@@ -1,0 +1,71 @@
+"""Networks on the CUDA engine vs golden outputs of the reference modules (fp32 engine)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import model_oracle as MO
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(1e-12, np.abs(b).max())
+
+
+def test_feature_extractor_vs_reference(rf):
+    g = golden("feature_extractor")
+    fe = rf.model.FeatureExtractor()
+    fe.load_state_dict(synth.feature_extractor_state(int(g["seed"])))
+    fe.cuda()
+    fe.eval()
+    y = fe(torch.from_numpy(g["x"]).cuda())
+    assert tuple(y.shape) == g["y"].shape
+    assert rel_err(y.cpu().numpy(), g["y"]) < 1e-4
+    # reload other weights: the folded cache must follow
+    fe.load_state_dict(synth.feature_extractor_state(5))
+    y2 = fe(torch.from_numpy(g["x"]).cuda())
+    ref2 = MO.feature_extractor(torch.from_numpy(g["x"]), synth.feature_extractor_state(5))
+    assert rel_err(y2.cpu().numpy(), ref2.numpy()) < 1e-4
+    fe.train()
+    with pytest.raises(RuntimeError):
+        fe(torch.from_numpy(g["x"]).cuda())
+
+
+def test_fine_heads_vs_reference(rf):
+    g = golden("fine_heads")
+    corr = rf.model.CorrNeigh(7)(torch.from_numpy(g["a"]).cuda(), torch.from_numpy(g["b"]).cuda())
+    assert np.abs(corr.cpu().numpy() - g["corr"]).max() < 1e-6
+    nf = rf.model.NetFlowCoarse(7)
+    nf.load_state_dict(synth.net_flow_coarse_state(1))
+    assert nf.cuda() is not None
+    nf.eval()
+    flow = nf(torch.from_numpy(g["corr"]).cuda(), False)
+    assert np.abs(flow.cpu().numpy() - g["flow"]).max() < 1e-6          # flow in [-1,1] units: << 1e-3
+    nm = rf.model.NetMatchability(7)
+    nm.load_state_dict(synth.net_matchability_state(2))
+    nm.cuda()
+    nm.eval()
+    m = nm(torch.from_numpy(g["corr"]).cuda(), False)
+    assert np.abs(m.cpu().numpy() - g["match"]).max() < 1e-6
+    grid = torch.zeros(1, 6, 8, 2).cuda()
+    _, fc = rf.model.predFlowCoarse(torch.from_numpy(g["corr"]).cuda(), nf, grid, up8X=False)
+    assert tuple(fc.shape) == (1, 6, 8, 2)
+
+
+def test_resnet50_conv4_vs_torchvision(rf):
+    g = golden("resnet50_conv4")
+    from ransac_flow_b200.coarseAlignFeatMatch import ResNet50Conv4
+    net = ResNet50Conv4(synth.resnet50_conv4_state(int(g["seed"])))
+    x = rf.ops.Ragged.from_nchw(torch.from_numpy(g["x"]).cuda())
+    y = net(x)
+    assert rel_err(y.to_nchw().cpu().numpy(), g["y"]) < 1e-4
+    # ragged batch: two different sizes in one pass == each alone
+    x2 = torch.randn(1, 3, 48, 80)
+    xs = rf.ops.Ragged(torch.cat([x.data, x2[0].permute(1, 2, 0).reshape(-1, 3).cuda()]), [(64, 96), (48, 80)])
+    ys = net(xs)
+    assert rel_err(ys.image(0).cpu().numpy(), g["y"]) < 1e-4
+    ref2 = MO.resnet50_conv4(x2, synth.resnet50_conv4_state(int(g["seed"])))
+    assert rel_err(ys.image(1).cpu().numpy(), ref2.numpy()) < 1e-4

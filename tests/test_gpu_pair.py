@@ -1,0 +1,154 @@
+"""The API level: CoarseAlign variants, PredFlowMask, the pair loop and getFlow against the
+reference's golden outputs and the CPU oracle (fp32 engine; flow tolerance 1e-3 from north_star)."""
+import numpy as np
+import PIL.Image as Image
+import pytest
+import torch
+
+from conftest import golden
+from oracle import pair_oracle as PO
+from oracle import synth
+from oracle import warp_oracle as WO
+
+pytestmark = pytest.mark.gpu
+FLOW_TOL = 1e-3
+
+
+def networks(rf):
+    net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
+           "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}
+    net["netFeatCoarse"].load_state_dict(synth.feature_extractor_state(0))
+    net["netFlowCoarse"].load_state_dict(synth.net_flow_coarse_state(1))
+    net["netMatch"].load_state_dict(synth.net_matchability_state(2))
+    for m in net.values():
+        m.cuda()
+        m.eval()
+    return net
+
+
+def oracle_net():
+    return {"netFeatCoarse": synth.feature_extractor_state(0), "netFlowCoarse": synth.net_flow_coarse_state(1),
+            "netMatch": synth.net_matchability_state(2)}
+
+
+class fixed_randint:
+    def __init__(self, arrays):
+        self.arrays = list(arrays)
+
+    def __enter__(self):
+        self.real = torch.randint
+        it = iter(self.arrays)
+        torch.randint = lambda high, size, **k: torch.from_numpy(next(it)).to(k.get("device", "cpu"))
+        return self
+
+    def __exit__(self, *a):
+        torch.randint = self.real
+
+
+def test_coarse_align_variant_C_vs_reference(rf):
+    g = golden("coarse_align_C")
+    c = rf.CoarseAlignC(3, 500, 0.05, "Homography", 128, scaleR=1.5, resnet_state_dict=synth.resnet50_conv4_state(0), verbose=False)
+    c.setSource(Image.fromarray(g["src"]))
+    c.setTarget(Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.Is), g["Is"]) and np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale.cpu().numpy(), g["WMulti"]) and np.array_equal(c.HMultiScale.cpu().numpy(), g["HMulti"])
+    assert np.abs(c.featt.cpu().numpy() - g["featt"]).max() < 1e-4
+    assert tuple(c.featsMultiScale.shape) == (1024, len(g["WMulti"]))
+    assert np.abs(c.featsMultiScale.sum(0).cpu().numpy() - g["feats_sum"]).max() < 1e-3
+    assert tuple(c.IsTensor.shape) == (1, 3, 96, 128) and float(c.IsTensor.max()) <= 1.0
+    with fixed_randint([g["samples"]]):
+        H, mask = c.getCoarse(np.zeros((c.It.size[1], c.It.size[0])))
+    assert len(c.match1) == int(g["nbMatch"])
+    np.testing.assert_allclose(H, g["H"], atol=1e-5)
+    assert H.dtype == np.float32 and np.array_equal(mask, g["inlierMask"])
+
+
+def test_coarse_align_variant_A_vs_reference(rf):
+    g = golden("coarse_align_A")
+    c = rf.CoarseAlignA(3, 500, 0.05, "Homography", 96, 2, False, 1.5, True, False,
+                        resnet_state_dict=synth.resnet50_conv4_state(0), verbose=False)
+    c.setPair(Image.fromarray(g["src"]), Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.It), g["It"])
+    for name, key in (("W1MutualMatch", "W1"), ("H1MutualMatch", "H1m"), ("W2MutualMatch", "W2"), ("H2MutualMatch", "H2m"),
+                      ("W2MutualMatchInt", "W2i"), ("H2MutualMatchInt", "H2i")):
+        assert np.array_equal(getattr(c, name).cpu().numpy(), g[key]), name
+    with fixed_randint([g["samples0"], g["samples1"]]):
+        H0 = c.getCoarse(np.zeros_like(g["Mt"]))
+        n0 = len(c.match1)
+        H1 = c.getCoarse(g["Mt"])
+    assert n0 == int(g["nbMatch0"]) and len(c.match1) == int(g["nbMatch1"])
+    np.testing.assert_allclose(H0, g["H0"], atol=1e-5)
+    np.testing.assert_allclose(H1, g["H1"], atol=1e-5)
+    # too few matches -> None (coarseAlignFeatMatch.py:171-172)
+    assert c.getCoarse(np.ones_like(g["Mt"])) is None
+
+
+@pytest.mark.parametrize("tag,m21", [("hpatch", False), ("corr", True)])
+def test_pred_flow_mask_vs_reference(rf, tag, m21):
+    g = golden("pred_flow_mask_" + tag)
+    net = networks(rf)
+    Is, It = torch.from_numpy(g["Is"]).cuda(), torch.from_numpy(g["It"]).cuda()
+    featt = torch.nn.functional.normalize(net["netFeatCoarse"](It))
+    flowCoarse = rf.kornia_geometry.HomographyWarper(48, 64).warp_grid(torch.from_numpy(g["H"]).cuda())
+    grid = rf.pipeline.base_grid(48, 64)
+    flow12, match, f8, m8 = rf.pipeline.PredFlowMask(Is, featt, flowCoarse, grid, net, with_match21=m21)
+    assert np.abs(f8 - g["flowDown8"]).max() < FLOW_TOL and np.abs(m8 - g["matchDown8"]).max() < FLOW_TOL
+    assert np.abs(flow12.cpu().numpy() - g["flow12"]).max() < FLOW_TOL
+    far = (np.abs(np.abs(g["flow12"]) - 1) > 1e-3).all(-1)[0]
+    assert np.abs(match - g["match"])[far].max() < FLOW_TOL
+    print("max |flow12 - ref| = %.3g" % np.abs(flow12.cpu().numpy() - g["flow12"]).max())
+
+
+def test_get_flow_all_vs_reference(rf):
+    g = golden("get_flow_all")
+    fg = rf.pipeline.getFlow_all(g["flow"], g["H"], g["mask"], 40, 56, th=float(g["th"]), multiH=True)
+    ref, m = WO.get_flow_all(g["flow"], g["H"], g["mask"], 40, 56, th=float(g["th"]), multiH=True)
+    far = (np.abs(m.numpy() - float(g["th"])) > 1e-4).all(0)[..., 0]     # merge picks flip only at the threshold
+    assert np.abs(fg.cpu().numpy() - g["flowGlobal"])[0][far].max() < 1e-5
+
+
+@pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
+def test_whole_pair_vs_oracle(rf, h, w, minSize, nbScale):
+    """L2 parity: the full path, same seeded samples on both sides."""
+    src, tgt, _ = synth.make_pair(11, h, w)
+    Is, It = Image.fromarray(src), Image.fromarray(tgt)
+    rsd = synth.resnet50_conv4_state(0)
+    oc = PO.CoarseAlignOracle(rsd, nbScale=nbScale, nbIter=1000, tolerance=0.05, minSize=minSize, scaleR=2, variant="A", seed=1000)
+    ref = PO.align_pair(oc, oracle_net(), Is, It, maxCoarse=0)
+    c = rf.CoarseAlignA(nbScale, 1000, 0.05, "Homography", minSize, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    with fixed_randint([oc.last_samples]):
+        out = rf.pipeline.align_pair(c, networks(rf), Is, It, maxCoarse=0)
+    # the match set: identical up to fp32-noise ties of the arg-max
+    m_ref = set(map(tuple, np.round(oc.match2[:, :2] * 1e4).astype(int).tolist()))
+    m_got = set(map(tuple, np.round(c.match2.cpu().numpy()[:, :2] * 1e4).astype(int).tolist()))
+    print("matches ref %d got %d sym-diff %d" % (len(m_ref), len(m_got), len(m_ref ^ m_got)))
+    assert len(m_ref ^ m_got) <= max(2, len(m_ref) // 50)
+    if len(m_ref ^ m_got) == 0:
+        assert out["H"].shape == ref["H"].shape
+        np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
+        d = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy()).max()
+        print("max |flow12 - oracle| = %.3g" % d)
+        assert d < FLOW_TOL
+        assert np.abs(out["flowDown8"] - ref["flowDown8"]).max() < FLOW_TOL
+
+
+def test_multi_hypothesis_loop_runs(rf):
+    src, tgt, _ = synth.make_pair(12, 96, 128)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False,
+                        resnet_state_dict=synth.resnet50_conv4_state(0), verbose=False)
+    torch.manual_seed(1000)
+    out = rf.pipeline.align_pair(c, networks(rf), Image.fromarray(src), Image.fromarray(tgt), maxCoarse=3, with_match21=True)
+    nH = len(out["flow12"])
+    assert 1 <= nH <= 4 and out["H"].shape == (nH, 3, 3) and out["flowDown8"].shape == (nH, 2, 12, 16)
+
+
+def test_device_preproc_pyramid_equals_host(rf):
+    src, tgt, _ = synth.make_pair(13, 120, 160)
+    rsd = synth.resnet50_conv4_state(0)
+    a = rf.CoarseAlignA(3, 100, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    b = rf.CoarseAlignA(3, 100, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    b.device_preproc = True
+    a.setPair(Image.fromarray(src), Image.fromarray(tgt))
+    b.setPair(Image.fromarray(src), Image.fromarray(tgt))
+    assert np.array_equal(np.asarray(a.It), np.asarray(b.It)) and np.array_equal(np.asarray(a.Is), np.asarray(b.Is))
+    assert torch.equal(a.featsMultiScale, b.featsMultiScale) and torch.equal(a._idx1, b._idx1)
