@@ -138,8 +138,8 @@ class _CoarseAlignBase:
     # -- features -------------------------------------------------------------------------------
     @staticmethod
     def _to_device_u8(I):
-        a = np.asarray(I, dtype=np.uint8)
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        a = np.array(I, dtype=np.uint8)          # writable copy
+        t = torch.from_numpy(a)
         return t.pin_memory().cuda(non_blocking=True)
 
     def _features(self, images):

@@ -30,24 +30,34 @@ def resizeImg(I, strideNet, minSize=400, mode=Image.LANCZOS):
     return I.resize((resizeW, resizeH), resample=mode)
 
 
+_wh_cache = {}
+
+
 def _wh(h, w, device):
-    r = torch.arange(0, h, device=device).view(-1, 1).expand(h, w).contiguous().view(-1)
-    c = torch.arange(0, w, device=device).view(1, -1).expand(h, w).contiguous().view(-1)
-    return r, c
+    """Row / column index of every cell of an (h, w) grid, flattened row-major, plus the cell-centre
+    coordinates.  Evaluated once per grid size with IEEE fp32 division on the host (torch's CUDA kernels
+    turn ``x / scalar`` into ``x * (1 / scalar)``, which is off by an ulp from utils/outil.py:22-23 as the
+    CPU evaluates it) and cached on the device."""
+    key = (int(h), int(w), str(device))
+    if key not in _wh_cache:
+        r = torch.arange(0, h).view(-1, 1).expand(h, w).contiguous().view(-1)
+        c = torch.arange(0, w).view(1, -1).expand(h, w).contiguous().view(-1)
+        W = ((r.float() + 0.5) / h - 0.5) * 2
+        H = ((c.float() + 0.5) / w - 0.5) * 2
+        _wh_cache[key] = tuple(t.to(device) for t in (r, c, W, H))
+    return _wh_cache[key]
 
 
 def getWHTensor(feat):
     """utils/outil.py:21-24: cell-centre coordinates in [-1, 1] ("W" = rows/y, "H" = cols/x)."""
-    h, w = feat.size(2), feat.size(3)
-    r, c = _wh(h, w, feat.device)
-    W = (r.float() + 0.5) / h
-    H = (c.float() + 0.5) / w
-    return (W - 0.5) * 2, (H - 0.5) * 2
+    _, _, W, H = _wh(feat.size(2), feat.size(3), feat.device)
+    return W, H
 
 
 def getWHTensor_Int(feat):
     """utils/outil.py:26-29."""
-    return _wh(feat.size(2), feat.size(3), feat.device)
+    r, c, _, _ = _wh(feat.size(2), feat.size(3), feat.device)
+    return r, c
 
 
 def _rows(feat):
