@@ -50,7 +50,7 @@ uint64_t rf_launch_count(void);
  * written.  featA [NA][C], featB [NB][C] (K-major rows = one feature vector).
  * Outputs: idx1/idx2 (int64, capacity >= min(NA,NB)) sorted by idx1, *count.
  * precision: 0 = exact fp32 FMA (SIMT), 1 = 3xTF32 on tcgen05 tensor cores. */
-size_t rf_corr_mutual_nn_workspace(int NA, int NB);
+size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precision);
 int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
                       int64_t* idx1_out, int64_t* idx2_out, int* count_out,
                       void* ws, size_t ws_bytes, int precision, void* stream);
@@ -86,8 +86,9 @@ int rf_build_matches(const int64_t* idx1, const int64_t* idx2, const int* count_
  * model/model.py:27-56,59-125,167-322; torchvision ResNet-50 bottlenecks.
  * x: ragged NHWC [sum HW][Cin]; w: [R*S*Cin][Cout] (tap-major, Cout contiguous);
  * bias [Cout] (nullable); residual: packed like y (nullable).
- * engine: 0 = fp32 SIMT implicit GEMM, 1 = TF32 tcgen05 implicit GEMM
- * (w_tc = same weights as [Cout][R*S*Cin], required for engine 1). */
+ * engine: 0 = fp32 SIMT implicit GEMM everywhere; 1 = TF32 tcgen05 implicit GEMM for the layers it
+ * supports (stride 1, Cin % 32 == 0, 1x1 / 3x3; w_tc = same weights as [Cout][R*S*Cin]), the exact-fp32
+ * SIMT kernel for the rest (3-channel stems, stride-2 convs). */
 int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,

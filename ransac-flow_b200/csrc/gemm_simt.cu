@@ -385,18 +385,26 @@ using namespace rf;
 
 // tensor-core engines live in gemm_tc.cu
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, cudaStream_t st);
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st);
+size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const float* w_tc, cudaStream_t st);
+bool rf_conv2d_tc_supported(const ConvParams& p);
 
-extern "C" size_t rf_corr_mutual_nn_workspace(int NA, int NB) {
-    return ((size_t)(NA > 0 ? NA : 0) + (size_t)(NB > 0 ? NB : 0)) * sizeof(unsigned long long) + 256;
+static size_t keys_bytes(int NA, int NB) {
+    return (((size_t)(NA > 0 ? NA : 0) + (size_t)(NB > 0 ? NB : 0)) * sizeof(unsigned long long) + 255) / 256 * 256;
+}
+
+extern "C" size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precision) {
+    size_t b = keys_bytes(NA, NB) + 256;
+    if (precision == 1) b += rf_corr_tc_workspace(NA > 0 ? NA : 0, NB > 0 ? NB : 0, C);
+    return b;
 }
 
 extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
                                  int64_t* idx1_out, int64_t* idx2_out, int* count_out,
                                  void* ws, size_t ws_bytes, int precision, void* stream) {
     RF_REQUIRE(NA >= 0 && NB >= 0 && C > 0 && (C % 4) == 0, "rf_corr_mutual_nn: bad sizes (C must be a multiple of 4)");
-    RF_REQUIRE(ws != nullptr && ws_bytes >= rf_corr_mutual_nn_workspace(NA, NB), "rf_corr_mutual_nn: workspace too small");
+    RF_REQUIRE(ws != nullptr && ws_bytes >= rf_corr_mutual_nn_workspace(NA, NB, C, precision), "rf_corr_mutual_nn: workspace too small");
     RF_REQUIRE(((uintptr_t)featA % 16) == 0 && ((uintptr_t)featB % 16) == 0, "rf_corr_mutual_nn: features must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(ws);
@@ -404,7 +412,7 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
     RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
     if (NA > 0 && NB > 0) {
         if (precision == 1) {
-            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, st);
+            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, static_cast<unsigned char*>(ws) + keys_bytes(NA, NB), st);
             if (rc) return rc;
         } else {
             dim3 grid((NB + 127) / 128, (NA + BM - 1) / BM);
@@ -430,8 +438,10 @@ extern "C" int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int 
     p.Mtot = set.out_pix[nimg];
     p.K = R * S * Cin;
     cudaStream_t st = as_stream(stream);
-    if (engine == 1) return rf_conv2d_tc(set, p, w_tc, st);
-    RF_REQUIRE(engine == 0, "rf_conv2d_nhwc: unknown engine");
+    RF_REQUIRE(engine == 0 || engine == 1, "rf_conv2d_nhwc: unknown engine");
+    // engine 1 = tcgen05 TF32 where the layer shape allows it (stride 1, Cin % 32 == 0); other layers
+    // (3-channel stems, stride-2 convs, 49-channel heads) run on the exact-fp32 SIMT engine below
+    if (engine == 1 && w_tc != nullptr && rf_conv2d_tc_supported(p)) return rf_conv2d_tc(set, p, w_tc, st);
     RF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "rf_conv2d_nhwc: pointers must be 16-byte aligned");
     const bool vec = (Cin % 16) == 0;
     const bool wide = Cout >= 128;

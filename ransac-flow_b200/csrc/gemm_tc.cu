@@ -1,10 +1,495 @@
-// tcgen05 / TMA tensor-core engine (placeholder until the kernels land in this file).
+// tcgen05 / TMEM / TMA tensor-core engine (sm_100a).
+//
+// One warp-specialised kernel, two epilogues:
+//   MODE_CONV : implicit-GEMM convolution (stride 1) over a ragged NHWC batch, TF32 operands,
+//               fp32 accumulation in TMEM, epilogue = folded-BN bias + residual + ReLU
+//               (model/model.py:27-56,59-125,167-322; torchvision ResNet-50 conv1..layer3);
+//   MODE_CORR : utils/outil.py:34-37 score = featA^T featB as 3xTF32 (hi*hi + lo*hi + hi*lo, fp32-grade
+//               accuracy so the arg-max agrees with an fp32 GEMM) with the row / column arg-max fused
+//               into the epilogue; the NA x NB matrix never leaves the SM.
+//
+// Data path per CTA (one 128-pixel x BN-channel output tile):
+//   warp 0  : TMA producer.  A tile = 3-D box (32 channels, tw, th) of the NHWC image at the tap's
+//             offset (out-of-bounds = zero padding for free), B tile = 2-D box (32 k, BN rows) of the
+//             K-major weight matrix; both land in 128B-swizzled shared memory, mbarrier complete_tx.
+//   warp 1  : allocates TMEM, issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x4 per stage from one
+//             thread, tcgen05.commit releases the stage / publishes the accumulator.
+//   warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns at a time straight from TMEM.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
+
+namespace rf {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BK = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int TC_A_BYTES = 128 * 128;     // 128 rows x 128 B
+
+struct alignas(64) TcParams {
+    CUtensorMap mapA[RF_MAX_IMGS];        // per image: (C, W, H) fp32, box (32, tw, th)
+    CUtensorMap mapAlo;                   // MODE_CORR: low part of A
+    CUtensorMap mapB;                     // (K, Cout) fp32, box (32, BN)
+    CUtensorMap mapBlo;                   // MODE_CORR: low part of B
+    int nimg;
+    int tile_start[RF_MAX_IMGS + 1];      // prefix sums of tiles per image
+    int tiles_x[RF_MAX_IMGS];
+    int tw[RF_MAX_IMGS];                  // tile width (tile height = 128 / tw)
+    int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
+    long long out_pix[RF_MAX_IMGS + 1];
+    int R, S, pad, Cin, Cout, relu;
+    const float* bias;
+    const float* residual;
+    float* y;
+    unsigned long long* rowbest;          // MODE_CORR
+    unsigned long long* colbest;
+    int NA, NB;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost arrival becomes a CUDA error (trap) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], TF32 operands, fp32 accumulate, M = 128, N from idesc
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups, bits [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                           // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// instruction descriptor: D fp32, A/B TF32, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+constexpr int MODE_CONV = 0, MODE_CORR = 1;
+
+template <int BN, int MODE>
+struct TcCfg {
+    static constexpr int NSPLIT = (MODE == MODE_CORR) ? 2 : 1;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_kernel(const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<BN, MODE>;
+    constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile decode ----
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = blockIdx.x - p.tile_start[img];
+    const int tw = p.tw[img], th = 128 / tw;
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    const int ox0 = txi * tw, oy0 = tyi * th;
+    const int n0 = blockIdx.y * BN;
+    const int kc = p.Cin / TC_BK;                 // 32-channel chunks per tap
+    const int KI = p.R * p.S * kc;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA[img]);
+        tma_prefetch_desc(&p.mapB);
+        if (NSPLIT == 2) { tma_prefetch_desc(&p.mapAlo); tma_prefetch_desc(&p.mapBlo); }
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            for (int it = 0; it < KI; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                const int tap = it / kc, cc = it - tap * kc;
+                const int r = tap / p.S, s = tap - r * p.S;
+                const int c0 = cc * TC_BK, x = ox0 + s - p.pad, y = oy0 + r - p.pad;
+                const int kcol = tap * p.Cin + c0;
+                tma_load_3d(sbase, &p.mapA[img], &full[st], c0, x, y);
+                tma_load_2d(sbase + NSPLIT * TC_A_BYTES, &p.mapB, &full[st], kcol, n0);
+                if (NSPLIT == 2) {
+                    tma_load_3d(sbase + TC_A_BYTES, &p.mapAlo, &full[st], c0, x, y);
+                    tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &p.mapBlo, &full[st], kcol, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            for (int it = 0; it < KI; ++it) {
+                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + NSPLIT * TC_A_BYTES;
+                const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {                       // UMMA_K = 8 tf32 = 32 bytes
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    if (NSPLIT == 2) {
+                        const uint64_t dalo = make_desc_sw128(sa + TC_A_BYTES), dblo = make_desc_sw128(sb + Cfg::B_BYTES);
+                        umma_tf32(tmem_base, dalo + adv, db + adv, idesc, (it | k) != 0 ? 1u : 0u);   // lo * hi
+                        umma_tf32(tmem_base, da + adv, dblo + adv, idesc, 1u);                         // hi * lo
+                        umma_tf32(tmem_base, da + adv, db + adv, idesc, 1u);                           // hi * hi
+                    } else {
+                        umma_tf32(tmem_base, da + adv, db + adv, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[st]);            // stage free once these MMAs have read it
+            }
+            umma_commit(tmem_full);                 // accumulator complete
+        }
+    } else {
+        // =============================== epilogue (warps 2..5) ===============================
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                // accumulator row = pixel inside the tile
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (MODE == MODE_CONV) {
+            const int py = m / tw, px = m - py * tw;
+            const int oy = oy0 + py, ox = ox0 + px;
+            const bool valid = (oy < p.Ho[img]) && (ox < p.Wo[img]);
+            const long long pix = p.out_pix[img] + (long long)oy * p.Wo[img] + ox;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                const int n = n0 + c * 32;
+                if (valid && n < p.Cout) {
+                    float* dst = p.y + pix * p.Cout + n;
+                    const float* res = p.residual ? p.residual + pix * p.Cout + n : nullptr;
+                    if (n + 32 <= p.Cout && (p.Cout & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                            if (res) { float4 rr = __ldg(reinterpret_cast<const float4*>(res + j)); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4*>(dst + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.Cout) {
+                                float o = __uint_as_float(v[j]);
+                                if (p.bias) o += __ldg(p.bias + n + j);
+                                if (res) o += __ldg(res + j);
+                                if (p.relu) o = fmaxf(o, 0.f);
+                                dst[j] = o;
+                            }
+                    }
+                }
+            }
+        } else {
+            // utils/outil.py:36-37: row arg-max (thread-local over this tile's columns), column arg-max via an
+            // smem transpose of the score tile (the pipeline stages are idle by now)
+            float* sS = reinterpret_cast<float*>(smem);
+            constexpr int LD = BN + 1;
+            const int row = ox0 + m;                // corr "image" is 1 x NA: tile = 128 consecutive rows of featA
+            const bool rvalid = row < p.NA;
+            unsigned long long best = 0ull;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c * 32 + j;
+                    const float s = __uint_as_float(v[j]);
+                    sS[m * LD + c * 32 + j] = s;
+                    if (col < p.NB) {
+                        unsigned long long k = pack_key(s, (uint32_t)col);
+                        best = k > best ? k : best;
+                    }
+                }
+            }
+            if (rvalid && best != 0ull) atomicMax(p.rowbest + row, best);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = (warp - 2) * 32 + lane;
+            const int rmax = min(128, p.NA - ox0);
+            for (int cidx = t; cidx < BN; cidx += 128) {
+                const int col = n0 + cidx;
+                if (col >= p.NB) continue;
+                unsigned long long cb = 0ull;
+                for (int rr = 0; rr < rmax; ++rr) {
+                    unsigned long long k = pack_key(sS[rr * LD + cidx], (uint32_t)(ox0 + rr));
+                    cb = k > cb ? k : cb;
+                }
+                if (cb != 0ull) atomicMax(p.colbest + col, cb);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = __ldg(x + i), h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    hi[i] = h;
+    lo[i] = l;
+}
+
+// ------------------------------------------------------------------ host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    unsigned long long d0, d1, d2;
+    unsigned b0, b1, b2;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&](unsigned long long v) { h ^= std::hash<unsigned long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.b2);
+        return h;
+    }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// fp32 tensor (d0 innermost, d1, d2), dense strides, box (b0, b1, b2), 128B swizzle, zero fill out of bounds
+static int get_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                   unsigned b0, unsigned b1, unsigned b2) {
+    MapKey key{ptr, d0, d1, d2, b0, b1, b2};
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail_msg("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 4ull, d0 * d1 * 4ull};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t es[3] = {1, 1, 1};
+    int rank = d2 > 0 ? 3 : 2;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu box %u,%u,%u)", (int)r, d0, d1, d2, b0, b1, b2);
+        return 3;
+    }
+    if (g_maps.size() > 8192) g_maps.clear();
+    g_maps[key] = *out;
+    return 0;
+}
+
+static int pick_tw(int Ho, int Wo) {
+    // tile = tw x (128/tw) output pixels: minimise the padded area
+    int best = 16;
+    long long best_area = -1;
+    const int cands[5] = {16, 32, 8, 64, 128};
+    for (int i = 0; i < 5; ++i) {
+        int tw = cands[i], th = 128 / tw;
+        long long area = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+        if (best_area < 0 || area < best_area) { best_area = area; best = tw; }
+    }
+    return best;
+}
+
+template <int BN, int MODE>
+static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st) {
+    using Cfg = TcCfg<BN, MODE>;
+    static bool attr = false;
+    if (!attr) {
+        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    tc_kernel<BN, MODE><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    RF_LAUNCHED();
+    return 0;
+}
+
+}  // namespace rf
+
 using namespace rf;
 
-int rf_corr_argmax_tc(const float*, int, const float*, int, int, unsigned long long*, unsigned long long*, cudaStream_t) {
-    return fail_msg("rf_corr_mutual_nn: precision=1 (tcgen05) engine is not available in this build");
+bool rf_conv2d_tc_supported(const ConvParams& p) {
+    return p.stride == 1 && (p.Cin % TC_BK) == 0 && (p.Cout % 4) == 0 && p.Cout >= 16 && p.R == p.S && (p.R == 1 || p.R == 3);
 }
-int rf_conv2d_tc(const ImgSet&, const ConvParams&, const float*, cudaStream_t) {
-    return fail_msg("rf_conv2d_nhwc: engine=1 (tcgen05) is not available in this build");
+
+int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cudaStream_t st) {
+    RF_REQUIRE(w_tc != nullptr, "rf_conv2d_nhwc: engine=1 needs w_tc ([Cout][R*S*Cin])");
+    RF_REQUIRE(rf_conv2d_tc_supported(cp), "rf_conv2d_nhwc: engine=1 needs stride 1, Cin % 32 == 0, Cout % 4 == 0, 1x1 or 3x3");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = cp.Cout >= 256 ? 256 : (cp.Cout >= 128 ? 128 : 64);
+    p.nimg = set.n;
+    int tiles = 0;
+    for (int i = 0; i < set.n; ++i) {
+        int tw = pick_tw(set.Ho[i], set.Wo[i]), th = 128 / tw;
+        p.tw[i] = tw;
+        p.tiles_x[i] = (set.Wo[i] + tw - 1) / tw;
+        p.tile_start[i] = tiles;
+        tiles += p.tiles_x[i] * ((set.Ho[i] + th - 1) / th);
+        p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
+        p.out_pix[i] = set.out_pix[i];
+        int rc = get_map(&p.mapA[i], cp.x + set.in_pix[i] * cp.Cin, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
+                         (unsigned long long)set.H[i], TC_BK, (unsigned)tw, (unsigned)th);
+        if (rc) return rc;
+    }
+    for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
+    p.out_pix[set.n] = set.out_pix[set.n];
+    int rc = get_map(&p.mapB, w_tc, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 0, TC_BK, (unsigned)BN, 0);
+    if (rc) return rc;
+    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
+    p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
+    const int nt = (cp.Cout + BN - 1) / BN;
+    if (BN == 256) return launch_tc<256, MODE_CONV>(p, tiles, nt, st);
+    if (BN == 128) return launch_tc<128, MODE_CONV>(p, tiles, nt, st);
+    return launch_tc<64, MODE_CONV>(p, tiles, nt, st);
+}
+
+size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }
+
+int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st) {
+    RF_REQUIRE((C % TC_BK) == 0, "rf_corr_mutual_nn: precision=1 needs C % 32 == 0");
+    uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+    float* Ahi = reinterpret_cast<float*>(base);
+    float* Alo = Ahi + (size_t)NA * C;
+    float* Bhi = Alo + (size_t)NA * C;
+    float* Blo = Bhi + (size_t)NB * C;
+    long long na4 = (long long)NA * C / 4, nb4 = (long long)NB * C / 4;
+    split_tf32_kernel<<<(unsigned)((na4 + 255) / 256), 256, 0, st>>>((const float4*)featA, (float4*)Ahi, (float4*)Alo, na4);
+    RF_LAUNCHED();
+    split_tf32_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (float4*)Bhi, (float4*)Blo, nb4);
+    RF_LAUNCHED();
+    constexpr int BN = 128;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.nimg = 1;
+    p.tw[0] = 128;
+    p.tiles_x[0] = (NA + 127) / 128;
+    p.tile_start[0] = 0;
+    for (int i = 1; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = p.tiles_x[0];
+    p.Ho[0] = 1; p.Wo[0] = NA;
+    int rc = get_map(&p.mapA[0], Ahi, (unsigned long long)C, (unsigned long long)NA, 1, TC_BK, 128, 1);
+    if (!rc) rc = get_map(&p.mapAlo, Alo, (unsigned long long)C, (unsigned long long)NA, 1, TC_BK, 128, 1);
+    if (!rc) rc = get_map(&p.mapB, Bhi, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
+    if (!rc) rc = get_map(&p.mapBlo, Blo, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
+    if (rc) return rc;
+    p.R = 1; p.S = 1; p.pad = 0; p.Cin = C; p.Cout = NB;
+    p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
+    return launch_tc<BN, MODE_CORR>(p, p.tiles_x[0], (NB + BN - 1) / BN, st);
 }

@@ -63,9 +63,7 @@ class FoldedConv:
         self.pad = (k // 2) if pad is None else pad
 
     def __call__(self, x, relu, residual=None, engine=None):
-        eng = _engine if engine is None else engine
-        if eng == ops.ENGINE_TF32 and (self.cin % 8 != 0):
-            eng = ops.ENGINE_FP32                      # 3-channel stems / 49-channel heads stay on the FMA engine
+        eng = _engine if engine is None else engine     # the library keeps unsupported shapes on the FMA engine
         return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_tc)
 
 

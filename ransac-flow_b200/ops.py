@@ -141,7 +141,7 @@ def corr_mutual_nn(featA, featB, precision=0):
     idx1 = torch.empty(cap, device=dev, dtype=torch.int64)
     idx2 = torch.empty(cap, device=dev, dtype=torch.int64)
     count = torch.zeros(1, device=dev, dtype=torch.int32)
-    wsz = lib.rf_corr_mutual_nn_workspace(NA, NB)
+    wsz = lib.rf_corr_mutual_nn_workspace(NA, NB, Cc, int(precision))
     ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
     check(lib.rf_corr_mutual_nn(ptr(featA), NA, ptr(featB), NB, Cc, ptr(idx1), ptr(idx2), ptr(count),
                                 ptr(ws), wsz, int(precision), stream()))

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(rf):
 
 def test_workspace_queries_are_host_only(rf):
     assert rf._lib.lib.rf_ransac_workspace(1000) >= 1000 * (4 + 36)
-    assert rf._lib.lib.rf_corr_mutual_nn_workspace(13065, 1200) >= (13065 + 1200) * 8
+    assert rf._lib.lib.rf_corr_mutual_nn_workspace(13065, 1200, 1024, 0) >= (13065 + 1200) * 8
 
 
 def test_lanczos_coefficients_match_pil(rf):

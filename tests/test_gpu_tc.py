@@ -1,0 +1,77 @@
+"""tcgen05 engine: TF32 implicit-GEMM convolution and 3xTF32 correlation vs fp32 references."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import outil_oracle as OO
+from test_gpu_matching import check_same
+from test_gpu_ops import ragged
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 4e-3          # two TF32-truncated operands (2^-10 each), fp32 accumulation
+
+
+@pytest.mark.parametrize("cin,cout,k,sizes", [
+    (64, 64, 3, [(24, 32), (9, 7)]), (64, 64, 1, [(16, 16)]), (64, 256, 1, [(13, 17), (6, 5), (1, 1)]),
+    (128, 128, 3, [(16, 16), (16, 16)]), (256, 64, 1, [(30, 40)]), (1024, 256, 1, [(15, 20), (30, 40)]),
+    (256, 256, 3, [(15, 20), (33, 25)]), (256, 1024, 1, [(20, 15), (40, 30)]), (512, 128, 1, [(60, 80)]),
+    (64, 48, 3, [(12, 20)]), (128, 16, 3, [(6, 8)]), (32, 32, 3, [(128, 3), (3, 128)])])
+@pytest.mark.parametrize("relu,res", [(True, True), (False, False)])
+def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res):
+    g = torch.Generator().manual_seed(cin + cout * 3 + k)
+    xs = [torch.randn(1, cin, h, w, generator=g) for h, w in sizes]
+    w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g)
+    refs = [F.conv2d(x, w, bias, padding=k // 2) for x in xs]
+    rs = [torch.randn(r.shape, generator=g) for r in refs] if res else None
+    if res:
+        refs = [a + b for a, b in zip(refs, rs)]
+    if relu:
+        refs = [F.relu(r) for r in refs]
+    wp = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous().cuda()
+    wtc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().cuda()
+    y = rf.ops.conv2d(ragged(rf, xs), wp, bias.cuda(), cout, k, 1, k // 2, relu, ragged(rf, rs) if res else None,
+                      rf.ops.ENGINE_TF32, wtc)
+    torch.cuda.synchronize()
+    for i, r in enumerate(refs):
+        got = y.image(i).cpu()
+        assert tuple(got.shape) == tuple(r.shape)
+        err = (got - r).abs().max().item()
+        assert err <= TF32_TOL * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
+
+
+def test_tf32_engine_falls_back_to_fp32_kernels_for_unsupported_shapes(rf):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 64, 16, 16, generator=g)
+    w = torch.randn(128, 64, 3, 3, generator=g) / 24
+    ref = F.conv2d(x, w, stride=2, padding=1)
+    wp = w.permute(2, 3, 1, 0).reshape(576, 128).contiguous().cuda()
+    wtc = w.permute(0, 2, 3, 1).reshape(128, 576).contiguous().cuda()
+    y = rf.ops.conv2d(ragged(rf, [x]), wp, None, 128, 3, 2, 1, False, None, rf.ops.ENGINE_TF32, wtc)
+    assert (y.image(0).cpu() - ref).abs().max().item() < 2e-5        # exact-fp32 SIMT path
+
+
+@pytest.mark.parametrize("C,NA,NB,seed", [(1024, 13065, 1200, 0), (1024, 2107, 300, 1), (64, 129, 127, 2), (256, 1, 1, 4),
+                                           (1024, 300, 1200, 5), (32, 500, 260, 6)])
+def test_corr_3xtf32_matches_fp32_argmax(rf, C, NA, NB, seed):
+    rs = np.random.RandomState(seed)
+    A = np.abs(rs.randn(C, NA)).astype(np.float32)
+    B = np.abs(rs.randn(C, NB)).astype(np.float32)
+    n = min(NA, NB) // 2
+    B[:, :n] = A[:, rs.permutation(NA)[:n]] + 0.1 * np.abs(rs.randn(C, n)).astype(np.float32)
+    A /= np.linalg.norm(A, axis=0, keepdims=True)
+    B /= np.linalg.norm(B, axis=0, keepdims=True)
+    if NB > 2:
+        B[:, 1] = 0
+    o1, o2, score = OO.mutualMatching(A, B, return_score=True)
+    rf.outil.corr_precision = 1
+    try:
+        i1, i2 = rf.outil.mutualMatching(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    finally:
+        rf.outil.corr_precision = 0
+    nd = check_same(i1.cpu().numpy(), i2.cpu().numpy(), o1, o2, score)
+    print("3xTF32 vs fp32 oracle: %d matches, %d differing (ambiguous) pairs" % (len(o1), nd))
+    # and against the library's own exact-fp32 kernel
+    j1, j2 = rf.outil.mutualMatching(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
+    check_same(i1.cpu().numpy(), i2.cpu().numpy(), j1.cpu().numpy(), j2.cpu().numpy(), score)
