@@ -69,6 +69,28 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
 def make_pairs(n):
     from oracle import synth
     return [synth.make_pair(i, 480, 640)[:2] for i in range(n)]
@@ -87,7 +109,7 @@ def run_reference(args, rank, world):
     import PIL.Image as Image
     import torch
     from oracle import pair_oracle as PO
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("RF_CPU_THREADS", "0")) or min(usable_cores(), 64)
     torch.set_num_threads(cores)
     rsd, fe, nf, nm = states()
     net = {"netFeatCoarse": fe, "netFlowCoarse": nf, "netMatch": nm}
@@ -225,25 +247,18 @@ def run_b200(args, rank, world, local):
                 "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": int(len(m1)),
                 "corr_plus_ransac_gbs": (abytes + 61e3) / ((corr_ms + ransac_ms) * 1e-3) / 1e9}
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores ----
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores,
+    # run as `bench.py --impl reference` in a child process so that it can be cut off ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import pair_oracle as PO
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        oc = PO.CoarseAlignOracle(rsd, nbScale=7, nbIter=1000, tolerance=0.05, minSize=480, scaleR=2, variant="A", seed=1000)
-        onet = {"netFeatCoarse": fe_sd, "netFlowCoarse": nf_sd, "netMatch": nm_sd}
-        s, t = pairs[0]
-        PO.align_pair(oc, onet, Image.fromarray(s), Image.fromarray(t), maxCoarse=0)             # warm-up pair
-        t0 = time.perf_counter()
-        npairs = 0
-        while npairs < 3 or (time.perf_counter() - t0 < 10 and npairs < 12):
-            s, t = pairs[npairs % len(pairs)]
-            PO.align_pair(oc, onet, Image.fromarray(s), Image.fromarray(t), maxCoarse=0)
-            npairs += 1
-        dt = time.perf_counter() - t0
-        cpu = {"value": npairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": "%d whole 480x640 pairs through oracle/pair_oracle.py (torch-CPU fp32, %d threads), %.1f s" % (npairs, torch.get_num_threads(), dt)}
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                               capture_output=True, text=True, timeout=240)
+            ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            cpu = ref["cpu_baseline"]
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "pairs/s", "cores": usable_cores(), "kind": "port",
+                   "sample": "CPU oracle did not finish 1+3 pairs in 240 s (%s)" % type(e).__name__}
 
     if rank == 0:
         d2h = int(480 * 640 * 4 + out["flowDown8"].nbytes + out["matchDown8"].nbytes + 9 * 4 + 64)

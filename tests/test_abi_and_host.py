@@ -115,3 +115,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_dropin_installs_the_reference_module_names(rf, tmp_path):
+    """The names the reference's drivers import by bare name resolve to this package."""
+    import runpy
+    import sys
+    from ransac_flow_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ("coarseAlignFeatMatch", "outil", "model", "kornia", "kornia.geometry")}
+    try:
+        for script, cls in (("x/quick_start/a.py", rf.CoarseAlignC), ("x/evaluation/evalYFCC/evaluation.py", rf.CoarseAlignB),
+                            ("x/evaluation/evalHpatch/evaluation.py", rf.CoarseAlignA)):
+            dropin.install(dropin.variant_for(script))
+            drv = tmp_path / "drv.py"
+            drv.write_text("from coarseAlignFeatMatch import CoarseAlign\nimport outil\nimport model as model\n"
+                           "import kornia.geometry as tgm\nW = tgm.HomographyWarper(4, 4)\n"
+                           "names = (outil.RANSAC, outil.Homography, outil.mutualMatching, outil.getWHTensor, model.FeatureExtractor,\n"
+                           "         model.CorrNeigh, model.NetFlowCoarse, model.NetMatchability, model.predFlowCoarse)\n")
+            ns = runpy.run_path(str(drv))
+            assert ns["CoarseAlign"] is cls and ns["outil"] is rf.outil and ns["model"] is rf.model
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

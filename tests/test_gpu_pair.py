@@ -107,9 +107,21 @@ def test_get_flow_all_vs_reference(rf):
     assert np.abs(fg.cpu().numpy() - g["flowGlobal"])[0][far].max() < 1e-5
 
 
+@pytest.fixture
+def engine(request, rf):
+    rf.model.set_engine(request.param)
+    rf.outil.corr_precision = 1 if request.param == "tf32" else 0
+    yield request.param
+    rf.model.set_engine("fp32")
+    rf.outil.corr_precision = 0
+
+
+@pytest.mark.parametrize("engine", ["fp32", "tf32"], indirect=True)
 @pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
-def test_whole_pair_vs_oracle(rf, h, w, minSize, nbScale):
-    """L2 parity: the full path, same seeded samples on both sides."""
+def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
+    """L2 parity: the full path, same seeded samples on both sides.  fp32 engine: the match set is
+    the oracle's up to arg-max ties.  tf32 engine (tcgen05 convs): features carry TF32 rounding, so the match set
+    may differ; the flow is compared when the coarse homographies agree."""
     src, tgt, _ = synth.make_pair(11, h, w)
     Is, It = Image.fromarray(src), Image.fromarray(tgt)
     rsd = synth.resnet50_conv4_state(0)
@@ -121,15 +133,18 @@ def test_whole_pair_vs_oracle(rf, h, w, minSize, nbScale):
     # the match set: identical up to fp32-noise ties of the arg-max
     m_ref = set(map(tuple, np.round(oc.match2[:, :2] * 1e4).astype(int).tolist()))
     m_got = set(map(tuple, np.round(c.match2.cpu().numpy()[:, :2] * 1e4).astype(int).tolist()))
-    print("matches ref %d got %d sym-diff %d" % (len(m_ref), len(m_got), len(m_ref ^ m_got)))
-    assert len(m_ref ^ m_got) <= max(2, len(m_ref) // 50)
+    print("[%s] matches ref %d got %d sym-diff %d" % (engine, len(m_ref), len(m_got), len(m_ref ^ m_got)))
+    if engine == "fp32":
+        assert len(m_ref ^ m_got) <= max(2, len(m_ref) // 50)
+    assert out["H"].shape == ref["H"].shape
+    dH = np.abs(out["H"] - ref["H"]).max()
+    d = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy()).max()
+    d8 = np.abs(out["flowDown8"] - ref["flowDown8"]).max()
+    print("[%s] max |H - oracle| = %.3g, max |flow12 - oracle| = %.3g, max |flowDown8 - oracle| = %.3g" % (engine, dH, d, d8))
     if len(m_ref ^ m_got) == 0:
-        assert out["H"].shape == ref["H"].shape
         np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
-        d = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy()).max()
-        print("max |flow12 - oracle| = %.3g" % d)
-        assert d < FLOW_TOL
-        assert np.abs(out["flowDown8"] - ref["flowDown8"]).max() < FLOW_TOL
+    if dH < 1e-5:
+        assert d < FLOW_TOL and d8 < FLOW_TOL
 
 
 def test_multi_hypothesis_loop_runs(rf):
