@@ -93,6 +93,25 @@ int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,
                    float* y, void* stream);
+/* A whole network in one call: `layers_host[n]` executed in order over a ragged batch.  Buffers are numbered
+ * "slots" (`slots_host[i]` = device pointer, caller-allocated); slot `layers[0].src` holds the input images
+ * (`hw_host` = their sizes) and every layer's output sizes follow from its input's.  This is what the Python
+ * mirrors of FeatureExtractor / NetFlowCoarse / NetMatchability / ResNet-50 conv4 call (one host call per
+ * network instead of one per layer). */
+#define RF_OP_CONV 0      /* conv + bias (+ residual slot) (+ ReLU) */
+#define RF_OP_MAXPOOL 1   /* k, stride, pad */
+#define RF_OP_BLUR 2      /* model/downsample.py: reflect-pad 1 + [1 2 1]^2/16, stride */
+#define RF_MAX_SLOTS 32
+typedef struct rf_layer {
+    int op;
+    int src, dst, res;              /* slot indices; res < 0 = none */
+    int Cin, Cout, k, stride, pad, relu;
+    const float* w;                 /* [k*k*Cin][Cout] */
+    const float* w_tc;              /* [Cout][k*k*Cin] */
+    const float* bias;              /* [Cout] or NULL */
+} rf_layer_t;
+int rf_run_layers(const rf_layer_t* layers_host, int n, void* const* slots_host, int nimg, const int* hw_host,
+                  int engine, void* stream);
 /* max pooling k x k / stride / zero-free padding: nn.MaxPool2d (model/model.py:71; torchvision resnet maxpool) */
 int rf_maxpool2d_nhwc(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad,
                       float* y, void* stream);
@@ -101,8 +120,9 @@ int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C,
 /* F.normalize(x, dim=1): y = x / max(||x||_2, 1e-12) per pixel over C (P = total pixels).
  * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
 int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
-/* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][k*k] */
-int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, float* out, void* stream);
+/* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][ldo], channels >= k*k are
+ * written as zeros (ldo = 64 makes the 49-channel volume a 128-byte-aligned operand for the conv engines) */
+int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, float* out, void* stream);
 /* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */
 int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream);
 /* model/model.py:306: sigmoid, NHWC [P][1] -> [P] */

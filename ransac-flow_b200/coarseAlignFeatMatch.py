@@ -27,6 +27,7 @@ from . import ops
 from . import outil
 from .model import FoldedConv
 from .ops import Ragged
+from .program import LayerProgram
 
 RESNET50_LAYERS = (("layer1", 64, 3, 1), ("layer2", 128, 4, 2), ("layer3", 256, 6, 2))
 
@@ -45,31 +46,27 @@ class ResNet50Conv4:
     def __init__(self, state_dict, device="cuda"):
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
               if torch.is_tensor(v) and v.dtype.is_floating_point}
-        self.stem = FoldedConv(sd["conv1.weight"], _BN(sd, "bn1"), stride=2, pad=3)
-        self.blocks = []
+        P = LayerProgram(3)
+        x = P.conv(0, FoldedConv(sd["conv1.weight"], _BN(sd, "bn1"), stride=2, pad=3), relu=True)
+        x = P.maxpool(x, 3, 2, 1)
         for layer, planes, blocks, stride in RESNET50_LAYERS:
             for b in range(blocks):
                 p = "%s.%d" % (layer, b)
                 s = stride if b == 0 else 1
-                e = {"c1": FoldedConv(sd[p + ".conv1.weight"], _BN(sd, p + ".bn1"), 1, pad=0),
-                     "c2": FoldedConv(sd[p + ".conv2.weight"], _BN(sd, p + ".bn2"), s, pad=1),
-                     "c3": FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0),
-                     "down": None}
+                out = P.conv(x, FoldedConv(sd[p + ".conv1.weight"], _BN(sd, p + ".bn1"), 1, pad=0), relu=True)
+                out = P.conv(out, FoldedConv(sd[p + ".conv2.weight"], _BN(sd, p + ".bn2"), s, pad=1), relu=True)
+                r = x
                 if (p + ".downsample.0.weight") in sd:
-                    e["down"] = FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0)
-                self.blocks.append(e)
-        self.out_channels = self.blocks[-1]["c3"].cout
+                    r = P.conv(x, FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0), relu=False)
+                x = P.conv(out, FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0), relu=True, res=r)
+        self.program = P
+        self.out_channels = P.chan[-1]
 
     def __call__(self, x):
-        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU)."""
-        x = self.stem(x, relu=True)
-        x = ops.maxpool2d(x, 3, 2, 1)
-        for e in self.blocks:
-            out = e["c1"](x, relu=True)
-            out = e["c2"](out, relu=True)
-            r = e["down"](x, relu=False) if e["down"] is not None else x
-            x = e["c3"](out, relu=True, residual=r)
-        return x
+        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU).  One library call for the
+        whole trunk; the output buffer belongs to the program (valid until the next call with these sizes)."""
+        out, ohw = self.program.run(x, rfmodel.get_engine())
+        return Ragged(out, ohw)
 
 
 def _load_resnet50_state(imageNet, resnet_state_dict):
@@ -300,7 +297,8 @@ class CoarseAlignC(_CoarseAlignBase):
         u8 = [im if torch.is_tensor(im) else self._to_device_u8(im) for im in images]
         hw = [(int(t.shape[0]), int(t.shape[1])) for t in u8]
         flat = torch.cat([t.reshape(-1, 3) for t in u8], dim=0) if len(u8) > 1 else u8[0].reshape(-1, 3)
-        return self.net(Ragged(ops.preproc_u8(flat, normalize=True), hw)), u8
+        f = self.net(Ragged(ops.preproc_u8(flat, normalize=True), hw))
+        return Ragged(f.data.clone(), f.hw), u8        # the program owns its output buffer: keep a private copy
 
     def getCoarse(self, Mt):
         with torch.no_grad():

@@ -100,7 +100,7 @@ __global__ void l2norm_kernel(const float* __restrict__ x, long long P, int C, c
 // model/model.py:129-160 CorrNeigh: out[n,r,c,i*k+j] = sum_ch x[n,r,c,ch] * y[n,r+i-k/2,c+j-k/2,ch]
 // one warp per output pixel, lanes over channels, k*k shuffled reductions
 // ---------------------------------------------------------------------------
-__global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k,
+__global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k, int ldo,
                                   float* __restrict__ out) {
     long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -132,9 +132,10 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (lane == 0) out[pix * (k * k) + i * k + j] = acc;
+            if (lane == 0) out[pix * ldo + i * k + j] = acc;
         }
     }
+    for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
 }
 
 // ---------------------------------------------------------------------------
@@ -371,11 +372,11 @@ extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t*
     return 0;
 }
 
-extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, float* out, void* stream) {
-    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k");
+extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, float* out, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, out);
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, out);
     RF_LAUNCHED();
     return 0;
 }

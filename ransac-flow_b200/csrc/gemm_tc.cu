@@ -39,7 +39,7 @@ struct alignas(64) TcParams {
     int tw[RF_MAX_IMGS];                  // tile width (tile height = 128 / tw)
     int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
     long long out_pix[RF_MAX_IMGS + 1];
-    int R, S, pad, Cin, Cout, relu;
+    int R, S, pad, stride, Cin, Cout, relu;
     const float* bias;
     const float* residual;
     float* y;
@@ -142,13 +142,17 @@ struct TcCfg {
     static constexpr int NSPLIT = (MODE == MODE_CORR) ? 2 : 1;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+    // two CTAs per SM (so one tile's epilogue overlaps the other's main loop): <= ~100 KB of stages each;
+    // the 3xTF32 correlation needs 64 KB per stage and keeps one CTA per SM with 3 stages
+    static constexpr int BUDGET = (MODE == MODE_CORR) ? 200 * 1024 : 100 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR) ? 1 : 2;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MODE>::CTAS_PER_SM)
 tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, MODE>;
     constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
@@ -199,7 +203,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
                 const int tap = it / kc, cc = it - tap * kc;
                 const int r = tap / p.S, s = tap - r * p.S;
-                const int c0 = cc * TC_BK, x = ox0 + s - p.pad, y = oy0 + r - p.pad;
+                const int c0 = cc * TC_BK, x = ox0 * p.stride + s - p.pad, y = oy0 * p.stride + r - p.pad;
                 const int kcol = tap * p.Cin + c0;
                 tma_load_3d(sbase, &p.mapA[img], &full[st], c0, x, y);
                 tma_load_2d(sbase + NSPLIT * TC_A_BYTES, &p.mapB, &full[st], kcol, n0);
@@ -354,24 +358,25 @@ static EncodeTiledFn get_encode() {
 struct MapKey {
     const void* ptr;
     unsigned long long d0, d1, d2;
-    unsigned b0, b1, b2;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2; }
+    unsigned b0, b1, b2, es;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && es == o.es; }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&](unsigned long long v) { h ^= std::hash<unsigned long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.b2);
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.b2); mix(k.es);
         return h;
     }
 };
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// fp32 tensor (d0 innermost, d1, d2), dense strides, box (b0, b1, b2), 128B swizzle, zero fill out of bounds
+// fp32 tensor (d0 innermost, d1, d2), dense strides, box of (b0, b1, b2) ELEMENTS LOADED, traversal stride `es` on
+// d1 / d2 (strided convolutions: every es-th pixel), 128B swizzle, zero fill out of bounds
 static int get_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
-                   unsigned b0, unsigned b1, unsigned b2) {
-    MapKey key{ptr, d0, d1, d2, b0, b1, b2};
+                   unsigned b0, unsigned b1, unsigned b2, unsigned es_ = 1) {
+    MapKey key{ptr, d0, d1, d2, b0, b1, b2, es_};
     std::lock_guard<std::mutex> g(g_map_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
@@ -379,8 +384,8 @@ static int get_map(CUtensorMap* out, const void* ptr, unsigned long long d0, uns
     if (!enc) return fail_msg("cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[3] = {d0, d1, d2};
     cuuint64_t strides[2] = {d0 * 4ull, d0 * d1 * 4ull};
-    cuuint32_t box[3] = {b0, b1, b2};
-    cuuint32_t es[3] = {1, 1, 1};
+    cuuint32_t box[3] = {b0, b1 * es_, b2 * es_};      // bounding box in tensor coordinates; ceil(box / stride) elements are loaded
+    cuuint32_t es[3] = {1, es_, es_};
     int rank = d2 > 0 ? 3 : 2;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -425,15 +430,15 @@ static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st
 using namespace rf;
 
 bool rf_conv2d_tc_supported(const ConvParams& p) {
-    return p.stride == 1 && (p.Cin % TC_BK) == 0 && (p.Cout % 4) == 0 && p.Cout >= 16 && p.R == p.S && (p.R == 1 || p.R == 3);
+    return (p.stride == 1 || p.stride == 2) && (p.Cin % TC_BK) == 0 && p.Cout >= 1 && p.R == p.S && (p.R == 1 || p.R == 3);
 }
 
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cudaStream_t st) {
     RF_REQUIRE(w_tc != nullptr, "rf_conv2d_nhwc: engine=1 needs w_tc ([Cout][R*S*Cin])");
-    RF_REQUIRE(rf_conv2d_tc_supported(cp), "rf_conv2d_nhwc: engine=1 needs stride 1, Cin % 32 == 0, Cout % 4 == 0, 1x1 or 3x3");
+    RF_REQUIRE(rf_conv2d_tc_supported(cp), "rf_conv2d_nhwc: engine=1 needs stride 1 or 2, Cin % 32 == 0, 1x1 or 3x3");
     TcParams p;
     memset(&p, 0, sizeof(p));
-    const int BN = cp.Cout >= 256 ? 256 : (cp.Cout >= 128 ? 128 : 64);
+    const int BN = cp.Cout > 64 ? 128 : 64;
     p.nimg = set.n;
     int tiles = 0;
     for (int i = 0; i < set.n; ++i) {
@@ -445,17 +450,16 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
         p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
         p.out_pix[i] = set.out_pix[i];
         int rc = get_map(&p.mapA[i], cp.x + set.in_pix[i] * cp.Cin, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
-                         (unsigned long long)set.H[i], TC_BK, (unsigned)tw, (unsigned)th);
+                         (unsigned long long)set.H[i], TC_BK, (unsigned)tw, (unsigned)th, (unsigned)cp.stride);
         if (rc) return rc;
     }
     for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
     p.out_pix[set.n] = set.out_pix[set.n];
     int rc = get_map(&p.mapB, w_tc, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 0, TC_BK, (unsigned)BN, 0);
     if (rc) return rc;
-    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
+    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
-    if (BN == 256) return launch_tc<256, MODE_CONV>(p, tiles, nt, st);
     if (BN == 128) return launch_tc<128, MODE_CONV>(p, tiles, nt, st);
     return launch_tc<64, MODE_CONV>(p, tiles, nt, st);
 }
@@ -489,7 +493,7 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     if (!rc) rc = get_map(&p.mapB, Bhi, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
     if (!rc) rc = get_map(&p.mapBlo, Blo, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
     if (rc) return rc;
-    p.R = 1; p.S = 1; p.pad = 0; p.Cin = C; p.Cout = NB;
+    p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
     return launch_tc<BN, MODE_CORR>(p, p.tiles_x[0], (NB + BN - 1) / BN, st);
 }

@@ -1,0 +1,44 @@
+// rf_run_layers: a whole conv network (ResNet-50 conv1..layer3, FeatureExtractor, the flow / matchability heads)
+// executed from ONE host call: the layer list is walked here, in C++, so the per-layer cost on the host is a
+// kernel launch (a few microseconds) instead of a Python -> ctypes round trip.
+#include "common.cuh"
+
+using namespace rf;
+
+extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
+    RF_REQUIRE(L != nullptr && n >= 1 && nimg >= 1 && nimg <= RF_MAX_IMGS, "rf_run_layers: bad arguments");
+    static thread_local int hw[RF_MAX_SLOTS][2 * RF_MAX_IMGS];
+    bool known[RF_MAX_SLOTS] = {false};
+    RF_REQUIRE(L[0].src >= 0 && L[0].src < RF_MAX_SLOTS, "rf_run_layers: bad input slot");
+    for (int i = 0; i < 2 * nimg; ++i) hw[L[0].src][i] = hw_host[i];
+    known[L[0].src] = true;
+    for (int li = 0; li < n; ++li) {
+        const rf_layer_t& l = L[li];
+        RF_REQUIRE(l.src >= 0 && l.src < RF_MAX_SLOTS && l.dst >= 0 && l.dst < RF_MAX_SLOTS && l.res < RF_MAX_SLOTS, "rf_run_layers: slot index out of range");
+        RF_REQUIRE(known[l.src], "rf_run_layers: layer reads a slot nothing has written");
+        RF_REQUIRE(l.dst != l.src && l.dst != l.res, "rf_run_layers: in-place layers are not supported");
+        const int* shw = hw[l.src];
+        const float* x = static_cast<const float*>(slots[l.src]);
+        float* y = static_cast<float*>(slots[l.dst]);
+        int rc = 0;
+        int k = l.k, stride = l.stride, pad = l.pad;
+        if (l.op == RF_OP_CONV) {
+            const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;
+            rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, l.w_tc, l.bias, res, l.Cout, k, k, stride, pad, l.relu, engine, y, stream);
+        } else if (l.op == RF_OP_MAXPOOL) {
+            rc = rf_maxpool2d_nhwc(x, nimg, shw, l.Cin, k, stride, pad, y, stream);
+        } else if (l.op == RF_OP_BLUR) {
+            k = 3; pad = 1;
+            rc = rf_blur_downsample_nhwc(x, nimg, shw, l.Cin, stride, y, stream);
+        } else {
+            return fail_msg("rf_run_layers: unknown op");
+        }
+        if (rc) return rc;
+        for (int i = 0; i < nimg; ++i) {
+            hw[l.dst][2 * i] = (shw[2 * i] + 2 * pad - k) / stride + 1;
+            hw[l.dst][2 * i + 1] = (shw[2 * i + 1] + 2 * pad - k) / stride + 1;
+        }
+        known[l.dst] = true;
+    }
+    return 0;
+}

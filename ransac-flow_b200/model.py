@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from . import ops
 from .ops import Ragged
+from .program import LayerProgram
 
 _engine = ops.ENGINE_FP32
 
@@ -47,8 +48,10 @@ def _init_like_reference(module):
 class FoldedConv:
     """conv weight (+ following eval-mode BatchNorm) packed for the kernels."""
 
-    def __init__(self, weight, bn=None, stride=1, pad=None, eps=None):
+    def __init__(self, weight, bn=None, stride=1, pad=None, eps=None, cin_pad=None):
         w = weight.detach().float()
+        if cin_pad is not None and cin_pad > w.shape[1]:          # zero input channels (49 -> 64 for the heads)
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
         cout, cin, k, _ = w.shape
         if bn is not None:
             e = bn.eps if eps is None else eps
@@ -137,37 +140,33 @@ class FeatureExtractor(_Engine):
         return nn.Sequential(*layers)
 
     def _fold_build(self):
-        f = {"stem": FoldedConv(self.conv1.weight, self.bn1, 1), "blocks": []}
+        """The whole network as one layer program (model/model.py:106-114 do_forward)."""
+        P = LayerProgram(3)
+        x = P.conv(0, FoldedConv(self.conv1.weight, self.bn1, 1), relu=True)        # conv1 + bn1 + relu
+        x = P.maxpool(x, 2, 1, 0)                                                    # MaxPool2d(2, stride 1)
+        x = P.blur(x, 2)                                                             # anti-aliased stride 2
         for layer in (self.layer1, self.layer2, self.layer3):
             for b in layer:
-                e = {"c1": FoldedConv(b.conv1.weight, b.bn1, b.stride), "c2": FoldedConv(b.conv2.weight, b.bn2, 1), "down": None}
+                out = P.conv(x, FoldedConv(b.conv1.weight, b.bn1, b.stride), relu=True)
+                r = x
                 if b.downsample is not None:
                     mods = list(b.downsample)
-                    e["down"] = (mods[0].stride if isinstance(mods[0], Downsample) else None,
-                                 FoldedConv(mods[-2].weight, mods[-1], 1, pad=0))
-                f["blocks"].append(e)
-        return f
+                    if isinstance(mods[0], Downsample):
+                        r = P.blur(r, mods[0].stride)
+                    r = P.conv(r, FoldedConv(mods[-2].weight, mods[-1], 1, pad=0), relu=False)
+                x = P.conv(out, FoldedConv(b.conv2.weight, b.bn2, 1), relu=True, res=r)   # conv2 + bn2 + residual + relu
+        return P
 
     def forward_ragged(self, x):
-        f = self._folded()
-        x = f["stem"](x, relu=True)                       # conv1 + bn1 + relu
-        x = ops.maxpool2d(x, 2, 1, 0)                     # MaxPool2d(2, stride 1)
-        x = ops.blur_downsample(x, 2)                     # anti-aliased stride 2
-        for e in f["blocks"]:
-            out = e["c1"](x, relu=True)
-            if e["down"] is not None:
-                bs, conv = e["down"]
-                r = ops.blur_downsample(x, bs) if bs is not None else x
-                r = conv(r, relu=False)
-            else:
-                r = x
-            x = e["c2"](out, relu=True, residual=r)       # conv2 + bn2 + residual + relu
-        return x
+        """Ragged [P, 3] -> Ragged [P/64, 256].  The returned buffer is owned by the program and valid until
+        the next forward with the same image sizes; callers normalise / copy it right away."""
+        out, ohw = self._folded().run(x, _engine)
+        return Ragged(out, ohw)
 
     def forward(self, x):
         self._check(x)
         with torch.no_grad():
-            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw()
+            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw().clone(memory_format=torch.channels_last)
 
 
 class CorrNeigh(nn.Module):
@@ -200,16 +199,28 @@ class _Head(_Engine):
         self.paddingSize = kernelSize // 2
         _init_like_reference(self)
 
+    CORR_LD = 64      # the k*k = 49-channel correlation volume is carried with 64 channels (15 zeros)
+
     def _fold_build(self):
-        return [FoldedConv(self.conv1.weight, self.bn1), FoldedConv(self.conv2.weight, self.bn2),
-                FoldedConv(self.conv3.weight, self.bn3), FoldedConv(self.conv4.weight, None)]
+        P = LayerProgram(self.CORR_LD)
+        x = P.conv(0, FoldedConv(self.conv1.weight, self.bn1, cin_pad=self.CORR_LD), relu=True)
+        x = P.conv(x, FoldedConv(self.conv2.weight, self.bn2), relu=True)
+        x = P.conv(x, FoldedConv(self.conv3.weight, self.bn3), relu=True)
+        P.conv(x, FoldedConv(self.conv4.weight, None), relu=False)
+        return P
+
+    def _padded(self, corr):
+        """Accept the reference's 49-channel volume or the library's 64-channel one."""
+        if corr.C == self.CORR_LD:
+            return corr
+        d = torch.zeros((corr.data.shape[0], self.CORR_LD), device=corr.data.device, dtype=torch.float32)
+        d[:, :corr.C] = corr.data
+        return Ragged(d, corr.hw)
 
     def trunk(self, corr):
-        f = self._folded()
-        x = f[0](corr, relu=True)
-        x = f[1](x, relu=True)
-        x = f[2](x, relu=True)
-        return f[3](x, relu=False)
+        corr = self._padded(corr)
+        out, ohw = self._folded().run(corr, _engine)
+        return Ragged(out, ohw)
 
 
 class NetFlowCoarse(_Head):

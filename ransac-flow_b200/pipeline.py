@@ -37,8 +37,9 @@ def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False,
         fs = fine_features(network["netFeatCoarse"], IsSample)
         ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
         k = network["netCorr"].kernelSize
-        corr12 = ops.corr_neigh(ft, fs, k)
-        corr21 = ops.corr_neigh(fs, ft, k)
+        ld = network["netFlowCoarse"].CORR_LD
+        corr12 = ops.corr_neigh(ft, fs, k, ld)
+        corr21 = ops.corr_neigh(fs, ft, k, ld)
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
         both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
         mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch

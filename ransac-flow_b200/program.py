@@ -1,0 +1,118 @@
+"""Layer programs: a network (list of conv / pool / blur layers with folded weights) compiled for one
+image-set signature and executed by ONE call into the library (``rf_run_layers``).
+
+The topology is written in Python next to the mirror of the reference module it belongs to
+(model.py, coarseAlignFeatMatch.py); this class only assigns buffer slots, sizes and caches the
+activation buffers (stable device pointers => the library's TMA-descriptor cache always hits).
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, need_cuda, stream
+
+RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR = 0, 1, 2
+RF_MAX_SLOTS = 32
+
+
+class rf_layer_t(C.Structure):
+    _fields_ = [("op", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
+                ("Cin", C.c_int), ("Cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("relu", C.c_int),
+                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p)]
+
+
+lib.rf_run_layers.restype = C.c_int
+lib.rf_run_layers.argtypes = [C.POINTER(rf_layer_t), C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+
+
+class LayerProgram:
+    """Symbolic tensors are integers; tensor 0 is the input."""
+
+    def __init__(self, cin):
+        self.ops = []            # (op, src, res, cin, cout, k, stride, pad, relu, folded)
+        self.chan = [cin]
+        self._keep = []          # folded weights (keeps the device tensors alive)
+        self._compiled = {}
+
+    # -- topology --------------------------------------------------------------------------------
+    def conv(self, src, fc, relu, res=None):
+        assert self.chan[src] == fc.cin, (self.chan[src], fc.cin)
+        self.ops.append((RF_OP_CONV, src, -1 if res is None else res, fc.cin, fc.cout, fc.k, fc.stride, fc.pad, int(relu), fc))
+        self._keep.append(fc)
+        self.chan.append(fc.cout)
+        return len(self.chan) - 1
+
+    def maxpool(self, src, k, stride, pad):
+        c = self.chan[src]
+        self.ops.append((RF_OP_MAXPOOL, src, -1, c, c, k, stride, pad, 0, None))
+        self.chan.append(c)
+        return len(self.chan) - 1
+
+    def blur(self, src, stride):
+        c = self.chan[src]
+        self.ops.append((RF_OP_BLUR, src, -1, c, c, 3, stride, 1, 0, None))
+        self.chan.append(c)
+        return len(self.chan) - 1
+
+    # -- compilation for one image-set signature --------------------------------------------------
+    def _compile(self, hw, device):
+        n_t = len(self.chan)
+        last_use = [0] * n_t
+        for i, o in enumerate(self.ops):
+            last_use[o[1]] = i
+            if o[2] >= 0:
+                last_use[o[2]] = i
+        last_use[n_t - 1] = len(self.ops)                       # the output outlives the program
+        # pixel counts per tensor
+        hws = [list(hw)]
+        for o in self.ops:
+            k, s, p = o[5], o[6], o[7]
+            hws.append([((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1) for h, w in hws[o[1]]])
+        elems = [sum(h * w for h, w in hws[t]) * self.chan[t] for t in range(n_t)]
+        # slot assignment: slot 0 = external input; others from a free list
+        slot_of, free, slot_elems = {0: 0}, [], [0]
+        layers = (rf_layer_t * len(self.ops))()
+        for i, o in enumerate(self.ops):
+            t_out = i + 1
+            # choose a free slot (prefer the smallest that fits, else the largest one and grow it)
+            if free:
+                fit = [s for s in free if slot_elems[s] >= elems[t_out]]
+                s = min(fit, key=lambda q: slot_elems[q]) if fit else max(free, key=lambda q: slot_elems[q])
+                free.remove(s)
+                slot_elems[s] = max(slot_elems[s], elems[t_out])
+            else:
+                s = len(slot_elems)
+                slot_elems.append(elems[t_out])
+            slot_of[t_out] = s
+            L = layers[i]
+            L.op, L.src, L.dst, L.res = o[0], slot_of[o[1]], s, (slot_of[o[2]] if o[2] >= 0 else -1)
+            L.Cin, L.Cout, L.k, L.stride, L.pad, L.relu = o[3], o[4], o[5], o[6], o[7], o[8]
+            fc = o[9]
+            if fc is not None:
+                L.w, L.w_tc = fc.w.data_ptr(), fc.w_tc.data_ptr()
+                L.bias = fc.bias.data_ptr() if fc.bias is not None else None
+            for t in {o[1], o[2]}:
+                if t > 0 and last_use[t] == i:
+                    free.append(slot_of[t])
+        assert len(slot_elems) <= RF_MAX_SLOTS
+        bufs = [None] + [torch.empty(max(1, e), device=device, dtype=torch.float32) for e in slot_elems[1:]]
+        out_slot = slot_of[n_t - 1]
+        chw = (C.c_int * (2 * len(hw)))(*[v for p in hw for v in p])
+        return dict(layers=layers, bufs=bufs, out_slot=out_slot, out_hw=hws[-1], out_elems=elems[-1], chw=chw, nslots=len(slot_elems))
+
+    def run(self, x, engine):
+        """x: ops.Ragged input -> (output buffer view [P_out, C_out] valid until the next run, out_hw)."""
+        need_cuda(x.data)
+        key = (tuple(x.hw), str(x.data.device))
+        if key not in self._compiled:
+            if len(self._compiled) > 16:
+                self._compiled.clear()
+            self._compiled[key] = self._compile(x.hw, x.data.device)
+        c = self._compiled[key]
+        slots = (C.c_void_p * c["nslots"])()
+        slots[0] = x.data.data_ptr()
+        for i in range(1, c["nslots"]):
+            slots[i] = c["bufs"][i].data_ptr()
+        check(lib.rf_run_layers(c["layers"], len(self.ops), slots, len(x.hw), c["chw"], int(engine), stream()))
+        out = c["bufs"][c["out_slot"]][:c["out_elems"]].view(-1, self.chan[-1])
+        return out, c["out_hw"]

@@ -13,17 +13,18 @@ TF32_TOL = 4e-3          # two TF32-truncated operands (2^-10 each), fp32 accumu
 
 
 @pytest.mark.parametrize("cin,cout,k,sizes", [
+    (64, 49, 3, [(6, 8)]), (128, 1, 3, [(6, 8), (6, 8)]), (64, 512, 3, [(60, 80)]),
     (64, 64, 3, [(24, 32), (9, 7)]), (64, 64, 1, [(16, 16)]), (64, 256, 1, [(13, 17), (6, 5), (1, 1)]),
     (128, 128, 3, [(16, 16), (16, 16)]), (256, 64, 1, [(30, 40)]), (1024, 256, 1, [(15, 20), (30, 40)]),
     (256, 256, 3, [(15, 20), (33, 25)]), (256, 1024, 1, [(20, 15), (40, 30)]), (512, 128, 1, [(60, 80)]),
     (64, 48, 3, [(12, 20)]), (128, 16, 3, [(6, 8)]), (32, 32, 3, [(128, 3), (3, 128)])])
-@pytest.mark.parametrize("relu,res", [(True, True), (False, False)])
-def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res):
+@pytest.mark.parametrize("relu,res,stride", [(True, True, 1), (False, False, 1), (True, False, 2)])
+def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res, stride):
     g = torch.Generator().manual_seed(cin + cout * 3 + k)
     xs = [torch.randn(1, cin, h, w, generator=g) for h, w in sizes]
     w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
     bias = torch.randn(cout, generator=g)
-    refs = [F.conv2d(x, w, bias, padding=k // 2) for x in xs]
+    refs = [F.conv2d(x, w, bias, stride=stride, padding=k // 2) for x in xs]
     rs = [torch.randn(r.shape, generator=g) for r in refs] if res else None
     if res:
         refs = [a + b for a, b in zip(refs, rs)]
@@ -31,7 +32,7 @@ def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res):
         refs = [F.relu(r) for r in refs]
     wp = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous().cuda()
     wtc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().cuda()
-    y = rf.ops.conv2d(ragged(rf, xs), wp, bias.cuda(), cout, k, 1, k // 2, relu, ragged(rf, rs) if res else None,
+    y = rf.ops.conv2d(ragged(rf, xs), wp, bias.cuda(), cout, k, stride, k // 2, relu, ragged(rf, rs) if res else None,
                       rf.ops.ENGINE_TF32, wtc)
     torch.cuda.synchronize()
     for i, r in enumerate(refs):
@@ -43,12 +44,12 @@ def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res):
 
 def test_tf32_engine_falls_back_to_fp32_kernels_for_unsupported_shapes(rf):
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(1, 64, 16, 16, generator=g)
-    w = torch.randn(128, 64, 3, 3, generator=g) / 24
-    ref = F.conv2d(x, w, stride=2, padding=1)
-    wp = w.permute(2, 3, 1, 0).reshape(576, 128).contiguous().cuda()
-    wtc = w.permute(0, 2, 3, 1).reshape(128, 576).contiguous().cuda()
-    y = rf.ops.conv2d(ragged(rf, [x]), wp, None, 128, 3, 2, 1, False, None, rf.ops.ENGINE_TF32, wtc)
+    x = torch.randn(1, 3, 16, 16, generator=g)                       # 3-channel stem: not a TMA-able operand
+    w = torch.randn(64, 3, 7, 7, generator=g) / 12
+    ref = F.conv2d(x, w, stride=2, padding=3)
+    wp = w.permute(2, 3, 1, 0).reshape(147, 64).contiguous().cuda()
+    wtc = w.permute(0, 2, 3, 1).reshape(64, 147).contiguous().cuda()
+    y = rf.ops.conv2d(ragged(rf, [x]), wp, None, 64, 7, 2, 3, False, None, rf.ops.ENGINE_TF32, wtc)
     assert (y.image(0).cpu() - ref).abs().max().item() < 2e-5        # exact-fp32 SIMT path
 
 
