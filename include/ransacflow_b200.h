@@ -121,8 +121,10 @@ int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C,
  * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
 int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
 /* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][ldo], channels >= k*k are
- * written as zeros (ldo = 64 makes the 49-channel volume a 128-byte-aligned operand for the conv engines) */
-int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, float* out, void* stream);
+ * written as zeros (ldo = 64 makes the 49-channel volume a 128-byte-aligned operand for the conv engines);
+ * round_tf32_out = 1 stores the values rounded to nearest TF32 (operand of the tensor-core heads) */
+int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
+                       float* out, void* stream);
 /* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */
 int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream);
 /* model/model.py:306: sigmoid, NHWC [P][1] -> [P] */

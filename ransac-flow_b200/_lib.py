@@ -29,7 +29,7 @@ SIGNATURES = {
     "rf_maxpool2d_nhwc": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp]),
     "rf_blur_downsample_nhwc": (i32, [vp, i32, vp, i32, i32, vp, vp]),
     "rf_l2norm_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),
-    "rf_corr_neigh_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "rf_corr_neigh_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "rf_run_layers": (i32, [vp, i32, vp, i32, vp, i32, vp]),
     "rf_softmax_flow": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "rf_sigmoid": (i32, [vp, i64, vp, vp]),

@@ -91,6 +91,7 @@ struct ConvParams {
     const float* residual;   // nullable, packed like y
     float* y;
     int Cin, Cout, R, S, stride, pad, relu;
+    int round_out;           // 1: round the output to TF32 (nearest) so that the tensor-core consumer's truncation is exact
     long long Mtot;          // total output pixels
     int K;                   // R*S*Cin
 };
@@ -107,6 +108,12 @@ __device__ __forceinline__ int find_img(const ImgSet& s, long long p) {
 __device__ __forceinline__ uint32_t f2ord(float f) {
     uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// round-to-nearest TF32 (10-bit mantissa); the tensor core itself truncates fp32 operands
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
 }
 __device__ __forceinline__ float ord2f(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);

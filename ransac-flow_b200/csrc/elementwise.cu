@@ -42,7 +42,7 @@ __global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-__global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int stride) {
+__global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int stride, int round_out) {
     const int c4n = C >> 2;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = set.out_pix[set.n] * c4n;
@@ -65,6 +65,7 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __r
             acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y); acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
         }
     }
+    if (round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
     reinterpret_cast<float4*>(y + pm * C)[c4] = acc;
 }
 
@@ -100,7 +101,7 @@ __global__ void l2norm_kernel(const float* __restrict__ x, long long P, int C, c
 // model/model.py:129-160 CorrNeigh: out[n,r,c,i*k+j] = sum_ch x[n,r,c,ch] * y[n,r+i-k/2,c+j-k/2,ch]
 // one warp per output pixel, lanes over channels, k*k shuffled reductions
 // ---------------------------------------------------------------------------
-__global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k, int ldo,
+__global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k, int ldo, int round_out,
                                   float* __restrict__ out) {
     long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -132,7 +133,7 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (lane == 0) out[pix * ldo + i * k + j] = acc;
+            if (lane == 0) out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
         }
     }
     for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
@@ -353,15 +354,19 @@ extern "C" int rf_maxpool2d_nhwc(const float* x, int nimg, const int* hw_host, i
     return 0;
 }
 
-extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C, int stride, float* y, void* stream) {
+int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream) {
     RF_REQUIRE((C % 4) == 0 && stride >= 1, "rf_blur_downsample_nhwc: C must be a multiple of 4");
     ImgSet set;
     RF_REQUIRE(make_imgset(set, nimg, hw_host, 3, stride, 1) == 0, "rf_blur_downsample_nhwc: bad image set");
     for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur_downsample_nhwc: reflect padding needs H, W >= 2");
     long long total = set.out_pix[nimg] * (C / 4);
-    blur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride);
+    blur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride, round_out);
     RF_LAUNCHED();
     return 0;
+}
+
+extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C, int stride, float* y, void* stream) {
+    return rf_blur_downsample_impl(x, nimg, hw_host, C, stride, 0, y, stream);
 }
 
 extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream) {
@@ -372,11 +377,11 @@ extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t*
     return 0;
 }
 
-extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, float* out, void* stream) {
+extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out, float* out, void* stream) {
     RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, out);
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out);
     RF_LAUNCHED();
     return 0;
 }

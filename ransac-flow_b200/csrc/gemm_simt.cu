@@ -362,6 +362,10 @@ conv_kernel(const __grid_constant__ ImgSet set, const ConvParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
+                if (p.round_out) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = round_tf32(v[j]);
+                }
                 *reinterpret_cast<float4*>(p.y + o) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
@@ -371,6 +375,7 @@ conv_kernel(const __grid_constant__ ImgSet set, const ConvParams p) {
                         if (p.bias) t += __ldg(p.bias + n + j);
                         if (p.residual) t += __ldg(p.residual + o + j);
                         if (p.relu) t = fmaxf(t, 0.f);
+                        if (p.round_out) t = round_tf32(t);
                         p.y[o + j] = t;
                     }
                 }
@@ -437,6 +442,9 @@ extern "C" int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int 
     p.Cin = Cin; p.Cout = Cout; p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.relu = relu;
     p.Mtot = set.out_pix[nimg];
     p.K = R * S * Cin;
+    // tensor-core engine: ReLU'd activations are the next conv's MMA operand; store them rounded to nearest TF32
+    // (the MMA truncates), which removes the truncation bias.  The fp32 engine never rounds.
+    p.round_out = (engine == 1 && relu) ? 1 : 0;
     cudaStream_t st = as_stream(stream);
     RF_REQUIRE(engine == 0 || engine == 1, "rf_conv2d_nhwc: unknown engine");
     // engine 1 = tcgen05 TF32 where the layer shape allows it (stride 1, Cin % 32 == 0); other layers

@@ -39,7 +39,7 @@ struct alignas(64) TcParams {
     int tw[RF_MAX_IMGS];                  // tile width (tile height = 128 / tw)
     int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
     long long out_pix[RF_MAX_IMGS + 1];
-    int R, S, pad, stride, Cin, Cout, relu;
+    int R, S, pad, stride, Cin, Cout, relu, round_out;
     const float* bias;
     const float* residual;
     float* y;
@@ -267,6 +267,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
                             if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
                             if (res) { float4 rr = __ldg(reinterpret_cast<const float4*>(res + j)); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
                             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
                             *reinterpret_cast<float4*>(dst + j) = o;
                         }
                     } else {
@@ -277,6 +278,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
                                 if (p.bias) o += __ldg(p.bias + n + j);
                                 if (res) o += __ldg(res + j);
                                 if (p.relu) o = fmaxf(o, 0.f);
+                                if (p.round_out) o = round_tf32(o);
                                 dst[j] = o;
                             }
                     }
@@ -457,7 +459,7 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     p.out_pix[set.n] = set.out_pix[set.n];
     int rc = get_map(&p.mapB, w_tc, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 0, TC_BK, (unsigned)BN, 0);
     if (rc) return rc;
-    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
+    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
     if (BN == 128) return launch_tc<128, MODE_CONV>(p, tiles, nt, st);

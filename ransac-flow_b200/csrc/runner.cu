@@ -5,6 +5,8 @@
 
 using namespace rf;
 
+int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
+
 extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
     RF_REQUIRE(L != nullptr && n >= 1 && nimg >= 1 && nimg <= RF_MAX_IMGS, "rf_run_layers: bad arguments");
     static thread_local int hw[RF_MAX_SLOTS][2 * RF_MAX_IMGS];
@@ -29,7 +31,7 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
             rc = rf_maxpool2d_nhwc(x, nimg, shw, l.Cin, k, stride, pad, y, stream);
         } else if (l.op == RF_OP_BLUR) {
             k = 3; pad = 1;
-            rc = rf_blur_downsample_nhwc(x, nimg, shw, l.Cin, stride, y, stream);
+            rc = rf_blur_downsample_impl(x, nimg, shw, l.Cin, stride, engine == 1 ? 1 : 0, y, stream);
         } else {
             return fail_msg("rf_run_layers: unknown op");
         }

@@ -61,7 +61,11 @@ class FoldedConv:
         else:
             self.bias = None
         self.w = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous()      # [R*S*Cin][Cout]
-        self.w_tc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()   # [Cout][R*S*Cin]
+        # tensor-core copy: [Cout][R*S*Cin], rounded to nearest-even TF32 once (the MMA would truncate)
+        wt = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()
+        bits = wt.view(torch.int32)
+        bits = (bits + 0xFFF + ((bits >> 13) & 1)) & ~0x1FFF
+        self.w_tc = bits.view(torch.float32).contiguous()
         self.cout, self.cin, self.k, self.stride = cout, cin, k, stride
         self.pad = (k // 2) if pad is None else pad
 

@@ -9,7 +9,7 @@ restated on the library's kernels (no file IO, no metrics: those stay in the dri
 import numpy as np
 import torch
 
-from . import ops
+from . import model, ops
 from .kornia_geometry import HomographyWarper
 from .ops import Ragged
 
@@ -38,8 +38,9 @@ def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False,
         ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
         k = network["netCorr"].kernelSize
         ld = network["netFlowCoarse"].CORR_LD
-        corr12 = ops.corr_neigh(ft, fs, k, ld)
-        corr21 = ops.corr_neigh(fs, ft, k, ld)
+        tc = model.get_engine() == ops.ENGINE_TF32
+        corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
+        corr21 = ops.corr_neigh(fs, ft, k, ld, tc)
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
         both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
         mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch
