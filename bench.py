@@ -171,7 +171,7 @@ def run_b200(args, rank, world, local):
         else:
             s, t = resident[i % len(resident)]
         torch.manual_seed(1000)                                                     # evalKITTI/evaluation.py:182
-        out = rf.pipeline.align_pair(coarse, net, s, t, maxCoarse=0)                # results come back as numpy (D2H)
+        out = rf.pipeline.align_pair_single(coarse, net, s, t)                      # results come back as numpy (one pinned D2H)
         flush.zero_()                                                               # L2 flush between steps
         return out
 

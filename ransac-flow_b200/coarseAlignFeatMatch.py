@@ -47,7 +47,7 @@ class ResNet50Conv4:
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
               if torch.is_tensor(v) and v.dtype.is_floating_point}
         P = LayerProgram(3)
-        x = P.conv(0, FoldedConv(sd["conv1.weight"], _BN(sd, "bn1"), stride=2, pad=3), relu=True)
+        x = P.stem(0, sd["conv1.weight"], _BN(sd, "bn1"), 2, 3)                      # 7x7/2 stem as im2col + 1x1 conv
         x = P.maxpool(x, 3, 2, 1)
         for layer, planes, blocks, stride in RESNET50_LAYERS:
             for b in range(blocks):
@@ -236,16 +236,42 @@ class CoarseAlignA(_CoarseAlignBase):
             self.ItTensor = self._to_tensor01(u8[nS])
             self._set_source_feats(feats, nS)
             self._set_target_feats(feats, nS)
-            # mutual matching once per pair (:139-147), kept on the device
+            # mutual matching once per pair (:139-147), kept on the device; the matched-coordinate attributes the
+            # reference caches (:140-147) are materialised lazily (they need the match count on the host)
             self._idx1, self._idx2, self._count = ops.corr_mutual_nn(self._feats_rows, self._featt_rows, outil.corr_precision)
+            self._mm = None
+
+    def _matched(self):
+        if self._mm is None:
             n = int(self._count.item())
-            index1, index2 = self._idx1[:n], self._idx2[:n]
-            self.W1MutualMatch = self.WMultiScale[index1]
-            self.H1MutualMatch = self.HMultiScale[index1]
-            self.W2MutualMatch = self.Wt[index2]
-            self.H2MutualMatch = self.Ht[index2]
-            self.W2MutualMatchInt = self.WtInt[index2]
-            self.H2MutualMatchInt = self.HtInt[index2]
+            i1, i2 = self._idx1[:n], self._idx2[:n]
+            self._mm = dict(W1MutualMatch=self.WMultiScale[i1], H1MutualMatch=self.HMultiScale[i1], W2MutualMatch=self.Wt[i2],
+                            H2MutualMatch=self.Ht[i2], W2MutualMatchInt=self.WtInt[i2], H2MutualMatchInt=self.HtInt[i2])
+        return self._mm
+
+    W1MutualMatch = property(lambda self: self._matched()["W1MutualMatch"])
+    H1MutualMatch = property(lambda self: self._matched()["H1MutualMatch"])
+    W2MutualMatch = property(lambda self: self._matched()["W2MutualMatch"])
+    H2MutualMatch = property(lambda self: self._matched()["H2MutualMatch"])
+    W2MutualMatchInt = property(lambda self: self._matched()["W2MutualMatchInt"])
+    H2MutualMatchInt = property(lambda self: self._matched()["H2MutualMatchInt"])
+
+    def getCoarse_device(self, Mt=None):
+        """Device-resident ``getCoarse``: no host synchronisation.  Returns (H [9], nbInlier [1], mask [NB], status [1],
+        match_count [1]) as CUDA tensors; ``status`` follows RF_RANSAC_* (0 = OK; 1/3 = the reference returns None).
+        The RANSAC samples are drawn as ``torch.randint(2**32 - 1) % M`` with M read on the device (the reference
+        draws ``torch.randint(M)`` on the host, which needs M there); callers that need the reference's exact
+        generator stream use ``getCoarse``."""
+        with torch.no_grad():
+            valid16 = None
+            if Mt is not None and np.any(Mt):
+                valid16 = self._mask16(Mt).reshape(-1).to(torch.uint8).contiguous()
+            match1, match2, _, cnt = ops.build_matches(self._idx1, self._idx2, self._count, self.WMultiScale, self.HMultiScale,
+                                                       self.Wt, self.Ht, valid16)
+            self.match1, self.match2, self._match_count = match1, match2, cnt
+            raw = torch.randint(2 ** 32 - 1, (self.nbIter, self.nbPoint), device=match1.device)
+            H, nb, mask, status = ops.ransac_homography(match1, match2, raw, self.tolerance, 100, cnt)
+            return H, nb, mask, status, cnt
 
     def getCoarse(self, Mt):
         with torch.no_grad():

@@ -38,6 +38,33 @@ __global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* 
 }
 
 // ---------------------------------------------------------------------------
+// im2col for the few-channel stems (3 -> 64): row p of the output holds the k*k*C patch of output pixel p in
+// (r, s, c) order, zero padded to Kpad (a multiple of 32 floats = one 128-byte swizzle row), so that the stem
+// becomes a 1x1 convolution the tensor-core engine can read with TMA.  One thread per (pixel, patch element).
+// ---------------------------------------------------------------------------
+__global__ void im2col_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y,
+                              int C, int k, int stride, int pad, int Kpad, int round_out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * Kpad;
+    if (t >= total) return;
+    long long pm = t / Kpad;
+    int e = (int)(t - pm * Kpad);
+    float v = 0.f;
+    if (e < k * k * C) {
+        int im = find_img(set, pm);
+        int local = (int)(pm - set.out_pix[im]);
+        int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+        int tap = e / C, c = e - tap * C;
+        int r = tap / k, sx = tap - r * k;
+        int iy = oy * stride - pad + r, ix = ox * stride - pad + sx;
+        if (iy >= 0 && iy < set.H[im] && ix >= 0 && ix < set.W[im])
+            v = __ldg(x + (set.in_pix[im] + (long long)iy * set.W[im] + ix) * C + c);
+        if (round_out) v = round_tf32(v);
+    }
+    y[t] = v;
+}
+
+// ---------------------------------------------------------------------------
 // model/downsample.py:12-46: ReflectionPad2d(1) + depthwise [1 2 1]x[1 2 1]/16, stride s
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
@@ -367,6 +394,17 @@ int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C,
 
 extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C, int stride, float* y, void* stream) {
     return rf_blur_downsample_impl(x, nimg, hw_host, C, stride, 0, y, stream);
+}
+
+int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, int round_out,
+                   float* y, void* stream) {
+    RF_REQUIRE(Kpad >= k * k * C && C >= 1, "rf_im2col: Kpad too small");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_im2col: bad image set");
+    long long total = set.out_pix[nimg] * Kpad;
+    im2col_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    RF_LAUNCHED();
+    return 0;
 }
 
 extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream) {

@@ -5,6 +5,8 @@
 
 using namespace rf;
 
+int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, int round_out,
+                   float* y, void* stream);
 int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
 
 extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
@@ -32,6 +34,8 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
         } else if (l.op == RF_OP_BLUR) {
             k = 3; pad = 1;
             rc = rf_blur_downsample_impl(x, nimg, shw, l.Cin, stride, engine == 1 ? 1 : 0, y, stream);
+        } else if (l.op == RF_OP_IM2COL) {
+            rc = rf_im2col_impl(x, nimg, shw, l.Cin, k, stride, pad, l.Cout, engine == 1 ? 1 : 0, y, stream);
         } else {
             return fail_msg("rf_run_layers: unknown op");
         }

@@ -146,7 +146,7 @@ class FeatureExtractor(_Engine):
     def _fold_build(self):
         """The whole network as one layer program (model/model.py:106-114 do_forward)."""
         P = LayerProgram(3)
-        x = P.conv(0, FoldedConv(self.conv1.weight, self.bn1, 1), relu=True)        # conv1 + bn1 + relu
+        x = P.stem(0, self.conv1.weight, self.bn1, 1, 1)                             # conv1 + bn1 + relu (im2col + 1x1)
         x = P.maxpool(x, 2, 1, 0)                                                    # MaxPool2d(2, stride 1)
         x = P.blur(x, 2)                                                             # anti-aliased stride 2
         for layer in (self.layer1, self.layer2, self.layer3):

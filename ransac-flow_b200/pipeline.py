@@ -27,12 +27,10 @@ def fine_features(netFeatCoarse, img):
     return Ragged(ops.l2norm(f.data), f.hw)
 
 
-def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False, align_corners=False):
-    """Same inputs/outputs as the reference function.  ``featt`` may be the (1,256,h8,w8) tensor the
-    reference passes or a Ragged from ``fine_features``.  ``grid`` is only used for its size (the
-    base grid is regenerated inside the fused composition kernel)."""
+def PredFlowMask_device(IsTensor, featt, flowCoarse, size, network, with_match21=False, align_corners=False):
+    """PredFlowMask without the device->host copies: returns CUDA tensors
+    (flow12 (1,H,W,2), match (1,1,H,W), flowDown8 (1,2,h8,w8), matchDown8 (2,1,h8,w8) = [match12, match21])."""
     with torch.no_grad():
-        H, W = grid.size()[1], grid.size()[2]
         IsSample = ops.grid_sample(IsTensor, flowCoarse, align_corners)
         fs = fine_features(network["netFeatCoarse"], IsSample)
         ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
@@ -44,13 +42,61 @@ def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False,
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
         both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
         mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch
-        match12Down8, match21Down8 = mboth[0:1], mboth[1:2]
-        flow12, match, _ = ops.compose_fine(flowDown8, match12Down8, match21Down8 if with_match21 else None, flowCoarse,
+        flow12, match, _ = ops.compose_fine(flowDown8, mboth[0:1], mboth[1:2] if with_match21 else None, flowCoarse,
                                             clamp=True, align_corners=align_corners)
-        out = torch.cat([match.reshape(-1), flowDown8.reshape(-1), mboth.reshape(-1)]).cpu().numpy()   # one D2H
-        n0, n1 = H * W, flowDown8.numel()
-        return (flow12, out[:n0].reshape(H, W), out[n0:n0 + n1].reshape(tuple(flowDown8.shape)),
-                out[n0 + n1:].reshape(1, 2, flowDown8.shape[2], flowDown8.shape[3]))
+        return flow12, match, flowDown8, mboth
+
+
+def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False, align_corners=False):
+    """Same inputs/outputs as the reference function (evaluation/evalHpatch/evaluation.py:23-55; ``with_match21``:
+    evaluation/evalCorr/evaluation.py:54).  ``featt`` may be the (1,256,h8,w8) tensor the reference passes or a Ragged
+    from ``fine_features``.  ``grid`` is only used for its size (the base grid is regenerated inside the fused
+    composition kernel)."""
+    H, W = grid.size()[1], grid.size()[2]
+    flow12, match, flowDown8, mboth = PredFlowMask_device(IsTensor, featt, flowCoarse, (H, W), network, with_match21, align_corners)
+    out = torch.cat([match.reshape(-1), flowDown8.reshape(-1), mboth.reshape(-1)]).cpu().numpy()   # one D2H
+    n0, n1 = H * W, flowDown8.numel()
+    return (flow12, out[:n0].reshape(H, W), out[n0:n0 + n1].reshape(tuple(flowDown8.shape)),
+            out[n0 + n1:].reshape(1, 2, flowDown8.shape[2], flowDown8.shape[3]))
+
+
+_pinned = {}
+
+
+def _to_host(t):
+    """One asynchronous D2H into a cached pinned buffer + a stream synchronise."""
+    key = (t.numel(), t.dtype)
+    if key not in _pinned:
+        _pinned[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+    h = _pinned[key]
+    h.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def align_pair_single(coarseModel, network, Is, It, with_match21=False):
+    """The single-hypothesis case of the evaluation loop (maxCoarse = 0, no background mask) with NO host
+    synchronisation until the results are fetched: matching, RANSAC (device-side match count), warp, fine flow and
+    composition are queued back to back, then one pinned D2H brings back status, H, the matchability map and the /8
+    tensors.  Same outputs as ``align_pair``."""
+    coarseModel.setPair(Is, It)
+    Itw, Ith = coarseModel.target_size
+    featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+    Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(None)
+    flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+    flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
+    packed = torch.cat([status.float(), cnt.float(), nb.float(), Hd, match.reshape(-1), f8.reshape(-1), mboth.reshape(-1)])
+    host = _to_host(packed).copy()
+    st, n0, n8 = int(host[0]), Ith * Itw, f8.numel()
+    if st != 0:                                    # the reference's `if bestPara is None: break` (evaluation.py:215-216)
+        if st == 2:
+            raise TypeError("'NoneType' object is not subscriptable")     # utils/outil.py:162
+        return dict(H=np.zeros((0,)), flowDown8=np.zeros((0,)), matchDown8=np.zeros((0,)), flow12=[], match=[])
+    H = host[3:12].reshape(1, 3, 3).astype(np.float32)
+    o = 12
+    return dict(H=H, flowDown8=host[o + n0:o + n0 + n8].reshape(tuple(f8.shape)),
+                matchDown8=host[o + n0 + n8:].reshape(1, 2, f8.shape[2], f8.shape[3]),
+                flow12=[flow12], match=[host[o:o + n0].reshape(Ith, Itw)], nbInlier=int(host[2]), nbMatch=int(host[1]))
 
 
 def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):

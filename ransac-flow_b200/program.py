@@ -11,7 +11,7 @@ import torch
 
 from ._lib import check, lib, need_cuda, stream
 
-RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR = 0, 1, 2
+RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL = 0, 1, 2, 3
 RF_MAX_SLOTS = 32
 
 
@@ -47,6 +47,24 @@ class LayerProgram:
         self.ops.append((RF_OP_MAXPOOL, src, -1, c, c, k, stride, pad, 0, None))
         self.chan.append(c)
         return len(self.chan) - 1
+
+    def im2col(self, src, k, stride, pad, kpad):
+        """k x k patches of a few-channel image as rows of ``kpad`` floats (the stem becomes a 1x1 conv)."""
+        c = self.chan[src]
+        assert kpad >= k * k * c
+        self.ops.append((RF_OP_IM2COL, src, -1, c, kpad, k, stride, pad, 0, None))
+        self.chan.append(kpad)
+        return len(self.chan) - 1
+
+    def stem(self, src, weight, bn, stride, pad):
+        """conv(k x k, few input channels) + BN + ReLU as im2col + 1x1 conv (tensor-core friendly)."""
+        from .model import FoldedConv
+        cout, cin, k, _ = weight.shape
+        kpad = (k * k * cin + 31) // 32 * 32
+        w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k * cin)          # (r, s, c) order
+        w = torch.nn.functional.pad(w, (0, kpad - k * k * cin)).reshape(cout, kpad, 1, 1)
+        x = self.im2col(src, k, stride, pad, kpad)
+        return self.conv(x, FoldedConv(w, bn, 1, pad=0), relu=True)
 
     def blur(self, src, stride):
         c = self.chan[src]

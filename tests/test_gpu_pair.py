@@ -181,3 +181,29 @@ def test_device_preproc_pyramid_equals_host(rf):
     b.setPair(Image.fromarray(src), Image.fromarray(tgt))
     assert np.array_equal(np.asarray(a.It), np.asarray(b.It)) and np.array_equal(np.asarray(a.Is), np.asarray(b.Is))
     assert torch.equal(a.featsMultiScale, b.featsMultiScale) and torch.equal(a._idx1, b._idx1)
+
+
+def test_async_single_hypothesis_path_equals_the_loop(rf):
+    """align_pair_single (no host sync until the final D2H) == align_pair(maxCoarse=0) when both use the same samples."""
+    src, tgt, _ = synth.make_pair(14, 96, 128)
+    Is, It = Image.fromarray(src), Image.fromarray(tgt)
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    raw = synth.draw_samples(5, 2 ** 31 - 1, 1000)
+    with fixed_randint([raw]):
+        a = rf.pipeline.align_pair_single(c, net, Is, It)
+    with fixed_randint([raw % a["nbMatch"]]):
+        b = rf.pipeline.align_pair(c, net, Is, It, maxCoarse=0)
+    assert np.array_equal(a["H"], b["H"])
+    assert np.array_equal(a["flowDown8"], b["flowDown8"]) and np.array_equal(a["matchDown8"], b["matchDown8"])
+    assert torch.equal(a["flow12"][0], b["flow12"][0]) and np.array_equal(a["match"][0], b["match"][0])
+
+
+def test_randint_modulo_stream_on_cuda(rf):
+    """Documented property used by getCoarse_device: report whether randint(2**32-1) % M equals randint(M) on this torch."""
+    torch.manual_seed(1000)
+    a = torch.randint(636, (1000, 4), device="cuda")
+    torch.manual_seed(1000)
+    b = torch.randint(2 ** 32 - 1, (1000, 4), device="cuda") % 636
+    print("randint(M) == randint(2**32-1) %% M on CUDA: %s" % bool((a == b).all()))
