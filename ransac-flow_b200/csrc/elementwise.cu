@@ -42,26 +42,35 @@ __global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* 
 // (r, s, c) order, zero padded to Kpad (a multiple of 32 floats = one 128-byte swizzle row), so that the stem
 // becomes a 1x1 convolution the tensor-core engine can read with TMA.  One thread per (pixel, patch element).
 // ---------------------------------------------------------------------------
+// grid: (ceil(Ho*Wo*Kpad/4 / 256), image); one thread per float4 of the output; 32-bit index math.
 __global__ void im2col_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y,
                               int C, int k, int stride, int pad, int Kpad, int round_out) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = set.out_pix[set.n] * Kpad;
-    if (t >= total) return;
-    long long pm = t / Kpad;
-    int e = (int)(t - pm * Kpad);
-    float v = 0.f;
-    if (e < k * k * C) {
-        int im = find_img(set, pm);
-        int local = (int)(pm - set.out_pix[im]);
-        int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
-        int tap = e / C, c = e - tap * C;
-        int r = tap / k, sx = tap - r * k;
-        int iy = oy * stride - pad + r, ix = ox * stride - pad + sx;
-        if (iy >= 0 && iy < set.H[im] && ix >= 0 && ix < set.W[im])
-            v = __ldg(x + (set.in_pix[im] + (long long)iy * set.W[im] + ix) * C + c);
-        if (round_out) v = round_tf32(v);
+    const int im = blockIdx.y;
+    const int q4 = Kpad >> 2;                                   // float4 per output row
+    const int Wo = set.Wo[im], H = set.H[im], W = set.W[im];
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)(set.Ho[im] * Wo) * (unsigned)q4;
+    if (idx >= total) return;
+    const unsigned local = idx / (unsigned)q4;
+    const int e0 = (int)(idx - local * (unsigned)q4) * 4;
+    const int oy = (int)(local / (unsigned)Wo), ox = (int)(local - (unsigned)oy * (unsigned)Wo);
+    const int kkc = k * k * C, kc = k * C;
+    const float* src = x + set.in_pix[im] * C;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j;
+        float t = 0.f;
+        if (e < kkc) {
+            const int r = e / kc, rem = e - r * kc;             // (r, s, c) order: rem = s*C + c is contiguous in the input row
+            const int iy = oy * stride - pad + r;
+            const int ixc = (ox * stride - pad) * C + rem;      // element offset inside the input row
+            if (iy >= 0 && iy < H && ixc >= 0 && ixc < W * C) t = __ldg(src + (long long)iy * W * C + ixc);
+            if (round_out) t = round_tf32(t);
+        }
+        v[j] = t;
     }
-    y[t] = v;
+    reinterpret_cast<float4*>(y + (set.out_pix[im] + local) * Kpad)[e0 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // ---------------------------------------------------------------------------
@@ -401,8 +410,14 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
     RF_REQUIRE(Kpad >= k * k * C && C >= 1, "rf_im2col: Kpad too small");
     ImgSet set;
     RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_im2col: bad image set");
-    long long total = set.out_pix[nimg] * Kpad;
-    im2col_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    RF_REQUIRE((Kpad & 3) == 0, "rf_im2col: Kpad must be a multiple of 4");
+    long long maxq = 0;
+    for (int i = 0; i < nimg; ++i) {
+        long long q = (long long)set.Ho[i] * set.Wo[i] * (Kpad / 4);
+        RF_REQUIRE(q < (1ll << 31), "rf_im2col: image too large for 32-bit indexing");
+        if (q > maxq) maxq = q;
+    }
+    im2col_kernel<<<dim3(blocks_for(maxq, 256), nimg), 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
     RF_LAUNCHED();
     return 0;
 }

@@ -30,6 +30,8 @@ constexpr int TC_A_BYTES = 128 * 128;     // 128 rows x 128 B
 
 struct alignas(64) TcParams {
     CUtensorMap mapA[RF_MAX_IMGS];        // per image: (C, W, H) fp32, box (32, tw, th)
+    CUtensorMap mapY[RF_MAX_IMGS];        // per image: output (Cout, Wo, Ho), box (32, tw, th)   [TMA-store epilogue]
+    CUtensorMap mapR[RF_MAX_IMGS];        // per image: residual, same geometry                   [TMA-load in the epilogue]
     CUtensorMap mapAlo;                   // MODE_CORR: low part of A
     CUtensorMap mapB;                     // (K, Cout) fp32, box (32, BN)
     CUtensorMap mapBlo;                   // MODE_CORR: low part of B
@@ -39,7 +41,7 @@ struct alignas(64) TcParams {
     int tw[RF_MAX_IMGS];                  // tile width (tile height = 128 / tw)
     int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
     long long out_pix[RF_MAX_IMGS + 1];
-    int R, S, pad, stride, Cin, Cout, relu, round_out;
+    int R, S, pad, stride, Cin, Cout, relu, round_out, tma_epi;
     const float* bias;
     const float* residual;
     float* y;
@@ -81,6 +83,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -161,7 +171,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* res_full = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -180,6 +191,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
+        mbar_init(res_full, 1);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -247,7 +259,45 @@ tc_kernel(const __grid_constant__ TcParams p) {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (MODE == MODE_CONV) {
+        if (MODE == MODE_CONV && p.tma_epi) {
+            // ---- bulk epilogue: residual tile in by TMA, result tile out by TMA; the pipeline stages are idle now and
+            // serve as staging: BN/32 boxes of (32 channels x tw x th) = 128 rows x 128 B, 128-byte swizzled ----
+            uint8_t* stg = smem;
+            const bool has_res = p.residual != nullptr;
+            if (has_res) {
+                if (warp == 2 && lane == 0) {
+                    mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c) tma_load_3d(stg + c * TC_A_BYTES, &p.mapR[img], res_full, n0 + c * 32, ox0, oy0);
+                }
+                mbar_wait(res_full, 0);
+            }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(trow + c * 32, v);
+                const int n = n0 + c * 32;
+                uint8_t* rowp = stg + c * TC_A_BYTES + m * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (p.bias && n + 4 * j < p.Cout) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                    if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *sp = o;
+                }
+            }
+            fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA (async proxy)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 2 && lane == 0) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c)
+                    if (n0 + c * 32 < p.Cout) tma_store_3d(&p.mapY[img], stg + c * TC_A_BYTES, n0 + c * 32, ox0, oy0);
+                tma_store_commit_and_wait_read();       // smem must stay valid until the bulk stores have read it
+            }
+        } else if (MODE == MODE_CONV) {
             const int py = m / tw, px = m - py * tw;
             const int oy = oy0 + py, ox = ox0 + px;
             const bool valid = (oy < p.Ho[img]) && (ox < p.Wo[img]);
@@ -454,6 +504,19 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
         int rc = get_map(&p.mapA[i], cp.x + set.in_pix[i] * cp.Cin, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
                          (unsigned long long)set.H[i], TC_BK, (unsigned)tw, (unsigned)th, (unsigned)cp.stride);
         if (rc) return rc;
+    }
+    // bulk (TMA) epilogue whenever the output rows are 16-byte aligned (Cout % 4 == 0)
+    p.tma_epi = ((cp.Cout & 3) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0) ? 1 : 0;
+    if (p.tma_epi) {
+        for (int i = 0; i < set.n; ++i) {
+            const unsigned tw = (unsigned)p.tw[i], th = 128u / tw;
+            int rc = get_map(&p.mapY[i], cp.y + set.out_pix[i] * cp.Cout, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], TC_BK, tw, th);
+            if (!rc && cp.residual)
+                rc = get_map(&p.mapR[i], cp.residual + set.out_pix[i] * cp.Cout, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], TC_BK, tw, th);
+            if (rc) return rc;
+        }
     }
     for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
     p.out_pix[set.n] = set.out_pix[set.n];
