@@ -43,8 +43,10 @@ __global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* 
 // becomes a 1x1 convolution the tensor-core engine can read with TMA.  One thread per (pixel, patch element).
 // ---------------------------------------------------------------------------
 // grid: (ceil(Ho*Wo*Kpad/4 / 256), image); one thread per float4 of the output; 32-bit index math.
+template <int KC, int CC, int KPADC>      // compile-time (k, C, Kpad) for the two stems (0 = runtime values)
 __global__ void im2col_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y,
-                              int C, int k, int stride, int pad, int Kpad, int round_out) {
+                              int C_, int k_, int stride, int pad, int Kpad_, int round_out) {
+    const int C = CC ? CC : C_, k = KC ? KC : k_, Kpad = KPADC ? KPADC : Kpad_;
     const int im = blockIdx.y;
     const int q4 = Kpad >> 2;                                   // float4 per output row
     const int Wo = set.Wo[im], H = set.H[im], W = set.W[im];
@@ -417,7 +419,10 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
         RF_REQUIRE(q < (1ll << 31), "rf_im2col: image too large for 32-bit indexing");
         if (q > maxq) maxq = q;
     }
-    im2col_kernel<<<dim3(blocks_for(maxq, 256), nimg), 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    dim3 grid(blocks_for(maxq, 256), nimg);
+    if (k == 7 && C == 3 && Kpad == 160) im2col_kernel<7, 3, 160><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    else if (k == 3 && C == 3 && Kpad == 32) im2col_kernel<3, 3, 32><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    else im2col_kernel<0, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
     RF_LAUNCHED();
     return 0;
 }

@@ -152,11 +152,11 @@ struct TcCfg {
     static constexpr int NSPLIT = (MODE == MODE_CORR) ? 2 : 1;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
-    // two CTAs per SM (so one tile's epilogue overlaps the other's main loop): <= ~100 KB of stages each;
+    // three CTAs per SM (so one tile's epilogue / prologue overlaps the others' main loops): <= 73 KB of stages each;
     // the 3xTF32 correlation needs 64 KB per stage and keeps one CTA per SM with 3 stages
-    static constexpr int BUDGET = (MODE == MODE_CORR) ? 200 * 1024 : 100 * 1024;
+    static constexpr int BUDGET = (MODE == MODE_CORR) ? 200 * 1024 : 73 * 1024;
     static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR) ? 1 : 2;
+    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR) ? 1 : 3;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };

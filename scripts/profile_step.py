@@ -61,3 +61,10 @@ for e in ev:
 print("engine %s: wall %.3f ms/step; GPU kernel time %.3f ms/step (busy %.0f%%), %d kernels/step" % (engine, wall * 1e3, tot / 1e3, 100 * tot / 1e3 / (wall * 1e3), len(ev) // N))
 for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:28]:
     print("%9.1f us/step %5.1f%% x%-4d %s" % (t / N, 100 * t / N / tot, c // N, k))
+if "--seq" in sys.argv:
+    evs = sorted(ev, key=lambda e: e.time_range.start)
+    per = len(evs) // N
+    print("---- kernel sequence of the last step (us) ----")
+    for e in evs[-per:]:
+        d = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        print("%8.1f  %s" % (d, e.name.split("(")[0].replace("void ", "")[:60]))
