@@ -147,24 +147,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
 
 constexpr int MODE_CONV = 0, MODE_CORR = 1;
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool DEEP = false>
 struct TcCfg {
     static constexpr int NSPLIT = (MODE == MODE_CORR) ? 2 : 1;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
     // three CTAs per SM (so one tile's epilogue / prologue overlaps the others' main loops): <= 73 KB of stages each;
     // the 3xTF32 correlation needs 64 KB per stage and keeps one CTA per SM with 3 stages
-    static constexpr int BUDGET = (MODE == MODE_CORR) ? 200 * 1024 : 73 * 1024;
+    // DEEP: K-deep layers (3x3 convs, wide 1x1) are bound by TMA round trips unless many stages are in flight:
+    // one CTA per SM with a ~200 KB ring instead of three CTAs with short rings
+    static constexpr int BUDGET = (MODE == MODE_CORR || DEEP) ? 200 * 1024 : 73 * 1024;
     static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR) ? 1 : 3;
+    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR || DEEP) ? 1 : 3;
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MODE>::CTAS_PER_SM)
+template <int BN, int MODE, bool DEEP>
+__global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MODE, DEEP>::CTAS_PER_SM)
 tc_kernel(const __grid_constant__ TcParams p) {
-    using Cfg = TcCfg<BN, MODE>;
+    using Cfg = TcCfg<BN, MODE, DEEP>;
     constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -177,14 +179,18 @@ tc_kernel(const __grid_constant__ TcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- tile decode ----
+    // conv: blockIdx.x = pixel tile, blockIdx.y = channel tile.  corr: swapped, so that the CTAs sharing one 128-row
+    // slab of featA (1 MB of hi+lo) are co-resident and the slab is fetched from DRAM once
+    const int mtile = (MODE == MODE_CORR) ? blockIdx.y : blockIdx.x;
+    const int ntile = (MODE == MODE_CORR) ? blockIdx.x : blockIdx.y;
     int img = 0;
 #pragma unroll
-    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
-    const int tloc = blockIdx.x - p.tile_start[img];
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mtile >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = mtile - p.tile_start[img];
     const int tw = p.tw[img], th = 128 / tw;
     const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
     const int ox0 = txi * tw, oy0 = tyi * th;
-    const int n0 = blockIdx.y * BN;
+    const int n0 = ntile * BN;
     const int kc = p.Cin / TC_BK;                 // 32-channel chunks per tap
     const int KI = p.R * p.S * kc;
 
@@ -464,15 +470,16 @@ static int pick_tw(int Ho, int Wo) {
     return best;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool DEEP>
 static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st) {
-    using Cfg = TcCfg<BN, MODE>;
+    using Cfg = TcCfg<BN, MODE, DEEP>;
     static bool attr = false;
     if (!attr) {
-        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr = true;
     }
-    tc_kernel<BN, MODE><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
+    tc_kernel<BN, MODE, DEEP><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
     RF_LAUNCHED();
     return 0;
 }
@@ -525,8 +532,9 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
-    if (BN == 128) return launch_tc<128, MODE_CONV>(p, tiles, nt, st);
-    return launch_tc<64, MODE_CONV>(p, tiles, nt, st);
+    const bool deep = cp.R * cp.S * (cp.Cin / TC_BK) >= 16;          // >= 16 K-steps of 32 channels
+    if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false>(p, tiles, nt, st);
+    return deep ? launch_tc<64, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false>(p, tiles, nt, st);
 }
 
 size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }
@@ -560,5 +568,5 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     if (rc) return rc;
     p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
-    return launch_tc<BN, MODE_CORR>(p, p.tiles_x[0], (NB + BN - 1) / BN, st);
+    return launch_tc<BN, MODE_CORR, false>(p, p.tiles_x[0], (NB + BN - 1) / BN, st);
 }
