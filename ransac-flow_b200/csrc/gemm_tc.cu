@@ -154,11 +154,12 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = NSPLIT * (TC_A_BYTES + B_BYTES);
     // three CTAs per SM (so one tile's epilogue / prologue overlaps the others' main loops): <= 73 KB of stages each;
     // the 3xTF32 correlation needs 64 KB per stage and keeps one CTA per SM with 3 stages
-    // DEEP: K-deep layers (3x3 convs, wide 1x1) are bound by TMA round trips unless many stages are in flight:
-    // one CTA per SM with a ~200 KB ring instead of three CTAs with short rings
-    static constexpr int BUDGET = (MODE == MODE_CORR || DEEP) ? 200 * 1024 : 73 * 1024;
+    // measured in sequence (profiles/): co-resident CTAs matter more than ring depth (one tile's prologue /
+    // epilogue hides behind the others' main loops, and the loop itself is L2->SM bandwidth bound).  K-deep layers
+    // (3x3, wide 1x1): 2 CTAs x 3 stages; short-K layers (1x1 expansions with residual): 3 CTAs x 2 stages
+    static constexpr int BUDGET = (MODE == MODE_CORR) ? 200 * 1024 : (DEEP ? 100 * 1024 : 73 * 1024);
     static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR || DEEP) ? 1 : 3;
+    static constexpr int CTAS_PER_SM = (MODE == MODE_CORR) ? 1 : (DEEP ? 2 : 3);
     static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
