@@ -407,6 +407,42 @@ extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_h
     return rf_blur_downsample_impl(x, nimg, hw_host, C, stride, 0, y, stream);
 }
 
+// Stem-specialised im2col: one CTA = one output row segment of TPX pixels.  The K input rows it needs are staged in
+// shared memory with coalesced loads, then the (r, s, c)-ordered patches are written as contiguous float4 rows.
+template <int K, int C, int KPAD, int STRIDE, int PAD, int TPX>
+__global__ void __launch_bounds__(256)
+im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int round_out) {
+    constexpr int INW = ((TPX - 1) * STRIDE + K) * C;          // floats of one staged input row
+    constexpr int Q4 = KPAD / 4;
+    __shared__ float sIn[K][INW + 1];
+    const int im = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * TPX;
+    const int Wo = set.Wo[im];
+    if (oy >= set.Ho[im] || ox0 >= Wo) return;
+    const int H = set.H[im], WC = set.W[im] * C;
+    const float* src = x + set.in_pix[im] * C;
+    const int col0 = (ox0 * STRIDE - PAD) * C;
+    for (int idx = threadIdx.x; idx < K * INW; idx += 256) {
+        const int r = idx / INW, j = idx - r * INW;
+        const int iy = oy * STRIDE - PAD + r, col = col0 + j;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && col >= 0 && col < WC) v = __ldg(src + (long long)iy * WC + col);
+        sIn[r][j] = round_out ? round_tf32(v) : v;
+    }
+    __syncthreads();
+    const int npx = min(TPX, Wo - ox0);
+    float4* dst = reinterpret_cast<float4*>(y + (set.out_pix[im] + (long long)oy * Wo + ox0) * KPAD);
+    for (int f = threadIdx.x; f < npx * Q4; f += 256) {
+        const int px = f / Q4, e0 = (f - px * Q4) * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j;
+            v[j] = (e < K * K * C) ? sIn[e / (K * C)][px * STRIDE * C + e % (K * C)] : 0.f;
+        }
+        dst[f] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, int round_out,
                    float* y, void* stream) {
     RF_REQUIRE(Kpad >= k * k * C && C >= 1, "rf_im2col: Kpad too small");
@@ -418,6 +454,18 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
         long long q = (long long)set.Ho[i] * set.Wo[i] * (Kpad / 4);
         RF_REQUIRE(q < (1ll << 31), "rf_im2col: image too large for 32-bit indexing");
         if (q > maxq) maxq = q;
+    }
+    int maxHo = 0, maxWo = 0;
+    for (int i = 0; i < nimg; ++i) { maxHo = set.Ho[i] > maxHo ? set.Ho[i] : maxHo; maxWo = set.Wo[i] > maxWo ? set.Wo[i] : maxWo; }
+    if (k == 7 && C == 3 && Kpad == 160 && stride == 2 && pad == 3) {          // ResNet-50 stem
+        im2col_smem_kernel<7, 3, 160, 2, 3, 64><<<dim3((maxWo + 63) / 64, maxHo, nimg), 256, 0, as_stream(stream)>>>(set, x, y, round_out);
+        RF_LAUNCHED();
+        return 0;
+    }
+    if (k == 3 && C == 3 && Kpad == 32 && stride == 1 && pad == 1) {           // FeatureExtractor stem
+        im2col_smem_kernel<3, 3, 32, 1, 1, 128><<<dim3((maxWo + 127) / 128, maxHo, nimg), 256, 0, as_stream(stream)>>>(set, x, y, round_out);
+        RF_LAUNCHED();
+        return 0;
     }
     dim3 grid(blocks_for(maxq, 256), nimg);
     if (k == 7 && C == 3 && Kpad == 160) im2col_kernel<7, 3, 160><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);

@@ -11,7 +11,7 @@
 // DLT null vector: LAPACK dgesdd on an 8x9 matrix returns Vh[8] = (G_1...G_8 e_9)^T
 // where G_i are the right Householder reflectors of the unblocked
 // lower-bidiagonalisation dgebd2 (sign included); the kernel runs exactly that
-// recurrence in fp64, one hypothesis per thread, matrix in shared memory.
+// recurrence in fp64, one hypothesis per thread, matrix in registers (fully unrolled).
 //
 // Scoring uses IEEE fp32 ops in a fixed order without FMA contraction so that
 // the inlier masks are bit-identical to oracle/outil_oracle.py.
@@ -38,68 +38,76 @@ __device__ __forceinline__ double dlapy2(double x, double y) {
     return w * sqrt(1.0 + q * q);
 }
 
-// 4-point DLT.  sA: this thread's 8x9 fp64 matrix, element (r,c) at sA[(r*9+c)*ld].
-// xs/ys: source (X) and target (Y) sample points.  Writes the unit-norm null
-// vector (LAPACK sign) as fp32 to h[9].
-__device__ void dlt_null_vector(double* sA, int ld, const float (&xu)[4], const float (&xv)[4],
-                                const float (&yu)[4], const float (&yv)[4], float* h_out) {
-#define A_(r, c) sA[((r) * 9 + (c)) * ld]
+// 4-point DLT, one hypothesis per thread, the 8x9 fp64 matrix held in REGISTERS (every loop below is fully
+// unrolled so all indices are compile-time constants).  Writes the unit-norm null vector (LAPACK's sign) as fp32.
+// Same operation order as the dgebd2 recurrence spelled out in oracle/outil_oracle.py::householder_null_vector.
+__device__ __forceinline__ void dlt_null_vector(const float (&xu)[4], const float (&xv)[4],
+                                                const float (&yu)[4], const float (&yv)[4], float* h_out) {
+    double A[8][9];
     // utils/outil.py:73-81: entries are fp32 products upcast to fp64
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float u = yu[i], v = yv[i], u_ = xu[i], v_ = xv[i];
-        int r0 = 2 * i, r1 = 2 * i + 1;
-        A_(r0, 0) = 0.0; A_(r0, 1) = 0.0; A_(r0, 2) = 0.0;
-        A_(r0, 3) = (double)(-u); A_(r0, 4) = (double)(-v); A_(r0, 5) = -1.0;
-        A_(r0, 6) = (double)__fmul_rn(v_, u); A_(r0, 7) = (double)__fmul_rn(v_, v); A_(r0, 8) = (double)v_;
-        A_(r1, 0) = (double)u; A_(r1, 1) = (double)v; A_(r1, 2) = 1.0;
-        A_(r1, 3) = 0.0; A_(r1, 4) = 0.0; A_(r1, 5) = 0.0;
-        A_(r1, 6) = (double)__fmul_rn(-u_, u); A_(r1, 7) = (double)__fmul_rn(-u_, v); A_(r1, 8) = (double)(-u_);
+        const float u = yu[i], v = yv[i], u_ = xu[i], v_ = xv[i];
+        A[2 * i][0] = 0.0; A[2 * i][1] = 0.0; A[2 * i][2] = 0.0;
+        A[2 * i][3] = (double)(-u); A[2 * i][4] = (double)(-v); A[2 * i][5] = -1.0;
+        A[2 * i][6] = (double)__fmul_rn(v_, u); A[2 * i][7] = (double)__fmul_rn(v_, v); A[2 * i][8] = (double)v_;
+        A[2 * i + 1][0] = (double)u; A[2 * i + 1][1] = (double)v; A[2 * i + 1][2] = 1.0;
+        A[2 * i + 1][3] = 0.0; A[2 * i + 1][4] = 0.0; A[2 * i + 1][5] = 0.0;
+        A[2 * i + 1][6] = (double)__fmul_rn(-u_, u); A[2 * i + 1][7] = (double)__fmul_rn(-u_, v); A[2 * i + 1][8] = (double)(-u_);
     }
     double taup[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         // ---- dlarfg: right reflector G_i annihilates A(i, i+1:8) ----
-        double alpha = A_(i, i);
+        const double alpha = A[i][i];
         double ss = 0.0;
-        for (int j = i + 1; j < 9; ++j) { double t = A_(i, j); ss += t * t; }
-        double xnorm = sqrt(ss);
+#pragma unroll
+        for (int j = i + 1; j < 9; ++j) ss += A[i][j] * A[i][j];
+        const double xnorm = sqrt(ss);
         double tau = 0.0;
         if (xnorm != 0.0) {
-            double beta = -dsign(dlapy2(alpha, xnorm), alpha);
+            const double beta = -dsign(dlapy2(alpha, xnorm), alpha);
             tau = (beta - alpha) / beta;
-            double scal = 1.0 / (alpha - beta);
-            for (int j = i + 1; j < 9; ++j) A_(i, j) *= scal;   // v_i (v_i[i] = 1 implicit)
-            // A(i,i) = beta is never read again
+            const double scal = 1.0 / (alpha - beta);
+#pragma unroll
+            for (int j = i + 1; j < 9; ++j) A[i][j] *= scal;        // v_i (v_i[i] = 1 implicit)
         }
         taup[i] = tau;
         // ---- dlarf('Right'): rows i+1..7, columns i..8 ----
         if (tau != 0.0) {
+#pragma unroll
             for (int r = i + 1; r < 8; ++r) {
-                double w = A_(r, i);
-                for (int j = i + 1; j < 9; ++j) w += A_(r, j) * A_(i, j);
-                double tw = tau * w;
-                A_(r, i) -= tw;
-                for (int j = i + 1; j < 9; ++j) A_(r, j) -= tw * A_(i, j);
+                double w = A[r][i];
+#pragma unroll
+                for (int j = i + 1; j < 9; ++j) w += A[r][j] * A[i][j];
+                const double tw = tau * w;
+                A[r][i] -= tw;
+#pragma unroll
+                for (int j = i + 1; j < 9; ++j) A[r][j] -= tw * A[i][j];
             }
         }
         // ---- left reflector H_i annihilates A(i+2:7, i), applied to A(i+1:7, i+1:8) ----
         if (i < 7) {
-            double al = A_(i + 1, i);
+            const double al = A[i + 1][i];
             double s2 = 0.0;
-            for (int r = i + 2; r < 8; ++r) { double t = A_(r, i); s2 += t * t; }
-            double xn = sqrt(s2);
+#pragma unroll
+            for (int r = i + 2; r < 8; ++r) s2 += A[r][i] * A[r][i];
+            const double xn = sqrt(s2);
             if (xn != 0.0) {
-                double beta = -dsign(dlapy2(al, xn), al);
-                double tauq = (beta - al) / beta;
-                double scal = 1.0 / (al - beta);
-                for (int r = i + 2; r < 8; ++r) A_(r, i) *= scal;   // u (u[i+1] = 1 implicit)
+                const double beta = -dsign(dlapy2(al, xn), al);
+                const double tauq = (beta - al) / beta;
+                const double scal = 1.0 / (al - beta);
+#pragma unroll
+                for (int r = i + 2; r < 8; ++r) A[r][i] *= scal;    // u (u[i+1] = 1 implicit)
+#pragma unroll
                 for (int j = i + 1; j < 9; ++j) {
-                    double w = A_(i + 1, j);
-                    for (int r = i + 2; r < 8; ++r) w += A_(r, i) * A_(r, j);
-                    double tw = tauq * w;
-                    A_(i + 1, j) -= tw;
-                    for (int r = i + 2; r < 8; ++r) A_(r, j) -= tw * A_(r, i);
+                    double w = A[i + 1][j];
+#pragma unroll
+                    for (int r = i + 2; r < 8; ++r) w += A[r][i] * A[r][j];
+                    const double tw = tauq * w;
+                    A[i + 1][j] -= tw;
+#pragma unroll
+                    for (int r = i + 2; r < 8; ++r) A[r][j] -= tw * A[r][i];
                 }
             }
         }
@@ -112,15 +120,14 @@ __device__ void dlt_null_vector(double* sA, int ld, const float (&xu)[4], const 
     for (int i = 7; i >= 0; --i) {
         double d = h[i];
 #pragma unroll
-        for (int j = i + 1; j < 9; ++j) d += A_(i, j) * h[j];
-        double td = taup[i] * d;
+        for (int j = i + 1; j < 9; ++j) d += A[i][j] * h[j];
+        const double td = taup[i] * d;
         h[i] -= td;
 #pragma unroll
-        for (int j = i + 1; j < 9; ++j) h[j] -= td * A_(i, j);
+        for (int j = i + 1; j < 9; ++j) h[j] -= td * A[i][j];
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) h_out[j] = (float)h[j];
-#undef A_
 }
 
 // fp32 determinant, partial-pivoting LU, no FMA: same op order as oracle det3().
@@ -175,7 +182,7 @@ __device__ __forceinline__ float reproj_error(const float* H, float x0, float x1
 }
 
 // G hypotheses per group (G in {32, 128}); blockDim = RANSAC_THREADS.
-// dynamic smem: double A[72][G] | float Hs[G][9] | int flags[G]
+// dynamic smem: float Hs[G][9] | int flags[G]
 __global__ void __launch_bounds__(RANSAC_THREADS)
 ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2, int M_host,
               const int* __restrict__ M_dev, const long long* __restrict__ samples, int nbIter,
@@ -183,8 +190,7 @@ ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2
               RansacHeader* hdr, int* counts, float* Hall, int* chunk_nz,
               float* H_out, long long* nbInlier_out, unsigned char* mask_out, int* status_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sA = reinterpret_cast<double*>(smem_raw);
-    float* sH = reinterpret_cast<float*>(sA + 72 * G);
+    float* sH = reinterpret_cast<float*>(smem_raw);
     int* sFlag = reinterpret_cast<int*>(sH + 9 * G);
     __shared__ int s_scan[RANSAC_THREADS / 32];
     __shared__ int s_misc[4];
@@ -222,7 +228,7 @@ ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2
                             yv[k] = match2[s[k] * 3 + 1];
                         }
                         float h[9];
-                        dlt_null_vector(sA + tid, G, xu, xv, yu, yv, h);
+                        dlt_null_vector(xu, xv, yu, yv, h);
 #pragma unroll
                         for (int k = 0; k < 9; ++k) { sH[tid * 9 + k] = h[k]; Hall[(long long)i * 9 + k] = h[k]; }
                         float det = det3_lu(h);
@@ -350,8 +356,6 @@ ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2
 }
 
 __global__ void dlt_kernel(const float* __restrict__ X, const float* __restrict__ Y, int N, float* __restrict__ H_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sA = reinterpret_cast<double*>(smem_raw);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float xu[4], xv[4], yu[4], yv[4];
@@ -361,7 +365,7 @@ __global__ void dlt_kernel(const float* __restrict__ X, const float* __restrict_
         yu[k] = Y[(i * 4 + k) * 3]; yv[k] = Y[(i * 4 + k) * 3 + 1];
     }
     float h[9];
-    dlt_null_vector(sA + threadIdx.x, blockDim.x, xu, xv, yu, yv, h);
+    dlt_null_vector(xu, xv, yu, yv, h);
 #pragma unroll
     for (int k = 0; k < 9; ++k) H_out[i * 9 + k] = h[k];
 }
@@ -456,12 +460,7 @@ extern "C" int rf_ransac_homography(const float* match1, const float* match2, in
     int G = (nbIter >= 128 * 2 * sms) ? 128 : 32;
     int nGroups = (nbIter + G - 1) / G;
     int grid = nGroups < 1 ? 1 : (nGroups < 4 * sms ? nGroups : 4 * sms);
-    size_t smem = (size_t)G * (72 * sizeof(double) + 9 * sizeof(float) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
-        RF_CUDA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * (72 * 8 + 9 * 4 + 4)));
-        attr_set = true;
-    }
+    size_t smem = (size_t)G * (9 * sizeof(float) + sizeof(int));
     ransac_kernel<<<grid, RANSAC_THREADS, smem, st>>>(match1, match2, M, M_dev, (const long long*)samples, nbIter, tolerance,
                                                       chunk, G, hdr, counts, Hall, chunk_nz, H_out,
                                                       (long long*)nbInlier_out, mask_out, status_out);
@@ -472,7 +471,7 @@ extern "C" int rf_ransac_homography(const float* match1, const float* match2, in
 extern "C" int rf_homography_dlt(const float* X, const float* Y, int N, float* H_out, void* stream) {
     if (N <= 0) return 0;
     const int threads = 64;
-    dlt_kernel<<<(N + threads - 1) / threads, threads, threads * 72 * sizeof(double), as_stream(stream)>>>(X, Y, N, H_out);
+    dlt_kernel<<<(N + threads - 1) / threads, threads, 0, as_stream(stream)>>>(X, Y, N, H_out);
     RF_LAUNCHED();
     return 0;
 }

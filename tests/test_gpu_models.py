@@ -69,3 +69,28 @@ def test_resnet50_conv4_vs_torchvision(rf):
     assert rel_err(ys.image(0).cpu().numpy(), g["y"]) < 1e-4
     ref2 = MO.resnet50_conv4(x2, synth.resnet50_conv4_state(int(g["seed"])))
     assert rel_err(ys.image(1).cpu().numpy(), ref2.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("k,cin,cout,stride,pad", [(5, 2, 16, 1, 2), (3, 4, 32, 2, 1), (7, 3, 64, 2, 3), (3, 3, 64, 1, 1)])
+@pytest.mark.parametrize("engine", ["fp32", "tf32"])
+def test_stem_as_im2col_plus_1x1(rf, k, cin, cout, stride, pad, engine):
+    """LayerProgram.stem (im2col + 1x1 conv) == conv + BN + ReLU, on a ragged batch (generic and specialised kernels)."""
+    import torch.nn.functional as F
+    from ransac_flow_b200.program import LayerProgram
+    from ransac_flow_b200.coarseAlignFeatMatch import _BN
+    g = torch.Generator().manual_seed(k * 10 + cin)
+    w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    sd = {"bn.weight": torch.rand(cout, generator=g) + 0.5, "bn.bias": torch.randn(cout, generator=g) * 0.1,
+          "bn.running_mean": torch.randn(cout, generator=g) * 0.1, "bn.running_var": torch.rand(cout, generator=g) + 0.5}
+    xs = [torch.randn(1, cin, 37, 150, generator=g), torch.randn(1, cin, 9, 11, generator=g)]
+    refs = [F.relu(F.batch_norm(F.conv2d(x, w, stride=stride, padding=pad), sd["bn.running_mean"], sd["bn.running_var"],
+                                sd["bn.weight"], sd["bn.bias"], False, 0.0, 1e-5)) for x in xs]
+    P = LayerProgram(cin)
+    P.stem(0, w.cuda(), _BN({k_: v.cuda() for k_, v in sd.items()}, "bn"), stride, pad)
+    data = torch.cat([x[0].permute(1, 2, 0).reshape(-1, cin) for x in xs]).contiguous().cuda()
+    out, ohw = P.run(rf.ops.Ragged(data, [(37, 150), (9, 11)]), 1 if engine == "tf32" else 0)
+    y = rf.ops.Ragged(out, ohw)
+    tol = 4e-3 if engine == "tf32" else 2e-5
+    for i, r in enumerate(refs):
+        assert tuple(y.image(i).shape) == tuple(r.shape)
+        assert (y.image(i).cpu() - r).abs().max().item() <= tol * max(1.0, r.abs().max().item())
