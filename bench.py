@@ -224,7 +224,8 @@ def run_b200(args, rank, world, local):
     torch.cuda.synchronize()
     corr_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     # RANSAC alone (latency-bound: reported as us/call)
-    m1, m2 = coarse.match1, coarse.match2
+    nm = int(out.get("nbMatch", len(coarse.match1)))
+    m1, m2 = coarse.match1[:nm].contiguous(), coarse.match2[:nm].contiguous()
     smp = torch.randint(len(m1), (1000, 4), device=dev)
     for _ in range(3):
         rf.ops.ransac_homography(m1, m2, smp, 0.05)
@@ -238,10 +239,18 @@ def run_b200(args, rank, world, local):
     flops = 2.0 * NA * NB * CFEAT
     abytes = 4.0 * CFEAT * (NA + NB) + 16.0 * len(m1)
     tf = flops / (corr_ms * 1e-3) / 1e12
-    tensor_peak = pk["bf16_tflops"] if args.engine == "tf32" else pk["bf16_tflops"]
-    roofline = {"kernel": "corr_argmax+mutual_finalize (rf_corr_mutual_nn, %s)" % ("3xTF32 tcgen05" if args.engine == "tf32" else "fp32 SIMT"),
-                "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": None,
-                "peak_source": pk["src"] + " bf16 dense (burst); TF32 nominal rate is half of it",
+    tensor_peak = pk["bf16_tflops"]
+    traffic = None
+    try:                                   # dram__bytes_read+write of the dominant launch, from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_corr_ncu.json")))
+        traffic = prof["launches"][0]["dram_traffic_bytes"] if args.engine == "tf32" else None
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % ("tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)" if args.engine == "tf32" else "corr_argmax_kernel (fp32 SIMT)"),
+                "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
+                "peak_source": pk["src"] + " bf16 dense GEMM (burst); kind::tf32 peaks at half of it and this kernel issues 3 TF32 MMAs per "
+                               "algorithmic MAC (3xTF32), i.e. executed-TF32 fraction = 6 x frac",
+                "executed_tf32_frac": (3 * tf) / (tensor_peak / 2) if args.engine == "tf32" else None,
                 "ms_per_launch": corr_ms, "algorithmic_gflop": flops / 1e9, "algorithmic_mb": abytes / 1e6,
                 "hbm_gbs_achieved": abytes / (corr_ms * 1e-3) / 1e9, "hbm_frac": abytes / (corr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": int(len(m1)),
@@ -282,7 +291,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 convs (TF32 operands, the reference's own cuDNN default on sm_80+) + 3xTF32 correlation; fp32: exact-FMA SIMT engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
