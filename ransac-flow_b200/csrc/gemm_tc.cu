@@ -17,6 +17,7 @@
 //   warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns at a time straight from TMEM.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -147,6 +148,90 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
 
 constexpr int MODE_CONV = 0, MODE_CORR = 1;
 
+// Convolution epilogue shared by the tap-streaming and the halo kernels (warps 2..5 = 128 threads, thread m owns
+// accumulator row m = pixel m of the tile): + folded-BN bias, + residual, ReLU, TF32 rounding, store.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const TcParams& p, int img, int ox0, int oy0, int tw, int n0, int m, uint32_t trow,
+                                              uint8_t* smem, uint64_t* res_full, int warp, int lane) {
+    if (p.tma_epi) {
+        // ---- bulk epilogue: residual tile in by TMA, result tile out by TMA; the pipeline stages are idle now and
+        // serve as staging: BN/32 boxes of (32 channels x tw x th) = 128 rows x 128 B, 128-byte swizzled ----
+        uint8_t* stg = smem;
+        const bool has_res = p.residual != nullptr;
+        if (has_res) {
+            if (warp == 2 && lane == 0) {
+                mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) tma_load_3d(stg + c * TC_A_BYTES, &p.mapR[img], res_full, n0 + c * 32, ox0, oy0);
+            }
+            mbar_wait(res_full, 0);
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            const int n = n0 + c * 32;
+            uint8_t* rowp = stg + c * TC_A_BYTES + m * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
+                float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                if (p.bias && n + 4 * j < p.Cout) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *sp = o;
+            }
+        }
+        fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA (async proxy)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c)
+                if (n0 + c * 32 < p.Cout) tma_store_3d(&p.mapY[img], stg + c * TC_A_BYTES, n0 + c * 32, ox0, oy0);
+            tma_store_commit_and_wait_read();       // smem must stay valid until the bulk stores have read it
+        }
+    } else {
+        const int py = m / tw, px = m - py * tw;
+        const int oy = oy0 + py, ox = ox0 + px;
+        const bool valid = (oy < p.Ho[img]) && (ox < p.Wo[img]);
+        const long long pix = p.out_pix[img] + (long long)oy * p.Wo[img] + ox;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            const int n = n0 + c * 32;
+            if (valid && n < p.Cout) {
+                float* dst = p.y + pix * p.Cout + n;
+                const float* res = p.residual ? p.residual + pix * p.Cout + n : nullptr;
+                if (n + 32 <= p.Cout && (p.Cout & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                        if (res) { float4 rr = __ldg(reinterpret_cast<const float4*>(res + j)); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < p.Cout) {
+                            float o = __uint_as_float(v[j]);
+                            if (p.bias) o += __ldg(p.bias + n + j);
+                            if (res) o += __ldg(res + j);
+                            if (p.relu) o = fmaxf(o, 0.f);
+                            if (p.round_out) o = round_tf32(o);
+                            dst[j] = o;
+                        }
+                }
+            }
+        }
+    }
+}
+
+
 template <int BN, int MODE, bool DEEP = false>
 struct TcCfg {
     static constexpr int NSPLIT = (MODE == MODE_CORR) ? 2 : 1;
@@ -266,81 +351,8 @@ tc_kernel(const __grid_constant__ TcParams p) {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (MODE == MODE_CONV && p.tma_epi) {
-            // ---- bulk epilogue: residual tile in by TMA, result tile out by TMA; the pipeline stages are idle now and
-            // serve as staging: BN/32 boxes of (32 channels x tw x th) = 128 rows x 128 B, 128-byte swizzled ----
-            uint8_t* stg = smem;
-            const bool has_res = p.residual != nullptr;
-            if (has_res) {
-                if (warp == 2 && lane == 0) {
-                    mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
-#pragma unroll
-                    for (int c = 0; c < BN / 32; ++c) tma_load_3d(stg + c * TC_A_BYTES, &p.mapR[img], res_full, n0 + c * 32, ox0, oy0);
-                }
-                mbar_wait(res_full, 0);
-            }
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                const int n = n0 + c * 32;
-                uint8_t* rowp = stg + c * TC_A_BYTES + m * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
-                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    if (p.bias && n + 4 * j < p.Cout) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-                    if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                    *sp = o;
-                }
-            }
-            fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA (async proxy)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-#pragma unroll
-                for (int c = 0; c < BN / 32; ++c)
-                    if (n0 + c * 32 < p.Cout) tma_store_3d(&p.mapY[img], stg + c * TC_A_BYTES, n0 + c * 32, ox0, oy0);
-                tma_store_commit_and_wait_read();       // smem must stay valid until the bulk stores have read it
-            }
-        } else if (MODE == MODE_CONV) {
-            const int py = m / tw, px = m - py * tw;
-            const int oy = oy0 + py, ox = ox0 + px;
-            const bool valid = (oy < p.Ho[img]) && (ox < p.Wo[img]);
-            const long long pix = p.out_pix[img] + (long long)oy * p.Wo[img] + ox;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(trow + c * 32, v);
-                const int n = n0 + c * 32;
-                if (valid && n < p.Cout) {
-                    float* dst = p.y + pix * p.Cout + n;
-                    const float* res = p.residual ? p.residual + pix * p.Cout + n : nullptr;
-                    if (n + 32 <= p.Cout && (p.Cout & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-                            if (res) { float4 rr = __ldg(reinterpret_cast<const float4*>(res + j)); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                            *reinterpret_cast<float4*>(dst + j) = o;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n + j < p.Cout) {
-                                float o = __uint_as_float(v[j]);
-                                if (p.bias) o += __ldg(p.bias + n + j);
-                                if (res) o += __ldg(res + j);
-                                if (p.relu) o = fmaxf(o, 0.f);
-                                if (p.round_out) o = round_tf32(o);
-                                dst[j] = o;
-                            }
-                    }
-                }
-            }
+        if (MODE == MODE_CONV) {
+            conv_epilogue<BN>(p, img, ox0, oy0, tw, n0, m, trow, smem, res_full, warp, lane);
         } else {
             // utils/outil.py:36-37: row arg-max (thread-local over this tile's columns), column arg-max via an
             // smem transpose of the score tile (the pipeline stages are idle by now)
@@ -379,6 +391,138 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 if (cb != 0ull) atomicMax(p.colbest + col, cb);
             }
         }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 / stride-1 convolutions with HALO REUSE.  The tap-streaming kernel above fetches the A tile nine times per
+// 32-channel chunk (once per tap, shifted by one pixel) and is bound by L2->SM operand bandwidth.  Here the CTA
+// owns an 8 x 16 pixel tile, loads its (8+2) x (16+2) halo ONCE per chunk (180 rows x 128 B, one TMA box) and the
+// nine taps are nine UMMA descriptors into the same shared memory: tap (r, s) starts (r*10 + s) rows into the halo
+// and its sixteen 8-row core groups are 10 rows (1280 B) apart - the descriptor's stride-byte-offset.  Two rings:
+// A (halo chunks) and B (one K-major weight tile per tap).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HALO_TW = 8, HALO_TH = 16;
+constexpr int HALO_LD = HALO_TW + 2;                                   // halo row pitch in pixels
+constexpr int HALO_A_BYTES = HALO_LD * (HALO_TH + 2) * 128;            // 23040
+constexpr int HALO_A_SLOT = 23 * 1024;                                 // 1024-byte aligned slot
+
+template <int BN>
+struct HaloCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int NA = 2;
+    static constexpr int NB = (BN == 128) ? 3 : 4;
+    static constexpr int RING_BYTES = NA * HALO_A_SLOT + NB * B_BYTES;
+    static constexpr int STG_BYTES = BN * 512;
+    static constexpr int DATA_BYTES = RING_BYTES > STG_BYTES ? RING_BYTES : STG_BYTES;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = BN <= 64 ? 64 : 128;
+};
+
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((HALO_LD * 128) >> 4) << 32;                       // 8-row core groups are one halo row pitch apart
+    d |= (uint64_t)1 << 46;
+    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;           // base offset: start is not 1024-byte aligned
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + NA * HALO_A_SLOT;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* emptyA = fullA + NA;
+    uint64_t* fullB = emptyA + NA;
+    uint64_t* emptyB = fullB + NB;
+    uint64_t* tmem_full = emptyB + NB;
+    uint64_t* res_full = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = blockIdx.x - p.tile_start[img];
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    const int ox0 = txi * HALO_TW, oy0 = tyi * HALO_TH;
+    const int n0 = blockIdx.y * BN;
+    const int kc = p.Cin / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(res_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[img]); tma_prefetch_desc(&p.mapB); }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ib = 0;
+            for (int cc = 0; cc < kc; ++cc) {
+                const int sa = cc % NA, pha = (cc / NA) & 1;
+                mbar_wait(&emptyA[sa], pha ^ 1);
+                mbar_expect_tx(&fullA[sa], HALO_A_BYTES);
+                tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[img], &fullA[sa], cc * TC_BK, ox0 - 1, oy0 - 1);
+                for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    const int sb = ib % NB, phb = (ib / NB) & 1;
+                    mbar_wait(&emptyB[sb], phb ^ 1);
+                    mbar_expect_tx(&fullB[sb], Cfg::B_BYTES);
+                    tma_load_2d(sB + sb * Cfg::B_BYTES, &p.mapB, &fullB[sb], tap * p.Cin + cc * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            int ib = 0;
+            for (int cc = 0; cc < kc; ++cc) {
+                const int sa = cc % NA, pha = (cc / NA) & 1;
+                mbar_wait(&fullA[sa], pha);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(sA + sa * HALO_A_SLOT);
+                for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    const int sb = ib % NB, phb = (ib / NB) & 1;
+                    mbar_wait(&fullB[sb], phb);
+                    tc_fence_after();
+                    const int r = tap / 3, sx = tap - r * 3;
+                    const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
+                    const uint64_t db = make_desc_sw128(smem_u32(sB + sb * Cfg::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        umma_tf32(tmem_base, make_desc_halo(aaddr + k * 32, desc_mode), db + (uint64_t)(k * 32 >> 4), idesc,
+                                  (cc | tap | k) != 0 ? 1u : 0u);
+                    umma_commit(&emptyB[sb]);
+                }
+                umma_commit(&emptyA[sa]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        conv_epilogue<BN>(p, img, ox0, oy0, HALO_TW, n0, m, tmem_base + ((uint32_t)(q * 32) << 16), smem, res_full, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -471,6 +615,28 @@ static int pick_tw(int Ho, int Wo) {
     return best;
 }
 
+static int halo_mode() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("RF_TC_HALO");
+        m = e ? atoi(e) : 0;
+    }
+    return m;
+}
+
+template <int BN>
+static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cudaStream_t st) {
+    using Cfg = HaloCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    tc_halo_kernel<BN><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
+    RF_LAUNCHED();
+    return 0;
+}
+
 template <int BN, int MODE, bool DEEP>
 static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st) {
     using Cfg = TcCfg<BN, MODE, DEEP>;
@@ -500,9 +666,10 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     memset(&p, 0, sizeof(p));
     const int BN = cp.Cout > 64 ? 128 : 64;
     p.nimg = set.n;
+    const int hmode = (cp.R == 3 && cp.stride == 1 && cp.pad == 1) ? halo_mode() : 0;
     int tiles = 0;
     for (int i = 0; i < set.n; ++i) {
-        int tw = pick_tw(set.Ho[i], set.Wo[i]), th = 128 / tw;
+        int tw = hmode ? HALO_TW : pick_tw(set.Ho[i], set.Wo[i]), th = 128 / tw;
         p.tw[i] = tw;
         p.tiles_x[i] = (set.Wo[i] + tw - 1) / tw;
         p.tile_start[i] = tiles;
@@ -510,7 +677,7 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
         p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
         p.out_pix[i] = set.out_pix[i];
         int rc = get_map(&p.mapA[i], cp.x + set.in_pix[i] * cp.Cin, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
-                         (unsigned long long)set.H[i], TC_BK, (unsigned)tw, (unsigned)th, (unsigned)cp.stride);
+                         (unsigned long long)set.H[i], TC_BK, (unsigned)(hmode ? tw + 2 : tw), (unsigned)(hmode ? th + 2 : th), (unsigned)cp.stride);
         if (rc) return rc;
     }
     // bulk (TMA) epilogue whenever the output rows are 16-byte aligned (Cout % 4 == 0)
@@ -533,6 +700,7 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
+    if (hmode) return BN == 128 ? launch_halo<128>(p, tiles, nt, hmode, st) : launch_halo<64>(p, tiles, nt, hmode, st);
     const bool deep = cp.R * cp.S * (cp.Cin / TC_BK) >= 16;          // >= 16 K-steps of 32 channels
     if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false>(p, tiles, nt, st);
     return deep ? launch_tc<64, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false>(p, tiles, nt, st);
