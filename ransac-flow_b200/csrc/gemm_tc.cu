@@ -429,7 +429,11 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)((HALO_LD * 128) >> 4) << 32;                       // 8-row core groups are one halo row pitch apart
     d |= (uint64_t)1 << 46;
-    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;           // base offset: start is not 1024-byte aligned
+    // The start address is NOT 1024-byte aligned and the groups are 1280 B apart.  Measured on B200 (round 1): the
+    // 128-byte swizzle of tcgen05.mma is a pure function of the shared-memory address bits (it matches what the TMA
+    // wrote for any row phase) and the descriptor's base-offset field must stay 0; setting it to (addr >> 7) & 7, as the
+    // PTX text suggests for unaligned starts, double-applies the phase and gives wrong results (mode 1, kept for the record).
+    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
     d |= (uint64_t)2 << 61;
     return d;
 }
@@ -618,8 +622,8 @@ static int pick_tw(int Ho, int Wo) {
 static int halo_mode() {
     static int m = -1;
     if (m < 0) {
-        const char* e = getenv("RF_TC_HALO");
-        m = e ? atoi(e) : 0;
+        const char* e = getenv("RF_TC_HALO");     // 0 = tap-streaming kernel, 2 = halo reuse (default), 1 = experiment (wrong)
+        m = e ? atoi(e) : 2;
     }
     return m;
 }
