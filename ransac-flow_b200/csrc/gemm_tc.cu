@@ -533,6 +533,223 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// PERSISTENT convolution kernel: one CTA per SM walks a static list of tiles.  Most layers of this workload have a
+// short K loop (1x1 convs: 2-32 steps; 3x3 on 64 channels: 2 halo chunks), so a one-tile-per-CTA kernel spends its
+// life in prologue / TMA round-trip / epilogue latency.  Here the three roles run decoupled across tiles:
+//   warp 0   : TMA producer - keeps the A ring (tap tiles, or halo chunks when HALO) and the B ring (weight tiles)
+//              full, running ahead into the next tile while the current one is multiplied;
+//   warp 1   : MMA issuer - two TMEM accumulators (2 x BN columns): tile i+1 accumulates while tile i drains;
+//   warps 2-5: epilogue - TMEM -> (+bias, +residual, ReLU, TF32 round) -> swizzled smem staging -> TMA store, two
+//              staging buffers so the residual tile of tile i+1 is prefetched while tile i is being stored.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, bool HALO>
+struct PCfg {
+    static constexpr int A_SLOT = HALO ? HALO_A_SLOT : TC_A_BYTES;
+    static constexpr int A_TX = HALO ? HALO_A_BYTES : TC_A_BYTES;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int NA = HALO ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int NB = HALO ? (BN == 128 ? 3 : 6) : NA;
+    static constexpr int STG = BN * 512;
+    static constexpr int OFF_B = NA * A_SLOT;
+    static constexpr int OFF_STG = OFF_B + NB * B_BYTES;
+    static constexpr int DATA_BYTES = OFF_STG + 2 * STG;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int TB = HALO ? 9 : 1;                 // B tiles consumed per A slot
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord { int img, ox0, oy0, tw, n0; };
+
+template <bool HALO>
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int tiles_m, int BN) {
+    TileCoord c;
+    const int nt = t / tiles_m, mt = t - nt * tiles_m;      // pixel tiles fastest: co-running CTAs share the weight tile
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mt >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = mt - p.tile_start[img];
+    c.img = img;
+    c.tw = HALO ? HALO_TW : p.tw[img];
+    const int th = 128 / c.tw;
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    c.ox0 = txi * c.tw;
+    c.oy0 = tyi * th;
+    c.n0 = nt * BN;
+    return c;
+}
+
+template <int BN, bool HALO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) {
+    using Cfg = PCfg<BN, HALO>;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::OFF_B;
+    uint8_t* sStg = smem + Cfg::OFF_STG;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* emptyA = fullA + NA;
+    uint64_t* fullB = emptyA + NA;
+    uint64_t* emptyB = fullB + NB;
+    uint64_t* tmem_full = emptyB + NB;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint64_t* res_full = tmem_empty + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = tiles_m * tiles_n;
+    const int kc = p.Cin / TC_BK;
+    const int NAI = HALO ? kc : p.R * p.S * kc;             // A slots per tile
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); mbar_init(&res_full[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t ia_cnt = 0, ib_cnt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord c = decode_tile<HALO>(p, t, tiles_m, BN);
+                for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
+                    const int sa = ia_cnt % NA;
+                    mbar_wait(&emptyA[sa], ((ia_cnt / NA) & 1) ^ 1);
+                    mbar_expect_tx(&fullA[sa], Cfg::A_TX);
+                    int tap = 0, cc = ia;
+                    if (HALO) {
+                        tma_load_3d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], ia * TC_BK, c.ox0 - 1, c.oy0 - 1);
+                    } else {
+                        tap = ia / kc;
+                        cc = ia - tap * kc;
+                        const int r = tap / p.S, sx = tap - r * p.S;
+                        tma_load_3d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], cc * TC_BK, c.ox0 * p.stride + sx - p.pad,
+                                    c.oy0 * p.stride + r - p.pad);
+                    }
+                    for (int jb = 0; jb < TB; ++jb, ++ib_cnt) {
+                        const int sb = ib_cnt % NB;
+                        mbar_wait(&emptyB[sb], ((ib_cnt / NB) & 1) ^ 1);
+                        mbar_expect_tx(&fullB[sb], Cfg::B_BYTES);
+                        const int btap = HALO ? jb : tap;
+                        tma_load_2d(sB + sb * Cfg::B_BYTES, &p.mapB, &fullB[sb], btap * p.Cin + cc * TC_BK, c.n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1;
+                mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
+                    const int sa = ia_cnt % NA;
+                    mbar_wait(&fullA[sa], (ia_cnt / NA) & 1);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA + sa * Cfg::A_SLOT);
+                    for (int jb = 0; jb < TB; ++jb, ++ib_cnt) {
+                        const int sb = ib_cnt % NB;
+                        mbar_wait(&fullB[sb], (ib_cnt / NB) & 1);
+                        tc_fence_after();
+                        const uint64_t db = make_desc_sw128(smem_u32(sB + sb * Cfg::B_BYTES));
+                        uint32_t aaddr = abase;
+                        if (HALO) { const int r = jb / 3, sx = jb - r * 3; aaddr += (uint32_t)((r * HALO_LD + sx) * 128); }
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            const uint64_t da = HALO ? make_desc_halo(aaddr + k * 32, 2) : (make_desc_sw128(aaddr) + (uint64_t)(k * 32 >> 4));
+                            umma_tf32(tacc, da, db + (uint64_t)(k * 32 >> 4), idesc, (ia | jb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&emptyB[sb]);
+                    }
+                    umma_commit(&emptyA[sa]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // =============================== epilogue (warps 2..5) ===============================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const bool leader = (warp == 2 && lane == 0);
+        const bool has_res = p.residual != nullptr;
+        if (leader && has_res && (int)blockIdx.x < total) {
+            const TileCoord c = decode_tile<HALO>(p, blockIdx.x, tiles_m, BN);
+            mbar_expect_tx(&res_full[0], (BN / 32) * TC_A_BYTES);
+#pragma unroll
+            for (int cb = 0; cb < BN / 32; ++cb) tma_load_3d(sStg + cb * TC_A_BYTES, &p.mapR[c.img], &res_full[0], c.n0 + cb * 32, c.ox0, c.oy0);
+        }
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            const TileCoord c = decode_tile<HALO>(p, t, tiles_m, BN);
+            uint8_t* stg = sStg + buf * Cfg::STG;
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // the leader's bookkeeping of the previous tile is done
+            mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(&res_full[buf], (ti >> 1) & 1);
+            const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(trow + cb * 32, v);
+                const int n = c.n0 + cb * 32;
+                uint8_t* rowp = stg + cb * TC_A_BYTES + m * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (p.bias && n + 4 * j < p.Cout) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                    if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *sp = o;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);                            // accumulator drained (128 arrivals)
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb)
+                    if (c.n0 + cb * 32 < p.Cout) tma_store_3d(&p.mapY[c.img], stg + cb * TC_A_BYTES, c.n0 + cb * 32, c.ox0, c.oy0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the other staging buffer has been read out
+                const int tn = t + gridDim.x;
+                if (has_res && tn < total) {
+                    const TileCoord cn = decode_tile<HALO>(p, tn, tiles_m, BN);
+                    uint8_t* stn = sStg + (buf ^ 1) * Cfg::STG;
+                    mbar_expect_tx(&res_full[buf ^ 1], (BN / 32) * TC_A_BYTES);
+#pragma unroll
+                    for (int cb = 0; cb < BN / 32; ++cb) tma_load_3d(stn + cb * TC_A_BYTES, &p.mapR[cn.img], &res_full[buf ^ 1], cn.n0 + cb * 32, cn.ox0, cn.oy0);
+                }
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 // hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
 __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,6 +845,30 @@ static int halo_mode() {
     return m;
 }
 
+static int persist_mode() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("RF_TC_PERSIST");
+        m = e ? atoi(e) : 0;
+    }
+    return m;
+}
+
+template <int BN, bool HALO>
+static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStream_t st) {
+    using Cfg = PCfg<BN, HALO>;
+    static bool attr = false;
+    if (!attr) {
+        RF_CUDA(cudaFuncSetAttribute(tc_persist_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    const int total = tiles_m * tiles_n;
+    const int grid = total < num_sms() ? total : num_sms();
+    tc_persist_kernel<BN, HALO><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles_m, tiles_n);
+    RF_LAUNCHED();
+    return 0;
+}
+
 template <int BN>
 static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
@@ -704,6 +945,10 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
+    if (persist_mode() && p.tma_epi) {
+        if (hmode) return BN == 128 ? launch_persist<128, true>(p, tiles, nt, st) : launch_persist<64, true>(p, tiles, nt, st);
+        return BN == 128 ? launch_persist<128, false>(p, tiles, nt, st) : launch_persist<64, false>(p, tiles, nt, st);
+    }
     if (hmode) return BN == 128 ? launch_halo<128>(p, tiles, nt, hmode, st) : launch_halo<64>(p, tiles, nt, hmode, st);
     const bool deep = cp.R * cp.S * (cp.Cin / TC_BK) >= 16;          // >= 16 K-steps of 32 channels
     if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false>(p, tiles, nt, st);
