@@ -204,3 +204,24 @@ def align_pair(coarse, net, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21
             break
     cat = lambda l: np.concatenate(l, axis=0) if l else np.zeros((0,))
     return dict(H=cat(Hs), flowDown8=cat(flows8), matchDown8=cat(matches8), flow12=flows, match=matches)
+
+
+def align2images(coarse, net, img1, img2):
+    """quick_start/align2images.py:53-97 (variant C coarse model, no clamp on the fine flow, netCorr(source, target))."""
+    coarse.setSource(img1)
+    coarse.setTarget(img2)
+    w, h = coarse.It.size
+    res = coarse.getCoarse(np.zeros((h, w)))
+    if res[0] is None:
+        return None
+    bestPrm, inlierMask = res
+    flowCoarse = WO.warp_grid(bestPrm[None], h, w)
+    img1_coarse = WO.grid_sample(coarse.IsTensor, flowCoarse)
+    feat1 = F.normalize(MO.feature_extractor(img1_coarse, net["netFeatCoarse"]))
+    feat2 = F.normalize(MO.feature_extractor(coarse.ItTensor, net["netFeatCoarse"]))
+    corr12 = MO.corr_neigh(feat1, feat2)
+    flowDown = MO.net_flow_coarse(corr12, net["netFlowCoarse"])
+    flow12, _ = WO.compose_fine(flowDown, flowCoarse, WO.base_grid(h, w), clamp=False)
+    img1_fine = WO.grid_sample(coarse.IsTensor, flow12)
+    return dict(bestPrm=bestPrm, inlierMask=inlierMask, flowCoarse=flowCoarse, img1_coarse=img1_coarse, flowDown=flowDown,
+                flow12=flow12, img1_fine=img1_fine)

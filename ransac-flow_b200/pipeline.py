@@ -74,11 +74,8 @@ def _to_host(t):
     return h.numpy()
 
 
-def align_pair_single(coarseModel, network, Is, It, with_match21=False):
-    """The single-hypothesis case of the evaluation loop (maxCoarse = 0, no background mask) with NO host
-    synchronisation until the results are fetched: matching, RANSAC (device-side match count), warp, fine flow and
-    composition are queued back to back, then one pinned D2H brings back status, H, the matchability map and the /8
-    tensors.  Same outputs as ``align_pair``."""
+def _single_device(coarseModel, network, Is, It, with_match21):
+    """Device part of the single-hypothesis path: everything queued on the current stream, nothing read back."""
     coarseModel.setPair(Is, It)
     Itw, Ith = coarseModel.target_size
     featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
@@ -86,17 +83,74 @@ def align_pair_single(coarseModel, network, Is, It, with_match21=False):
     flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
     flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
     packed = torch.cat([status.float(), cnt.float(), nb.float(), Hd, match.reshape(-1), f8.reshape(-1), mboth.reshape(-1)])
-    host = _to_host(packed).copy()
-    st, n0, n8 = int(host[0]), Ith * Itw, f8.numel()
+    return packed, flow12, (Ith, Itw), tuple(f8.shape)
+
+
+def _unpack_single(host, flow12, size, f8shape):
+    Ith, Itw = size
+    st, n0, n8 = int(host[0]), Ith * Itw, int(np.prod(f8shape))
     if st != 0:                                    # the reference's `if bestPara is None: break` (evaluation.py:215-216)
         if st == 2:
             raise TypeError("'NoneType' object is not subscriptable")     # utils/outil.py:162
-        return dict(H=np.zeros((0,)), flowDown8=np.zeros((0,)), matchDown8=np.zeros((0,)), flow12=[], match=[])
+        return dict(H=np.zeros((0,)), flowDown8=np.zeros((0,)), matchDown8=np.zeros((0,)), flow12=[], match=[],
+                    nbInlier=0, nbMatch=int(host[1]))
     H = host[3:12].reshape(1, 3, 3).astype(np.float32)
     o = 12
-    return dict(H=H, flowDown8=host[o + n0:o + n0 + n8].reshape(tuple(f8.shape)),
-                matchDown8=host[o + n0 + n8:].reshape(1, 2, f8.shape[2], f8.shape[3]),
+    return dict(H=H, flowDown8=host[o + n0:o + n0 + n8].reshape(f8shape),
+                matchDown8=host[o + n0 + n8:].reshape(1, 2, f8shape[2], f8shape[3]),
                 flow12=[flow12], match=[host[o:o + n0].reshape(Ith, Itw)], nbInlier=int(host[2]), nbMatch=int(host[1]))
+
+
+def align_pair_single(coarseModel, network, Is, It, with_match21=False):
+    """The single-hypothesis case of the evaluation loop (maxCoarse = 0, no background mask) with NO host
+    synchronisation until the results are fetched: matching, RANSAC (device-side match count), warp, fine flow and
+    composition are queued back to back, then one pinned D2H brings back status, H, the matchability map and the /8
+    tensors.  Same outputs as ``align_pair``."""
+    packed, flow12, size, f8shape = _single_device(coarseModel, network, Is, It, with_match21)
+    return _unpack_single(_to_host(packed).copy(), flow12, size, f8shape)
+
+
+class GraphedAligner:
+    """``align_pair_single`` captured once in a CUDA graph per input size and replayed per pair: the ~140 kernel
+    launches of a pair (pyramid, ResNet-50 trunk, matching, RANSAC, fine flow) cost one graph launch on the host.
+    Inputs are copied into static device buffers (H2D when they are host tensors / arrays); the RANSAC samples are
+    drawn inside the graph (torch's graph-safe Philox offsets), so successive replays use fresh samples."""
+
+    def __init__(self, coarseModel, network, with_match21=False, warmup=2):
+        self.coarse, self.net, self.m21, self.warmup = coarseModel, network, with_match21, warmup
+        self.coarse.device_preproc = True
+        self.graphs = {}
+
+    def _build(self, Is, It):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        s_in = torch.empty(tuple(Is.shape), dtype=torch.uint8, device=dev)
+        t_in = torch.empty(tuple(It.shape), dtype=torch.uint8, device=dev)
+        s_in.copy_(Is)
+        t_in.copy_(It)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                       # eager runs: func attributes, TMA maps, caches, buffers
+                _single_device(self.coarse, self.net, s_in, t_in, self.m21)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            packed, flow12, size, f8shape = _single_device(self.coarse, self.net, s_in, t_in, self.m21)
+        return dict(graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape)
+
+    def __call__(self, Is, It):
+        """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
+        if isinstance(Is, np.ndarray):
+            Is, It = torch.from_numpy(Is), torch.from_numpy(It)
+        key = (tuple(Is.shape), tuple(It.shape))
+        if key not in self.graphs:
+            self.graphs[key] = self._build(Is, It)
+        c = self.graphs[key]
+        c["s_in"].copy_(Is, non_blocking=True)
+        c["t_in"].copy_(It, non_blocking=True)
+        c["graph"].replay()
+        return _unpack_single(_to_host(c["packed"]).copy(), c["flow12"], c["size"], c["f8shape"])
 
 
 def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):
@@ -133,6 +187,31 @@ def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, wit
             break
     cat = lambda l: np.concatenate(l, axis=0) if l else np.zeros((0,))
     return dict(H=cat(Hs), flowDown8=cat(flows8), matchDown8=cat(matches8), flow12=flows, match=matches)
+
+
+def align2images(coarseModel, network, img1, img2, align_corners=False):
+    """quick_start/align2images.py:53-97 without the matplotlib / file output: coarse homography from the variant-C
+    CoarseAlign, coarse warp, fine flow (no clamp, align2images.py:91-94) and the finely aligned source.
+    Note the reference calls ``netCorr(feat_source, feat_target)`` here (align2images.py:89, SURVEY A.3 #9)."""
+    with torch.no_grad():
+        coarseModel.setSource(img1)
+        coarseModel.setTarget(img2)
+        w, h = coarseModel.target_size
+        bestPrm, inlierMask = coarseModel.getCoarse(np.zeros((h, w)))
+        if bestPrm is None:
+            return None
+        Hd = torch.from_numpy(bestPrm).unsqueeze(0).cuda()
+        flowCoarse = HomographyWarper(h, w).warp_grid(Hd)
+        img1_coarse = ops.grid_sample(coarseModel.IsTensor, flowCoarse, align_corners)
+        feat1 = fine_features(network["netFeatCoarse"], img1_coarse)
+        feat2 = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+        k = network["netCorr"].kernelSize
+        corr12 = ops.corr_neigh(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, model.get_engine() == ops.ENGINE_TF32)
+        flowDown = network["netFlowCoarse"].forward_ragged(corr12)
+        flow12, _, _ = ops.compose_fine(flowDown, None, None, flowCoarse, clamp=False, align_corners=align_corners, want_match=False)
+        img1_fine = ops.grid_sample(coarseModel.IsTensor, flow12, align_corners)
+        return dict(bestPrm=bestPrm, inlierMask=inlierMask, flowCoarse=flowCoarse, img1_coarse=img1_coarse, flowDown=flowDown,
+                    flow12=flow12, img1_fine=img1_fine)
 
 
 def getFlow_all(flow, param, match, outH, outW, th=0.95, multiH=True, with_match21=False):

@@ -207,3 +207,67 @@ def test_randint_modulo_stream_on_cuda(rf):
     torch.manual_seed(1000)
     b = torch.randint(2 ** 32 - 1, (1000, 4), device="cuda") % 636
     print("randint(M) == randint(2**32-1) %% M on CUDA: %s" % bool((a == b).all()))
+
+
+def test_config1_quick_start_align2images_vs_oracle(rf):
+    """BASELINE config 1: a 240x320 pair through quick_start/align2images.py semantics (variant C, ResizeMaxSize,
+    minSize 320, nbScale 7, scaleR 1.2, one homography) against the CPU oracle with the same samples."""
+    src, tgt, _ = synth.make_pair(21, 240, 320)
+    Is, It = Image.fromarray(src), Image.fromarray(tgt)
+    rsd = synth.resnet50_conv4_state(0)
+    oc = PO.CoarseAlignOracle(rsd, nbScale=7, nbIter=1000, tolerance=0.05, minSize=320, scaleR=1.2, variant="C", seed=1000)
+    ref = PO.align2images(oc, oracle_net(), Is, It)
+    assert oc.featsMultiScale.shape[1] == 2107 and oc.featt.shape[2] * oc.featt.shape[3] == 300       # SURVEY A.5
+    c = rf.CoarseAlignC(7, 1000, 0.05, "Homography", 320, scaleR=1.2, resnet_state_dict=rsd, verbose=False)
+    with fixed_randint([oc.last_samples]):
+        out = rf.pipeline.align2images(c, networks(rf), Is, It)
+    assert ref is not None and out is not None
+    same = len(c.match1) == len(oc.match1) and np.array_equal(c.match2.cpu().numpy(), oc.match2)
+    print("config1: matches %d/%d identical=%s" % (len(c.match1), len(oc.match1), same))
+    if same:
+        np.testing.assert_allclose(out["bestPrm"], ref["bestPrm"], atol=1e-5)
+        assert np.array_equal(out["inlierMask"], ref["inlierMask"])
+        assert np.abs(out["flowDown"].cpu().numpy() - ref["flowDown"].numpy()).max() < FLOW_TOL
+        assert np.abs(out["flow12"].cpu().numpy() - ref["flow12"].numpy()).max() < FLOW_TOL
+        assert np.abs(out["img1_fine"].cpu().numpy() - ref["img1_fine"].numpy()).max() < 5e-3
+
+
+def test_coarse_align_variant_B_api(rf):
+    """evalYFCC variant: C's API with ResizeMinSize; use_cuda=False and segNet=True are refused loudly."""
+    src, tgt, _ = synth.make_pair(22, 96, 128)
+    rsd = synth.resnet50_conv4_state(0)
+    b = rf.CoarseAlignB(3, 500, 0.05, "Homography", 96, 1, True, True, True, False, 1.5, resnet_state_dict=rsd, verbose=False)
+    b.setSource(Image.fromarray(src))
+    b.setTarget(Image.fromarray(tgt))
+    assert b.It.size == (128, 96)
+    torch.manual_seed(1000)
+    H, mask = b.getCoarse(np.zeros((96, 128)))
+    assert H is not None and H.shape == (3, 3) and mask.shape == (6, 8)
+    with pytest.raises(rf._lib.RFError):
+        rf.CoarseAlignB(3, 500, 0.05, "Homography", 96, 1, True, False, True, False, 1.5, resnet_state_dict=rsd, verbose=False)
+    with pytest.raises(NotImplementedError):
+        rf.CoarseAlignB(3, 500, 0.05, "Homography", 96, 1, True, True, True, True, 1.5, resnet_state_dict=rsd, verbose=False)
+
+
+def test_graphed_aligner_replays_match_eager(rf):
+    """GraphedAligner (CUDA graph per input size) == align_pair_single on the same inputs, over several replays and
+    for two different pairs through the same graph (the samples differ per replay, so compare what is sample independent
+    and the full result against an eager run with the graph's own H)."""
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    ga = rf.pipeline.GraphedAligner(c, net)
+    for seed in (15, 16, 15):
+        src, tgt, _ = synth.make_pair(seed, 96, 128)
+        s, t = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+        out = ga(s, t)
+        assert out["H"].shape == (1, 3, 3) and out["nbMatch"] > 4 and out["nbInlier"] >= 4
+        # eager fine stage with the graph's H must give the graph's flow
+        c2 = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+        c2.setPair(Image.fromarray(src), Image.fromarray(tgt))
+        featt = rf.pipeline.fine_features(net["netFeatCoarse"], c2.ItTensor)
+        fc = rf.ops.warp_grid(torch.from_numpy(out["H"]).cuda(), 96, 128)
+        f12, m, f8, _ = rf.pipeline.PredFlowMask_device(c2.IsTensor, featt, fc, (96, 128), net)
+        assert np.abs(f8.cpu().numpy() - out["flowDown8"]).max() < 1e-6
+        assert torch.allclose(f12, out["flow12"][0], atol=1e-6)
+    assert len(ga.graphs) == 1

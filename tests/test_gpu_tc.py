@@ -76,3 +76,19 @@ def test_corr_3xtf32_matches_fp32_argmax(rf, C, NA, NB, seed):
     # and against the library's own exact-fp32 kernel
     j1, j2 = rf.outil.mutualMatching(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
     check_same(i1.cpu().numpy(), i2.cpu().numpy(), j1.cpu().numpy(), j2.cpu().numpy(), score)
+
+
+def test_corr_kitti_shape_both_engines_agree(rf):
+    """BASELINE config 5 shape (KITTI at coarseSize 800): NA = 25747, NB = 8250, C = 1024 (435 GFLOP, 850 MB score
+    matrix in the reference).  The 3xTF32 tensor-core kernel and the exact-fp32 kernel must produce the same pairs."""
+    g = torch.Generator().manual_seed(0)
+    A = torch.nn.functional.normalize(torch.rand(25747, 1024, generator=g), dim=1).cuda()
+    B = torch.nn.functional.normalize(torch.rand(8250, 1024, generator=g), dim=1).cuda()
+    B[:3000] = torch.nn.functional.normalize(A[torch.randperm(25747, generator=g)[:3000].cuda()] + 0.05 * torch.rand(3000, 1024, device="cuda"), dim=1)
+    i1, i2, n1 = rf.ops.corr_mutual_nn(A, B, 1)
+    j1, j2, n2 = rf.ops.corr_mutual_nn(A, B, 0)
+    n1, n2 = int(n1.item()), int(n2.item())
+    a = set(zip(i1[:n1].tolist(), i2[:n1].tolist()))
+    b = set(zip(j1[:n2].tolist(), j2[:n2].tolist()))
+    print("KITTI-shaped correlation: %d / %d pairs, %d differ" % (n1, n2, len(a ^ b)))
+    assert n1 >= 3000 and len(a ^ b) <= 2          # arg-max ties below fp32 accumulation noise only
