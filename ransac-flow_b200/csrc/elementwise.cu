@@ -108,6 +108,44 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __r
 }
 
 // ---------------------------------------------------------------------------
+// FeatureExtractor stem tail fused (model/model.py:71-72): MaxPool2d(2, stride 1) followed by the anti-aliased
+// stride-2 blur (reflect-pad 1, [1 2 1]^2/16).  The (H-1) x (W-1) pooled map is never written: each output reads
+// the 4 x 4 input window its 3 x 3 pooled neighbourhood covers (78.6 MB in, 19.7 MB out at 480x640 instead of
+// 78.6 + 78.6 + 78.6 + 19.7).
+// ---------------------------------------------------------------------------
+__global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int round_out) {
+    const int c4n = C >> 2;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * c4n;
+    if (t >= total) return;
+    long long pm = t / c4n;
+    int c4 = (int)(t - pm * c4n);
+    int im = find_img(set, pm);
+    int local = (int)(pm - set.out_pix[im]);
+    int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+    const int H = set.H[im], W = set.W[im];
+    const int Hp = H - 1, Wp = W - 1;                       // pooled map size
+    const float4* base = reinterpret_cast<const float4*>(x + set.in_pix[im] * C) + c4;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int py = reflect1(oy * 2 - 1 + r, Hp);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int px = reflect1(ox * 2 - 1 + s, Wp);
+            const float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
+            float4 a = __ldg(base + ((long long)py * W + px) * c4n), b = __ldg(base + ((long long)py * W + px + 1) * c4n);
+            float4 c = __ldg(base + ((long long)(py + 1) * W + px) * c4n), d = __ldg(base + ((long long)(py + 1) * W + px + 1) * c4n);
+            float4 m = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
+                                   fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
+            acc.x = fmaf(wgt, m.x, acc.x); acc.y = fmaf(wgt, m.y, acc.y); acc.z = fmaf(wgt, m.z, acc.z); acc.w = fmaf(wgt, m.w, acc.w);
+        }
+    }
+    if (round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+    reinterpret_cast<float4*>(y + pm * C)[c4] = acc;
+}
+
+// ---------------------------------------------------------------------------
 // F.normalize(dim=1): one warp per pixel (coarseAlignFeatMatch.py:106,124; evaluation.py:26,184)
 // ---------------------------------------------------------------------------
 __global__ void l2norm_kernel(const float* __restrict__ x, long long P, int C, const unsigned char* __restrict__ mask, float* __restrict__ y) {
@@ -399,6 +437,18 @@ int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C,
     for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur_downsample_nhwc: reflect padding needs H, W >= 2");
     long long total = set.out_pix[nimg] * (C / 4);
     blur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride, round_out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// output size of maxpool(2,1) + blur(stride 2): ((H-1) + 2 - 3)/2 + 1 = make_imgset with k = 4, stride 2, pad 1
+int rf_poolblur_impl(const float* x, int nimg, const int* hw_host, int C, int round_out, float* y, void* stream) {
+    RF_REQUIRE((C % 4) == 0, "rf_poolblur: C must be a multiple of 4");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 4, 2, 1) == 0, "rf_poolblur: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 3 && set.W[i] >= 3, "rf_poolblur: needs H, W >= 3");
+    long long total = set.out_pix[nimg] * (C / 4);
+    poolblur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, round_out);
     RF_LAUNCHED();
     return 0;
 }

@@ -158,10 +158,25 @@ corr_argmax_kernel(const float* __restrict__ A, int NA, const float* __restrict_
     }
 }
 
-// single CTA: mutual test + order-preserving compaction (utils/outil.py:38-44)
+// mutual test (utils/outil.py:38-42), fully parallel: rowbest[i] is overwritten with (1 << 63 | j) when (i, j) is a
+// mutual nearest-neighbour pair with non-zero score, else 0
+__global__ void mutual_flag_kernel(unsigned long long* __restrict__ rowbest, const unsigned long long* __restrict__ colbest, int NA) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NA) return;
+    unsigned long long rk = rowbest[i], out = 0ull;
+    if (rk != 0ull) {
+        uint32_t j = key_index(rk);
+        float v = key_value(rk);
+        unsigned long long ck = __ldg(colbest + j);
+        if (key_index(ck) == (uint32_t)i && (__fmul_rn(v, v) > 0.f)) out = (1ull << 63) | (unsigned long long)j;     // keepMax > 0
+    }
+    rowbest[i] = out;
+}
+
+// single CTA: order-preserving compaction of the flagged rows (utils/outil.py:43-44: nonzero() is row-major)
 __global__ void __launch_bounds__(1024)
-mutual_finalize_kernel(const unsigned long long* __restrict__ rowbest, const unsigned long long* __restrict__ colbest,
-                       int NA, int NB, long long* __restrict__ idx1, long long* __restrict__ idx2, int* __restrict__ count) {
+mutual_compact_kernel(const unsigned long long* __restrict__ flagged, int NA, long long* __restrict__ idx1, long long* __restrict__ idx2,
+                      int* __restrict__ count) {
     __shared__ int s_scan[32];
     __shared__ int s_off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -169,17 +184,8 @@ mutual_finalize_kernel(const unsigned long long* __restrict__ rowbest, const uns
     __syncthreads();
     for (int base = 0; base < NA; base += 1024) {
         int i = base + tid;
-        int keep = 0;
-        uint32_t j = 0;
-        if (i < NA) {
-            unsigned long long rk = rowbest[i];
-            if (rk != 0ull) {
-                j = key_index(rk);
-                float v = key_value(rk);
-                unsigned long long ck = colbest[j];
-                keep = (key_index(ck) == (uint32_t)i) && (__fmul_rn(v, v) > 0.f);     // keepMax > 0
-            }
-        }
+        unsigned long long f = (i < NA) ? flagged[i] : 0ull;
+        int keep = (f >> 63) ? 1 : 0;
         int incl = keep;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -194,7 +200,7 @@ mutual_finalize_kernel(const unsigned long long* __restrict__ rowbest, const uns
         if (keep) {
             int o = off + wofs + incl - 1;
             idx1[o] = i;
-            idx2[o] = j;
+            idx2[o] = (long long)(f & 0xFFFFFFFFull);
         }
         __syncthreads();
         if (tid == 0) s_off = off + total;
@@ -425,7 +431,11 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
             RF_LAUNCHED();
         }
     }
-    mutual_finalize_kernel<<<1, 1024, 0, st>>>(rowbest, colbest, NA, NB, (long long*)idx1_out, (long long*)idx2_out, count_out);
+    if (NA > 0) {
+        mutual_flag_kernel<<<(NA + 255) / 256, 256, 0, st>>>(rowbest, colbest, NA);
+        RF_LAUNCHED();
+    }
+    mutual_compact_kernel<<<1, 1024, 0, st>>>(rowbest, NA, (long long*)idx1_out, (long long*)idx2_out, count_out);
     RF_LAUNCHED();
     return 0;
 }

@@ -845,6 +845,15 @@ static int halo_mode() {
     return m;
 }
 
+static int corr_tile_n() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("RF_CORR_BN");
+        m = e ? atoi(e) : 256;
+    }
+    return m;
+}
+
 static int persist_mode() {
     static int m = -1;
     if (m < 0) {
@@ -970,7 +979,10 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     RF_LAUNCHED();
     split_tf32_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (float4*)Bhi, (float4*)Blo, nb4);
     RF_LAUNCHED();
-    constexpr int BN = 128;
+    // 256-wide score tiles when the target has enough cells: the featA slab (hi + lo) is fetched once per 256 columns,
+    // which is what the L2->SM bound cares about (96 KB per K-step for 24 MMAs instead of 64 KB for 12)
+    const bool wide = NB > 128 && corr_tile_n() == 256;
+    const int BN = wide ? 256 : 128;
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.nimg = 1;
@@ -986,5 +998,6 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     if (rc) return rc;
     p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
-    return launch_tc<BN, MODE_CORR, false>(p, p.tiles_x[0], (NB + BN - 1) / BN, st);
+    if (wide) return launch_tc<256, MODE_CORR, false>(p, p.tiles_x[0], (NB + 255) / 256, st);
+    return launch_tc<128, MODE_CORR, false>(p, p.tiles_x[0], (NB + 127) / 128, st);
 }

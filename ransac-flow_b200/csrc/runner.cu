@@ -7,6 +7,7 @@ using namespace rf;
 
 int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, int round_out,
                    float* y, void* stream);
+int rf_poolblur_impl(const float* x, int nimg, const int* hw_host, int C, int round_out, float* y, void* stream);
 int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
 
 extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
@@ -34,6 +35,9 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
         } else if (l.op == RF_OP_BLUR) {
             k = 3; pad = 1;
             rc = rf_blur_downsample_impl(x, nimg, shw, l.Cin, stride, engine == 1 ? 1 : 0, y, stream);
+        } else if (l.op == RF_OP_POOLBLUR) {
+            k = 4; stride = 2; pad = 1;                 // size rule of maxpool(2,1) followed by blur(3, stride 2, pad 1)
+            rc = rf_poolblur_impl(x, nimg, shw, l.Cin, engine == 1 ? 1 : 0, y, stream);
         } else if (l.op == RF_OP_IM2COL) {
             rc = rf_im2col_impl(x, nimg, shw, l.Cin, k, stride, pad, l.Cout, engine == 1 ? 1 : 0, y, stream);
         } else {

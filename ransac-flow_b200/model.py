@@ -147,8 +147,7 @@ class FeatureExtractor(_Engine):
         """The whole network as one layer program (model/model.py:106-114 do_forward)."""
         P = LayerProgram(3)
         x = P.stem(0, self.conv1.weight, self.bn1, 1, 1)                             # conv1 + bn1 + relu (im2col + 1x1)
-        x = P.maxpool(x, 2, 1, 0)                                                    # MaxPool2d(2, stride 1)
-        x = P.blur(x, 2)                                                             # anti-aliased stride 2
+        x = P.poolblur(x)                                                            # MaxPool2d(2, 1) + anti-aliased stride 2, fused
         for layer in (self.layer1, self.layer2, self.layer3):
             for b in layer:
                 out = P.conv(x, FoldedConv(b.conv1.weight, b.bn1, b.stride), relu=True)

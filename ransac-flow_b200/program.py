@@ -11,7 +11,7 @@ import torch
 
 from ._lib import check, lib, need_cuda, stream
 
-RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL = 0, 1, 2, 3
+RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR = 0, 1, 2, 3, 4
 RF_MAX_SLOTS = 32
 
 
@@ -45,6 +45,13 @@ class LayerProgram:
     def maxpool(self, src, k, stride, pad):
         c = self.chan[src]
         self.ops.append((RF_OP_MAXPOOL, src, -1, c, c, k, stride, pad, 0, None))
+        self.chan.append(c)
+        return len(self.chan) - 1
+
+    def poolblur(self, src):
+        """MaxPool2d(2, stride 1) + anti-aliased stride-2 blur in one pass (same output size rule as k=4, s=2, p=1)."""
+        c = self.chan[src]
+        self.ops.append((RF_OP_POOLBLUR, src, -1, c, c, 4, 2, 1, 0, None))
         self.chan.append(c)
         return len(self.chan) - 1
 
