@@ -42,15 +42,20 @@ inline int fail_msg(const char* msg) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
+
 inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 // ragged NHWC batch descriptor passed by value to kernels

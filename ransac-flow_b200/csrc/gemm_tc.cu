@@ -866,10 +866,11 @@ static int persist_mode() {
 template <int BN, bool HALO>
 static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStream_t st) {
     using Cfg = PCfg<BN, HALO>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
         RF_CUDA(cudaFuncSetAttribute(tc_persist_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
+        attr[dev] = true;
     }
     const int total = tiles_m * tiles_n;
     const int grid = total < num_sms() ? total : num_sms();
@@ -881,10 +882,11 @@ static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStrea
 template <int BN>
 static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
         RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
+        attr[dev] = true;
     }
     tc_halo_kernel<BN><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
     RF_LAUNCHED();
@@ -894,10 +896,11 @@ static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cud
 template <int BN, int MODE, bool DEEP>
 static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st) {
     using Cfg = TcCfg<BN, MODE, DEEP>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
         RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr = true;
+        attr[dev] = true;
     }
     dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
     tc_kernel<BN, MODE, DEEP><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
