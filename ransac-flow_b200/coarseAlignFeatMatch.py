@@ -264,7 +264,10 @@ class CoarseAlignA(_CoarseAlignBase):
         generator stream use ``getCoarse``."""
         with torch.no_grad():
             valid16 = None
-            if Mt is not None and np.any(Mt):
+            if torch.is_tensor(Mt):                          # device-resident mask (480x640 float, 1 = masked)
+                MtTensor = ops.upsample_bilinear((1 - Mt).reshape(1, 1, Mt.shape[-2], Mt.shape[-1]).float(), (self.W2, self.H2))
+                valid16 = (MtTensor > 0.5).reshape(-1).to(torch.uint8).contiguous()
+            elif Mt is not None and np.any(Mt):
                 valid16 = self._mask16(Mt).reshape(-1).to(torch.uint8).contiguous()
             match1, match2, _, cnt = ops.build_matches(self._idx1, self._idx2, self._count, self.WMultiScale, self.HMultiScale,
                                                        self.Wt, self.Ht, valid16)

@@ -189,6 +189,51 @@ def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, wit
     return dict(H=cat(Hs), flowDown8=cat(flows8), matchDown8=cat(matches8), flow12=flows, match=matches)
 
 
+def align_pair_device(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):
+    """The multi-hypothesis loop of evaluation/evalHpatch/evaluation.py:211-243 with the masks kept on the device:
+    per hypothesis only the two scalars the host needs to steer the loop (RANSAC status, new-region matchability mean)
+    cross the bus instead of the full-resolution matchability map, and the accepted results are fetched once at the
+    end.  Same outputs as ``align_pair`` (plus ``nbMatch`` per hypothesis)."""
+    coarseModel.setPair(Is, It)
+    Itw, Ith = coarseModel.target_size
+    dev = coarseModel.ItTensor.device
+    bg = torch.ones((Ith, Itw), device=dev) if It_bg is None else torch.as_tensor(It_bg, dtype=torch.float32, device=dev)
+    featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+    Mask = torch.zeros((Ith, Itw), device=dev)
+    acc = []
+    nbCoarse = 0
+    while nbCoarse <= maxCoarse:
+        fgMask = ((Mask + (1 - bg)) > 0.5).float()
+        Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(fgMask if nbCoarse > 0 or It_bg is not None else None)
+        flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+        flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
+        newreg = (match[0, 0] * (1 - fgMask)).mean()
+        ctl = _to_host(torch.cat([status.float(), newreg.reshape(1), cnt.float()])).copy()        # 12 bytes per hypothesis
+        st = int(ctl[0])
+        if st == 2:
+            raise TypeError("'NoneType' object is not subscriptable")     # utils/outil.py:162
+        if st != 0:
+            break                                                          # bestPara is None (evaluation.py:215-216)
+        if float(ctl[1]) > maskRegionTh or nbCoarse == 0:
+            acc.append((Hd, f8, mboth, flow12, match, int(ctl[2])))
+            matchFine = match[0, 0] if nbCoarse == 0 else match[0, 0] * (1 - fgMask)
+            nbCoarse += 1
+            Mask = ((Mask + matchFine) >= 1.0).float()
+        else:
+            break
+    if not acc:
+        return dict(H=np.zeros((0,)), flowDown8=np.zeros((0,)), matchDown8=np.zeros((0,)), flow12=[], match=[], nbMatch=[])
+    packed = torch.cat([torch.cat([a[0], a[1].reshape(-1), a[2].reshape(-1), a[4].reshape(-1)]) for a in acc])
+    host = _to_host(packed).copy().reshape(len(acc), -1)
+    n8 = acc[0][1].numel()
+    f8shape = tuple(acc[0][1].shape)
+    return dict(H=host[:, :9].reshape(-1, 3, 3).astype(np.float32),
+                flowDown8=host[:, 9:9 + n8].reshape((len(acc),) + f8shape[1:]),
+                matchDown8=host[:, 9 + n8:9 + 2 * n8].reshape(len(acc), 2, f8shape[2], f8shape[3]),
+                flow12=[a[3] for a in acc], match=[host[i, 9 + 2 * n8:].reshape(Ith, Itw) for i in range(len(acc))],
+                nbMatch=[a[5] for a in acc])
+
+
 def align2images(coarseModel, network, img1, img2, align_corners=False):
     """quick_start/align2images.py:53-97 without the matplotlib / file output: coarse homography from the variant-C
     CoarseAlign, coarse warp, fine flow (no clamp, align2images.py:91-94) and the finely aligned source.

@@ -271,3 +271,27 @@ def test_graphed_aligner_replays_match_eager(rf):
         assert np.abs(f8.cpu().numpy() - out["flowDown8"]).max() < 1e-6
         assert torch.allclose(f12, out["flow12"][0], atol=1e-6)
     assert len(ga.graphs) == 1
+
+
+def test_device_resident_multi_hypothesis_loop_equals_host_loop(rf):
+    """align_pair_device (masks on the device, 12 bytes per hypothesis to the host) == align_pair (host numpy masks, the
+    reference's loop) when both see the same samples."""
+    src, tgt, _ = synth.make_pair(12, 96, 128)
+    Is, It = Image.fromarray(src), Image.fromarray(tgt)
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    raws = [synth.draw_samples(30 + k, 2 ** 31 - 1, 1000) for k in range(6)]
+    with fixed_randint(raws):
+        a = rf.pipeline.align_pair_device(c, net, Is, It, maxCoarse=3, with_match21=True)
+    nH = len(a["flow12"])
+    assert 1 <= nH <= 4 and len(a["nbMatch"]) == nH
+    # the host loop draws one sample set per getCoarse call, including a last rejected / failed one
+    counts = a["nbMatch"] + [a["nbMatch"][-1]] * 3
+    with fixed_randint([raws[k] % max(counts[k], 1) for k in range(6)]):
+        b = rf.pipeline.align_pair(c, net, Is, It, maxCoarse=3, with_match21=True)
+    n = min(nH, len(b["flow12"]))
+    assert n >= 1
+    np.testing.assert_allclose(a["H"][:n], b["H"][:n], atol=1e-6)
+    np.testing.assert_allclose(a["flowDown8"][:n], b["flowDown8"][:n], atol=1e-6)
+    np.testing.assert_allclose(a["match"][0], b["match"][0], atol=1e-6)
