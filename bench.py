@@ -212,6 +212,45 @@ def run_b200(args, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     assert allr.shape[0] == args.steps * world
 
+    # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, mean of 5 pairs) ----
+    def stage_breakdown():
+        names = ["pyramid+preproc+resnet50_conv4(8 imgs)+l2norm", "corr+mutual_nn", "fine_features(target)", "build_matches+ransac",
+                 "warp_grid+PredFlowMask"]
+        acc = np.zeros(len(names))
+        reps = 5
+        for rep in range(reps + 1):
+            s_, t_ = resident[rep % len(resident)]
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            saved = rf.ops.corr_mutual_nn
+            marks = {}
+
+            def corr_hook(*a, **k):                                  # setPair ends with the correlation: split it out
+                marks["pre"] = torch.cuda.Event(enable_timing=True)
+                marks["pre"].record()
+                return saved(*a, **k)
+            rf.ops.corr_mutual_nn = corr_hook
+            try:
+                evs[0].record()
+                coarse.setPair(s_, t_)
+            finally:
+                rf.ops.corr_mutual_nn = saved
+            evs[2].record()
+            Itw, Ith = coarse.target_size
+            featt = rf.pipeline.fine_features(net["netFeatCoarse"], coarse.ItTensor)
+            evs[3].record()
+            Hd, nb, mask, status, cnt = coarse.getCoarse_device(None)
+            evs[4].record()
+            fc = rf.ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+            rf.pipeline.PredFlowMask_device(coarse.IsTensor, featt, fc, (Ith, Itw), net)
+            evs[5].record()
+            torch.cuda.synchronize()
+            if rep == 0:
+                continue
+            acc += np.array([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
+                             evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
+        return {n: round(float(v / reps), 4) for n, v in zip(names, acc)}
+    stages = stage_breakdown() if rank == 0 else None
+
     # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----
     fa, ft = coarse._feats_rows, coarse._featt_rows
     st = torch.cuda.current_stream()
@@ -284,7 +323,7 @@ def run_b200(args, rank, world, local):
                        "launch": "one CUDA graph per pair" if args.graph else "stream launches"},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * 480 * 640 * 3,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages_ms": stages,
         }
         print(json.dumps(line))
 

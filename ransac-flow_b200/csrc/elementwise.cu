@@ -265,6 +265,54 @@ __global__ void preproc_kernel(const unsigned char* __restrict__ img, long long 
 // PIL ImagingResample (8 bits per channel, fixed point, one pass)
 // ---------------------------------------------------------------------------
 #define RF_PRECISION_BITS 22
+__device__ __forceinline__ unsigned char clip8(int ss) {
+    int v = ss >> RF_PRECISION_BITS;
+    return (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+// horizontal pass: one thread per output PIXEL (all channels), so the coefficient row is walked once
+__global__ void resample_h_kernel(const unsigned char* __restrict__ in, int in_h, int in_w, int ch, const int* __restrict__ bounds,
+                                  const int* __restrict__ kk, int ksize, int out_w, unsigned char* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)in_h * out_w) return;
+    const int ox = (int)(t % out_w), oy = (int)(t / out_w);
+    const int lo = bounds[2 * ox], cnt = bounds[2 * ox + 1];
+    const int* k = kk + (long long)ox * ksize;
+    const unsigned char* row = in + ((long long)oy * in_w + lo) * ch;
+    if (ch == 3) {
+        int s0 = 1 << (RF_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+        for (int x = 0; x < cnt; ++x) {
+            const int kx = __ldg(k + x);
+            s0 += (int)row[3 * x] * kx; s1 += (int)row[3 * x + 1] * kx; s2 += (int)row[3 * x + 2] * kx;
+        }
+        unsigned char* o = out + t * 3;
+        o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+    } else {
+        for (int c = 0; c < ch; ++c) {
+            int ss = 1 << (RF_PRECISION_BITS - 1);
+            for (int x = 0; x < cnt; ++x) ss += (int)row[(long long)x * ch + c] * __ldg(k + x);
+            out[t * ch + c] = clip8(ss);
+        }
+    }
+}
+// vertical pass: one thread per 4 consecutive bytes of an output row (rows are W*ch bytes, a multiple of 4 here)
+__global__ void resample_v_kernel(const unsigned char* __restrict__ in, int in_h, int row_bytes, const int* __restrict__ bounds,
+                                  const int* __restrict__ kk, int ksize, int out_h, unsigned char* __restrict__ out) {
+    const int q = row_bytes >> 2;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)out_h * q) return;
+    const int xq = (int)(t % q), oy = (int)(t / q);
+    const int lo = bounds[2 * oy], cnt = bounds[2 * oy + 1];
+    const int* k = kk + (long long)oy * ksize;
+    const unsigned int* col = reinterpret_cast<const unsigned int*>(in + (long long)lo * row_bytes) + xq;
+    int s0 = 1 << (RF_PRECISION_BITS - 1), s1 = s0, s2 = s0, s3 = s0;
+    for (int y = 0; y < cnt; ++y) {
+        const unsigned int v = __ldg(col + (long long)y * q);
+        const int ky = __ldg(k + y);
+        s0 += (int)(v & 0xFF) * ky; s1 += (int)((v >> 8) & 0xFF) * ky; s2 += (int)((v >> 16) & 0xFF) * ky; s3 += (int)(v >> 24) * ky;
+    }
+    reinterpret_cast<unsigned int*>(out)[t] = (unsigned)clip8(s0) | ((unsigned)clip8(s1) << 8) | ((unsigned)clip8(s2) << 16) | ((unsigned)clip8(s3) << 24);
+}
+// generic fallback (any row length / alignment): one thread per output byte
 __global__ void resample_u8_kernel(const unsigned char* __restrict__ in, int in_h, int in_w, int ch, int horizontal,
                                    const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int out_size,
                                    unsigned char* __restrict__ out) {
@@ -286,8 +334,7 @@ __global__ void resample_u8_kernel(const unsigned char* __restrict__ in, int in_
         const unsigned char* col = in + (long long)ox * ch + c;
         for (int y = 0; y < cnt; ++y) ss += (int)col[(long long)(y + lo) * in_w * ch] * k[y];
     }
-    int v = ss >> RF_PRECISION_BITS;
-    out[t] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    out[t] = clip8(ss);
 }
 
 // ---------------------------------------------------------------------------
@@ -568,6 +615,17 @@ extern "C" int rf_resample_u8(const uint8_t* in, int in_h, int in_w, int channel
                               const int* bounds, const int* kk, int ksize, int out_size, uint8_t* out, void* stream) {
     long long total = (long long)(horizontal ? in_h : out_size) * (horizontal ? out_size : in_w) * channels;
     if (total <= 0) return 0;
+    if (horizontal) {
+        resample_h_kernel<<<blocks_for((long long)in_h * out_size, 256), 256, 0, as_stream(stream)>>>(in, in_h, in_w, channels, bounds, kk, ksize, out_size, out);
+        RF_LAUNCHED();
+        return 0;
+    }
+    const long long row_bytes = (long long)in_w * channels;
+    if ((row_bytes & 3) == 0 && ((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+        resample_v_kernel<<<blocks_for((long long)out_size * (row_bytes >> 2), 256), 256, 0, as_stream(stream)>>>(in, in_h, (int)row_bytes, bounds, kk, ksize, out_size, out);
+        RF_LAUNCHED();
+        return 0;
+    }
     resample_u8_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(in, in_h, in_w, channels, horizontal, bounds, kk, ksize, out_size, out);
     RF_LAUNCHED();
     return 0;
