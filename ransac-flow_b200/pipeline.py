@@ -9,7 +9,7 @@ restated on the library's kernels (no file IO, no metrics: those stay in the dri
 import numpy as np
 import torch
 
-from . import model, ops
+from . import _lib, model, ops
 from .kornia_geometry import HomographyWarper
 from .ops import Ragged
 
@@ -120,6 +120,7 @@ class GraphedAligner:
         self.coarse, self.net, self.m21, self.warmup = coarseModel, network, with_match21, warmup
         self.coarse.device_preproc = True
         self.graphs = {}
+        self.replayed_kernels = 0       # library kernels executed through graph replays (they bypass rf_launch_count)
 
     def _build(self, Is, It):
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -135,9 +136,10 @@ class GraphedAligner:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             packed, flow12, size, f8shape = _single_device(self.coarse, self.net, s_in, t_in, self.m21)
-        return dict(graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape)
+        return dict(n_kernels=_lib.launch_count() - n0, graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape)
 
     def __call__(self, Is, It):
         """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
@@ -150,6 +152,7 @@ class GraphedAligner:
         c["s_in"].copy_(Is, non_blocking=True)
         c["t_in"].copy_(It, non_blocking=True)
         c["graph"].replay()
+        self.replayed_kernels += c["n_kernels"]
         return _unpack_single(_to_host(c["packed"]).copy(), c["flow12"], c["size"], c["f8shape"])
 
 
