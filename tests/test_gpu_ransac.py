@@ -99,3 +99,35 @@ def test_mirror_api_matches_reference_types(rf):
     us = torch.from_numpy(OO.unique_samples(g["samples"])[:100]).cuda()
     H21, cnt = rf.outil.ScoreRANSAC(torch.from_numpy(g["match1"]).cuda(), torch.from_numpy(g["match2"]).cuda(), 0.05, us, rf.outil.Homography)
     assert np.array_equal(cnt.cpu().numpy(), g["chunk0_counts"])
+
+
+def test_fuzz_many_seeds_bit_exact(rf):
+    """40 random configurations (M 4..1500, nbIter 1..3000, inlier fraction 0..1, grid / continuous coordinates,
+    tolerance 0.005..0.1): status, inlier count and inlier mask bit-exact against the oracle, H within 2e-7."""
+    rs = np.random.RandomState(2024)
+    n_ok = n_none = n_nomodel = 0
+    for case in range(40):
+        M = int(rs.choice([4, 5, 8, 37, 100, 333, 636, 1200, 1500]))
+        nbIter = int(rs.choice([1, 7, 99, 100, 101, 250, 1000, 3000]))
+        frac = float(rs.choice([0.0, 0.1, 0.3, 0.6, 0.9, 1.0]))
+        tol = float(rs.choice([0.005, 0.02, 0.05, 0.1]))
+        seed = 5000 + case
+        m1, m2, _ = synth.make_matches(seed, M, frac, grid=(30, 40) if case % 3 == 0 else None)
+        samples = synth.draw_samples(seed, M, nbIter)
+        try:
+            Ho, nbo, inlo, _ = OO.RANSAC_from_samples(m1, m2, samples, tol)
+            expect = 0 if Ho is not None else 1
+        except TypeError:
+            expect = 2
+        H, nb, mask, st = run_kernel(rf, m1, m2, samples, tol)
+        assert st == expect, (case, M, nbIter, frac, tol, st, expect)
+        if expect == 0:
+            n_ok += 1
+            assert nb == int(nbo) and np.array_equal(mask, inlo), (case, M, nbIter, frac, tol)
+            np.testing.assert_allclose(H, Ho, rtol=0, atol=2e-7)
+        elif expect == 1:
+            n_none += 1
+        else:
+            n_nomodel += 1
+    print("fuzz: %d ok, %d None, %d no-model" % (n_ok, n_none, n_nomodel))
+    assert n_ok >= 20
