@@ -750,6 +750,163 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 / stride-1 / 64 -> 64 channel convolutions (ResNet-50 layer1 conv2, FeatureExtractor layer1): K is only two
+// 32-channel chunks, so a tile is ~1.2 us of MMA work and one-tile CTAs live mostly in launch / TMA / epilogue
+// latency.  All 18 weight tiles (9 taps x 2 chunks x 8 KB = 144 KB) fit in shared memory: this persistent kernel loads
+// them ONCE per CTA, then streams halo tiles (2 x 23 KB) through a two-slot ring while two TMEM accumulators let the
+// epilogue of tile i overlap the MMAs of tile i+1.  Per tile only the 46 KB halo crosses L2->SM.
+// ------------------------------------------------------------------------------------------------------------
+struct ResBCfg {
+    static constexpr int BN = 64, KC = 2, NTAP = 9, NA = 2;
+    static constexpr int B_TILE = BN * 128;                                 // 8 KB
+    static constexpr int B_BYTES = KC * NTAP * B_TILE;                      // 144 KB
+    static constexpr int OFF_A = B_BYTES;
+    static constexpr int OFF_STG = OFF_A + NA * HALO_A_SLOT;
+    static constexpr int STG = BN * 512;                                    // 32 KB
+    static constexpr int DATA_BYTES = OFF_STG + STG;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 128;                                   // two 64-column accumulators
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
+    using Cfg = ResBCfg;
+    constexpr int BN = Cfg::BN, NA = Cfg::NA;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;
+    uint8_t* sA = smem + Cfg::OFF_A;
+    uint8_t* sStg = smem + Cfg::OFF_STG;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* emptyA = fullA + NA;
+    uint64_t* fullB = emptyA + NA;              // [1]
+    uint64_t* tmem_full = fullB + 1;            // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint64_t* res_full = tmem_empty + 2;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = tiles_m;                  // Cout = 64: a single channel tile
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        mbar_init(fullB, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        mbar_init(res_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the whole weight set, once: tile (cc, tap) at sB + (cc * 9 + tap) * 8 KB
+            mbar_expect_tx(fullB, Cfg::B_BYTES);
+            for (int cc = 0; cc < Cfg::KC; ++cc)
+                for (int tap = 0; tap < Cfg::NTAP; ++tap)
+                    tma_load_2d(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE, &p.mapB, fullB, tap * p.Cin + cc * TC_BK, 0);
+            uint32_t ia = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord c = decode_tile<true>(p, t, tiles_m, BN);
+                for (int cc = 0; cc < Cfg::KC; ++cc, ++ia) {
+                    const int sa = ia % NA;
+                    mbar_wait(&emptyA[sa], ((ia / NA) & 1) ^ 1);
+                    mbar_expect_tx(&fullA[sa], HALO_A_BYTES);
+                    tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[c.img], &fullA[sa], cc * TC_BK, c.ox0 - 1, c.oy0 - 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            mbar_wait(fullB, 0);
+            tc_fence_after();
+            uint32_t ia = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const uint32_t buf = ti & 1;
+                mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int cc = 0; cc < Cfg::KC; ++cc, ++ia) {
+                    const int sa = ia % NA;
+                    mbar_wait(&fullA[sa], (ia / NA) & 1);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA + sa * HALO_A_SLOT);
+#pragma unroll
+                    for (int tap = 0; tap < Cfg::NTAP; ++tap) {
+                        const int r = tap / 3, sx = tap - r * 3;
+                        const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
+                        const uint64_t db = make_desc_sw128(smem_u32(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k)
+                            umma_tf32(tacc, make_desc_halo(aaddr + k * 32, 2), db + (uint64_t)(k * 32 >> 4), idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&emptyA[sa]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const bool leader = (warp == 2 && lane == 0);
+        const bool has_res = p.residual != nullptr;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            const TileCoord c = decode_tile<true>(p, t, tiles_m, BN);
+            if (leader) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // staging buffer has been read out
+                if (has_res) {
+                    mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
+#pragma unroll
+                    for (int cb = 0; cb < BN / 32; ++cb) tma_load_3d(sStg + cb * TC_A_BYTES, &p.mapR[c.img], res_full, cb * 32, c.ox0, c.oy0);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(res_full, ti & 1);
+            const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(trow + cb * 32, v);
+                const int n = cb * 32;
+                uint8_t* rowp = sStg + cb * TC_A_BYTES + m * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                    if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *sp = o;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) tma_store_3d(&p.mapY[c.img], sStg + cb * TC_A_BYTES, cb * 32, c.ox0, c.oy0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 // hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
 __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -863,6 +1020,28 @@ static int persist_mode() {
     return m;
 }
 
+static int resb_mode() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("RF_TC_RESB");
+        m = e ? atoi(e) : 0;
+    }
+    return m;
+}
+
+static int launch_resb(const TcParams& p, int tiles_m, cudaStream_t st) {
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        RF_CUDA(cudaFuncSetAttribute(tc_resb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ResBCfg::SMEM_BYTES));
+        attr[dev] = true;
+    }
+    const int grid = tiles_m < num_sms() ? tiles_m : num_sms();
+    tc_resb_kernel<<<grid, TC_THREADS, ResBCfg::SMEM_BYTES, st>>>(p, tiles_m);
+    RF_LAUNCHED();
+    return 0;
+}
+
 template <int BN, bool HALO>
 static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStream_t st) {
     using Cfg = PCfg<BN, HALO>;
@@ -957,6 +1136,7 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
+    if (hmode && resb_mode() && p.tma_epi && cp.Cin == 64 && cp.Cout == 64) return launch_resb(p, tiles, st);
     if (persist_mode() && p.tma_epi) {
         if (hmode) return BN == 128 ? launch_persist<128, true>(p, tiles, nt, st) : launch_persist<64, true>(p, tiles, nt, st);
         return BN == 128 ? launch_persist<128, false>(p, tiles, nt, st) : launch_persist<64, false>(p, tiles, nt, st);
