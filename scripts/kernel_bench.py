@@ -46,6 +46,15 @@ elif which == "ransac":
         s = torch.from_numpy(synth.draw_samples(1, 636, nb)).to(dev)
         m, mn = timed(lambda: rf.ops.ransac_homography(t1, t2, s, 0.05))
         print("ransac nbIter=%d M=636: mean %.1f us, min %.1f us" % (nb, m * 1e3, mn * 1e3))
+elif which == "c64":
+    sizes = [(240, 320), (200, 264), (160, 212), (120, 160), (100, 132), (80, 104), (60, 80), (120, 160)]   # layer1 grids of config 2
+    P = sum(h * w for h, w in sizes)
+    x = rf.ops.Ragged(torch.randn(P, 64, device=dev), sizes)
+    w = torch.randn(64, 64, 3, 3, device=dev) / 24
+    fc = rf.model.FoldedConv(w, None, 1)
+    m, mn = timed(lambda: fc(x, relu=True, engine=1))
+    fl = 2.0 * P * 64 * 64 * 9 / 1e9
+    print("conv3x3 64->64 on %d px (RF_TC_RESB=%s): mean %.1f us -> %.1f TFLOP/s" % (P, os.environ.get("RF_TC_RESB", "0"), m * 1e3, fl / m))
 else:
     sizes = [(60, 80), (50, 66), (40, 53), (30, 40), (25, 33), (20, 26), (15, 20), (30, 40)]      # layer3 grids of config 2
     P = sum(h * w for h, w in sizes)
