@@ -108,15 +108,66 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], TF32 operands, fp32 accumulate, M = 128, N from idesc
+// Called by ALL 32 lanes of the (converged) MMA warp with warp-uniform operands; one elected lane issues.  Keeping the
+// control flow and the descriptors warp-uniform lets the compiler hold them in uniform registers: issuing from a
+// divergent `if (lane == 0)` branch cost ~14 SASS instructions (ELECT / R2UR.BROADCAST per operand) per MMA and made
+// the single issuing thread, not the tensor pipe, the bottleneck (profiles/README.md).
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .pred e;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+
+// Four MMAs (the four K = 8 steps of one 32-wide, 128-byte-swizzled K block) from ONE elected lane with one
+// elect.sync: descriptors advance by 32 bytes (+2 in the 16-byte address field) per step.  `acc_first` = 0 makes the
+// first MMA overwrite the accumulator.
+__device__ __forceinline__ void umma_tf32_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a1, b1, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a2, b2, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %3, t;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
+}
+// 3xTF32: per K step lo*hi, hi*lo, hi*hi (12 MMAs per K block)
+__device__ __forceinline__ void umma_3xtf32_x4(uint32_t tmem_d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 ah, al, bh, bl;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, t;\n\t"
+        "add.u64 ah, %1, 2;\n\tadd.u64 al, %2, 2;\n\tadd.u64 bh, %3, 2;\n\tadd.u64 bl, %4, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %5, t;\n\t"
+        "add.u64 ah, %1, 4;\n\tadd.u64 al, %2, 4;\n\tadd.u64 bh, %3, 4;\n\tadd.u64 bl, %4, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %5, t;\n\t"
+        "add.u64 ah, %1, 6;\n\tadd.u64 al, %2, 6;\n\tadd.u64 bh, %3, 6;\n\tadd.u64 bl, %4, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %5, t;\n\t}"
+        ::"r"(tmem_d), "l"(ahi), "l"(alo), "l"(bhi), "l"(blo), "r"(idesc), "r"(acc_first) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -134,7 +185,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // shared-memory matrix descriptor: K-major tile, 128-byte swizzle, 8-row atoms 1024 B apart
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);          // start address, bits [0,14)
+    d |= (uint64_t)(saddr >> 4);                      // start address, bits [0,14) (shared addresses are < 256 KB)
     d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major), bits [16,30)
     d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups, bits [32,46)
     d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell), bits [46,48)
@@ -319,7 +370,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
             constexpr uint32_t idesc = make_idesc_tf32(BN);
             for (int it = 0; it < KI; ++it) {
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
@@ -328,17 +379,10 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
                 const uint32_t sb = sa + NSPLIT * TC_A_BYTES;
                 const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                       // UMMA_K = 8 tf32 = 32 bytes
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                    if (NSPLIT == 2) {
-                        const uint64_t dalo = make_desc_sw128(sa + TC_A_BYTES), dblo = make_desc_sw128(sb + Cfg::B_BYTES);
-                        umma_tf32(tmem_base, dalo + adv, db + adv, idesc, (it | k) != 0 ? 1u : 0u);   // lo * hi
-                        umma_tf32(tmem_base, da + adv, dblo + adv, idesc, 1u);                         // hi * lo
-                        umma_tf32(tmem_base, da + adv, db + adv, idesc, 1u);                           // hi * hi
-                    } else {
-                        umma_tf32(tmem_base, da + adv, db + adv, idesc, (it | k) != 0 ? 1u : 0u);
-                    }
+                if (NSPLIT == 2) {
+                    umma_3xtf32_x4(tmem_base, da, make_desc_sw128(sa + TC_A_BYTES), db, make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
+                } else {
+                    umma_tf32_x4(tmem_base, da, db, idesc, it != 0 ? 1u : 0u);      // 4 x (UMMA_K = 8 tf32 = 32 bytes)
                 }
                 umma_commit(&empty[st]);            // stage free once these MMAs have read it
             }
@@ -425,7 +469,7 @@ struct HaloCfg {
 
 __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
     uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(saddr >> 4);
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)((HALO_LD * 128) >> 4) << 32;                       // 8-row core groups are one halo row pitch apart
     d |= (uint64_t)1 << 46;
@@ -496,7 +540,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
             constexpr uint32_t idesc = make_idesc_tf32(BN);
             int ib = 0;
             for (int cc = 0; cc < kc; ++cc) {
@@ -511,10 +555,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
                     const int r = tap / 3, sx = tap - r * 3;
                     const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
                     const uint64_t db = make_desc_sw128(smem_u32(sB + sb * Cfg::B_BYTES));
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        umma_tf32(tmem_base, make_desc_halo(aaddr + k * 32, desc_mode), db + (uint64_t)(k * 32 >> 4), idesc,
-                                  (cc | tap | k) != 0 ? 1u : 0u);
+                    umma_tf32_x4(tmem_base, make_desc_halo(aaddr, desc_mode), db, idesc, (cc | tap) != 0 ? 1u : 0u);
                     umma_commit(&emptyB[sb]);
                 }
                 umma_commit(&emptyA[sa]);
@@ -652,7 +693,7 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
             constexpr uint32_t idesc = make_idesc_tf32(BN);
             uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
@@ -672,11 +713,7 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
                         const uint64_t db = make_desc_sw128(smem_u32(sB + sb * Cfg::B_BYTES));
                         uint32_t aaddr = abase;
                         if (HALO) { const int r = jb / 3, sx = jb - r * 3; aaddr += (uint32_t)((r * HALO_LD + sx) * 128); }
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k) {
-                            const uint64_t da = HALO ? make_desc_halo(aaddr + k * 32, 2) : (make_desc_sw128(aaddr) + (uint64_t)(k * 32 >> 4));
-                            umma_tf32(tacc, da, db + (uint64_t)(k * 32 >> 4), idesc, (ia | jb | k) != 0 ? 1u : 0u);
-                        }
+                        umma_tf32_x4(tacc, HALO ? make_desc_halo(aaddr, 2) : make_desc_sw128(aaddr), db, idesc, (ia | jb) != 0 ? 1u : 0u);
                         umma_commit(&emptyB[sb]);
                     }
                     umma_commit(&emptyA[sa]);
@@ -822,7 +859,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
             constexpr uint32_t idesc = make_idesc_tf32(BN);
             mbar_wait(fullB, 0);
             tc_fence_after();
@@ -842,9 +879,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
                         const int r = tap / 3, sx = tap - r * 3;
                         const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
                         const uint64_t db = make_desc_sw128(smem_u32(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE));
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; ++k)
-                            umma_tf32(tacc, make_desc_halo(aaddr + k * 32, 2), db + (uint64_t)(k * 32 >> 4), idesc, (cc | tap | k) != 0 ? 1u : 0u);
+                        umma_tf32_x4(tacc, make_desc_halo(aaddr, 2), db, idesc, (cc | tap) != 0 ? 1u : 0u);
                     }
                     umma_commit(&emptyA[sa]);
                 }
