@@ -203,8 +203,8 @@ constexpr int MODE_CONV = 0, MODE_CORR = 1;
 // accumulator row m = pixel m of the tile): + folded-BN bias, + residual, ReLU, TF32 rounding, store.
 template <int BN>
 __device__ __forceinline__ void conv_epilogue(const TcParams& p, int img, int ox0, int oy0, int tw, int n0, int m, uint32_t trow,
-                                              uint8_t* smem, uint64_t* res_full, int warp, int lane, bool force_direct = false) {
-    if (p.tma_epi && !force_direct) {
+                                              uint8_t* smem, uint64_t* res_full, int warp, int lane) {
+    if (p.tma_epi) {
         // ---- bulk epilogue: residual tile in by TMA, result tile out by TMA; the pipeline stages are idle now and
         // serve as staging: BN/32 boxes of (32 channels x tw x th) = 128 rows x 128 B, 128-byte swizzled ----
         uint8_t* stg = smem;
@@ -792,17 +792,18 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
 // 3x3 / stride-1 / 64 -> 64 channel convolutions (ResNet-50 layer1 conv2, FeatureExtractor layer1): K is only two
 // 32-channel chunks, so a tile is ~1.2 us of MMA work and one-tile CTAs live mostly in launch / TMA / epilogue
 // latency.  All 18 weight tiles (9 taps x 2 chunks x 8 KB = 144 KB) fit in shared memory: this persistent kernel loads
-// them ONCE per CTA, then streams halo chunks (23 KB each) through a three-slot ring while two TMEM accumulators let the
-// epilogue of tile i (straight from TMEM to global memory: no smem left for staging) overlap the MMAs of tile i+1.
-// Per tile only the 46 KB halo crosses L2->SM.
+// them ONCE per CTA, then streams halo tiles (2 x 23 KB) through a two-slot ring while two TMEM accumulators let the
+// epilogue of tile i overlap the MMAs of tile i+1.  Per tile only the 46 KB halo crosses L2->SM.
 // ------------------------------------------------------------------------------------------------------------
 struct ResBCfg {
-    static constexpr int BN = 64, KC = 2, NTAP = 9, NA = 3;
+    static constexpr int BN = 64, KC = 2, NTAP = 9, NA = 2;
     static constexpr int B_TILE = BN * 128;                                 // 8 KB
     static constexpr int B_BYTES = KC * NTAP * B_TILE;                      // 144 KB
     static constexpr int OFF_A = B_BYTES;
-    static constexpr int DATA_BYTES = OFF_A + NA * HALO_A_SLOT;             // 144 KB of weights + 3 halo slots = 213 KB:
-    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;              // no room for store staging -> direct epilogue
+    static constexpr int OFF_STG = OFF_A + NA * HALO_A_SLOT;
+    static constexpr int STG = BN * 512;                                    // 32 KB
+    static constexpr int DATA_BYTES = OFF_STG + STG;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 128;                                   // two 64-column accumulators
 };
 
@@ -814,12 +815,14 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;
     uint8_t* sA = smem + Cfg::OFF_A;
+    uint8_t* sStg = smem + Cfg::OFF_STG;
     uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
     uint64_t* emptyA = fullA + NA;
     uint64_t* fullB = emptyA + NA;              // [1]
     uint64_t* tmem_full = fullB + 1;            // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_full = tmem_empty + 2;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = tiles_m;                  // Cout = 64: a single channel tile
 
@@ -827,9 +830,10 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         mbar_init(fullB, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        mbar_init(res_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
     if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -885,18 +889,53 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
     } else {
         const int q = warp & 3;
         const int m = q * 32 + lane;
+        const bool leader = (warp == 2 && lane == 0);
+        const bool has_res = p.residual != nullptr;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1;
             const TileCoord c = decode_tile<true>(p, t, tiles_m, BN);
+            if (leader) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // staging buffer has been read out
+                if (has_res) {
+                    mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
+#pragma unroll
+                    for (int cb = 0; cb < BN / 32; ++cb) tma_load_3d(sStg + cb * TC_A_BYTES, &p.mapR[c.img], res_full, cb * 32, c.ox0, c.oy0);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-            // straight from TMEM to global memory (each thread owns one pixel row of 64 channels = 256 contiguous bytes)
-            conv_epilogue<BN>(p, c.img, c.ox0, c.oy0, HALO_TW, 0, m, tmem_base + buf * BN + ((uint32_t)(q * 32) << 16), nullptr, nullptr,
-                              warp, lane, /*force_direct=*/true);
+            if (has_res) mbar_wait(res_full, ti & 1);
+            const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(trow + cb * 32, v);
+                const int n = cb * 32;
+                uint8_t* rowp = sStg + cb * TC_A_BYTES + m * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* sp = reinterpret_cast<float4*>(rowp + ((j ^ (m & 7)) << 4));
+                    float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    if (p.bias) { float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                    if (has_res) { float4 rr = *sp; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                    *sp = o;
+                }
+            }
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+#pragma unroll
+                for (int cb = 0; cb < BN / 32; ++cb) tma_store_3d(&p.mapY[c.img], sStg + cb * TC_A_BYTES, cb * 32, c.ox0, c.oy0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -1019,8 +1058,8 @@ static int persist_mode() {
 static int resb_mode() {
     static int m = -1;
     if (m < 0) {
-        const char* e = getenv("RF_TC_RESB");     // weights-resident persistent kernel for 64 -> 64 3x3 convs (default on)
-        m = e ? atoi(e) : 1;
+        const char* e = getenv("RF_TC_RESB");     // weights-resident persistent kernel for 64 -> 64 3x3 convs (default on);
+        m = e ? atoi(e) : 1;                      // a 3-slot / direct-store variant measured no faster (332 vs 320 us per pair)
     }
     return m;
 }
