@@ -221,19 +221,25 @@ class CoarseAlignA(_CoarseAlignBase):
                  segNet=True, resnet_state_dict=None, verbose=True):
         self._setup(nbScale, nbIter, tolerance, transform, minSize, scaleR, imageNet, segNet, resnet_state_dict, verbose)
 
-    def setPair(self, Is_org, It_org):
+    def setPair(self, Is_org, It_org, after_preproc=None):
+        """``after_preproc`` (optional callable): invoked as soon as ``ItTensor`` / ``IsTensor`` exist, before the ResNet
+        trunk is queued - the pair pipeline uses it to start the target's fine features on a second stream."""
         with torch.no_grad():
             ws, hs = self._size_of(Is_org)
             sizes = [self._target_size(ws, hs, int(self.minSize * s)) for s in self.scaleList]
             IsList = self._pyramid(Is_org, sizes)
             wt, ht = self._size_of(It_org)
             ItR = self._pyramid(It_org, [self._target_size(wt, ht, self.minSize)])[0]
-            feats, u8 = self._features(IsList + [ItR])            # 7 scales + target: one ragged batch
+            imgs = IsList + [ItR]
+            u8 = [im if torch.is_tensor(im) else self._to_device_u8(im) for im in imgs]
             nS = len(IsList)
             mid = len(self.scaleList) // 2
             self.Is, self.It = self._as_pil(IsList[mid]), self._as_pil(ItR)
             self.IsTensor = self._to_tensor01(u8[mid])
             self.ItTensor = self._to_tensor01(u8[nS])
+            if after_preproc is not None:
+                after_preproc()
+            feats, _ = self._features(u8)                         # 7 scales + target: one ragged batch
             self._set_source_feats(feats, nS)
             self._set_target_feats(feats, nS)
             # mutual matching once per pair (:139-147), kept on the device; the matched-coordinate attributes the

@@ -61,6 +61,14 @@ def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False,
 
 
 _pinned = {}
+_side = {}
+
+
+def _side_stream():
+    d = torch.cuda.current_device()
+    if d not in _side:
+        _side[d] = torch.cuda.Stream(device=d)
+    return _side[d]
 
 
 def _to_host(t):
@@ -76,11 +84,23 @@ def _to_host(t):
 
 def _single_device(coarseModel, network, Is, It, with_match21):
     """Device part of the single-hypothesis path: everything queued on the current stream, nothing read back."""
-    coarseModel.setPair(Is, It)
+    # the target's fine features do not depend on the coarse stage: queue them on a second stream as soon as the resized
+    # target exists, so they fill the SMs that the small late layers of the ResNet trunk, the matching and RANSAC leave idle
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    box = {}
+
+    def start_target_features():
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            box["featt"] = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+    coarseModel.setPair(Is, It, after_preproc=start_target_features)
     Itw, Ith = coarseModel.target_size
-    featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
     Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(None)
     flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+    main.wait_stream(side)
+    featt = box["featt"]
+    featt.data.record_stream(main)
     flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
     packed = torch.cat([status.float(), cnt.float(), nb.float(), Hd, match.reshape(-1), f8.reshape(-1), mboth.reshape(-1)])
     return packed, flow12, (Ith, Itw), tuple(f8.shape)
