@@ -192,38 +192,24 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
     float4 xv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) xv[q] = (lane + 32 * q < c4n) ? __ldg(xs + lane + 32 * q) : make_float4(0, 0, 0, 0);
-    // one row of the k x k window at a time, its (up to 8) taps as independent accumulators: the loads of all taps of the
-    // row are in flight together (the per-tap version was bound by one load + shuffle chain after the other)
     for (int i = 0; i < k; ++i) {
-        const int yr = r + i - pad;
-        float acc[8];
+        int yr = r + i - pad;
+        for (int j = 0; j < k; ++j) {
+            int yc = c + j - pad;
+            float acc = 0.f;
+            if (yr >= 0 && yr < h && yc >= 0 && yc < w) {
+                const float4* ys = reinterpret_cast<const float4*>(y + (((long long)n * h + yr) * w + yc) * C);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        if (yr >= 0 && yr < h) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int yc = c + j - pad;
-                if (j < k && yc >= 0 && yc < w) {
-                    const float4* ys = reinterpret_cast<const float4*>(y + (((long long)n * h + yr) * w + yc) * C);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (lane + 32 * q < c4n) {
-                            float4 v = __ldg(ys + lane + 32 * q);
-                            acc[j] = fmaf(xv[q].x, v.x, acc[j]); acc[j] = fmaf(xv[q].y, v.y, acc[j]);
-                            acc[j] = fmaf(xv[q].z, v.z, acc[j]); acc[j] = fmaf(xv[q].w, v.w, acc[j]);
-                        }
-                }
+                for (int q = 0; q < 8; ++q)
+                    if (lane + 32 * q < c4n) {
+                        float4 v = __ldg(ys + lane + 32 * q);
+                        acc = fmaf(xv[q].x, v.x, acc); acc = fmaf(xv[q].y, v.y, acc);
+                        acc = fmaf(xv[q].z, v.z, acc); acc = fmaf(xv[q].w, v.w, acc);
+                    }
             }
-        }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], d);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < k) out[pix * ldo + i * k + j] = round_out ? round_tf32(acc[j]) : acc[j];
+            for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane == 0) out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
         }
     }
     for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
@@ -595,7 +581,7 @@ extern "C" int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t*
 }
 
 extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out, float* out, void* stream) {
-    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && k <= 7 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k <= 7, ldo >= k*k");
+    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
     corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out);
