@@ -295,3 +295,23 @@ def test_device_resident_multi_hypothesis_loop_equals_host_loop(rf):
     np.testing.assert_allclose(a["H"][:n], b["H"][:n], atol=1e-6)
     np.testing.assert_allclose(a["flowDown8"][:n], b["flowDown8"][:n], atol=1e-6)
     np.testing.assert_allclose(a["match"][0], b["match"][0], atol=1e-6)
+
+
+def test_kitti_shaped_pair_runs(rf):
+    """BASELINE config 5 shape: 376x1241 pair at coarseSize 800 (nbScale 3, scaleR 1.2 -> source grids 198x60 / 165x50 / 137x41,
+    NA = 25747; target 165x50, NB = 8250), one hypothesis through the sync-free path.  No oracle at this size (minutes on the
+    CPU): checks sizes, finiteness and that the coarse homography of a synthetic homography pair is recovered."""
+    src, tgt, Hgt = synth.make_pair(31, 376, 1241)
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 800, 2, False, 1.2, True, False, resnet_state_dict=rsd, verbose=False)
+    c.device_preproc = True
+    torch.manual_seed(1000)
+    out = rf.pipeline.align_pair_single(c, net, torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda())
+    assert c._feats_rows.shape == (25747, 1024) and c._featt_rows.shape == (8250, 1024)
+    assert out["H"].shape == (1, 3, 3) and np.isfinite(out["H"]).all() and out["nbMatch"] >= 4
+    h, w = c.target_size[1], c.target_size[0]
+    assert (h, w) == (800, 2640) and out["flow12"][0].shape == (1, h, w, 2) and torch.isfinite(out["flow12"][0]).all()
+    assert out["flowDown8"].shape == (1, 2, h // 8, w // 8)
+    Hn = out["H"][0] / out["H"][0][2, 2]
+    print("KITTI-shaped pair: %d matches, %d inliers, |H - Hgt|max = %.3f" % (out["nbMatch"], out["nbInlier"], np.abs(Hn - Hgt / Hgt[2, 2]).max()))
