@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - image-pairs/sec on synthetic 480x640 pairs (BASELINE.json config 2).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--engine fp32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--engine fp32|tf32|f16]
 
 One "step" = one pair through the whole hot path (variant-A CoarseAlign.setPair -> getCoarse ->
 warp_grid -> PredFlowMask), nbScale 7, scaleR 2, nbIter 1000, one hypothesis.  Prints ONE JSON line
@@ -147,7 +147,7 @@ def run_b200(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     rf.model.set_engine(args.engine)
-    rf.outil.corr_precision = 1 if args.engine == "tf32" else 0
+    rf.outil.corr_precision = 0 if args.engine == "fp32" else 1
     rsd, fe_sd, nf_sd, nm_sd = states()
     net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
            "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}
@@ -285,14 +285,14 @@ def run_b200(args, rank, world, local):
     traffic = None
     try:                                   # dram__bytes_read+write of the dominant launch, from the committed ncu --set full capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_corr_ncu.json")))
-        traffic = prof["launches"][0]["dram_traffic_bytes"] if args.engine == "tf32" else None
+        traffic = prof["launches"][0]["dram_traffic_bytes"] if args.engine != "fp32" else None
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % ("tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)" if args.engine == "tf32" else "corr_argmax_kernel (fp32 SIMT)"),
+    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % ("tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)" if args.engine != "fp32" else "corr_argmax_kernel (fp32 SIMT)"),
                 "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
                 "peak_source": pk["src"] + " bf16 dense GEMM (burst); kind::tf32 peaks at half of it and this kernel issues 3 TF32 MMAs per "
                                "algorithmic MAC (3xTF32), i.e. executed-TF32 fraction = 6 x frac",
-                "executed_tf32_frac": (3 * tf) / (tensor_peak / 2) if args.engine == "tf32" else None,
+                "executed_tf32_frac": (3 * tf) / (tensor_peak / 2) if args.engine != "fp32" else None,
                 "ms_per_launch": corr_ms, "algorithmic_gflop": flops / 1e9, "algorithmic_mb": abytes / 1e6,
                 "hbm_gbs_achieved": abytes / (corr_ms * 1e-3) / 1e9, "hbm_frac": abytes / (corr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": int(len(m1)),
@@ -316,7 +316,7 @@ def run_b200(args, rank, world, local):
         line = {
             "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.engine == "fp32" else "tf32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 trunk (fp32 accumulate) + tf32 fine-flow nets + 3xTF32 correlation"}[args.engine], "data": "synthetic",
             "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded i %% %d" % world,
                        "l2": "256 MiB buffer written between steps (L2 flush); activations per step also exceed the 126 MB L2",
                        "preprocessing": "7-scale LANCZOS pyramid on the GPU (bit-exact PIL emulation)",
@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "tf32"), choices=["fp32", "tf32"],
+    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "tf32"), choices=["fp32", "tf32", "f16"],
                     help="tf32: tcgen05 convs (TF32 operands, the reference's own cuDNN default on sm_80+) + 3xTF32 correlation; fp32: exact-FMA SIMT engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the ~140 kernels of a pair one by one instead of replaying a CUDA graph")

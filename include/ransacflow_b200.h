@@ -88,7 +88,14 @@ int rf_build_matches(const int64_t* idx1, const int64_t* idx2, const int* count_
  * bias [Cout] (nullable); residual: packed like y (nullable).
  * engine: 0 = fp32 SIMT implicit GEMM everywhere; 1 = TF32 tcgen05 implicit GEMM for the layers it
  * supports (stride 1, Cin % 32 == 0, 1x1 / 3x3; w_tc = same weights as [Cout][R*S*Cin]), the exact-fp32
- * SIMT kernel for the rest (3-channel stems, stride-2 convs). */
+ * SIMT kernel for the rest (3-channel stems, stride-2 convs);
+ * 2 = fp16 tcgen05 implicit GEMM: x, residual, y and w_tc ([Cout][R*S*Cin]) hold IEEE fp16 elements behind the
+ * same pointers (10-bit mantissa like TF32, half the HBM bytes, twice the tensor rate), fp32 accumulation and fp32
+ * bias, outputs saturated to +-65504; needs Cin % 64 == 0, Cout % 8 == 0, 1x1 / 3x3, stride 1 / 2 and fails otherwise
+ * (no fallback).  Used for the ResNet-50 conv4 trunk. */
+#define RF_ENGINE_FP32 0
+#define RF_ENGINE_TF32 1
+#define RF_ENGINE_F16 2
 int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,
@@ -111,7 +118,10 @@ typedef struct rf_layer {
     const float* w;                 /* [k*k*Cin][Cout] */
     const float* w_tc;              /* [Cout][k*k*Cin] */
     const float* bias;              /* [Cout] or NULL */
+    const void* w_f16;              /* [Cout][k*k*Cin] fp16, engine 2 only (NULL otherwise) */
 } rf_layer_t;
+/* engine 2: every slot except the input holds fp16; the input slot (fp32 image) must feed an RF_OP_IM2COL whose Cout
+ * (row length) is a multiple of 64; RF_OP_MAXPOOL runs in fp16; RF_OP_BLUR / RF_OP_POOLBLUR are not available. */
 int rf_run_layers(const rf_layer_t* layers_host, int n, void* const* slots_host, int nimg, const int* hw_host,
                   int engine, void* stream);
 /* max pooling k x k / stride / zero-free padding: nn.MaxPool2d (model/model.py:71; torchvision resnet maxpool) */
@@ -122,6 +132,8 @@ int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C,
 /* F.normalize(x, dim=1): y = x / max(||x||_2, 1e-12) per pixel over C (P = total pixels).
  * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
 int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
+/* same with fp16 input (the engine-2 trunk's output), fp32 output; C % 8 == 0 */
+int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mask, float* y, void* stream);
 /* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][ldo], channels >= k*k are
  * written as zeros (ldo = 64 makes the 49-channel volume a 128-byte-aligned operand for the conv engines);
  * round_tf32_out = 1 stores the values rounded to nearest TF32 (operand of the tensor-core heads) */

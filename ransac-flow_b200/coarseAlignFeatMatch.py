@@ -44,10 +44,16 @@ class ResNet50Conv4:
     variant model/resnet50.py:107-168 has the same trunk) on the library's conv kernels."""
 
     def __init__(self, state_dict, device="cuda"):
-        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
-              if torch.is_tensor(v) and v.dtype.is_floating_point}
+        self._sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
+                    if torch.is_tensor(v) and v.dtype.is_floating_point}
+        self.program = self._build(32)            # fp32 activations: 'fp32' / 'tf32' engines
+        self._program_f16 = None                  # fp16 activations ('f16' engine), built on first use
+        self.out_channels = self.program.chan[-1]
+
+    def _build(self, kalign):
+        sd = self._sd
         P = LayerProgram(3)
-        x = P.stem(0, sd["conv1.weight"], _BN(sd, "bn1"), 2, 3)                      # 7x7/2 stem as im2col + 1x1 conv
+        x = P.stem(0, sd["conv1.weight"], _BN(sd, "bn1"), 2, 3, kalign)              # 7x7/2 stem as im2col + 1x1 conv
         x = P.maxpool(x, 3, 2, 1)
         for layer, planes, blocks, stride in RESNET50_LAYERS:
             for b in range(blocks):
@@ -59,13 +65,19 @@ class ResNet50Conv4:
                 if (p + ".downsample.0.weight") in sd:
                     r = P.conv(x, FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0), relu=False)
                 x = P.conv(out, FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0), relu=True, res=r)
-        self.program = P
-        self.out_channels = P.chan[-1]
+        return P
 
     def __call__(self, x):
-        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU).  One library call for the
-        whole trunk; the output buffer belongs to the program (valid until the next call with these sizes)."""
-        out, ohw = self.program.run(x, rfmodel.get_engine())
+        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU; fp16 rows under the 'f16' engine,
+        which ``ops.l2norm`` turns into fp32).  One library call for the whole trunk; the output buffer belongs to the
+        program (valid until the next call with these sizes)."""
+        eng = rfmodel.get_engine()
+        if eng == ops.ENGINE_F16:
+            if self._program_f16 is None:
+                self._program_f16 = self._build(64)      # stem patches padded to a multiple of 64 halves
+            out, ohw = self._program_f16.run(x, eng)
+        else:
+            out, ohw = self.program.run(x, eng)
         return Ragged(out, ohw)
 
 

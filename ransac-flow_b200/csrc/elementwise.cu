@@ -3,6 +3,8 @@
 // pre-processing, homography grids, bilinear sampling and the fused
 // fine-flow composition.  All NHWC fp32, coalesced along channels, vectorised
 // (float4) where the channel count allows.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rf {
@@ -35,6 +37,40 @@ __global__ void maxpool_kernel(const __grid_constant__ ImgSet set, const float* 
         }
     }
     reinterpret_cast<float4*>(y + pm * C)[c4] = m;
+}
+
+// fp16 variant (engine 2): one thread per (output pixel, 8 channels)
+__global__ void maxpool_f16_kernel(const __grid_constant__ ImgSet set, const __half* __restrict__ x, __half* __restrict__ y,
+                                   int C, int k, int stride, int pad) {
+    const int c8n = C >> 3;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * c8n;
+    if (t >= total) return;
+    long long pm = t / c8n;
+    int c8 = (int)(t - pm * c8n);
+    int im = find_img(set, pm);
+    int local = (int)(pm - set.out_pix[im]);
+    int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+    const int H = set.H[im], W = set.W[im];
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m[4] = {ninf, ninf, ninf, ninf};
+    for (int r = 0; r < k; ++r) {
+        int iy = oy * stride - pad + r;
+        if (iy < 0 || iy >= H) continue;
+        for (int s = 0; s < k; ++s) {
+            int ix = ox * stride - pad + s;
+            if (ix < 0 || ix >= W) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (set.in_pix[im] + (long long)iy * W + ix) * C) + c8);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
+        }
+    }
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ho[e] = m[e];
+    reinterpret_cast<uint4*>(y + pm * C)[c8] = o;
 }
 
 // ---------------------------------------------------------------------------
@@ -170,6 +206,37 @@ __global__ void l2norm_kernel(const float* __restrict__ x, long long P, int C, c
     for (int c = lane; c < c4n; c += 32) {
         float4 v = __ldg(src + c);
         dst[c] = make_float4(__fdiv_rn(v.x, denom), __fdiv_rn(v.y, denom), __fdiv_rn(v.z, denom), __fdiv_rn(v.w, denom));
+    }
+}
+
+// fp16 input (engine-2 trunk output), fp32 arithmetic and output
+__global__ void l2norm_f16_kernel(const __half* __restrict__ x, long long P, int C, const unsigned char* __restrict__ mask, float* __restrict__ y) {
+    long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (pix >= P) return;
+    const uint4* src = reinterpret_cast<const uint4*>(x + pix * C);
+    float4* dst = reinterpret_cast<float4*>(y + pix * C);
+    const int c8n = C >> 3;
+    if (mask != nullptr && mask[pix] == 0) {
+        for (int c = lane; c < 2 * c8n; c += 32) dst[c] = make_float4(0, 0, 0, 0);
+        return;
+    }
+    float ss = 0.f;
+    for (int c = lane; c < c8n; c += 32) {
+        const uint4 v = __ldg(src + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < c8n; c += 32) {
+        const uint4 v = __ldg(src + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        dst[2 * c] = make_float4(__fdiv_rn(f0.x, denom), __fdiv_rn(f0.y, denom), __fdiv_rn(f1.x, denom), __fdiv_rn(f1.y, denom));
+        dst[2 * c + 1] = make_float4(__fdiv_rn(f2.x, denom), __fdiv_rn(f2.y, denom), __fdiv_rn(f3.x, denom), __fdiv_rn(f3.y, denom));
     }
 }
 
@@ -506,9 +573,9 @@ extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_h
 
 // Stem-specialised im2col: one CTA = one output row segment of TPX pixels.  The K input rows it needs are staged in
 // shared memory with coalesced loads, then the (r, s, c)-ordered patches are written as contiguous float4 rows.
-template <int K, int C, int KPAD, int STRIDE, int PAD, int TPX>
+template <int K, int C, int KPAD, int STRIDE, int PAD, int TPX, typename OutT = float>
 __global__ void __launch_bounds__(256)
-im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int round_out) {
+im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, OutT* __restrict__ y, int round_out) {
     constexpr int INW = ((TPX - 1) * STRIDE + K) * C;          // floats of one staged input row
     constexpr int Q4 = KPAD / 4;
     __shared__ float sIn[K][INW + 1];
@@ -527,6 +594,26 @@ im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__
     }
     __syncthreads();
     const int npx = min(TPX, Wo - ox0);
+    if constexpr (sizeof(OutT) == 2) {
+        // engine 2: rows of KPAD halves, eight per 16-byte store
+        constexpr int Q8 = KPAD / 8;
+        uint4* dst8 = reinterpret_cast<uint4*>(y + (set.out_pix[im] + (long long)oy * Wo + ox0) * KPAD);
+        for (int f = threadIdx.x; f < npx * Q8; f += 256) {
+            const int px = f / Q8, e0 = (f - px * Q8) * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = e0 + j;
+                v[j] = (e < K * K * C) ? sIn[e / (K * C)][px * STRIDE * C + e % (K * C)] : 0.f;
+            }
+            uint4 o;
+            __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ho[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            dst8[f] = o;
+        }
+        return;
+    }
     float4* dst = reinterpret_cast<float4*>(y + (set.out_pix[im] + (long long)oy * Wo + ox0) * KPAD);
     for (int f = threadIdx.x; f < npx * Q4; f += 256) {
         const int px = f / Q4, e0 = (f - px * Q4) * 4;
@@ -568,6 +655,38 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
     if (k == 7 && C == 3 && Kpad == 160) im2col_kernel<7, 3, 160><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
     else if (k == 3 && C == 3 && Kpad == 32) im2col_kernel<3, 3, 32><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
     else im2col_kernel<0, 0, 0><<<grid, 256, 0, as_stream(stream)>>>(set, x, y, C, k, stride, pad, Kpad, round_out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// engine 2 (fp16 activations): the ResNet-50 stem's patches as rows of 192 halves; max pooling in fp16
+int rf_im2col_f16_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y_f16, void* stream) {
+    RF_REQUIRE(k == 7 && C == 3 && Kpad == 192 && stride == 2 && pad == 3, "rf_im2col (engine 2): only the ResNet-50 stem (7x7/2, 3 channels, Kpad 192)");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_im2col: bad image set");
+    int maxHo = 0, maxWo = 0;
+    for (int i = 0; i < nimg; ++i) { maxHo = set.Ho[i] > maxHo ? set.Ho[i] : maxHo; maxWo = set.Wo[i] > maxWo ? set.Wo[i] : maxWo; }
+    im2col_smem_kernel<7, 3, 192, 2, 3, 64, __half><<<dim3((maxWo + 63) / 64, maxHo, nimg), 256, 0, as_stream(stream)>>>(
+        set, x, static_cast<__half*>(y_f16), 0);
+    RF_LAUNCHED();
+    return 0;
+}
+
+int rf_maxpool_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int k, int stride, int pad, void* y_f16, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && k >= 1 && stride >= 1, "rf_maxpool (engine 2): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_maxpool: bad image set");
+    long long total = set.out_pix[nimg] * (C / 8);
+    maxpool_f16_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x_f16), static_cast<__half*>(y_f16), C, k, stride, pad);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mask, float* y, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && P >= 0, "rf_l2norm_f16_nhwc: C must be a multiple of 8");
+    RF_REQUIRE(((uintptr_t)x_f16 % 16) == 0 && ((uintptr_t)y % 16) == 0, "rf_l2norm_f16_nhwc: pointers must be 16-byte aligned");
+    if (P == 0) return 0;
+    l2norm_f16_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x_f16), P, C, mask, y);
     RF_LAUNCHED();
     return 0;
 }

@@ -16,6 +16,7 @@
 //             thread, tcgen05.commit releases the stage / publishes the accumulator.
 //   warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns at a time straight from TMEM.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -27,6 +28,8 @@ namespace rf {
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BK = 32;                 // fp32 elements per 128-byte swizzle row
+constexpr int TC_BK_F16 = 64;             // fp16 elements per 128-byte swizzle row (engine 2)
+template <bool F16> constexpr int tc_bk() { return F16 ? TC_BK_F16 : TC_BK; }
 constexpr int TC_A_BYTES = 128 * 128;     // 128 rows x 128 B
 
 struct alignas(64) TcParams {
@@ -138,6 +141,27 @@ __device__ __forceinline__ void umma_tf32_x4(uint32_t tmem_d, uint64_t adesc, ui
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], a3, b3, %3, t;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
 }
+// fp16 operands (engine 2): same 128-byte K block, now 64 channels = four K = 16 steps; 10-bit mantissa like TF32, half
+// the bytes per element and twice the tensor rate
+__device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc_first) : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc_first) {
+    if constexpr (F16) umma_f16_x4(tmem_d, adesc, bdesc, idesc, acc_first);
+    else umma_tf32_x4(tmem_d, adesc, bdesc, idesc, acc_first);
+}
 // 3xTF32: per K step lo*hi, hi*lo, hi*hi (12 MMAs per K block)
 __device__ __forceinline__ void umma_3xtf32_x4(uint32_t tmem_d, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc, uint32_t acc_first) {
     asm volatile(
@@ -197,13 +221,88 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return F16 ? make_idesc_f16(n) : make_idesc_tf32(n); }
+
 constexpr int MODE_CONV = 0, MODE_CORR = 1;
 
 // Convolution epilogue shared by the tap-streaming and the halo kernels (warps 2..5 = 128 threads, thread m owns
 // accumulator row m = pixel m of the tile): + folded-BN bias, + residual, ReLU, TF32 rounding, store.
+// fp16 epilogue core (engine 2): thread m's accumulator row -> + bias, + residual, ReLU, saturate -> fp16 into the
+// 128-byte-swizzled staging boxes (64 channels x 128 pixels x 2 B = 16 KB each; the residual boxes were TMA-loaded into
+// the same place).  32 accumulator columns = 64 bytes = four 16-byte chunks of the pixel's 128-byte row.
 template <int BN>
+__device__ __forceinline__ void epi_rows_f16(const float* __restrict__ bias, int Cout, int relu, bool has_res, int n0, int m,
+                                             uint32_t trow, uint8_t* stg) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        const int n = n0 + c * 32;
+        uint8_t* rowp = stg + (c >> 1) * TC_A_BYTES + m * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int chunk = (c & 1) * 4 + j;
+            uint4* sp = reinterpret_cast<uint4*>(rowp + ((chunk ^ (m & 7)) << 4));
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
+            if (bias && n + 8 * j < Cout) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n + 8 * j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 8 * j + 4));
+                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+            }
+            if (has_res) {
+                const uint4 rr = *sp;
+                const __half2* h = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); o[2 * e] += f.x; o[2 * e + 1] += f.y; }
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+            }
+            uint4 out;
+            __half2* ho = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)         // saturate instead of overflowing to inf
+                ho[e] = __floats2half2_rn(fminf(fmaxf(o[2 * e], -65504.f), 65504.f), fminf(fmaxf(o[2 * e + 1], -65504.f), 65504.f));
+            *sp = out;
+        }
+    }
+}
+
+template <int BN, bool F16 = false>
 __device__ __forceinline__ void conv_epilogue(const TcParams& p, int img, int ox0, int oy0, int tw, int n0, int m, uint32_t trow,
                                               uint8_t* smem, uint64_t* res_full, int warp, int lane) {
+    if constexpr (F16) {
+        // engine 2: always the bulk path (the host requires Cout % 8 == 0); boxes of 64 fp16 channels
+        constexpr int NBOX = BN / 64;
+        uint8_t* stg = smem;
+        const bool has_res = p.residual != nullptr;
+        if (has_res) {
+            if (warp == 2 && lane == 0) {
+                mbar_expect_tx(res_full, NBOX * TC_A_BYTES);
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) tma_load_3d(stg + b * TC_A_BYTES, &p.mapR[img], res_full, n0 + b * 64, ox0, oy0);
+            }
+            mbar_wait(res_full, 0);
+        }
+        epi_rows_f16<BN>(p.bias, p.Cout, p.relu, has_res, n0, m, trow, stg);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b)
+                if (n0 + b * 64 < p.Cout) tma_store_3d(&p.mapY[img], stg + b * TC_A_BYTES, n0 + b * 64, ox0, oy0);
+            tma_store_commit_and_wait_read();
+        }
+        return;
+    }
     if (p.tma_epi) {
         // ---- bulk epilogue: residual tile in by TMA, result tile out by TMA; the pipeline stages are idle now and
         // serve as staging: BN/32 boxes of (32 channels x tw x th) = 128 rows x 128 B, 128-byte swizzled ----
@@ -300,11 +399,13 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MODE, bool DEEP>
+template <int BN, int MODE, bool DEEP, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, TcCfg<BN, MODE, DEEP>::CTAS_PER_SM)
 tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, MODE, DEEP>;
     constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
+    constexpr int BK = tc_bk<F16>();              // channels per 128-byte K block
+    static_assert(!(F16 && MODE == MODE_CORR), "the correlation runs 3xTF32");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -328,7 +429,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
     const int ox0 = txi * tw, oy0 = tyi * th;
     const int n0 = ntile * BN;
-    const int kc = p.Cin / TC_BK;                 // 32-channel chunks per tap
+    const int kc = p.Cin / BK;                    // K blocks (32 fp32 / 64 fp16 channels) per tap
     const int KI = p.R * p.S * kc;
 
     if (threadIdx.x == 0) {
@@ -358,7 +459,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
                 const int tap = it / kc, cc = it - tap * kc;
                 const int r = tap / p.S, s = tap - r * p.S;
-                const int c0 = cc * TC_BK, x = ox0 * p.stride + s - p.pad, y = oy0 * p.stride + r - p.pad;
+                const int c0 = cc * BK, x = ox0 * p.stride + s - p.pad, y = oy0 * p.stride + r - p.pad;
                 const int kcol = tap * p.Cin + c0;
                 tma_load_3d(sbase, &p.mapA[img], &full[st], c0, x, y);
                 tma_load_2d(sbase + NSPLIT * TC_A_BYTES, &p.mapB, &full[st], kcol, n0);
@@ -371,7 +472,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            constexpr uint32_t idesc = make_idesc<F16>(BN);
             for (int it = 0; it < KI; ++it) {
                 const int st = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&full[st], ph);
@@ -382,7 +483,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 if (NSPLIT == 2) {
                     umma_3xtf32_x4(tmem_base, da, make_desc_sw128(sa + TC_A_BYTES), db, make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
                 } else {
-                    umma_tf32_x4(tmem_base, da, db, idesc, it != 0 ? 1u : 0u);      // 4 x (UMMA_K = 8 tf32 = 32 bytes)
+                    umma_x4<F16>(tmem_base, da, db, idesc, it != 0 ? 1u : 0u);      // 4 x (UMMA_K = 8 tf32 / 16 fp16 = 32 bytes)
                 }
                 umma_commit(&empty[st]);            // stage free once these MMAs have read it
             }
@@ -396,7 +497,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         if (MODE == MODE_CONV) {
-            conv_epilogue<BN>(p, img, ox0, oy0, tw, n0, m, trow, smem, res_full, warp, lane);
+            conv_epilogue<BN, F16>(p, img, ox0, oy0, tw, n0, m, trow, smem, res_full, warp, lane);
         } else {
             // utils/outil.py:36-37: row arg-max (thread-local over this tile's columns), column arg-max via an
             // smem transpose of the score tile (the pipeline stages are idle by now)
@@ -482,11 +583,12 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
     return d;
 }
 
-template <int BN>
+template <int BN, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
     using Cfg = HaloCfg<BN>;
     constexpr int NA = Cfg::NA, NB = Cfg::NB;
+    constexpr int BK = tc_bk<F16>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -507,7 +609,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
     const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
     const int ox0 = txi * HALO_TW, oy0 = tyi * HALO_TH;
     const int n0 = blockIdx.y * BN;
-    const int kc = p.Cin / TC_BK;
+    const int kc = p.Cin / BK;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
@@ -530,18 +632,18 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
                 const int sa = cc % NA, pha = (cc / NA) & 1;
                 mbar_wait(&emptyA[sa], pha ^ 1);
                 mbar_expect_tx(&fullA[sa], HALO_A_BYTES);
-                tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[img], &fullA[sa], cc * TC_BK, ox0 - 1, oy0 - 1);
+                tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[img], &fullA[sa], cc * BK, ox0 - 1, oy0 - 1);
                 for (int tap = 0; tap < 9; ++tap, ++ib) {
                     const int sb = ib % NB, phb = (ib / NB) & 1;
                     mbar_wait(&emptyB[sb], phb ^ 1);
                     mbar_expect_tx(&fullB[sb], Cfg::B_BYTES);
-                    tma_load_2d(sB + sb * Cfg::B_BYTES, &p.mapB, &fullB[sb], tap * p.Cin + cc * TC_BK, n0);
+                    tma_load_2d(sB + sb * Cfg::B_BYTES, &p.mapB, &fullB[sb], tap * p.Cin + cc * BK, n0);
                 }
             }
         }
     } else if (warp == 1) {
         {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            constexpr uint32_t idesc = make_idesc<F16>(BN);
             int ib = 0;
             for (int cc = 0; cc < kc; ++cc) {
                 const int sa = cc % NA, pha = (cc / NA) & 1;
@@ -555,7 +657,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
                     const int r = tap / 3, sx = tap - r * 3;
                     const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
                     const uint64_t db = make_desc_sw128(smem_u32(sB + sb * Cfg::B_BYTES));
-                    umma_tf32_x4(tmem_base, make_desc_halo(aaddr, desc_mode), db, idesc, (cc | tap) != 0 ? 1u : 0u);
+                    umma_x4<F16>(tmem_base, make_desc_halo(aaddr, desc_mode), db, idesc, (cc | tap) != 0 ? 1u : 0u);
                     umma_commit(&emptyB[sb]);
                 }
                 umma_commit(&emptyA[sa]);
@@ -567,7 +669,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
         const int m = q * 32 + lane;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        conv_epilogue<BN>(p, img, ox0, oy0, HALO_TW, n0, m, tmem_base + ((uint32_t)(q * 32) << 16), smem, res_full, warp, lane);
+        conv_epilogue<BN, F16>(p, img, ox0, oy0, HALO_TW, n0, m, tmem_base + ((uint32_t)(q * 32) << 16), smem, res_full, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -795,22 +897,26 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
 // them ONCE per CTA, then streams halo tiles (2 x 23 KB) through a two-slot ring while two TMEM accumulators let the
 // epilogue of tile i overlap the MMAs of tile i+1.  Per tile only the 46 KB halo crosses L2->SM.
 // ------------------------------------------------------------------------------------------------------------
+// fp16 (engine 2): 64 channels are ONE 128-byte K block, so the weights are 72 KB and the halo ring gets four slots
+template <bool F16>
 struct ResBCfg {
-    static constexpr int BN = 64, KC = 2, NTAP = 9, NA = 2;
+    static constexpr int BN = 64, KC = F16 ? 1 : 2, NTAP = 9, NA = F16 ? 4 : 2;
     static constexpr int B_TILE = BN * 128;                                 // 8 KB
-    static constexpr int B_BYTES = KC * NTAP * B_TILE;                      // 144 KB
+    static constexpr int B_BYTES = KC * NTAP * B_TILE;                      // 144 KB (72 KB fp16)
     static constexpr int OFF_A = B_BYTES;
     static constexpr int OFF_STG = OFF_A + NA * HALO_A_SLOT;
-    static constexpr int STG = BN * 512;                                    // 32 KB
+    static constexpr int STG = F16 ? BN * 256 : BN * 512;                   // 32 KB (16 KB fp16)
     static constexpr int DATA_BYTES = OFF_STG + STG;
     static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;
     static constexpr int TMEM_COLS = 128;                                   // two 64-column accumulators
 };
 
+template <bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
-    using Cfg = ResBCfg;
+    using Cfg = ResBCfg<F16>;
     constexpr int BN = Cfg::BN, NA = Cfg::NA;
+    constexpr int BK = tc_bk<F16>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;
@@ -846,7 +952,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
             mbar_expect_tx(fullB, Cfg::B_BYTES);
             for (int cc = 0; cc < Cfg::KC; ++cc)
                 for (int tap = 0; tap < Cfg::NTAP; ++tap)
-                    tma_load_2d(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE, &p.mapB, fullB, tap * p.Cin + cc * TC_BK, 0);
+                    tma_load_2d(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE, &p.mapB, fullB, tap * p.Cin + cc * BK, 0);
             uint32_t ia = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TileCoord c = decode_tile<true>(p, t, tiles_m, BN);
@@ -854,13 +960,13 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
                     const int sa = ia % NA;
                     mbar_wait(&emptyA[sa], ((ia / NA) & 1) ^ 1);
                     mbar_expect_tx(&fullA[sa], HALO_A_BYTES);
-                    tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[c.img], &fullA[sa], cc * TC_BK, c.ox0 - 1, c.oy0 - 1);
+                    tma_load_3d(sA + sa * HALO_A_SLOT, &p.mapA[c.img], &fullA[sa], cc * BK, c.ox0 - 1, c.oy0 - 1);
                 }
             }
         }
     } else if (warp == 1) {
         {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
-            constexpr uint32_t idesc = make_idesc_tf32(BN);
+            constexpr uint32_t idesc = make_idesc<F16>(BN);
             mbar_wait(fullB, 0);
             tc_fence_after();
             uint32_t ia = 0, ti = 0;
@@ -879,7 +985,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
                         const int r = tap / 3, sx = tap - r * 3;
                         const uint32_t aaddr = abase + (uint32_t)((r * HALO_LD + sx) * 128);
                         const uint64_t db = make_desc_sw128(smem_u32(sB + (cc * Cfg::NTAP + tap) * Cfg::B_TILE));
-                        umma_tf32_x4(tacc, make_desc_halo(aaddr, 2), db, idesc, (cc | tap) != 0 ? 1u : 0u);
+                        umma_x4<F16>(tacc, make_desc_halo(aaddr, 2), db, idesc, (cc | tap) != 0 ? 1u : 0u);
                     }
                     umma_commit(&emptyA[sa]);
                 }
@@ -891,6 +997,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
         const int m = q * 32 + lane;
         const bool leader = (warp == 2 && lane == 0);
         const bool has_res = p.residual != nullptr;
+        constexpr int NBOX = Cfg::STG / TC_A_BYTES;                 // staging boxes of 128 bytes per pixel: 2 (fp32) / 1 (fp16)
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1;
@@ -898,9 +1005,9 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
             if (leader) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // staging buffer has been read out
                 if (has_res) {
-                    mbar_expect_tx(res_full, (BN / 32) * TC_A_BYTES);
+                    mbar_expect_tx(res_full, NBOX * TC_A_BYTES);
 #pragma unroll
-                    for (int cb = 0; cb < BN / 32; ++cb) tma_load_3d(sStg + cb * TC_A_BYTES, &p.mapR[c.img], res_full, cb * 32, c.ox0, c.oy0);
+                    for (int cb = 0; cb < NBOX; ++cb) tma_load_3d(sStg + cb * TC_A_BYTES, &p.mapR[c.img], res_full, cb * BK, c.ox0, c.oy0);
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -908,8 +1015,9 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
             tc_fence_after();
             if (has_res) mbar_wait(res_full, ti & 1);
             const uint32_t trow = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+            if constexpr (F16) epi_rows_f16<BN>(p.bias, p.Cout, p.relu, has_res, 0, m, trow, sStg);
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
+            for (int cb = 0; cb < (F16 ? 0 : BN / 32); ++cb) {
                 uint32_t v[32];
                 tmem_ld32(trow + cb * 32, v);
                 const int n = cb * 32;
@@ -931,7 +1039,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (leader) {
 #pragma unroll
-                for (int cb = 0; cb < BN / 32; ++cb) tma_store_3d(&p.mapY[c.img], sStg + cb * TC_A_BYTES, cb * 32, c.ox0, c.oy0);
+                for (int cb = 0; cb < NBOX; ++cb) tma_store_3d(&p.mapY[c.img], sStg + cb * TC_A_BYTES, cb * BK, c.ox0, c.oy0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -974,36 +1082,36 @@ static EncodeTiledFn get_encode() {
 struct MapKey {
     const void* ptr;
     unsigned long long d0, d1, d2;
-    unsigned b0, b1, b2, es;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && es == o.es; }
+    unsigned b0, b1, b2, es, esize;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && es == o.es && esize == o.esize; }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = std::hash<const void*>()(k.ptr);
         auto mix = [&](unsigned long long v) { h ^= std::hash<unsigned long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.b2); mix(k.es);
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.b2); mix(k.es); mix(k.esize);
         return h;
     }
 };
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// fp32 tensor (d0 innermost, d1, d2), dense strides, box of (b0, b1, b2) ELEMENTS LOADED, traversal stride `es` on
-// d1 / d2 (strided convolutions: every es-th pixel), 128B swizzle, zero fill out of bounds
+// fp32 (esize 4) or fp16 (esize 2) tensor (d0 innermost, d1, d2), dense strides, box of (b0, b1, b2) ELEMENTS LOADED,
+// traversal stride `es` on d1 / d2 (strided convolutions: every es-th pixel), 128B swizzle, zero fill out of bounds
 static int get_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2,
-                   unsigned b0, unsigned b1, unsigned b2, unsigned es_ = 1) {
-    MapKey key{ptr, d0, d1, d2, b0, b1, b2, es_};
+                   unsigned b0, unsigned b1, unsigned b2, unsigned es_ = 1, unsigned esize = 4) {
+    MapKey key{ptr, d0, d1, d2, b0, b1, b2, es_, esize};
     std::lock_guard<std::mutex> g(g_map_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return 0; }
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail_msg("cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 4ull, d0 * d1 * 4ull};
+    cuuint64_t strides[2] = {d0 * (unsigned long long)esize, d0 * d1 * (unsigned long long)esize};
     cuuint32_t box[3] = {b0, b1 * es_, b2 * es_};      // bounding box in tensor coordinates; ceil(box / stride) elements are loaded
     cuuint32_t es[3] = {1, es_, es_};
     int rank = d2 > 0 ? 3 : 2;
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1064,15 +1172,16 @@ static int resb_mode() {
     return m;
 }
 
+template <bool F16>
 static int launch_resb(const TcParams& p, int tiles_m, cudaStream_t st) {
     static bool attr[64] = {false};
     const int dev = current_device();
     if (!attr[dev]) {
-        RF_CUDA(cudaFuncSetAttribute(tc_resb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ResBCfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_resb_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ResBCfg<F16>::SMEM_BYTES));
         attr[dev] = true;
     }
     const int grid = tiles_m < num_sms() ? tiles_m : num_sms();
-    tc_resb_kernel<<<grid, TC_THREADS, ResBCfg::SMEM_BYTES, st>>>(p, tiles_m);
+    tc_resb_kernel<F16><<<grid, TC_THREADS, ResBCfg<F16>::SMEM_BYTES, st>>>(p, tiles_m);
     RF_LAUNCHED();
     return 0;
 }
@@ -1093,31 +1202,31 @@ static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStrea
     return 0;
 }
 
-template <int BN>
+template <int BN, bool F16 = false>
 static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
     static bool attr[64] = {false};
     const int dev = current_device();
     if (!attr[dev]) {
-        RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr[dev] = true;
     }
-    tc_halo_kernel<BN><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
+    tc_halo_kernel<BN, F16><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
     RF_LAUNCHED();
     return 0;
 }
 
-template <int BN, int MODE, bool DEEP>
+template <int BN, int MODE, bool DEEP, bool F16 = false>
 static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st) {
     using Cfg = TcCfg<BN, MODE, DEEP>;
     static bool attr[64] = {false};
     const int dev = current_device();
     if (!attr[dev]) {
-        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr[dev] = true;
     }
     dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
-    tc_kernel<BN, MODE, DEEP><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    tc_kernel<BN, MODE, DEEP, F16><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
     RF_LAUNCHED();
     return 0;
 }
@@ -1129,13 +1238,24 @@ using namespace rf;
 bool rf_conv2d_tc_supported(const ConvParams& p) {
     return (p.stride == 1 || p.stride == 2) && (p.Cin % TC_BK) == 0 && p.Cout >= 1 && p.R == p.S && (p.R == 1 || p.R == 3);
 }
+// engine 2: fp16 activations / weights; every layer must fit (there is no fp16 SIMT path to fall back to)
+bool rf_conv2d_f16_supported(const ConvParams& p) {
+    return (p.stride == 1 || p.stride == 2) && (p.Cin % TC_BK_F16) == 0 && p.Cout >= 8 && (p.Cout % 8) == 0 && p.R == p.S && (p.R == 1 || p.R == 3);
+}
 
-int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cudaStream_t st) {
-    RF_REQUIRE(w_tc != nullptr, "rf_conv2d_nhwc: engine=1 needs w_tc ([Cout][R*S*Cin])");
-    RF_REQUIRE(rf_conv2d_tc_supported(cp), "rf_conv2d_nhwc: engine=1 needs stride 1 or 2, Cin % 32 == 0, 1x1 or 3x3");
+// f16 = false: x / residual / y fp32, w_tc fp32 [Cout][K] (TF32-rounded).  f16 = true: the same pointers hold IEEE fp16.
+int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cudaStream_t st, bool f16) {
+    RF_REQUIRE(w_tc != nullptr, "rf_conv2d_nhwc: tensor-core engines need w_tc ([Cout][R*S*Cin])");
+    RF_REQUIRE(f16 ? rf_conv2d_f16_supported(cp) : rf_conv2d_tc_supported(cp),
+               "rf_conv2d_nhwc: tensor-core engines need stride 1 or 2, 1x1 or 3x3, Cin % 32 == 0 (fp16: Cin % 64 == 0, Cout % 8 == 0)");
     TcParams p;
     memset(&p, 0, sizeof(p));
     const int BN = cp.Cout > 64 ? 128 : 64;
+    const unsigned esz = f16 ? 2u : 4u;
+    const unsigned bk = f16 ? TC_BK_F16 : TC_BK;
+    const char* xb = reinterpret_cast<const char*>(cp.x);
+    const char* rb = reinterpret_cast<const char*>(cp.residual);
+    char* yb = reinterpret_cast<char*>(cp.y);
     p.nimg = set.n;
     const int hmode = (cp.R == 3 && cp.stride == 1 && cp.pad == 1) ? halo_mode() : 0;
     int tiles = 0;
@@ -1147,37 +1267,44 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const float* w_tc, cud
         tiles += p.tiles_x[i] * ((set.Ho[i] + th - 1) / th);
         p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
         p.out_pix[i] = set.out_pix[i];
-        int rc = get_map(&p.mapA[i], cp.x + set.in_pix[i] * cp.Cin, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
-                         (unsigned long long)set.H[i], TC_BK, (unsigned)(hmode ? tw + 2 : tw), (unsigned)(hmode ? th + 2 : th), (unsigned)cp.stride);
+        int rc = get_map(&p.mapA[i], xb + set.in_pix[i] * cp.Cin * esz, (unsigned long long)cp.Cin, (unsigned long long)set.W[i],
+                         (unsigned long long)set.H[i], bk, (unsigned)(hmode ? tw + 2 : tw), (unsigned)(hmode ? th + 2 : th), (unsigned)cp.stride, esz);
         if (rc) return rc;
     }
-    // bulk (TMA) epilogue whenever the output rows are 16-byte aligned (Cout % 4 == 0)
-    p.tma_epi = ((cp.Cout & 3) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0) ? 1 : 0;
+    // bulk (TMA) epilogue whenever the output rows are 16-byte aligned (fp32: Cout % 4 == 0; fp16: Cout % 8 == 0, required)
+    p.tma_epi = (((cp.Cout * esz) & 15) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0) ? 1 : 0;
+    RF_REQUIRE(!f16 || p.tma_epi, "rf_conv2d_nhwc: engine 2 needs 16-byte aligned y / residual");
     if (p.tma_epi) {
         for (int i = 0; i < set.n; ++i) {
             const unsigned tw = (unsigned)p.tw[i], th = 128u / tw;
-            int rc = get_map(&p.mapY[i], cp.y + set.out_pix[i] * cp.Cout, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
-                             (unsigned long long)set.Ho[i], TC_BK, tw, th);
+            int rc = get_map(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * esz, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], bk, tw, th, 1, esz);
             if (!rc && cp.residual)
-                rc = get_map(&p.mapR[i], cp.residual + set.out_pix[i] * cp.Cout, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
-                             (unsigned long long)set.Ho[i], TC_BK, tw, th);
+                rc = get_map(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * esz, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], bk, tw, th, 1, esz);
             if (rc) return rc;
         }
     }
     for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
     p.out_pix[set.n] = set.out_pix[set.n];
-    int rc = get_map(&p.mapB, w_tc, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 0, TC_BK, (unsigned)BN, 0);
+    int rc = get_map(&p.mapB, w_tc, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 0, bk, (unsigned)BN, 0, 1, esz);
     if (rc) return rc;
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
-    if (hmode && resb_mode() && p.tma_epi && cp.Cin == 64 && cp.Cout == 64) return launch_resb(p, tiles, st);
+    const bool deep = cp.K >= 512;                                   // >= 16 K-steps of 32 fp32 channels (8 of 64 fp16)
+    if (f16) {
+        if (hmode && resb_mode() && cp.Cin == 64 && cp.Cout == 64) return launch_resb<true>(p, tiles, st);
+        if (hmode) return BN == 128 ? launch_halo<128, true>(p, tiles, nt, hmode, st) : launch_halo<64, true>(p, tiles, nt, hmode, st);
+        if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false, true>(p, tiles, nt, st);
+        return deep ? launch_tc<64, MODE_CONV, true, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false, true>(p, tiles, nt, st);
+    }
+    if (hmode && resb_mode() && p.tma_epi && cp.Cin == 64 && cp.Cout == 64) return launch_resb<false>(p, tiles, st);
     if (persist_mode() && p.tma_epi) {
         if (hmode) return BN == 128 ? launch_persist<128, true>(p, tiles, nt, st) : launch_persist<64, true>(p, tiles, nt, st);
         return BN == 128 ? launch_persist<128, false>(p, tiles, nt, st) : launch_persist<64, false>(p, tiles, nt, st);
     }
     if (hmode) return BN == 128 ? launch_halo<128>(p, tiles, nt, hmode, st) : launch_halo<64>(p, tiles, nt, hmode, st);
-    const bool deep = cp.R * cp.S * (cp.Cin / TC_BK) >= 16;          // >= 16 K-steps of 32 channels
     if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false>(p, tiles, nt, st);
     return deep ? launch_tc<64, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false>(p, tiles, nt, st);
 }

@@ -18,13 +18,20 @@ _engine = ops.ENGINE_FP32
 
 
 def set_engine(engine):
-    """'fp32' (exact FMA, SIMT) or 'tf32' (tcgen05 tensor cores)."""
+    """'fp32' (exact FMA, SIMT), 'tf32' (tcgen05 tensor cores, fp32 activations) or 'f16' (tcgen05 with fp16
+    activations for the ResNet-50 trunk; the fine-flow networks stay on 'tf32')."""
     global _engine
-    _engine = {"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32}[engine] if isinstance(engine, str) else int(engine)
+    _engine = ({"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32, "f16": ops.ENGINE_F16}[engine]
+               if isinstance(engine, str) else int(engine))
 
 
 def get_engine():
     return _engine
+
+
+def fine_engine():
+    """Engine of FeatureExtractor / NetFlowCoarse / NetMatchability: fp32 activations, so 'f16' maps to 'tf32'."""
+    return min(_engine, ops.ENGINE_TF32)
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -66,11 +73,20 @@ class FoldedConv:
         bits = wt.view(torch.int32)
         bits = (bits + 0xFFF + ((bits >> 13) & 1)) & ~0x1FFF
         self.w_tc = bits.view(torch.float32).contiguous()
+        self._wt = wt
+        self._w_f16 = None
         self.cout, self.cin, self.k, self.stride = cout, cin, k, stride
         self.pad = (k // 2) if pad is None else pad
 
+    @property
+    def w_f16(self):
+        """[Cout][R*S*Cin] fp16 (round to nearest), the engine-2 operand; built on first use."""
+        if self._w_f16 is None:
+            self._w_f16 = self._wt.to(torch.float16).contiguous()
+        return self._w_f16
+
     def __call__(self, x, relu, residual=None, engine=None):
-        eng = _engine if engine is None else engine     # the library keeps unsupported shapes on the FMA engine
+        eng = fine_engine() if engine is None else engine     # the library keeps unsupported shapes on the FMA engine
         return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_tc)
 
 
@@ -163,7 +179,7 @@ class FeatureExtractor(_Engine):
     def forward_ragged(self, x):
         """Ragged [P, 3] -> Ragged [P/64, 256].  The returned buffer is owned by the program and valid until
         the next forward with the same image sizes; callers normalise / copy it right away."""
-        out, ohw = self._folded().run(x, _engine)
+        out, ohw = self._folded().run(x, fine_engine())
         return Ragged(out, ohw)
 
     def forward(self, x):
@@ -222,7 +238,7 @@ class _Head(_Engine):
 
     def trunk(self, corr):
         corr = self._padded(corr)
-        out, ohw = self._folded().run(corr, _engine)
+        out, ohw = self._folded().run(corr, fine_engine())
         return Ragged(out, ohw)
 
 

@@ -15,6 +15,7 @@ from ._lib import check, lib, need_cuda, ptr, stream
 
 ENGINE_FP32 = 0      # exact fp32 FMA (SIMT)
 ENGINE_TF32 = 1      # tcgen05 tensor cores, TF32 operands, fp32 accumulate
+ENGINE_F16 = 2       # tcgen05 tensor cores, fp16 activations + weights in HBM, fp32 accumulate (ResNet-50 trunk)
 
 
 class Ragged:
@@ -67,7 +68,11 @@ def conv2d(x, w_packed, bias, Cout, k, stride, pad, relu, residual=None, engine=
     """conv + folded-BN bias (+ residual) (+ ReLU) on a ragged NHWC batch."""
     need_cuda(x.data, w_packed, bias, residual.data if residual is not None else None)
     ohw = _out_hw(x.hw, k, stride, pad)
-    y = torch.empty((sum(h * w for h, w in ohw), Cout), device=x.data.device, dtype=torch.float32)
+    if int(engine) == ENGINE_F16:      # x, residual, w_tc fp16 -> y fp16
+        assert x.data.dtype == torch.float16 and w_tc is not None and w_tc.dtype == torch.float16
+        assert residual is None or residual.data.dtype == torch.float16
+    y = torch.empty((sum(h * w for h, w in ohw), Cout), device=x.data.device,
+                    dtype=torch.float16 if int(engine) == ENGINE_F16 else torch.float32)
     check(lib.rf_conv2d_nhwc(ptr(x.data), x.n, x._c, x.C, ptr(w_packed), ptr(w_tc), ptr(bias),
                              ptr(residual.data) if residual is not None else None,
                              Cout, k, k, stride, pad, int(relu), int(engine), ptr(y), stream()))
@@ -93,6 +98,10 @@ def blur_downsample(x, stride):
 def l2norm(x2d, mask=None):
     """x2d [P, C] -> x / max(||x||, 1e-12) per row; rows with mask == 0 become zeros."""
     need_cuda(x2d, mask)
+    if x2d.dtype == torch.float16:      # engine-2 trunk output: fp16 in, fp32 out
+        y = torch.empty(x2d.shape, device=x2d.device, dtype=torch.float32)
+        check(lib.rf_l2norm_f16_nhwc(ptr(x2d), x2d.shape[0], x2d.shape[1], ptr(mask), ptr(y), stream()))
+        return y
     y = torch.empty_like(x2d)
     check(lib.rf_l2norm_nhwc(ptr(x2d), x2d.shape[0], x2d.shape[1], ptr(mask), ptr(y), stream()))
     return y

@@ -18,7 +18,7 @@ RF_MAX_SLOTS = 32
 class rf_layer_t(C.Structure):
     _fields_ = [("op", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
                 ("Cin", C.c_int), ("Cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("relu", C.c_int),
-                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p)]
+                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("w_f16", C.c_void_p)]
 
 
 lib.rf_run_layers.restype = C.c_int
@@ -63,11 +63,12 @@ class LayerProgram:
         self.chan.append(kpad)
         return len(self.chan) - 1
 
-    def stem(self, src, weight, bn, stride, pad):
-        """conv(k x k, few input channels) + BN + ReLU as im2col + 1x1 conv (tensor-core friendly)."""
+    def stem(self, src, weight, bn, stride, pad, kalign=32):
+        """conv(k x k, few input channels) + BN + ReLU as im2col + 1x1 conv (tensor-core friendly).  ``kalign`` = channels
+        per 128-byte K block of the engine that will run the program (32 fp32, 64 fp16)."""
         from .model import FoldedConv
         cout, cin, k, _ = weight.shape
-        kpad = (k * k * cin + 31) // 32 * 32
+        kpad = (k * k * cin + kalign - 1) // kalign * kalign
         w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k * cin)          # (r, s, c) order
         w = torch.nn.functional.pad(w, (0, kpad - k * k * cin)).reshape(cout, kpad, 1, 1)
         x = self.im2col(src, k, stride, pad, kpad)
@@ -80,7 +81,7 @@ class LayerProgram:
         return len(self.chan) - 1
 
     # -- compilation for one image-set signature --------------------------------------------------
-    def _compile(self, hw, device):
+    def _compile(self, hw, device, f16=False):
         n_t = len(self.chan)
         last_use = [0] * n_t
         for i, o in enumerate(self.ops):
@@ -115,12 +116,14 @@ class LayerProgram:
             fc = o[9]
             if fc is not None:
                 L.w, L.w_tc = fc.w.data_ptr(), fc.w_tc.data_ptr()
+                L.w_f16 = fc.w_f16.data_ptr() if f16 else None
                 L.bias = fc.bias.data_ptr() if fc.bias is not None else None
             for t in {o[1], o[2]}:
                 if t > 0 and last_use[t] == i:
                     free.append(slot_of[t])
         assert len(slot_elems) <= RF_MAX_SLOTS
-        bufs = [None] + [torch.empty(max(1, e), device=device, dtype=torch.float32) for e in slot_elems[1:]]
+        # engine 2: every intermediate (and the output) is fp16
+        bufs = [None] + [torch.empty(max(8, e), device=device, dtype=torch.float16 if f16 else torch.float32) for e in slot_elems[1:]]
         out_slot = slot_of[n_t - 1]
         chw = (C.c_int * (2 * len(hw)))(*[v for p in hw for v in p])
         return dict(layers=layers, bufs=bufs, out_slot=out_slot, out_hw=hws[-1], out_elems=elems[-1], chw=chw, nslots=len(slot_elems))
@@ -128,11 +131,12 @@ class LayerProgram:
     def run(self, x, engine):
         """x: ops.Ragged input -> (output buffer view [P_out, C_out] valid until the next run, out_hw)."""
         need_cuda(x.data)
-        key = (tuple(x.hw), str(x.data.device))
+        f16 = int(engine) == 2
+        key = (tuple(x.hw), str(x.data.device), f16)
         if key not in self._compiled:
             if len(self._compiled) > 16:
                 self._compiled.clear()
-            self._compiled[key] = self._compile(x.hw, x.data.device)
+            self._compiled[key] = self._compile(x.hw, x.data.device, f16)
         c = self._compiled[key]
         slots = (C.c_void_p * c["nslots"])()
         slots[0] = x.data.data_ptr()

@@ -71,6 +71,37 @@ def test_resnet50_conv4_vs_torchvision(rf):
     assert rel_err(ys.image(1).cpu().numpy(), ref2.numpy()) < 1e-4
 
 
+def test_resnet50_conv4_f16_engine(rf):
+    """Engine 'f16': the trunk with fp16 activations (stem im2col -> 192-half rows, fp16 max-pool, every bottleneck on
+    tcgen05 kind::f16).  10-bit operands like TF32: close to the fp32 golden output, and ragged == alone."""
+    g = golden("resnet50_conv4")
+    from ransac_flow_b200.coarseAlignFeatMatch import ResNet50Conv4
+    net = ResNet50Conv4(synth.resnet50_conv4_state(int(g["seed"])))
+    x = rf.ops.Ragged.from_nchw(torch.from_numpy(g["x"]).cuda())
+    rf.model.set_engine("f16")
+    try:
+        y = net(x)
+        assert y.data.dtype == torch.float16
+        y1 = y.to_nchw().float().cpu().numpy()
+        e1 = rel_err(y1, g["y"])
+        x2 = torch.randn(1, 3, 48, 80)
+        xs = rf.ops.Ragged(torch.cat([x.data, x2[0].permute(1, 2, 0).reshape(-1, 3).cuda()]), [(64, 96), (48, 80)])
+        ys = net(xs)
+        y2 = ys.image(0).float().cpu().numpy()
+        ref2 = MO.resnet50_conv4(x2, synth.resnet50_conv4_state(int(g["seed"])))
+        e2 = rel_err(ys.image(1).float().cpu().numpy(), ref2.numpy())
+        # normalised rows (what the matcher sees)
+        n = rf.ops.l2norm(ys.data)
+        assert n.dtype == torch.float32
+        ref_n = torch.nn.functional.normalize(ys.data.float(), dim=1)
+        assert (n - ref_n).abs().max().item() < 1e-6
+    finally:
+        rf.model.set_engine("fp32")
+    print("f16 trunk: rel err %.3g (alone), %.3g (ragged second image)" % (e1, e2))
+    assert e1 < 1e-2 and e2 < 1e-2
+    assert np.array_equal(y1, y2)                 # tiles never mix images: bit-identical alone vs in a ragged batch
+
+
 @pytest.mark.parametrize("k,cin,cout,stride,pad", [(5, 2, 16, 1, 2), (3, 4, 32, 2, 1), (7, 3, 64, 2, 3), (3, 3, 64, 1, 1)])
 @pytest.mark.parametrize("engine", ["fp32", "tf32"])
 def test_stem_as_im2col_plus_1x1(rf, k, cin, cout, stride, pad, engine):

@@ -110,13 +110,13 @@ def test_get_flow_all_vs_reference(rf):
 @pytest.fixture
 def engine(request, rf):
     rf.model.set_engine(request.param)
-    rf.outil.corr_precision = 1 if request.param == "tf32" else 0
+    rf.outil.corr_precision = 1 if request.param in ("tf32", "f16") else 0
     yield request.param
     rf.model.set_engine("fp32")
     rf.outil.corr_precision = 0
 
 
-@pytest.mark.parametrize("engine", ["fp32", "tf32"], indirect=True)
+@pytest.mark.parametrize("engine", ["fp32", "tf32", "f16"], indirect=True)
 @pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
 def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
     """L2 parity: the full path, same seeded samples on both sides.  fp32 engine: the match set is

@@ -42,6 +42,49 @@ def test_conv2d_tf32(rf, cin, cout, k, sizes, relu, res, stride):
         assert err <= TF32_TOL * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
 
 
+F16_TOL = 2e-3           # fp16 output rounding (2^-11 relative) + fp32 accumulation order
+
+
+@pytest.mark.parametrize("cin,cout,k,sizes", [
+    (64, 64, 3, [(24, 32), (9, 7)]), (64, 64, 3, [(120, 160), (60, 80), (33, 47)]), (64, 64, 1, [(16, 16)]),
+    (64, 256, 1, [(13, 17), (6, 5), (1, 1)]), (128, 128, 3, [(16, 16), (16, 16)]), (256, 64, 1, [(30, 40)]),
+    (1024, 256, 1, [(15, 20), (30, 40)]), (256, 256, 3, [(15, 20), (33, 25)]), (256, 1024, 1, [(20, 15), (40, 30)]),
+    (512, 128, 1, [(60, 80)]), (192, 64, 1, [(37, 53)]), (64, 48, 3, [(12, 20)]), (128, 8, 3, [(6, 8)]), (512, 2048, 1, [(9, 5)])])
+@pytest.mark.parametrize("relu,res,stride", [(True, True, 1), (False, False, 1), (True, False, 2)])
+def test_conv2d_f16(rf, cin, cout, k, sizes, relu, res, stride):
+    """Engine 2: fp16 activations and weights through tcgen05 kind::f16, fp32 accumulation, fp16 output.  The
+    reference is an fp32 convolution of the same fp16-rounded operands."""
+    g = torch.Generator().manual_seed(cin + cout * 3 + k)
+    xs = [torch.randn(1, cin, h, w, generator=g).half() for h, w in sizes]
+    w = (torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)).half()
+    bias = torch.randn(cout, generator=g)
+    refs = [F.conv2d(x.float(), w.float(), bias, stride=stride, padding=k // 2) for x in xs]
+    rs = [torch.randn(r.shape, generator=g).half() for r in refs] if res else None
+    if res:
+        refs = [a + b.float() for a, b in zip(refs, rs)]
+    if relu:
+        refs = [F.relu(r) for r in refs]
+    wtc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().cuda()
+    y = rf.ops.conv2d(ragged(rf, xs), None, bias.cuda(), cout, k, stride, k // 2, relu, ragged(rf, rs) if res else None,
+                      rf.ops.ENGINE_F16, wtc)
+    torch.cuda.synchronize()
+    assert y.data.dtype == torch.float16
+    for i, r in enumerate(refs):
+        got = y.image(i).float().cpu()
+        assert tuple(got.shape) == tuple(r.shape)
+        err = (got - r).abs().max().item()
+        assert err <= F16_TOL * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
+
+
+def test_f16_engine_saturates_and_rejects_unsupported_shapes(rf):
+    x = torch.full((1, 64, 4, 4), 200.0).half()
+    w = torch.full((8, 64, 1, 1), 100.0).half()
+    y = rf.ops.conv2d(ragged(rf, [x]), None, None, 8, 1, 1, 0, False, None, rf.ops.ENGINE_F16, w.reshape(8, 64).cuda())
+    assert torch.isfinite(y.data.float()).all() and float(y.data.float().max()) == 65504.0
+    with pytest.raises(rf._lib.RFError):     # Cin % 64 != 0: no fp16 path and no silent fallback
+        rf.ops.conv2d(ragged(rf, [x[:, :32]]), None, None, 8, 1, 1, 0, False, None, rf.ops.ENGINE_F16, w.reshape(8, 64)[:, :32].contiguous().cuda())
+
+
 def test_tf32_engine_falls_back_to_fp32_kernels_for_unsupported_shapes(rf):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, 3, 16, 16, generator=g)                       # 3-channel stem: not a TMA-able operand
