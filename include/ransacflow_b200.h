@@ -96,6 +96,8 @@ int rf_build_matches(const int64_t* idx1, const int64_t* idx2, const int* count_
 #define RF_ENGINE_FP32 0
 #define RF_ENGINE_TF32 1
 #define RF_ENGINE_F16 2
+#define RF_ENGINE_F16_OUT32 3   /* engine 2 operands, fp32 output rounded to TF32 after ReLU (3x3 / stride 1 / no residual):
+                                   the layer that hands over from fp16 activations to a TF32 layer */
 int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,
@@ -119,9 +121,12 @@ typedef struct rf_layer {
     const float* w_tc;              /* [Cout][k*k*Cin] */
     const float* bias;              /* [Cout] or NULL */
     const void* w_f16;              /* [Cout][k*k*Cin] fp16, engine 2 only (NULL otherwise) */
+    int flags;                      /* engine 2 only: RF_LAYER_* */
 } rf_layer_t;
-/* engine 2: every slot except the input holds fp16; the input slot (fp32 image) must feed an RF_OP_IM2COL whose Cout
- * (row length) is a multiple of 64; RF_OP_MAXPOOL runs in fp16; RF_OP_BLUR / RF_OP_POOLBLUR are not available. */
+#define RF_LAYER_OUT_F32 1          /* conv: fp16 operands, fp32 output (RF_ENGINE_F16_OUT32) */
+#define RF_LAYER_TF32 2             /* conv: fp32 input and output on the TF32 engine (e.g. a 49-channel head after an OUT_F32 layer) */
+/* engine 2: slots hold fp16 except the input of an RF_OP_IM2COL (the fp32 image; row length = Cout % 64 == 0), the
+ * output of an RF_LAYER_OUT_F32 conv and the input / output of an RF_LAYER_TF32 conv; pooling and blur run in fp16. */
 int rf_run_layers(const rf_layer_t* layers_host, int n, void* const* slots_host, int nimg, const int* hw_host,
                   int engine, void* stream);
 /* max pooling k x k / stride / zero-free padding: nn.MaxPool2d (model/model.py:71; torchvision resnet maxpool) */
@@ -136,7 +141,8 @@ int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, floa
 int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mask, float* y, void* stream);
 /* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][ldo], channels >= k*k are
  * written as zeros (ldo = 64 makes the 49-channel volume a 128-byte-aligned operand for the conv engines);
- * round_tf32_out = 1 stores the values rounded to nearest TF32 (operand of the tensor-core heads) */
+ * round_tf32_out = 1 stores the values rounded to nearest TF32 (operand of the tensor-core heads);
+ * round_tf32_out = 2 stores fp16 (out then holds N*h*w*ldo halves: the operand of the engine-2 heads) */
 int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
                        float* out, void* stream);
 /* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */

@@ -116,18 +116,53 @@ __global__ void im2col_kernel(const __grid_constant__ ImgSet set, const float* _
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-__global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int stride, int round_out) {
-    const int c4n = C >> 2;
+// 16-byte vectors of the activation type: 4 floats or 8 halves; arithmetic is always fp32
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4], int round_out) {
+        float4 t = make_float4(v[0], v[1], v[2], v[3]);
+        if (round_out) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+        *reinterpret_cast<float4*>(p) = t;
+    }
+};
+template <> struct Vec16<__half> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(__half* p, const float (&v)[8], int) {
+        uint4 t;
+        __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    }
+};
+
+template <typename T>
+__global__ void blur_kernel(const __grid_constant__ ImgSet set, const T* __restrict__ x, T* __restrict__ y, int C, int stride, int round_out) {
+    constexpr int VN = Vec16<T>::N;
+    const int cvn = C / VN;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = set.out_pix[set.n] * c4n;
+    long long total = set.out_pix[set.n] * cvn;
     if (t >= total) return;
-    long long pm = t / c4n;
-    int c4 = (int)(t - pm * c4n);
+    long long pm = t / cvn;
+    int cv = (int)(t - pm * cvn);
     int im = find_img(set, pm);
     int local = (int)(pm - set.out_pix[im]);
     int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
     const int H = set.H[im], W = set.W[im];
-    float4 acc = make_float4(0, 0, 0, 0);
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         int iy = reflect1(oy * stride - 1 + r, H);
@@ -135,12 +170,13 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __r
         for (int s = 0; s < 3; ++s) {
             int ix = reflect1(ox * stride - 1 + s, W);
             float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
-            float4 v = __ldg(reinterpret_cast<const float4*>(x + (set.in_pix[im] + (long long)iy * W + ix) * C) + c4);
-            acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y); acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+            float v[VN];
+            Vec16<T>::load(x + (set.in_pix[im] + (long long)iy * W + ix) * C + cv * VN, v);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
         }
     }
-    if (round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
-    reinterpret_cast<float4*>(y + pm * C)[c4] = acc;
+    Vec16<T>::store(y + pm * C + cv * VN, acc, round_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -149,20 +185,24 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const float* __r
 // the 4 x 4 input window its 3 x 3 pooled neighbourhood covers (78.6 MB in, 19.7 MB out at 480x640 instead of
 // 78.6 + 78.6 + 78.6 + 19.7).
 // ---------------------------------------------------------------------------
-__global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, float* __restrict__ y, int C, int round_out) {
-    const int c4n = C >> 2;
+template <typename T>
+__global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const T* __restrict__ x, T* __restrict__ y, int C, int round_out) {
+    constexpr int VN = Vec16<T>::N;
+    const int cvn = C / VN;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = set.out_pix[set.n] * c4n;
+    long long total = set.out_pix[set.n] * cvn;
     if (t >= total) return;
-    long long pm = t / c4n;
-    int c4 = (int)(t - pm * c4n);
+    long long pm = t / cvn;
+    int cv = (int)(t - pm * cvn);
     int im = find_img(set, pm);
     int local = (int)(pm - set.out_pix[im]);
     int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
     const int H = set.H[im], W = set.W[im];
     const int Hp = H - 1, Wp = W - 1;                       // pooled map size
-    const float4* base = reinterpret_cast<const float4*>(x + set.in_pix[im] * C) + c4;
-    float4 acc = make_float4(0, 0, 0, 0);
+    const T* base = x + set.in_pix[im] * C + cv * VN;
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int py = reflect1(oy * 2 - 1 + r, Hp);
@@ -170,15 +210,16 @@ __global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const float*
         for (int s = 0; s < 3; ++s) {
             const int px = reflect1(ox * 2 - 1 + s, Wp);
             const float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
-            float4 a = __ldg(base + ((long long)py * W + px) * c4n), b = __ldg(base + ((long long)py * W + px + 1) * c4n);
-            float4 c = __ldg(base + ((long long)(py + 1) * W + px) * c4n), d = __ldg(base + ((long long)(py + 1) * W + px + 1) * c4n);
-            float4 m = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y)),
-                                   fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w)));
-            acc.x = fmaf(wgt, m.x, acc.x); acc.y = fmaf(wgt, m.y, acc.y); acc.z = fmaf(wgt, m.z, acc.z); acc.w = fmaf(wgt, m.w, acc.w);
+            float a[VN], b[VN], c[VN], d[VN];
+            Vec16<T>::load(base + ((long long)py * W + px) * C, a);
+            Vec16<T>::load(base + ((long long)py * W + px + 1) * C, b);
+            Vec16<T>::load(base + ((long long)(py + 1) * W + px) * C, c);
+            Vec16<T>::load(base + ((long long)(py + 1) * W + px + 1) * C, d);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[e] = fmaf(wgt, fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e])), acc[e]);
         }
     }
-    if (round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
-    reinterpret_cast<float4*>(y + pm * C)[c4] = acc;
+    Vec16<T>::store(y + pm * C + cv * VN, acc, round_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -276,10 +317,17 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
             }
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (lane == 0) out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
+            if (lane == 0) {
+                if (round_out == 2) reinterpret_cast<__half*>(out)[pix * ldo + i * k + j] = __float2half_rn(acc);
+                else out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
+            }
         }
     }
-    for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
+    if (round_out == 2) {
+        for (int c = k * k + lane; c < ldo; c += 32) reinterpret_cast<__half*>(out)[pix * ldo + c] = __float2half_rn(0.f);
+    } else {
+        for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -550,7 +598,7 @@ int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C,
     RF_REQUIRE(make_imgset(set, nimg, hw_host, 3, stride, 1) == 0, "rf_blur_downsample_nhwc: bad image set");
     for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur_downsample_nhwc: reflect padding needs H, W >= 2");
     long long total = set.out_pix[nimg] * (C / 4);
-    blur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride, round_out);
+    blur_kernel<float><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, stride, round_out);
     RF_LAUNCHED();
     return 0;
 }
@@ -562,7 +610,7 @@ int rf_poolblur_impl(const float* x, int nimg, const int* hw_host, int C, int ro
     RF_REQUIRE(make_imgset(set, nimg, hw_host, 4, 2, 1) == 0, "rf_poolblur: bad image set");
     for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 3 && set.W[i] >= 3, "rf_poolblur: needs H, W >= 3");
     long long total = set.out_pix[nimg] * (C / 4);
-    poolblur_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, round_out);
+    poolblur_kernel<float><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, x, y, C, round_out);
     RF_LAUNCHED();
     return 0;
 }
@@ -661,13 +709,43 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
 
 // engine 2 (fp16 activations): the ResNet-50 stem's patches as rows of 192 halves; max pooling in fp16
 int rf_im2col_f16_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y_f16, void* stream) {
-    RF_REQUIRE(k == 7 && C == 3 && Kpad == 192 && stride == 2 && pad == 3, "rf_im2col (engine 2): only the ResNet-50 stem (7x7/2, 3 channels, Kpad 192)");
+    const bool resnet = (k == 7 && C == 3 && Kpad == 192 && stride == 2 && pad == 3);
+    const bool fe = (k == 3 && C == 3 && Kpad == 64 && stride == 1 && pad == 1);
+    RF_REQUIRE(resnet || fe, "rf_im2col (engine 2): only the ResNet-50 stem (7x7/2, Kpad 192) and the FeatureExtractor stem (3x3/1, Kpad 64)");
     ImgSet set;
     RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_im2col: bad image set");
     int maxHo = 0, maxWo = 0;
     for (int i = 0; i < nimg; ++i) { maxHo = set.Ho[i] > maxHo ? set.Ho[i] : maxHo; maxWo = set.Wo[i] > maxWo ? set.Wo[i] : maxWo; }
+    if (fe) {
+        im2col_smem_kernel<3, 3, 64, 1, 1, 128, __half><<<dim3((maxWo + 127) / 128, maxHo, nimg), 256, 0, as_stream(stream)>>>(
+            set, x, static_cast<__half*>(y_f16), 0);
+        RF_LAUNCHED();
+        return 0;
+    }
     im2col_smem_kernel<7, 3, 192, 2, 3, 64, __half><<<dim3((maxWo + 63) / 64, maxHo, nimg), 256, 0, as_stream(stream)>>>(
         set, x, static_cast<__half*>(y_f16), 0);
+    RF_LAUNCHED();
+    return 0;
+}
+
+int rf_blur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int stride, void* y_f16, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && stride >= 1, "rf_blur (engine 2): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 3, stride, 1) == 0, "rf_blur: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur: reflect padding needs H, W >= 2");
+    long long total = set.out_pix[nimg] * (C / 8);
+    blur_kernel<__half><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x_f16), static_cast<__half*>(y_f16), C, stride, 0);
+    RF_LAUNCHED();
+    return 0;
+}
+
+int rf_poolblur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, void* y_f16, void* stream) {
+    RF_REQUIRE((C % 8) == 0, "rf_poolblur (engine 2): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 4, 2, 1) == 0, "rf_poolblur: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 3 && set.W[i] >= 3, "rf_poolblur: needs H, W >= 3");
+    long long total = set.out_pix[nimg] * (C / 8);
+    poolblur_kernel<__half><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x_f16), static_cast<__half*>(y_f16), C, 0);
     RF_LAUNCHED();
     return 0;
 }

@@ -398,7 +398,7 @@ using namespace rf;
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
                       unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st);
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
-int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16);
+int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
 bool rf_conv2d_tc_supported(const ConvParams& p);
 
 static size_t keys_bytes(int NA, int NB) {
@@ -454,14 +454,16 @@ extern "C" int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int 
     p.K = R * S * Cin;
     // tensor-core engine: ReLU'd activations are the next conv's MMA operand; store them rounded to nearest TF32
     // (the MMA truncates), which removes the truncation bias.  The fp32 engine never rounds.
-    p.round_out = (engine == 1 && relu) ? 1 : 0;
+    p.round_out = ((engine == RF_ENGINE_TF32 || engine == RF_ENGINE_F16_OUT32) && relu) ? 1 : 0;
     cudaStream_t st = as_stream(stream);
-    RF_REQUIRE(engine == RF_ENGINE_FP32 || engine == RF_ENGINE_TF32 || engine == RF_ENGINE_F16, "rf_conv2d_nhwc: unknown engine");
-    // engine 2 = tcgen05 with fp16 activations and weights (x, residual, y, w_tc hold IEEE halves); no SIMT fallback
-    if (engine == RF_ENGINE_F16) return rf_conv2d_tc(set, p, w_tc, st, true);
+    RF_REQUIRE(engine >= RF_ENGINE_FP32 && engine <= RF_ENGINE_F16_OUT32, "rf_conv2d_nhwc: unknown engine");
+    // engine 2 = tcgen05 with fp16 activations and weights (x, residual, y, w_tc hold IEEE halves); no SIMT fallback.
+    // engine 3 = the same with an fp32 (TF32-rounded after ReLU) output: the hand-over to a TF32 layer
+    if (engine == RF_ENGINE_F16) return rf_conv2d_tc(set, p, w_tc, st, true, false);
+    if (engine == RF_ENGINE_F16_OUT32) return rf_conv2d_tc(set, p, w_tc, st, true, true);
     // engine 1 = tcgen05 TF32 where the layer shape allows it (stride 1, Cin % 32 == 0); other layers
     // (3-channel stems, stride-2 convs, 49-channel heads) run on the exact-fp32 SIMT engine below
-    if (engine == 1 && w_tc != nullptr && rf_conv2d_tc_supported(p)) return rf_conv2d_tc(set, p, w_tc, st, false);
+    if (engine == 1 && w_tc != nullptr && rf_conv2d_tc_supported(p)) return rf_conv2d_tc(set, p, w_tc, st, false, false);
     RF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "rf_conv2d_nhwc: pointers must be 16-byte aligned");
     const bool vec = (Cin % 16) == 0;
     const bool wide = Cout >= 128;

@@ -583,7 +583,8 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
     return d;
 }
 
-template <int BN, bool F16 = false>
+// OUT32 (with F16): fp16 operands, fp32 output through the fp32 epilogue (the layer feeding a TF32 / fp32 consumer)
+template <int BN, bool F16 = false, bool OUT32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
     using Cfg = HaloCfg<BN>;
@@ -669,7 +670,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
         const int m = q * 32 + lane;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        conv_epilogue<BN, F16>(p, img, ox0, oy0, HALO_TW, n0, m, tmem_base + ((uint32_t)(q * 32) << 16), smem, res_full, warp, lane);
+        conv_epilogue<BN, F16 && !OUT32>(p, img, ox0, oy0, HALO_TW, n0, m, tmem_base + ((uint32_t)(q * 32) << 16), smem, res_full, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -1202,16 +1203,16 @@ static int launch_persist(const TcParams& p, int tiles_m, int tiles_n, cudaStrea
     return 0;
 }
 
-template <int BN, bool F16 = false>
+template <int BN, bool F16 = false, bool OUT32 = false>
 static int launch_halo(const TcParams& p, int tiles, int ntiles_n, int mode, cudaStream_t st) {
     using Cfg = HaloCfg<BN>;
     static bool attr[64] = {false};
     const int dev = current_device();
     if (!attr[dev]) {
-        RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_halo_kernel<BN, F16, OUT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr[dev] = true;
     }
-    tc_halo_kernel<BN, F16><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
+    tc_halo_kernel<BN, F16, OUT32><<<dim3(tiles, ntiles_n), TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mode);
     RF_LAUNCHED();
     return 0;
 }
@@ -1244,7 +1245,8 @@ bool rf_conv2d_f16_supported(const ConvParams& p) {
 }
 
 // f16 = false: x / residual / y fp32, w_tc fp32 [Cout][K] (TF32-rounded).  f16 = true: the same pointers hold IEEE fp16.
-int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cudaStream_t st, bool f16) {
+// out32 (with f16): y is fp32 (3x3 / stride 1 layers only, no residual) - the hand-over from fp16 layers to a TF32 consumer.
+int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cudaStream_t st, bool f16, bool out32) {
     RF_REQUIRE(w_tc != nullptr, "rf_conv2d_nhwc: tensor-core engines need w_tc ([Cout][R*S*Cin])");
     RF_REQUIRE(f16 ? rf_conv2d_f16_supported(cp) : rf_conv2d_tc_supported(cp),
                "rf_conv2d_nhwc: tensor-core engines need stride 1 or 2, 1x1 or 3x3, Cin % 32 == 0 (fp16: Cin % 64 == 0, Cout % 8 == 0)");
@@ -1253,6 +1255,10 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cuda
     const int BN = cp.Cout > 64 ? 128 : 64;
     const unsigned esz = f16 ? 2u : 4u;
     const unsigned bk = f16 ? TC_BK_F16 : TC_BK;
+    const unsigned esz_y = (f16 && !out32) ? 2u : 4u;                // output (and residual) element size
+    const unsigned bk_y = (f16 && !out32) ? TC_BK_F16 : TC_BK;
+    RF_REQUIRE(!out32 || (f16 && cp.R == 3 && cp.stride == 1 && cp.pad == 1 && cp.residual == nullptr && halo_mode() != 0),
+               "rf_conv2d_nhwc: engine 3 (fp16 operands, fp32 output) covers 3x3 / stride 1 / pad 1 layers without residual");
     const char* xb = reinterpret_cast<const char*>(cp.x);
     const char* rb = reinterpret_cast<const char*>(cp.residual);
     char* yb = reinterpret_cast<char*>(cp.y);
@@ -1272,16 +1278,16 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cuda
         if (rc) return rc;
     }
     // bulk (TMA) epilogue whenever the output rows are 16-byte aligned (fp32: Cout % 4 == 0; fp16: Cout % 8 == 0, required)
-    p.tma_epi = (((cp.Cout * esz) & 15) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0) ? 1 : 0;
-    RF_REQUIRE(!f16 || p.tma_epi, "rf_conv2d_nhwc: engine 2 needs 16-byte aligned y / residual");
+    p.tma_epi = (((cp.Cout * esz_y) & 15) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0) ? 1 : 0;
+    RF_REQUIRE(!f16 || out32 || p.tma_epi, "rf_conv2d_nhwc: engine 2 needs 16-byte aligned y / residual");
     if (p.tma_epi) {
         for (int i = 0; i < set.n; ++i) {
             const unsigned tw = (unsigned)p.tw[i], th = 128u / tw;
-            int rc = get_map(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * esz, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
-                             (unsigned long long)set.Ho[i], bk, tw, th, 1, esz);
+            int rc = get_map(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * esz_y, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], bk_y, tw, th, 1, esz_y);
             if (!rc && cp.residual)
-                rc = get_map(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * esz, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
-                             (unsigned long long)set.Ho[i], bk, tw, th, 1, esz);
+                rc = get_map(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * esz_y, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i],
+                             (unsigned long long)set.Ho[i], bk_y, tw, th, 1, esz_y);
             if (rc) return rc;
         }
     }
@@ -1293,6 +1299,7 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cuda
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
     const bool deep = cp.K >= 512;                                   // >= 16 K-steps of 32 fp32 channels (8 of 64 fp16)
+    if (f16 && out32) return BN == 128 ? launch_halo<128, true, true>(p, tiles, nt, hmode, st) : launch_halo<64, true, true>(p, tiles, nt, hmode, st);
     if (f16) {
         if (hmode && resb_mode() && cp.Cin == 64 && cp.Cout == 64) return launch_resb<true>(p, tiles, st);
         if (hmode) return BN == 128 ? launch_halo<128, true>(p, tiles, nt, hmode, st) : launch_halo<64, true>(p, tiles, nt, hmode, st);

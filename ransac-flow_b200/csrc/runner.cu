@@ -10,6 +10,8 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
 int rf_poolblur_impl(const float* x, int nimg, const int* hw_host, int C, int round_out, float* y, void* stream);
 int rf_im2col_f16_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y_f16, void* stream);
 int rf_maxpool_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int k, int stride, int pad, void* y_f16, void* stream);
+int rf_blur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int stride, void* y_f16, void* stream);
+int rf_poolblur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, void* y_f16, void* stream);
 int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
 
 extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
@@ -32,18 +34,25 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
         if (engine == RF_ENGINE_F16) {
             // fp16 activations: the (fp32) input image may only feed the stem's im2col; everything after it is fp16
             if (l.op == RF_OP_CONV) {
-                RF_REQUIRE(l.src != L[0].src, "rf_run_layers (engine 2): the fp32 input slot must feed an im2col layer");
                 const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;
-                rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, static_cast<const float*>(l.w_f16), l.bias, res, l.Cout, k, k, stride, pad, l.relu,
-                                    RF_ENGINE_F16, y, stream);
+                if (l.flags & RF_LAYER_TF32)          // fp32 in / out on the TF32 engine (SIMT for shapes it does not cover)
+                    rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, l.w_tc, l.bias, res, l.Cout, k, k, stride, pad, l.relu, RF_ENGINE_TF32, y, stream);
+                else
+                    rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, static_cast<const float*>(l.w_f16), l.bias, res, l.Cout, k, k, stride, pad, l.relu,
+                                        (l.flags & RF_LAYER_OUT_F32) ? RF_ENGINE_F16_OUT32 : RF_ENGINE_F16, y, stream);
             } else if (l.op == RF_OP_MAXPOOL) {
-                RF_REQUIRE(l.src != L[0].src, "rf_run_layers (engine 2): the fp32 input slot must feed an im2col layer");
                 rc = rf_maxpool_f16_impl(x, nimg, shw, l.Cin, k, stride, pad, y, stream);
+            } else if (l.op == RF_OP_BLUR) {
+                k = 3; pad = 1;
+                rc = rf_blur_f16_impl(x, nimg, shw, l.Cin, stride, y, stream);
+            } else if (l.op == RF_OP_POOLBLUR) {
+                k = 4; stride = 2; pad = 1;
+                rc = rf_poolblur_f16_impl(x, nimg, shw, l.Cin, y, stream);
             } else if (l.op == RF_OP_IM2COL) {
                 RF_REQUIRE(l.src == L[0].src, "rf_run_layers (engine 2): im2col reads the fp32 input slot");
                 rc = rf_im2col_f16_impl(x, nimg, shw, l.Cin, k, stride, pad, l.Cout, y, stream);
             } else {
-                return fail_msg("rf_run_layers (engine 2): only conv / maxpool / im2col layers have an fp16 path");
+                return fail_msg("rf_run_layers: unknown op");
             }
         } else if (l.op == RF_OP_CONV) {
             const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;

@@ -18,10 +18,12 @@ _engine = ops.ENGINE_FP32
 
 
 def set_engine(engine):
-    """'fp32' (exact FMA, SIMT), 'tf32' (tcgen05 tensor cores, fp32 activations) or 'f16' (tcgen05 with fp16
-    activations for the ResNet-50 trunk; the fine-flow networks stay on 'tf32')."""
-    global _engine
-    _engine = ({"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32, "f16": ops.ENGINE_F16}[engine]
+    """'fp32' (exact FMA, SIMT), 'tf32' (tcgen05 tensor cores, fp32 activations), 'f16' (tcgen05 with fp16
+    activations: ResNet-50 trunk, FeatureExtractor and the 3x3 body of the heads; the 49- / 1-channel head outputs
+    stay TF32 / fp32) or 'f16-trunk' (fp16 trunk only, fine-flow networks on 'tf32')."""
+    global _engine, _fine_f16
+    _fine_f16 = engine != "f16-trunk"
+    _engine = ({"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32, "f16": ops.ENGINE_F16, "f16-trunk": ops.ENGINE_F16}[engine]
                if isinstance(engine, str) else int(engine))
 
 
@@ -29,9 +31,12 @@ def get_engine():
     return _engine
 
 
+_fine_f16 = True
+
+
 def fine_engine():
-    """Engine of FeatureExtractor / NetFlowCoarse / NetMatchability: fp32 activations, so 'f16' maps to 'tf32'."""
-    return min(_engine, ops.ENGINE_TF32)
+    """Engine of FeatureExtractor / NetFlowCoarse / NetMatchability ('f16-trunk' keeps them on 'tf32')."""
+    return _engine if (_engine < ops.ENGINE_F16 or _fine_f16) else ops.ENGINE_TF32
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -86,20 +91,23 @@ class FoldedConv:
         return self._w_f16
 
     def __call__(self, x, relu, residual=None, engine=None):
-        eng = fine_engine() if engine is None else engine     # the library keeps unsupported shapes on the FMA engine
+        eng = min(fine_engine(), ops.ENGINE_TF32) if engine is None else engine     # fp32 activations here; the library keeps unsupported shapes on the FMA engine
         return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_tc)
 
 
 class _Engine(nn.Module):
     """Caches folded weights; rebuilt whenever parameters change or move."""
 
-    def _folded(self):
+    def _folded(self, f16=False):
+        """The layer program for fp32 activations (f16 = False) or for the fp16 engine."""
         ver = tuple((p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
         if getattr(self, "_fold_ver", None) != ver:
-            with torch.no_grad():
-                self._fold = self._fold_build()
+            self._fold = {}
             self._fold_ver = ver
-        return self._fold
+        if f16 not in self._fold:
+            with torch.no_grad():
+                self._fold[f16] = self._fold_build(f16)
+        return self._fold[f16]
 
     def _check(self, *xs):
         if self.training:
@@ -159,10 +167,10 @@ class FeatureExtractor(_Engine):
             layers.append(block(self.inplanes, planes, 1, None))
         return nn.Sequential(*layers)
 
-    def _fold_build(self):
+    def _fold_build(self, f16=False):
         """The whole network as one layer program (model/model.py:106-114 do_forward)."""
         P = LayerProgram(3)
-        x = P.stem(0, self.conv1.weight, self.bn1, 1, 1)                             # conv1 + bn1 + relu (im2col + 1x1)
+        x = P.stem(0, self.conv1.weight, self.bn1, 1, 1, 64 if f16 else 32)          # conv1 + bn1 + relu (im2col + 1x1)
         x = P.poolblur(x)                                                            # MaxPool2d(2, 1) + anti-aliased stride 2, fused
         for layer in (self.layer1, self.layer2, self.layer3):
             for b in layer:
@@ -179,13 +187,14 @@ class FeatureExtractor(_Engine):
     def forward_ragged(self, x):
         """Ragged [P, 3] -> Ragged [P/64, 256].  The returned buffer is owned by the program and valid until
         the next forward with the same image sizes; callers normalise / copy it right away."""
-        out, ohw = self._folded().run(x, fine_engine())
-        return Ragged(out, ohw)
+        eng = fine_engine()
+        out, ohw = self._folded(eng == ops.ENGINE_F16).run(x, eng)
+        return Ragged(out, ohw)                 # fp16 rows under the fp16 engine (ops.l2norm returns fp32 either way)
 
     def forward(self, x):
         self._check(x)
         with torch.no_grad():
-            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw().clone(memory_format=torch.channels_last)
+            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw().float().clone(memory_format=torch.channels_last)
 
 
 class CorrNeigh(nn.Module):
@@ -220,25 +229,28 @@ class _Head(_Engine):
 
     CORR_LD = 64      # the k*k = 49-channel correlation volume is carried with 64 channels (15 zeros)
 
-    def _fold_build(self):
+    def _fold_build(self, f16=False):
+        # under the fp16 engine conv1..conv3 read fp16; conv3 writes fp32 and the 49- / 1-channel conv4 stays on TF32
         P = LayerProgram(self.CORR_LD)
         x = P.conv(0, FoldedConv(self.conv1.weight, self.bn1, cin_pad=self.CORR_LD), relu=True)
         x = P.conv(x, FoldedConv(self.conv2.weight, self.bn2), relu=True)
-        x = P.conv(x, FoldedConv(self.conv3.weight, self.bn3), relu=True)
-        P.conv(x, FoldedConv(self.conv4.weight, None), relu=False)
+        x = P.conv(x, FoldedConv(self.conv3.weight, self.bn3), relu=True, out_f32=True)
+        P.conv(x, FoldedConv(self.conv4.weight, None), relu=False, tf32=True)
         return P
 
-    def _padded(self, corr):
-        """Accept the reference's 49-channel volume or the library's 64-channel one."""
-        if corr.C == self.CORR_LD:
+    def _padded(self, corr, dtype):
+        """Accept the reference's 49-channel volume or the library's 64-channel one (fp32, or fp16 for the fp16 engine)."""
+        if corr.C == self.CORR_LD and corr.data.dtype == dtype:
             return corr
-        d = torch.zeros((corr.data.shape[0], self.CORR_LD), device=corr.data.device, dtype=torch.float32)
-        d[:, :corr.C] = corr.data
+        d = torch.zeros((corr.data.shape[0], self.CORR_LD), device=corr.data.device, dtype=dtype)
+        d[:, :min(corr.C, self.kernelSize ** 2)] = corr.data[:, :self.kernelSize ** 2].to(dtype)
         return Ragged(d, corr.hw)
 
     def trunk(self, corr):
-        corr = self._padded(corr)
-        out, ohw = self._folded().run(corr, fine_engine())
+        eng = fine_engine()
+        f16 = eng == ops.ENGINE_F16
+        corr = self._padded(corr, torch.float16 if f16 else torch.float32)
+        out, ohw = self._folded(f16).run(corr, eng)
         return Ragged(out, ohw)
 
 

@@ -109,11 +109,13 @@ def l2norm(x2d, mask=None):
 
 def corr_neigh(x, y, k, ldo=None, round_tf32=False):
     """x, y: Ragged with identical (h, w) per image -> Ragged with ``ldo`` (default k*k) channels; channels
-    beyond k*k are zeros (ldo = 64 gives the heads a 128-byte aligned K-major operand)."""
+    beyond k*k are zeros (ldo = 64 gives the heads a 128-byte aligned K-major operand).  ``round_tf32``: 0 / False =
+    plain fp32, 1 / True = fp32 rounded to TF32, 2 = fp16 output (operand of the fp16-engine heads)."""
     need_cuda(x.data, y.data)
+    assert x.data.dtype == torch.float32 and y.data.dtype == torch.float32
     h, w = x.hw[0]
     ldo = k * k if ldo is None else int(ldo)
-    out = torch.empty((x.data.shape[0], ldo), device=x.data.device, dtype=torch.float32)
+    out = torch.empty((x.data.shape[0], ldo), device=x.data.device, dtype=torch.float16 if int(round_tf32) == 2 else torch.float32)
     check(lib.rf_corr_neigh_nhwc(ptr(x.data), ptr(y.data), x.n, h, w, x.C, k, ldo, int(round_tf32), ptr(out), stream()))
     return Ragged(out, x.hw)
 

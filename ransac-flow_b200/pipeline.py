@@ -36,7 +36,7 @@ def PredFlowMask_device(IsTensor, featt, flowCoarse, size, network, with_match21
         ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
         k = network["netCorr"].kernelSize
         ld = network["netFlowCoarse"].CORR_LD
-        tc = model.fine_engine() == ops.ENGINE_TF32
+        tc = model.fine_engine()            # 0 plain fp32, 1 TF32-rounded, 2 fp16: the operand type of the heads
         corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
         corr21 = ops.corr_neigh(fs, ft, k, ld, tc)
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
@@ -274,7 +274,7 @@ def align2images(coarseModel, network, img1, img2, align_corners=False):
         feat1 = fine_features(network["netFeatCoarse"], img1_coarse)
         feat2 = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
         k = network["netCorr"].kernelSize
-        corr12 = ops.corr_neigh(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, model.fine_engine() == ops.ENGINE_TF32)
+        corr12 = ops.corr_neigh(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, model.fine_engine())
         flowDown = network["netFlowCoarse"].forward_ragged(corr12)
         flow12, _, _ = ops.compose_fine(flowDown, None, None, flowCoarse, clamp=False, align_corners=align_corners, want_match=False)
         img1_fine = ops.grid_sample(coarseModel.IsTensor, flow12, align_corners)

@@ -13,12 +13,13 @@ from ._lib import check, lib, need_cuda, stream
 
 RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR = 0, 1, 2, 3, 4
 RF_MAX_SLOTS = 32
+RF_LAYER_OUT_F32, RF_LAYER_TF32 = 1, 2
 
 
 class rf_layer_t(C.Structure):
     _fields_ = [("op", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
                 ("Cin", C.c_int), ("Cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("relu", C.c_int),
-                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("w_f16", C.c_void_p)]
+                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("w_f16", C.c_void_p), ("flags", C.c_int)]
 
 
 lib.rf_run_layers.restype = C.c_int
@@ -32,11 +33,15 @@ class LayerProgram:
         self.ops = []            # (op, src, res, cin, cout, k, stride, pad, relu, folded)
         self.chan = [cin]
         self._keep = []          # folded weights (keeps the device tensors alive)
+        self.flags = {}          # op index -> RF_LAYER_* (fp16 engine only)
         self._compiled = {}
 
     # -- topology --------------------------------------------------------------------------------
-    def conv(self, src, fc, relu, res=None):
+    def conv(self, src, fc, relu, res=None, out_f32=False, tf32=False):
+        """``out_f32`` / ``tf32`` only matter under the fp16 engine: the layer that hands fp32 to a TF32 layer, and that
+        TF32 layer (fp32 in and out; e.g. the 49- / 1-channel head outputs, which stay fp32)."""
         assert self.chan[src] == fc.cin, (self.chan[src], fc.cin)
+        self.flags[len(self.ops)] = (RF_LAYER_OUT_F32 if out_f32 else 0) | (RF_LAYER_TF32 if tf32 else 0)
         self.ops.append((RF_OP_CONV, src, -1 if res is None else res, fc.cin, fc.cout, fc.k, fc.stride, fc.pad, int(relu), fc))
         self._keep.append(fc)
         self.chan.append(fc.cout)
@@ -94,7 +99,19 @@ class LayerProgram:
         for o in self.ops:
             k, s, p = o[5], o[6], o[7]
             hws.append([((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1) for h, w in hws[o[1]]])
-        elems = [sum(h * w for h, w in hws[t]) * self.chan[t] for t in range(n_t)]
+        # element size per tensor: fp32 everywhere, except under the fp16 engine (fp32 only for the image an im2col
+        # reads and around RF_LAYER_OUT_F32 / RF_LAYER_TF32 convs)
+        esize = [4] * n_t
+        if f16:
+            esize[0] = 4 if self.ops[0][0] == RF_OP_IM2COL else 2
+            for i, o in enumerate(self.ops):
+                fl = self.flags.get(i, 0)
+                esize[i + 1] = 4 if fl else 2
+                if fl & RF_LAYER_TF32:
+                    assert esize[o[1]] == 4, "a TF32 layer under the fp16 engine needs an fp32 input (out_f32 on its producer)"
+                elif o[0] != RF_OP_IM2COL:
+                    assert esize[o[1]] == 2 and (o[2] < 0 or esize[o[2]] == 2), "fp16 layer fed by an fp32 tensor"
+        elems = [sum(h * w for h, w in hws[t]) * self.chan[t] * esize[t] for t in range(n_t)]        # BYTES per tensor
         # slot assignment: slot 0 = external input; others from a free list
         slot_of, free, slot_elems = {0: 0}, [], [0]
         layers = (rf_layer_t * len(self.ops))()
@@ -117,16 +134,17 @@ class LayerProgram:
             if fc is not None:
                 L.w, L.w_tc = fc.w.data_ptr(), fc.w_tc.data_ptr()
                 L.w_f16 = fc.w_f16.data_ptr() if f16 else None
+                L.flags = self.flags.get(i, 0) if f16 else 0
                 L.bias = fc.bias.data_ptr() if fc.bias is not None else None
             for t in {o[1], o[2]}:
                 if t > 0 and last_use[t] == i:
                     free.append(slot_of[t])
         assert len(slot_elems) <= RF_MAX_SLOTS
-        # engine 2: every intermediate (and the output) is fp16
-        bufs = [None] + [torch.empty(max(8, e), device=device, dtype=torch.float16 if f16 else torch.float32) for e in slot_elems[1:]]
+        bufs = [None] + [torch.empty(max(16, e), device=device, dtype=torch.uint8) for e in slot_elems[1:]]       # bytes
         out_slot = slot_of[n_t - 1]
         chw = (C.c_int * (2 * len(hw)))(*[v for p in hw for v in p])
-        return dict(layers=layers, bufs=bufs, out_slot=out_slot, out_hw=hws[-1], out_elems=elems[-1], chw=chw, nslots=len(slot_elems))
+        return dict(layers=layers, bufs=bufs, out_slot=out_slot, out_hw=hws[-1], out_elems=elems[-1], chw=chw, nslots=len(slot_elems),
+                    out_dtype=torch.float16 if esize[-1] == 2 else torch.float32, in_dtype=torch.float16 if esize[0] == 2 else torch.float32)
 
     def run(self, x, engine):
         """x: ops.Ragged input -> (output buffer view [P_out, C_out] valid until the next run, out_hw)."""
@@ -138,10 +156,11 @@ class LayerProgram:
                 self._compiled.clear()
             self._compiled[key] = self._compile(x.hw, x.data.device, f16)
         c = self._compiled[key]
+        assert x.data.dtype == c["in_dtype"], (x.data.dtype, c["in_dtype"])
         slots = (C.c_void_p * c["nslots"])()
         slots[0] = x.data.data_ptr()
         for i in range(1, c["nslots"]):
             slots[i] = c["bufs"][i].data_ptr()
         check(lib.rf_run_layers(c["layers"], len(self.ops), slots, len(x.hw), c["chw"], int(engine), stream()))
-        out = c["bufs"][c["out_slot"]][:c["out_elems"]].view(-1, self.chan[-1])
+        out = c["bufs"][c["out_slot"]][:c["out_elems"]].view(c["out_dtype"]).view(-1, self.chan[-1])
         return out, c["out_hw"]

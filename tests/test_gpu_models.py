@@ -71,6 +71,37 @@ def test_resnet50_conv4_vs_torchvision(rf):
     assert rel_err(ys.image(1).cpu().numpy(), ref2.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("engine", ["tf32", "f16"])
+def test_fine_networks_on_tensor_core_engines(rf, engine):
+    """FeatureExtractor and the two heads through the nn.Module API on the tcgen05 engines.  'f16': fp16 activations
+    (stem patches of 64 halves, fp16 pool+blur / blur, kind::f16 convs; conv3 of the heads hands fp32 to the TF32 conv4).
+    10-bit operands either way: outputs close to the fp32 golden values, flow error far below 1e-3."""
+    g = golden("feature_extractor")
+    h = golden("fine_heads")
+    fe = rf.model.FeatureExtractor()
+    fe.load_state_dict(synth.feature_extractor_state(int(g["seed"])))
+    nf = rf.model.NetFlowCoarse(7)
+    nf.load_state_dict(synth.net_flow_coarse_state(1))
+    nm = rf.model.NetMatchability(7)
+    nm.load_state_dict(synth.net_matchability_state(2))
+    for m in (fe, nf, nm):
+        m.cuda()
+        m.eval()
+    rf.model.set_engine(engine)
+    try:
+        y = fe(torch.from_numpy(g["x"]).cuda())
+        flow = nf(torch.from_numpy(h["corr"]).cuda(), False)
+        match = nm(torch.from_numpy(h["corr"]).cuda(), False)
+    finally:
+        rf.model.set_engine("fp32")
+    assert y.dtype == torch.float32 and flow.dtype == torch.float32 and match.dtype == torch.float32
+    e_fe = rel_err(y.cpu().numpy(), g["y"])
+    e_flow = np.abs(flow.cpu().numpy() - h["flow"]).max()
+    e_match = np.abs(match.cpu().numpy() - h["match"]).max()
+    print("[%s] FeatureExtractor rel err %.3g, flow err %.3g, matchability err %.3g" % (engine, e_fe, e_flow, e_match))
+    assert e_fe < 1e-2 and e_flow < 2e-4 and e_match < 1e-3
+
+
 def test_resnet50_conv4_f16_engine(rf):
     """Engine 'f16': the trunk with fp16 activations (stem im2col -> 192-half rows, fp16 max-pool, every bottleneck on
     tcgen05 kind::f16).  10-bit operands like TF32: close to the fp32 golden output, and ragged == alone."""
