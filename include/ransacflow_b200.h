@@ -112,6 +112,8 @@ int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
 #define RF_OP_BLUR 2      /* model/downsample.py: reflect-pad 1 + [1 2 1]^2/16, stride */
 #define RF_OP_IM2COL 3    /* k x k x Cin patches (r, s, c order) zero-padded to Cout floats per output pixel: few-channel stems */
 #define RF_OP_POOLBLUR 4  /* MaxPool2d(2, stride 1) + blur stride 2 fused (model/model.py:71-72) */
+#define RF_OP_STEM7 5     /* engine 2 only: ResNet-50 stem fused (7x7 / stride 2 / pad 3 on the 3-channel fp32 image + bias + ReLU ->
+                             fp16, 64 channels) without the im2col matrix; w_f16 = [64][192] in (r, s, c) order, zero padded */
 #define RF_MAX_SLOTS 32
 typedef struct rf_layer {
     int op;

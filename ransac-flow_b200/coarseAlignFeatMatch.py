@@ -53,7 +53,10 @@ class ResNet50Conv4:
     def _build(self, kalign):
         sd = self._sd
         P = LayerProgram(3)
-        x = P.stem(0, sd["conv1.weight"], _BN(sd, "bn1"), 2, 3, kalign)              # 7x7/2 stem as im2col + 1x1 conv
+        if kalign == 64 and os.environ.get("RF_STEM_FUSED", "1") != "0":
+            x = P.stem7_fused(0, sd["conv1.weight"], _BN(sd, "bn1"))                 # fp16 engine: patches built in shared memory
+        else:
+            x = P.stem(0, sd["conv1.weight"], _BN(sd, "bn1"), 2, 3, kalign)          # 7x7/2 stem as im2col + 1x1 conv
         x = P.maxpool(x, 3, 2, 1)
         for layer, planes, blocks, stride in RESNET50_LAYERS:
             for b in range(blocks):

@@ -633,12 +633,21 @@ im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__
     const int H = set.H[im], WC = set.W[im] * C;
     const float* src = x + set.in_pix[im] * C;
     const int col0 = (ox0 * STRIDE - PAD) * C;
-    for (int idx = threadIdx.x; idx < K * INW; idx += 256) {
+    // all global loads first (independent: one DRAM latency for the whole window), then the shared-memory stores
+    constexpr int NLD = (K * INW + 255) / 256;
+    float stage[NLD];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int idx = threadIdx.x + i * 256;
         const int r = idx / INW, j = idx - r * INW;
         const int iy = oy * STRIDE - PAD + r, col = col0 + j;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && col >= 0 && col < WC) v = __ldg(src + (long long)iy * WC + col);
-        sIn[r][j] = round_out ? round_tf32(v) : v;
+        stage[i] = (idx < K * INW && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int r = idx / INW, j = idx - r * INW;
+        if (idx < K * INW) sIn[r][j] = round_out ? round_tf32(stage[i]) : stage[i];
     }
     __syncthreads();
     const int npx = min(TPX, Wo - ox0);

@@ -46,6 +46,8 @@ struct alignas(64) TcParams {
     int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
     long long out_pix[RF_MAX_IMGS + 1];
     int R, S, pad, stride, Cin, Cout, relu, round_out, tma_epi;
+    int stages;                           // fp16 tap-streaming kernel: ring depth chosen per layer on the host
+    int res_pf;                           // fp16 tap-streaming kernel: residual tile prefetched into its own staging at CTA start
     const float* bias;
     const float* residual;
     float* y;
@@ -278,14 +280,16 @@ __device__ __forceinline__ void epi_rows_f16(const float* __restrict__ bias, int
 
 template <int BN, bool F16 = false>
 __device__ __forceinline__ void conv_epilogue(const TcParams& p, int img, int ox0, int oy0, int tw, int n0, int m, uint32_t trow,
-                                              uint8_t* smem, uint64_t* res_full, int warp, int lane) {
+                                              uint8_t* smem, uint64_t* res_full, int warp, int lane, bool res_issued = false) {
     if constexpr (F16) {
-        // engine 2: always the bulk path (the host requires Cout % 8 == 0); boxes of 64 fp16 channels
+        // engine 2: always the bulk path (the host requires Cout % 8 == 0); boxes of 64 fp16 channels.  `smem` is the
+        // staging area: the idle pipeline stages, or the dedicated residual staging when the producer warp already
+        // issued the residual loads at CTA start (res_issued)
         constexpr int NBOX = BN / 64;
         uint8_t* stg = smem;
         const bool has_res = p.residual != nullptr;
         if (has_res) {
-            if (warp == 2 && lane == 0) {
+            if (!res_issued && warp == 2 && lane == 0) {
                 mbar_expect_tx(res_full, NBOX * TC_A_BYTES);
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) tma_load_3d(stg + b * TC_A_BYTES, &p.mapR[img], res_full, n0 + b * 64, ox0, oy0);
@@ -406,9 +410,15 @@ tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
     constexpr int BK = tc_bk<F16>();              // channels per 128-byte K block
     static_assert(!(F16 && MODE == MODE_CORR), "the correlation runs 3xTF32");
+    // fp16 convolutions: ring depth per layer (<= STAGES) and, for layers with a residual, a dedicated staging area
+    // behind the ring that the producer fills at CTA start (more bytes in flight per SM, one DRAM latency less per CTA)
+    const int NST = F16 ? p.stages : STAGES;
+    const bool res_pf = F16 && p.res_pf;
+    constexpr int RES_BYTES = (BN / 64) * TC_A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* res_stg = smem + NST * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(res_stg + (res_pf ? RES_BYTES : 0));
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* res_full = tmem_full + 1;
@@ -433,7 +443,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     const int KI = p.R * p.S * kc;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init(res_full, 1);
         fence_barrier_init();
@@ -453,7 +463,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             for (int it = 0; it < KI; ++it) {
-                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                const int st = it % NST, ph = (it / NST) & 1;
                 mbar_wait(&empty[st], ph ^ 1);
                 uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
@@ -467,6 +477,11 @@ tc_kernel(const __grid_constant__ TcParams p) {
                     tma_load_3d(sbase + TC_A_BYTES, &p.mapAlo, &full[st], c0, x, y);
                     tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &p.mapBlo, &full[st], kcol, n0);
                 }
+                if (F16 && it == 0 && res_pf) {       // right behind the first operand tiles: the residual tile
+                    mbar_expect_tx(res_full, RES_BYTES);
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b) tma_load_3d(res_stg + b * TC_A_BYTES, &p.mapR[img], res_full, n0 + b * 64, ox0, oy0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -474,7 +489,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         {   // whole warp, warp-uniform control flow; umma_* elect the issuing lane
             constexpr uint32_t idesc = make_idesc<F16>(BN);
             for (int it = 0; it < KI; ++it) {
-                const int st = it % STAGES, ph = (it / STAGES) & 1;
+                const int st = it % NST, ph = (it / NST) & 1;
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
@@ -497,7 +512,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         if (MODE == MODE_CONV) {
-            conv_epilogue<BN, F16>(p, img, ox0, oy0, tw, n0, m, trow, smem, res_full, warp, lane);
+            conv_epilogue<BN, F16>(p, img, ox0, oy0, tw, n0, m, trow, res_pf ? res_stg : smem, res_full, warp, lane, res_pf);
         } else {
             // utils/outil.py:36-37: row arg-max (thread-local over this tile's columns), column arg-max via an
             // smem transpose of the score tile (the pipeline stages are idle by now)
@@ -1051,6 +1066,149 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// ResNet-50 stem, fused (engine 2): conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
+// fp16 NHWC, without materialising the im2col matrix (350 MB written and read back per pair at 480x640 x 8 images).
+// One CTA = 16 x 8 output pixels x 64 channels:
+//   warps 0-3 : stage the 37 x 21 x 3 input window in shared memory (coalesced, zero padded), then each thread builds
+//               ITS pixel's 147-long (r, s, c) patch as fp16 directly in the 128-byte-swizzled K-major layout the
+//               UMMA descriptors expect (three K blocks of 64; 148..191 are zeros), fence.proxy.async, arrive;
+//   warp 4    : TMA-loads the 64 x 192 fp16 weights, issues 12 tcgen05.mma kind::f16 (M 128, N 64, K 16), commits;
+//   warps 0-3 : epilogue - TMEM -> + bias, ReLU -> fp16 swizzled staging (the A tile's first block) -> one TMA store.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int STEM_TW = 16, STEM_TH = 8, STEM_K = 7, STEM_C = 3, STEM_KK = 147, STEM_KB = 3;
+constexpr int STEM_IN_W = ((STEM_TW - 1) * 2 + STEM_K) * STEM_C;          // 111 floats per staged input row
+constexpr int STEM_IN_H = (STEM_TH - 1) * 2 + STEM_K;                     // 21 rows
+constexpr int STEM_IN_LD = 112;
+constexpr int STEM_B_TILE = 64 * 128;                                     // 8 KB per K block
+constexpr int STEM_OFF_B = STEM_KB * TC_A_BYTES;                          // 48 KB
+constexpr int STEM_OFF_IN = STEM_OFF_B + STEM_KB * STEM_B_TILE;           // 72 KB
+constexpr int STEM_OFF_BAR = STEM_OFF_IN + STEM_IN_H * STEM_IN_LD * 4;    // + 9408 B
+constexpr int STEM_SMEM = STEM_OFF_BAR + 64 + 1024;
+constexpr int STEM_THREADS = 160;
+
+struct alignas(64) StemParams {
+    CUtensorMap mapB;                     // weights fp16 [64][192], box (64, 64)
+    CUtensorMap mapY[RF_MAX_IMGS];        // output fp16 (64, Wo, Ho), box (64, 16, 8)
+    int nimg;
+    int tile_start[RF_MAX_IMGS + 1];
+    int tiles_x[RF_MAX_IMGS];
+    int H[RF_MAX_IMGS], W[RF_MAX_IMGS];
+    long long in_pix[RF_MAX_IMGS];
+    const float* x;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(STEM_THREADS, 2)
+stem7_f16_kernel(const __grid_constant__ StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STEM_OFF_B;
+    float* sIn = reinterpret_cast<float*>(smem + STEM_OFF_IN);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + STEM_OFF_BAR);
+    uint64_t* bar_a = bar_b + 1;
+    uint64_t* bar_mma = bar_a + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = blockIdx.x - p.tile_start[img];
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    const int ox0 = txi * STEM_TW, oy0 = tyi * STEM_TH;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_a, 128);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[img]); }
+        tmem_alloc(tmem_slot, 64);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_b, STEM_KB * STEM_B_TILE);
+#pragma unroll
+            for (int kb = 0; kb < STEM_KB; ++kb) tma_load_2d(sB + kb * STEM_B_TILE, &p.mapB, bar_b, kb * 64, 0);
+        }
+        mbar_wait(bar_b, 0);
+        mbar_wait(bar_a, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_f16(64);
+#pragma unroll
+        for (int kb = 0; kb < STEM_KB; ++kb)
+            umma_f16_x4(tmem_base, make_desc_sw128(smem_u32(sA + kb * TC_A_BYTES)), make_desc_sw128(smem_u32(sB + kb * STEM_B_TILE)), idesc, kb != 0 ? 1u : 0u);
+        umma_commit(bar_mma);
+    } else {
+        const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = accumulator row
+        // ---- stage the input window: rows 2*oy0-3 .. +20, float columns (2*ox0-3)*3 .. +110 ----
+        const int H = p.H[img], WC = p.W[img] * STEM_C;
+        const float* src = p.x + p.in_pix[img] * STEM_C;
+        const int iy0 = oy0 * 2 - 3, col0 = (ox0 * 2 - 3) * STEM_C;
+        // all loads first (independent, one DRAM latency), then the shared-memory stores
+        constexpr int NLD = (STEM_IN_H * STEM_IN_W + 127) / 128;         // 19 per thread
+        float stage[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int idx = m + i * 128;
+            const int r = idx / STEM_IN_W, j = idx - r * STEM_IN_W;
+            const int iy = iy0 + r, col = col0 + j;
+            stage[i] = (idx < STEM_IN_H * STEM_IN_W && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int idx = m + i * 128;
+            const int r = idx / STEM_IN_W, j = idx - r * STEM_IN_W;
+            if (idx < STEM_IN_H * STEM_IN_W) sIn[r * STEM_IN_LD + j] = stage[i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- this pixel's patch, (r, s, c) order: element k = r*21 + s*3 + c sits at sIn[2*py + r][6*px + (k % 21)] ----
+        const int py = m >> 4, px = m & 15;
+        const float* base = sIn + (2 * py) * STEM_IN_LD + 6 * px;
+#pragma unroll
+        for (int kb = 0; kb < STEM_KB; ++kb) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 o;
+                __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
+                    const float a = k0 < STEM_KK ? base[(k0 / 21) * STEM_IN_LD + (k0 % 21)] : 0.f;
+                    const float b = k1 < STEM_KK ? base[(k1 / 21) * STEM_IN_LD + (k1 % 21)] : 0.f;
+                    ho[e] = __floats2half2_rn(a, b);
+                }
+                *reinterpret_cast<uint4*>(sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4)) = o;
+            }
+        }
+        fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_a);
+        // ---- epilogue ----
+        mbar_wait(bar_mma, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        epi_rows_f16<64>(p.bias, 64, 1, false, 0, m, trow, sA);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (m == 0) {
+            tma_store_3d(&p.mapY[img], sA, 0, ox0, oy0);
+            tma_store_commit_and_wait_read();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 64);
+}
+
 // hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact in fp32)
 __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1164,6 +1322,15 @@ static int persist_mode() {
     return m;
 }
 
+static int respf_mode() {
+    static int m = -1;
+    if (m < 0) {
+        const char* e = getenv("RF_TC_RESPF");    // fp16 1x1 convs with a residual: prefetch the residual tile at CTA start.
+        m = e ? atoi(e) : 0;                      // Measured (profiles/README.md): -2 % end to end - the extra staging costs a resident CTA
+    }
+    return m;
+}
+
 static int resb_mode() {
     static int m = -1;
     if (m < 0) {
@@ -1223,10 +1390,25 @@ static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st
     static bool attr[64] = {false};
     const int dev = current_device();
     if (!attr[dev]) {
-        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        RF_CUDA(cudaFuncSetAttribute(tc_kernel<BN, MODE, DEEP, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES + (F16 ? (BN / 64) * TC_A_BYTES : 0)));
         attr[dev] = true;
     }
     dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
+    if (F16) {
+        // ring depth: never more stages than K blocks; with a prefetched residual two stages (+ its staging) keep two or
+        // three CTAs resident per SM
+        TcParams q = p;
+        const int KI = p.R * p.S * (p.Cin / TC_BK_F16);
+        q.res_pf = (p.residual != nullptr && respf_mode()) ? 1 : 0;
+        int stages = KI < Cfg::STAGES ? KI : Cfg::STAGES;
+        if (q.res_pf && stages > 2) stages = 2;
+        q.stages = stages;
+        const int smem = stages * Cfg::STAGE_BYTES + (q.res_pf ? (BN / 64) * TC_A_BYTES : 0) + 1024 + 256;
+        tc_kernel<BN, MODE, DEEP, F16><<<grid, TC_THREADS, smem, st>>>(q);
+        RF_LAUNCHED();
+        return 0;
+    }
     tc_kernel<BN, MODE, DEEP, F16><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
     RF_LAUNCHED();
     return 0;
@@ -1314,6 +1496,42 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cuda
     if (hmode) return BN == 128 ? launch_halo<128>(p, tiles, nt, hmode, st) : launch_halo<64>(p, tiles, nt, hmode, st);
     if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false>(p, tiles, nt, st);
     return deep ? launch_tc<64, MODE_CONV, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false>(p, tiles, nt, st);
+}
+
+// engine 2: fused ResNet-50 stem (see stem7_f16_kernel).  x fp32 [sum HW][3], w_f16 [64][192] ((r, s, c) order, zero
+// padded), bias fp32 [64], y fp16 [sum HoWo][64]
+int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* w_f16, const float* bias, void* y_f16, void* stream) {
+    RF_REQUIRE(x != nullptr && w_f16 != nullptr && y_f16 != nullptr, "rf_stem7: null pointer");
+    RF_REQUIRE(((uintptr_t)y_f16 % 16) == 0 && ((uintptr_t)w_f16 % 16) == 0, "rf_stem7: pointers must be 16-byte aligned");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 7, 2, 3) == 0, "rf_stem7: bad image set");
+    StemParams p;
+    memset(&p, 0, sizeof(p));
+    p.nimg = nimg;
+    int tiles = 0;
+    for (int i = 0; i < nimg; ++i) {
+        p.tiles_x[i] = (set.Wo[i] + STEM_TW - 1) / STEM_TW;
+        p.tile_start[i] = tiles;
+        tiles += p.tiles_x[i] * ((set.Ho[i] + STEM_TH - 1) / STEM_TH);
+        p.H[i] = set.H[i]; p.W[i] = set.W[i];
+        p.in_pix[i] = set.in_pix[i];
+        int rc = get_map(&p.mapY[i], static_cast<char*>(y_f16) + set.out_pix[i] * 64 * 2, 64ull, (unsigned long long)set.Wo[i],
+                         (unsigned long long)set.Ho[i], 64, STEM_TW, STEM_TH, 1, 2);
+        if (rc) return rc;
+    }
+    for (int i = nimg; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
+    int rc = get_map(&p.mapB, w_f16, 192ull, 64ull, 0, 64, 64, 0, 1, 2);
+    if (rc) return rc;
+    p.x = x; p.bias = bias;
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        RF_CUDA(cudaFuncSetAttribute(stem7_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
+        attr[dev] = true;
+    }
+    stem7_f16_kernel<<<tiles, STEM_THREADS, STEM_SMEM, as_stream(stream)>>>(p);
+    RF_LAUNCHED();
+    return 0;
 }
 
 size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }

@@ -10,6 +10,7 @@ int rf_im2col_impl(const float* x, int nimg, const int* hw_host, int C, int k, i
 int rf_poolblur_impl(const float* x, int nimg, const int* hw_host, int C, int round_out, float* y, void* stream);
 int rf_im2col_f16_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y_f16, void* stream);
 int rf_maxpool_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int k, int stride, int pad, void* y_f16, void* stream);
+int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* w_f16, const float* bias, void* y_f16, void* stream);
 int rf_blur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int stride, void* y_f16, void* stream);
 int rf_poolblur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, void* y_f16, void* stream);
 int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
@@ -48,6 +49,10 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
             } else if (l.op == RF_OP_POOLBLUR) {
                 k = 4; stride = 2; pad = 1;
                 rc = rf_poolblur_f16_impl(x, nimg, shw, l.Cin, y, stream);
+            } else if (l.op == RF_OP_STEM7) {
+                RF_REQUIRE(l.src == L[0].src && l.Cin == 3 && l.Cout == 64 && k == 7 && stride == 2 && pad == 3 && l.relu,
+                           "rf_run_layers: RF_OP_STEM7 is the ResNet-50 stem on the fp32 input slot");
+                rc = rf_stem7_f16_impl(x, nimg, shw, l.w_f16, l.bias, y, stream);
             } else if (l.op == RF_OP_IM2COL) {
                 RF_REQUIRE(l.src == L[0].src, "rf_run_layers (engine 2): im2col reads the fp32 input slot");
                 rc = rf_im2col_f16_impl(x, nimg, shw, l.Cin, k, stride, pad, l.Cout, y, stream);

@@ -11,7 +11,7 @@ import torch
 
 from ._lib import check, lib, need_cuda, stream
 
-RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR = 0, 1, 2, 3, 4
+RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR, RF_OP_STEM7 = 0, 1, 2, 3, 4, 5
 RF_MAX_SLOTS = 32
 RF_LAYER_OUT_F32, RF_LAYER_TF32 = 1, 2
 
@@ -79,6 +79,21 @@ class LayerProgram:
         x = self.im2col(src, k, stride, pad, kpad)
         return self.conv(x, FoldedConv(w, bn, 1, pad=0), relu=True)
 
+    def stem7_fused(self, src, weight, bn):
+        """fp16 engine only: the ResNet-50 stem (7x7 / 2 / pad 3, 3 -> 64, BN, ReLU) in one kernel that builds the patches
+        in shared memory (no im2col matrix in HBM).  Same packed weights as ``stem(kalign=64)``."""
+        from .model import FoldedConv
+        cout, cin, k, _ = weight.shape
+        assert (cout, cin, k) == (64, 3, 7) and self.chan[src] == 3
+        w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+        w = torch.nn.functional.pad(w, (0, 192 - k * k * cin)).reshape(cout, 192, 1, 1)
+        fc = FoldedConv(w, bn, 1, pad=0)
+        self.ops.append((RF_OP_STEM7, src, -1, 3, 64, 7, 2, 3, 1, fc))
+        self._keep.append(fc)
+        self.chan.append(64)
+        self.f16_only = True
+        return len(self.chan) - 1
+
     def blur(self, src, stride):
         c = self.chan[src]
         self.ops.append((RF_OP_BLUR, src, -1, c, c, 3, stride, 1, 0, None))
@@ -103,13 +118,13 @@ class LayerProgram:
         # reads and around RF_LAYER_OUT_F32 / RF_LAYER_TF32 convs)
         esize = [4] * n_t
         if f16:
-            esize[0] = 4 if self.ops[0][0] == RF_OP_IM2COL else 2
+            esize[0] = 4 if self.ops[0][0] in (RF_OP_IM2COL, RF_OP_STEM7) else 2
             for i, o in enumerate(self.ops):
                 fl = self.flags.get(i, 0)
                 esize[i + 1] = 4 if fl else 2
                 if fl & RF_LAYER_TF32:
                     assert esize[o[1]] == 4, "a TF32 layer under the fp16 engine needs an fp32 input (out_f32 on its producer)"
-                elif o[0] != RF_OP_IM2COL:
+                elif o[0] not in (RF_OP_IM2COL, RF_OP_STEM7):
                     assert esize[o[1]] == 2 and (o[2] < 0 or esize[o[2]] == 2), "fp16 layer fed by an fp32 tensor"
         elems = [sum(h * w for h, w in hws[t]) * self.chan[t] * esize[t] for t in range(n_t)]        # BYTES per tensor
         # slot assignment: slot 0 = external input; others from a free list
@@ -150,6 +165,7 @@ class LayerProgram:
         """x: ops.Ragged input -> (output buffer view [P_out, C_out] valid until the next run, out_hw)."""
         need_cuda(x.data)
         f16 = int(engine) == 2
+        assert f16 or not getattr(self, "f16_only", False), "this program uses fp16-engine-only layers"
         key = (tuple(x.hw), str(x.data.device), f16)
         if key not in self._compiled:
             if len(self._compiled) > 16:
