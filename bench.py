@@ -147,7 +147,7 @@ def run_b200(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     rf.model.set_engine(args.engine)
-    rf.outil.corr_precision = 0 if args.engine == "fp32" else 1
+    rf.outil.corr_precision = {"fp32": 0, "tf32": 1}.get(args.engine, 2)      # exact fp32 / 3xTF32 / fp16 split
     rsd, fe_sd, nf_sd, nm_sd = states()
     net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
            "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}
@@ -284,15 +284,21 @@ def run_b200(args, rank, world, local):
     tensor_peak = pk["bf16_tflops"]
     traffic = None
     try:                                   # dram__bytes_read+write of the dominant launch, from the committed ncu --set full capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_corr_ncu.json")))
-        traffic = prof["launches"][0]["dram_traffic_bytes"] if args.engine != "fp32" else None
+        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_f16_ncu.json"}[rf.outil.corr_precision]
+        prof = json.load(open(os.path.join(ROOT, "profiles", pf)))
+        traffic = [l for l in prof["launches"] if "tc_kernel" in l["kernel"]][0]["dram_traffic_bytes"]
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % ("tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)" if args.engine != "fp32" else "corr_argmax_kernel (fp32 SIMT)"),
+    prec = rf.outil.corr_precision
+    kname = {0: "corr_argmax_kernel (fp32 SIMT)", 1: "tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)",
+             2: "tc_kernel<128,MODE_CORR,f16> (fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
+    # tensor work actually issued per algorithmic MAC: 3 MMAs either way; kind::tf32 runs at half the bf16/f16 rate
+    executed = {0: None, 1: (3 * tf) / (tensor_peak / 2), 2: (3 * tf) / tensor_peak}[prec]
+    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % kname,
                 "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
-                "peak_source": pk["src"] + " bf16 dense GEMM (burst); kind::tf32 peaks at half of it and this kernel issues 3 TF32 MMAs per "
-                               "algorithmic MAC (3xTF32), i.e. executed-TF32 fraction = 6 x frac",
-                "executed_tf32_frac": (3 * tf) / (tensor_peak / 2) if args.engine != "fp32" else None,
+                "peak_source": pk["src"] + " bf16 dense GEMM (burst); fp32-grade scores need 3 tensor MMAs per algorithmic MAC (split operands), "
+                               "so the executed tensor fraction is 3 x frac for the fp16 split (6 x for 3xTF32, whose MMAs run at half rate)",
+                "executed_tensor_frac": executed,
                 "ms_per_launch": corr_ms, "algorithmic_gflop": flops / 1e9, "algorithmic_mb": abytes / 1e6,
                 "hbm_gbs_achieved": abytes / (corr_ms * 1e-3) / 1e9, "hbm_frac": abytes / (corr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                 "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": int(len(m1)),
@@ -316,7 +322,8 @@ def run_b200(args, rank, world, local):
         line = {
             "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 trunk (fp32 accumulate) + tf32 fine-flow nets + 3xTF32 correlation"}[args.engine], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 (conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; 3xTF32 correlation; fp32/fp64 RANSAC)",
+                      "f16-trunk": "f16 trunk + tf32 fine-flow nets"}[args.engine], "data": "synthetic",
             "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded i %% %d" % world,
                        "l2": "256 MiB buffer written between steps (L2 flush); activations per step also exceed the 126 MB L2",
                        "preprocessing": "7-scale LANCZOS pyramid on the GPU (bit-exact PIL emulation)",
@@ -334,8 +341,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "tf32"), choices=["fp32", "tf32", "f16"],
-                    help="tf32: tcgen05 convs (TF32 operands, the reference's own cuDNN default on sm_80+) + 3xTF32 correlation; fp32: exact-FMA SIMT engine")
+    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "f16"), choices=["fp32", "tf32", "f16", "f16-trunk"],
+                    help="f16: tcgen05 convs with fp16 activations (default); tf32: tcgen05 convs with fp32 activations / TF32 operands; f16-trunk: fp16 trunk + tf32 fine-flow nets; fp32: exact-FMA SIMT engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the ~140 kernels of a pair one by one instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -49,7 +49,9 @@ uint64_t rf_launch_count(void);
  * utils/outil.py:32-45 mutualMatching, fused: the NA x NB score matrix is never
  * written.  featA [NA][C], featB [NB][C] (K-major rows = one feature vector).
  * Outputs: idx1/idx2 (int64, capacity >= min(NA,NB)) sorted by idx1, *count.
- * precision: 0 = exact fp32 FMA (SIMT), 1 = 3xTF32 on tcgen05 tensor cores. */
+ * precision: 0 = exact fp32 FMA (SIMT); 1 = 3xTF32 on tcgen05 tensor cores (hi*hi + lo*hi + hi*lo, C % 32 == 0);
+ * 2 = fp16 split on tcgen05 (x = hi + lo * 2^-11 in fp16, cross terms in a second TMEM accumulator, C % 64 == 0): the
+ * same 22 significand bits with half the MMAs per channel. */
 size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precision);
 int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
                       int64_t* idx1_out, int64_t* idx2_out, int* count_out,

@@ -396,7 +396,7 @@ using namespace rf;
 
 // tensor-core engines live in gemm_tc.cu
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st);
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision);
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
 bool rf_conv2d_tc_supported(const ConvParams& p);
@@ -407,7 +407,7 @@ static size_t keys_bytes(int NA, int NB) {
 
 extern "C" size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precision) {
     size_t b = keys_bytes(NA, NB) + 256;
-    if (precision == 1) b += rf_corr_tc_workspace(NA > 0 ? NA : 0, NB > 0 ? NB : 0, C);
+    if (precision == 1 || precision == 2) b += rf_corr_tc_workspace(NA > 0 ? NA : 0, NB > 0 ? NB : 0, C);
     return b;
 }
 
@@ -422,8 +422,9 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
     unsigned long long* colbest = rowbest + NA;
     RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
     if (NA > 0 && NB > 0) {
-        if (precision == 1) {
-            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, static_cast<unsigned char*>(ws) + keys_bytes(NA, NB), st);
+        RF_REQUIRE(precision >= 0 && precision <= 2, "rf_corr_mutual_nn: precision is 0 (fp32 SIMT), 1 (3xTF32) or 2 (fp16 split)");
+        if (precision >= 1) {
+            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, static_cast<unsigned char*>(ws) + keys_bytes(NA, NB), st, precision);
             if (rc) return rc;
         } else {
             dim3 grid((NB + 127) / 128, (NA + BM - 1) / BM);

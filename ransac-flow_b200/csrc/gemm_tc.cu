@@ -188,6 +188,33 @@ __device__ __forceinline__ void umma_3xtf32_x4(uint32_t tmem_d, uint64_t ahi, ui
         "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %5, t;\n\t}"
         ::"r"(tmem_d), "l"(ahi), "l"(alo), "l"(bhi), "l"(blo), "r"(idesc), "r"(acc_first) : "memory");
 }
+// fp16 split (correlation precision 2): x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11).  Per K = 16 step
+// lo*hi and hi*lo accumulate into `tmem_x` (scaled by 2^11), hi*hi into `tmem_d`; the epilogue adds tmem_x * 2^-11.  Same
+// 22 significand bits as 3xTF32 at half the MMAs per channel (K = 16 per instruction instead of 8).
+__device__ __forceinline__ void umma_f16split_x4(uint32_t tmem_d, uint32_t tmem_x, uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo,
+                                                 uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 ah, al, bh, bl;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %5, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %6, p;\n\t"
+        "add.u64 ah, %2, 2;\n\tadd.u64 al, %3, 2;\n\tadd.u64 bh, %4, 2;\n\tadd.u64 bl, %5, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %6, t;\n\t"
+        "add.u64 ah, %2, 4;\n\tadd.u64 al, %3, 4;\n\tadd.u64 bh, %4, 4;\n\tadd.u64 bl, %5, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %6, t;\n\t"
+        "add.u64 ah, %2, 6;\n\tadd.u64 al, %3, 6;\n\tadd.u64 bh, %4, 6;\n\tadd.u64 bl, %5, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], al, bh, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bl, %6, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %6, t;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_x), "l"(ahi), "l"(alo), "l"(bhi), "l"(blo), "r"(idesc), "r"(acc_first) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -409,11 +436,13 @@ tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, MODE, DEEP>;
     constexpr int STAGES = Cfg::STAGES, NSPLIT = Cfg::NSPLIT;
     constexpr int BK = tc_bk<F16>();              // channels per 128-byte K block
-    static_assert(!(F16 && MODE == MODE_CORR), "the correlation runs 3xTF32");
+    constexpr bool CORR16 = F16 && MODE == MODE_CORR;                 // correlation with fp16-split operands: two accumulators
+    constexpr int TMEM_COLS = CORR16 ? 2 * Cfg::TMEM_COLS : Cfg::TMEM_COLS;
+    static_assert(TMEM_COLS <= 512, "TMEM");
     // fp16 convolutions: ring depth per layer (<= STAGES) and, for layers with a residual, a dedicated staging area
     // behind the ring that the producer fills at CTA start (more bytes in flight per SM, one DRAM latency less per CTA)
-    const int NST = F16 ? p.stages : STAGES;
-    const bool res_pf = F16 && p.res_pf;
+    const int NST = (F16 && MODE == MODE_CONV) ? p.stages : STAGES;
+    const bool res_pf = F16 && MODE == MODE_CONV && p.res_pf;
     constexpr int RES_BYTES = (BN / 64) * TC_A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -453,7 +482,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
         tma_prefetch_desc(&p.mapB);
         if (NSPLIT == 2) { tma_prefetch_desc(&p.mapAlo); tma_prefetch_desc(&p.mapBlo); }
     }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -495,7 +524,9 @@ tc_kernel(const __grid_constant__ TcParams p) {
                 const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
                 const uint32_t sb = sa + NSPLIT * TC_A_BYTES;
                 const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
-                if (NSPLIT == 2) {
+                if (CORR16) {
+                    umma_f16split_x4(tmem_base, tmem_base + BN, da, make_desc_sw128(sa + TC_A_BYTES), db, make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
+                } else if (NSPLIT == 2) {
                     umma_3xtf32_x4(tmem_base, da, make_desc_sw128(sa + TC_A_BYTES), db, make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
                 } else {
                     umma_x4<F16>(tmem_base, da, db, idesc, it != 0 ? 1u : 0u);      // 4 x (UMMA_K = 8 tf32 / 16 fp16 = 32 bytes)
@@ -525,6 +556,12 @@ tc_kernel(const __grid_constant__ TcParams p) {
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(trow + c * 32, v);
+                if (CORR16) {                       // + the cross terms, accumulated at 2^11 scale in the second accumulator
+                    uint32_t x[32];
+                    tmem_ld32(trow + BN + c * 32, x);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(x[j]), 0.00048828125f, __uint_as_float(v[j])));
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int col = n0 + c * 32 + j;
@@ -554,7 +591,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 
@@ -1222,6 +1259,22 @@ __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restri
     lo[i] = l;
 }
 
+// fp16 split for the correlation (precision 2): hi = fp16(x), lo = fp16((x - hi) * 2^11)
+__global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(x + i);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * 2048.f, (v.y - f0.y) * 2048.f);
+    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * 2048.f, (v.w - f1.y) * 2048.f);
+    uint2 ho, lo2;
+    ho.x = *reinterpret_cast<const uint32_t*>(&h0); ho.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo2.x = *reinterpret_cast<const uint32_t*>(&l0); lo2.y = *reinterpret_cast<const uint32_t*>(&l1);
+    hi[i] = ho;
+    lo[i] = lo2;
+}
+
 // ------------------------------------------------------------------ host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1395,7 +1448,7 @@ static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st
         attr[dev] = true;
     }
     dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
-    if (F16) {
+    if (F16 && MODE == MODE_CONV) {
         // ring depth: never more stages than K blocks; with a prefetched residual two stages (+ its staging) keep two or
         // three CTAs resident per SM
         TcParams q = p;
@@ -1537,21 +1590,31 @@ int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* 
 size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }
 
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st) {
-    RF_REQUIRE((C % TC_BK) == 0, "rf_corr_mutual_nn: precision=1 needs C % 32 == 0");
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision) {
+    const bool f16 = precision == 2;
+    RF_REQUIRE((C % (f16 ? TC_BK_F16 : TC_BK)) == 0, "rf_corr_mutual_nn: precision 1 needs C % 32 == 0, precision 2 C % 64 == 0");
     uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
-    float* Ahi = reinterpret_cast<float*>(base);
-    float* Alo = Ahi + (size_t)NA * C;
-    float* Bhi = Alo + (size_t)NA * C;
-    float* Blo = Bhi + (size_t)NB * C;
+    const size_t esz = f16 ? 2 : 4;
+    char* Ahi = reinterpret_cast<char*>(base);
+    char* Alo = Ahi + (size_t)NA * C * esz;
+    char* Bhi = Alo + (size_t)NA * C * esz;
+    char* Blo = Bhi + (size_t)NB * C * esz;
     long long na4 = (long long)NA * C / 4, nb4 = (long long)NB * C / 4;
-    split_tf32_kernel<<<(unsigned)((na4 + 255) / 256), 256, 0, st>>>((const float4*)featA, (float4*)Ahi, (float4*)Alo, na4);
-    RF_LAUNCHED();
-    split_tf32_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (float4*)Bhi, (float4*)Blo, nb4);
-    RF_LAUNCHED();
-    // optional 256-wide score tiles (RF_CORR_BN=256): the featA slab (hi + lo) is fetched once per 256 columns
-    const bool wide = NB > 128 && corr_tile_n() == 256;
+    if (f16) {
+        split_f16_kernel<<<(unsigned)((na4 + 255) / 256), 256, 0, st>>>((const float4*)featA, (uint2*)Ahi, (uint2*)Alo, na4);
+        RF_LAUNCHED();
+        split_f16_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (uint2*)Bhi, (uint2*)Blo, nb4);
+        RF_LAUNCHED();
+    } else {
+        split_tf32_kernel<<<(unsigned)((na4 + 255) / 256), 256, 0, st>>>((const float4*)featA, (float4*)Ahi, (float4*)Alo, na4);
+        RF_LAUNCHED();
+        split_tf32_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (float4*)Bhi, (float4*)Blo, nb4);
+        RF_LAUNCHED();
+    }
+    // optional 256-wide score tiles (RF_CORR_BN=256, 3xTF32 only): the featA slab (hi + lo) is fetched once per 256 columns
+    const bool wide = !f16 && NB > 128 && corr_tile_n() == 256;
     const int BN = wide ? 256 : 128;
+    const unsigned bk = f16 ? TC_BK_F16 : TC_BK, es = (unsigned)esz;
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.nimg = 1;
@@ -1560,13 +1623,14 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     p.tile_start[0] = 0;
     for (int i = 1; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = p.tiles_x[0];
     p.Ho[0] = 1; p.Wo[0] = NA;
-    int rc = get_map(&p.mapA[0], Ahi, (unsigned long long)C, (unsigned long long)NA, 1, TC_BK, 128, 1);
-    if (!rc) rc = get_map(&p.mapAlo, Alo, (unsigned long long)C, (unsigned long long)NA, 1, TC_BK, 128, 1);
-    if (!rc) rc = get_map(&p.mapB, Bhi, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
-    if (!rc) rc = get_map(&p.mapBlo, Blo, (unsigned long long)C, (unsigned long long)NB, 0, TC_BK, BN, 0);
+    int rc = get_map(&p.mapA[0], Ahi, (unsigned long long)C, (unsigned long long)NA, 1, bk, 128, 1, 1, es);
+    if (!rc) rc = get_map(&p.mapAlo, Alo, (unsigned long long)C, (unsigned long long)NA, 1, bk, 128, 1, 1, es);
+    if (!rc) rc = get_map(&p.mapB, Bhi, (unsigned long long)C, (unsigned long long)NB, 0, bk, BN, 0, 1, es);
+    if (!rc) rc = get_map(&p.mapBlo, Blo, (unsigned long long)C, (unsigned long long)NB, 0, bk, BN, 0, 1, es);
     if (rc) return rc;
     p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
+    if (f16) return launch_tc<128, MODE_CORR, false, true>(p, p.tiles_x[0], (NB + 127) / 128, st);
     if (wide) return launch_tc<256, MODE_CORR, false>(p, p.tiles_x[0], (NB + 255) / 256, st);
     return launch_tc<128, MODE_CORR, false>(p, p.tiles_x[0], (NB + 127) / 128, st);
 }

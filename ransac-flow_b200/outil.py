@@ -15,7 +15,7 @@ from ._lib import RFError
 
 RF_RANSAC_OK, RF_RANSAC_NONE, RF_RANSAC_NO_MODEL, RF_RANSAC_TOO_FEW = 0, 1, 2, 3
 
-# precision of the dense correlation: 0 = exact fp32 FMA, 1 = 3xTF32 on tcgen05
+# precision of the dense correlation: 0 = exact fp32 FMA, 1 = 3xTF32 on tcgen05, 2 = fp16 split on tcgen05
 corr_precision = 0
 
 

@@ -36,7 +36,7 @@ if which == "corr":
     g = torch.Generator(device="cpu").manual_seed(0)
     A = torch.nn.functional.normalize(torch.rand(13065, 1024, generator=g), dim=1).to(dev)
     B = torch.nn.functional.normalize(torch.rand(1200, 1024, generator=g), dim=1).to(dev)
-    for prec in (1, 0):
+    for prec in (2, 1, 0):
         m, mn = timed(lambda: rf.ops.corr_mutual_nn(A, B, prec))
         print("corr_mutual_nn precision=%d: mean %.1f us, min %.1f us -> %.1f TFLOP/s algorithmic" % (prec, m * 1e3, mn * 1e3, 32.108544 / m))
 elif which == "ransac":

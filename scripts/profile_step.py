@@ -14,7 +14,7 @@ import ransac_flow_b200 as rf  # noqa: E402
 
 engine = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 rf.model.set_engine(engine)
-rf.outil.corr_precision = 0 if engine == "fp32" else 1
+rf.outil.corr_precision = {"fp32": 0, "tf32": 1}.get(engine, 2)
 rsd, fe_sd, nf_sd, nm_sd = bench.states()
 net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
        "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}

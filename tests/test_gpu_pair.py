@@ -110,7 +110,7 @@ def test_get_flow_all_vs_reference(rf):
 @pytest.fixture
 def engine(request, rf):
     rf.model.set_engine(request.param)
-    rf.outil.corr_precision = 1 if request.param in ("tf32", "f16") else 0
+    rf.outil.corr_precision = {"fp32": 0, "tf32": 1, "f16": 2}[request.param]
     yield request.param
     rf.model.set_engine("fp32")
     rf.outil.corr_precision = 0

@@ -98,7 +98,11 @@ def test_tf32_engine_falls_back_to_fp32_kernels_for_unsupported_shapes(rf):
 
 @pytest.mark.parametrize("C,NA,NB,seed", [(1024, 13065, 1200, 0), (1024, 2107, 300, 1), (64, 129, 127, 2), (256, 1, 1, 4),
                                            (1024, 300, 1200, 5), (32, 500, 260, 6)])
-def test_corr_3xtf32_matches_fp32_argmax(rf, C, NA, NB, seed):
+@pytest.mark.parametrize("precision", [1, 2])
+def test_corr_3xtf32_matches_fp32_argmax(rf, C, NA, NB, seed, precision):
+    """precision 1 = 3xTF32, 2 = fp16 split (hi + lo * 2^-11, two TMEM accumulators): both carry 22 significand bits."""
+    if precision == 2 and C % 64:
+        pytest.skip("fp16 split needs C % 64 == 0")
     rs = np.random.RandomState(seed)
     A = np.abs(rs.randn(C, NA)).astype(np.float32)
     B = np.abs(rs.randn(C, NB)).astype(np.float32)
@@ -109,13 +113,13 @@ def test_corr_3xtf32_matches_fp32_argmax(rf, C, NA, NB, seed):
     if NB > 2:
         B[:, 1] = 0
     o1, o2, score = OO.mutualMatching(A, B, return_score=True)
-    rf.outil.corr_precision = 1
+    rf.outil.corr_precision = precision
     try:
         i1, i2 = rf.outil.mutualMatching(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
     finally:
         rf.outil.corr_precision = 0
     nd = check_same(i1.cpu().numpy(), i2.cpu().numpy(), o1, o2, score)
-    print("3xTF32 vs fp32 oracle: %d matches, %d differing (ambiguous) pairs" % (len(o1), nd))
+    print("precision %d vs fp32 oracle: %d matches, %d differing (ambiguous) pairs" % (precision, len(o1), nd))
     # and against the library's own exact-fp32 kernel
     j1, j2 = rf.outil.mutualMatching(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
     check_same(i1.cpu().numpy(), i2.cpu().numpy(), j1.cpu().numpy(), j2.cpu().numpy(), score)
@@ -128,10 +132,12 @@ def test_corr_kitti_shape_both_engines_agree(rf):
     A = torch.nn.functional.normalize(torch.rand(25747, 1024, generator=g), dim=1).cuda()
     B = torch.nn.functional.normalize(torch.rand(8250, 1024, generator=g), dim=1).cuda()
     B[:3000] = torch.nn.functional.normalize(A[torch.randperm(25747, generator=g)[:3000].cuda()] + 0.05 * torch.rand(3000, 1024, device="cuda"), dim=1)
-    i1, i2, n1 = rf.ops.corr_mutual_nn(A, B, 1)
     j1, j2, n2 = rf.ops.corr_mutual_nn(A, B, 0)
-    n1, n2 = int(n1.item()), int(n2.item())
-    a = set(zip(i1[:n1].tolist(), i2[:n1].tolist()))
+    n2 = int(n2.item())
     b = set(zip(j1[:n2].tolist(), j2[:n2].tolist()))
-    print("KITTI-shaped correlation: %d / %d pairs, %d differ" % (n1, n2, len(a ^ b)))
-    assert n1 >= 3000 and len(a ^ b) <= 2          # arg-max ties below fp32 accumulation noise only
+    for precision in (1, 2):
+        i1, i2, n1 = rf.ops.corr_mutual_nn(A, B, precision)
+        n1 = int(n1.item())
+        a = set(zip(i1[:n1].tolist(), i2[:n1].tolist()))
+        print("KITTI-shaped correlation, precision %d: %d / %d pairs, %d differ" % (precision, n1, n2, len(a ^ b)))
+        assert n1 >= 3000 and len(a ^ b) <= 2          # arg-max ties below fp32 accumulation noise only
