@@ -48,6 +48,7 @@ struct alignas(64) TcParams {
     int R, S, pad, stride, Cin, Cout, relu, round_out, tma_epi;
     int stages;                           // fp16 tap-streaming kernel: ring depth chosen per layer on the host
     int res_pf;                           // fp16 tap-streaming kernel: residual tile prefetched into its own staging at CTA start
+    int raster_n;                         // convolutions: channel tiles fastest in the grid (CTAs of one pixel tile run together)
     const float* bias;
     const float* residual;
     float* y;
@@ -458,8 +459,9 @@ tc_kernel(const __grid_constant__ TcParams p) {
     // ---- tile decode ----
     // conv: blockIdx.x = pixel tile, blockIdx.y = channel tile.  corr: swapped, so that the CTAs sharing one 128-row
     // slab of featA (1 MB of hi+lo) are co-resident and the slab is fetched from DRAM once
-    const int mtile = (MODE == MODE_CORR) ? blockIdx.y : blockIdx.x;
-    const int ntile = (MODE == MODE_CORR) ? blockIdx.x : blockIdx.y;
+    const bool nfast = (MODE == MODE_CORR) || p.raster_n;
+    const int mtile = nfast ? blockIdx.y : blockIdx.x;
+    const int ntile = nfast ? blockIdx.x : blockIdx.y;
     int img = 0;
 #pragma unroll
     for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mtile >= p.tile_start[j]) ? 1 : 0;
@@ -765,7 +767,12 @@ struct TileCoord { int img, ox0, oy0, tw, n0; };
 template <bool HALO>
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int tiles_m, int BN) {
     TileCoord c;
-    const int nt = t / tiles_m, mt = t - nt * tiles_m;      // pixel tiles fastest: co-running CTAs share the weight tile
+    int nt = t / tiles_m, mt = t - nt * tiles_m;            // pixel tiles fastest: co-running CTAs share the weight tile
+    if (p.raster_n) {                                       // channel tiles fastest: co-running CTAs share the pixel tile
+        const int tiles_n = (p.Cout + BN - 1) / BN;
+        mt = t / tiles_n;
+        nt = t - mt * tiles_n;
+    }
     int img = 0;
 #pragma unroll
     for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mt >= p.tile_start[j]) ? 1 : 0;
@@ -1104,6 +1111,143 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// PIPELINED persistent fp16 convolution (tap streaming: 1x1 of any stride, 3x3 / stride 2).  ncu on the one-tile-per-CTA
+// kernel (profiles/r1_f16_layers_ncu.json) shows every such layer latency bound - DRAM <= 55 %, L2 <= 32 %, tensor
+// pipe <= 28 %, a CTA lives ~10 us for ~1 us of work: operand load -> MMA -> residual load -> epilogue -> store drain
+// are serial inside a CTA and at most four CTAs fit an SM.  Here one CTA per SM software-pipelines tiles:
+//   warp 0     : TMA producer - residual tile of tile i (into staging buffer i & 1, as soon as the store of tile i-2
+//                has read it out) and the K blocks of tile i into an NS-deep ring; runs ahead across tiles;
+//   warp 1     : MMA issuer - accumulator i & 1 of two, so tile i+1 multiplies while tile i drains;
+//   warps 2-5  : epilogue group 0 (even tiles), warps 6-9: epilogue group 1 (odd tiles) - TMEM -> + bias, + residual,
+//                ReLU -> fp16 swizzled staging -> TMA store; two groups so that two epilogues overlap.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct PipeCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int NS = BN == 128 ? 4 : 6;
+    static constexpr int STG = (BN / 64) * TC_A_BYTES;                      // fp16 staging: BN / 64 boxes of 16 KB
+    static constexpr int OFF_STG = NS * STAGE_BYTES;
+    static constexpr int DATA_BYTES = OFF_STG + 2 * STG;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int THREADS = 320;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(PipeCfg<BN>::THREADS, 1)
+tc_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) {
+    using Cfg = PipeCfg<BN>;
+    constexpr int NS = Cfg::NS, NBOX = BN / 64, BK = TC_BK_F16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sStg = smem + Cfg::OFF_STG;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* empty = full + NS;
+    uint64_t* tmem_full = empty + NS;           // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
+    uint64_t* res_full = tmem_empty + 2;        // [2]
+    uint64_t* stg_free = res_full + 2;          // [2] the group's leader: the TMA store has read the staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = tiles_m * tiles_n;
+    const int kc = p.Cin / BK;
+    const int KI = p.R * p.S * kc;
+    const bool has_res = p.residual != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); mbar_init(&res_full[i], 1); mbar_init(&stg_free[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t cnt = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const TileCoord c = decode_tile<false>(p, t, tiles_m, BN);
+                if (has_res) {
+                    const uint32_t g = ti & 1;
+                    mbar_wait(&stg_free[g], ((ti >> 1) & 1) ^ 1);        // tile ti-2's store has read this buffer (passes at once for ti < 2)
+                    mbar_expect_tx(&res_full[g], Cfg::STG);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_3d(sStg + g * Cfg::STG + b * TC_A_BYTES, &p.mapR[c.img], &res_full[g], c.n0 + b * 64, c.ox0, c.oy0);
+                }
+                for (int it = 0; it < KI; ++it, ++cnt) {
+                    const int st = cnt % NS;
+                    mbar_wait(&empty[st], ((cnt / NS) & 1) ^ 1);
+                    uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                    const int tap = it / kc, cc = it - tap * kc;
+                    const int r = tap / p.S, sx = tap - r * p.S;
+                    tma_load_3d(sbase, &p.mapA[c.img], &full[st], cc * BK, c.ox0 * p.stride + sx - p.pad, c.oy0 * p.stride + r - p.pad);
+                    tma_load_2d(sbase + TC_A_BYTES, &p.mapB, &full[st], tap * p.Cin + cc * BK, c.n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (whole warp, warp-uniform) ===============================
+        constexpr uint32_t idesc = make_idesc_f16(BN);
+        uint32_t cnt = 0, ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * BN;
+            for (int it = 0; it < KI; ++it, ++cnt) {
+                const int st = cnt % NS;
+                mbar_wait(&full[st], (cnt / NS) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+                umma_f16_x4(tacc, make_desc_sw128(sa), make_desc_sw128(sa + TC_A_BYTES), idesc, it != 0 ? 1u : 0u);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(&tmem_full[buf]);
+        }
+    } else {
+        // =============================== epilogue groups ===============================
+        const uint32_t g = (uint32_t)(warp - 2) >> 2;                       // 0: warps 2-5, 1: warps 6-9
+        const int q = warp & 3;                                             // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+        uint8_t* stg = sStg + g * Cfg::STG;
+        uint32_t k = 0;                                                     // this group's tile counter
+        for (int t = blockIdx.x + (int)g * (int)gridDim.x; t < total; t += 2 * gridDim.x, ++k) {
+            const TileCoord c = decode_tile<false>(p, t, tiles_m, BN);
+            // the leader comes here only after the previous store has read the staging buffer
+            if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            mbar_wait(&tmem_full[g], k & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(&res_full[g], k & 1);
+            const uint32_t trow = tmem_base + g * BN + ((uint32_t)(q * 32) << 16);
+            epi_rows_f16<BN>(p.bias, p.Cout, p.relu, has_res, c.n0, m, trow, stg);
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[g]);                                    // accumulator drained (128 arrivals)
+            fence_proxy_async();
+            if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (leader) {
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b)
+                    if (c.n0 + b * 64 < p.Cout) tma_store_3d(&p.mapY[c.img], stg + b * TC_A_BYTES, c.n0 + b * 64, c.ox0, c.oy0);
+                tma_store_commit_and_wait_read();
+                if (has_res) mbar_arrive(&stg_free[g]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // ResNet-50 stem, fused (engine 2): conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
 // fp16 NHWC, without materialising the im2col matrix (350 MB written and read back per pair at 480x640 x 8 images).
 // One CTA = 16 x 8 output pixels x 64 channels:
@@ -1376,12 +1520,8 @@ static int persist_mode() {
 }
 
 static int respf_mode() {
-    static int m = -1;
-    if (m < 0) {
-        const char* e = getenv("RF_TC_RESPF");    // fp16 1x1 convs with a residual: prefetch the residual tile at CTA start.
-        m = e ? atoi(e) : 0;                      // Measured (profiles/README.md): -2 % end to end - the extra staging costs a resident CTA
-    }
-    return m;
+    const char* e = getenv("RF_TC_RESPF");    // fp16 1x1 convs with a residual: prefetch the residual tile at CTA start.
+    return e ? atoi(e) : 0;                     // Measured (profiles/README.md): -2 % end to end - the extra staging costs a resident CTA
 }
 
 static int resb_mode() {
@@ -1403,6 +1543,32 @@ static int launch_resb(const TcParams& p, int tiles_m, cudaStream_t st) {
     }
     const int grid = tiles_m < num_sms() ? tiles_m : num_sms();
     tc_resb_kernel<F16><<<grid, TC_THREADS, ResBCfg<F16>::SMEM_BYTES, st>>>(p, tiles_m);
+    RF_LAUNCHED();
+    return 0;
+}
+
+static int raster_mode() {
+    const char* e = getenv("RF_TC_RASTER");    // 1 (default): channel tiles fastest for the tap-streaming conv kernels - the CTAs
+    return e ? atoi(e) : 1;                     // of one pixel tile run together (A once from HBM, whole output rows); +2 % per pair
+}
+
+static int pipe_mode() {
+    const char* e = getenv("RF_TC_PIPE");    // pipelined persistent kernel for the fp16 tap-streaming convs: 0 never, 1 always,
+    return e ? atoi(e) : 2;                     // 2 (default) where it measured faster: >= 4 K blocks and >= 2 tiles per SM
+}
+
+template <int BN>
+static int launch_pipe(const TcParams& p, int tiles_m, int tiles_n, cudaStream_t st) {
+    using Cfg = PipeCfg<BN>;
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        RF_CUDA(cudaFuncSetAttribute(tc_pipe_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr[dev] = true;
+    }
+    const int total = tiles_m * tiles_n;
+    const int grid = total < num_sms() ? total : num_sms();
+    tc_pipe_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles_m, tiles_n);
     RF_LAUNCHED();
     return 0;
 }
@@ -1447,7 +1613,7 @@ static int launch_tc(const TcParams& p, int tiles, int ntiles_n, cudaStream_t st
                                      Cfg::SMEM_BYTES + (F16 ? (BN / 64) * TC_A_BYTES : 0)));
         attr[dev] = true;
     }
-    dim3 grid = (MODE == MODE_CORR) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
+    dim3 grid = (MODE == MODE_CORR || p.raster_n) ? dim3(ntiles_n, tiles) : dim3(tiles, ntiles_n);
     if (F16 && MODE == MODE_CONV) {
         // ring depth: never more stages than K blocks; with a prefetched residual two stages (+ its staging) keep two or
         // three CTAs resident per SM
@@ -1533,11 +1699,15 @@ int rf_conv2d_tc(const ImgSet& set, const ConvParams& cp, const void* w_tc, cuda
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu; p.round_out = cp.round_out;
     p.bias = cp.bias; p.residual = cp.residual; p.y = cp.y;
     const int nt = (cp.Cout + BN - 1) / BN;
+    p.raster_n = (raster_mode() && tiles <= 65535) ? 1 : 0;
     const bool deep = cp.K >= 512;                                   // >= 16 K-steps of 32 fp32 channels (8 of 64 fp16)
     if (f16 && out32) return BN == 128 ? launch_halo<128, true, true>(p, tiles, nt, hmode, st) : launch_halo<64, true, true>(p, tiles, nt, hmode, st);
     if (f16) {
         if (hmode && resb_mode() && cp.Cin == 64 && cp.Cout == 64) return launch_resb<true>(p, tiles, st);
         if (hmode) return BN == 128 ? launch_halo<128, true>(p, tiles, nt, hmode, st) : launch_halo<64, true>(p, tiles, nt, hmode, st);
+        const int pm = pipe_mode();
+        if (pm == 1 || (pm == 2 && cp.K >= 4 * TC_BK_F16 && (long long)tiles * nt >= 2ll * num_sms()))
+            return BN == 128 ? launch_pipe<128>(p, tiles, nt, st) : launch_pipe<64>(p, tiles, nt, st);
         if (BN == 128) return deep ? launch_tc<128, MODE_CONV, true, true>(p, tiles, nt, st) : launch_tc<128, MODE_CONV, false, true>(p, tiles, nt, st);
         return deep ? launch_tc<64, MODE_CONV, true, true>(p, tiles, nt, st) : launch_tc<64, MODE_CONV, false, true>(p, tiles, nt, st);
     }

@@ -76,6 +76,36 @@ def test_conv2d_f16(rf, cin, cout, k, sizes, relu, res, stride):
         assert err <= F16_TOL * max(1.0, r.abs().max().item()), (err, r.abs().max().item())
 
 
+@pytest.mark.parametrize("env", [{"RF_TC_PIPE": "1"}, {"RF_TC_PIPE": "0", "RF_TC_RASTER": "0"}, {"RF_TC_PIPE": "0", "RF_TC_RESPF": "1"},
+                                 {"RF_TC_PIPE": "1", "RF_TC_RASTER": "0"}])
+@pytest.mark.parametrize("cin,cout,k,stride,res,sizes", [
+    (64, 256, 1, 1, True, [(120, 160), (60, 80), (33, 47)]), (256, 64, 1, 1, False, [(120, 160), (31, 17)]),
+    (512, 1024, 1, 2, False, [(60, 80), (30, 44)]), (128, 128, 3, 2, False, [(64, 96), (37, 41)]),
+    (256, 1024, 1, 1, True, [(30, 40), (60, 80), (15, 20)]), (128, 512, 1, 1, True, [(9, 7)])])
+def test_conv2d_f16_kernel_variants(rf, monkeypatch, env, cin, cout, k, stride, res, sizes):
+    """The same fp16 convolutions through every tap-streaming kernel variant (the switches are read per call): the
+    pipelined persistent kernel (two epilogue groups, producer-issued residual prefetch), pixel-tile-fastest raster,
+    and the residual-prefetching one-tile kernel.  All must agree with the fp32 reference."""
+    for kk, v in env.items():
+        monkeypatch.setenv(kk, v)
+    g = torch.Generator().manual_seed(cin + cout + k + stride)
+    xs = [torch.randn(1, cin, h, w, generator=g).half() for h, w in sizes]
+    w = (torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)).half()
+    bias = torch.randn(cout, generator=g)
+    refs = [F.conv2d(x.float(), w.float(), bias, stride=stride, padding=k // 2) for x in xs]
+    rs = [torch.randn(r.shape, generator=g).half() for r in refs] if res else None
+    if res:
+        refs = [a + b.float() for a, b in zip(refs, rs)]
+    refs = [F.relu(r) for r in refs]
+    wtc = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().cuda()
+    y = rf.ops.conv2d(ragged(rf, xs), None, bias.cuda(), cout, k, stride, k // 2, True, ragged(rf, rs) if res else None,
+                      rf.ops.ENGINE_F16, wtc)
+    torch.cuda.synchronize()
+    for i, r in enumerate(refs):
+        err = (y.image(i).float().cpu() - r).abs().max().item()
+        assert err <= F16_TOL * max(1.0, r.abs().max().item()), (env, err, r.abs().max().item())
+
+
 def test_f16_engine_saturates_and_rejects_unsupported_shapes(rf):
     x = torch.full((1, 64, 4, 4), 200.0).half()
     w = torch.full((8, 64, 1, 1), 100.0).half()
