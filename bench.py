@@ -92,12 +92,12 @@ def usable_cores():
 
 
 def make_pairs(n):
-    from oracle import synth
+    import synthdata as synth                        # workload generator (repo root); nothing under oracle/ on the B200 arm
     return [synth.make_pair(i, 480, 640)[:2] for i in range(n)]
 
 
 def states():
-    from oracle import synth
+    import synthdata as synth
     return (synth.resnet50_conv4_state(0), synth.feature_extractor_state(0), synth.net_flow_coarse_state(1),
             synth.net_matchability_state(2))
 
@@ -149,34 +149,51 @@ def run_b200(args, rank, world, local):
     rf.model.set_engine(args.engine)
     rf.outil.corr_precision = {"fp32": 0, "tf32": 1}.get(args.engine, 2)      # exact fp32 / 3xTF32 / fp16 split
     rsd, fe_sd, nf_sd, nm_sd = states()
-    net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
-           "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}
-    net["netFeatCoarse"].load_state_dict(fe_sd)
-    net["netFlowCoarse"].load_state_dict(nf_sd)
-    net["netMatch"].load_state_dict(nm_sd)
-    for m in net.values():
-        m.cuda()
-        m.eval()
-    coarse = rf.CoarseAlignA(7, 1000, 0.05, "Homography", 480, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
-    coarse.device_preproc = True
+
+    def make_models():
+        """A fresh (CoarseAlign, networks) set: same weights, own activation buffers / pair state."""
+        net = {"netFeatCoarse": rf.model.FeatureExtractor(), "netCorr": rf.model.CorrNeigh(7),
+               "netFlowCoarse": rf.model.NetFlowCoarse(7), "netMatch": rf.model.NetMatchability(7)}
+        net["netFeatCoarse"].load_state_dict(fe_sd)
+        net["netFlowCoarse"].load_state_dict(nf_sd)
+        net["netMatch"].load_state_dict(nm_sd)
+        for m in net.values():
+            m.cuda()
+            m.eval()
+        c = rf.CoarseAlignA(7, 1000, 0.05, "Homography", 480, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+        c.device_preproc = True
+        return c, net
+    coarse, net = make_models()
+    lanes = max(1, args.lanes) if args.graph else 1
     pairs = make_pairs(4)
     host = [(torch.from_numpy(s).pin_memory(), torch.from_numpy(t).pin_memory()) for s, t in pairs]
     resident = [(s.to(dev), t.to(dev)) for s, t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    aligner = rf.pipeline.GraphedAligner(coarse, net) if args.graph else None
+    aligner = rf.pipeline.GraphedAligner(coarse, net) if (args.graph and lanes == 1) else None
+    multi = rf.pipeline.ConcurrentAligner(make_models, lanes) if lanes > 1 else None
+    if multi is not None:
+        multi.prepare(*resident[0])
+
+    def replayed():
+        return (aligner.replayed_kernels if aligner is not None else 0) + (multi.replayed_kernels if multi is not None else 0)
 
     def step(i, from_host):
-        s, t = (host if from_host else resident)[i % len(host)]                     # pinned host (H2D inside) or HBM-resident
-        if aligner is not None:
-            out = aligner(s, t)                                                     # one CUDA-graph launch + one pinned D2H
+        """One step = `lanes` pairs (1 unless --lanes): returns the list of per-pair results."""
+        src = host if from_host else resident                                       # pinned host (H2D inside) or HBM-resident
+        if multi is not None:
+            outs = multi([src[(i * lanes + k) % len(src)] for k in range(lanes)])    # lanes graphs side by side, one D2H each
         else:
-            if from_host:
-                s, t = s.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
-            torch.manual_seed(1000)                                                 # evalKITTI/evaluation.py:182
-            out = rf.pipeline.align_pair_single(coarse, net, s, t)                  # results come back as numpy (one pinned D2H)
+            s, t = src[i % len(src)]
+            if aligner is not None:
+                outs = [aligner(s, t)]                                              # one CUDA-graph launch + one pinned D2H
+            else:
+                if from_host:
+                    s, t = s.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
+                torch.manual_seed(1000)                                             # evalKITTI/evaluation.py:182
+                outs = [rf.pipeline.align_pair_single(coarse, net, s, t)]           # results come back as numpy (one pinned D2H)
         flush.zero_()                                                               # L2 flush between steps
-        return out
+        return outs
 
     def timed(from_host, K, W):
         for i in range(W):
@@ -185,24 +202,26 @@ def run_b200(args, rank, world, local):
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = rf._lib.launch_count() + (aligner.replayed_kernels if aligner is not None else 0)
+        l0 = rf._lib.launch_count() + replayed()
         e0.record()
         recs = []
         for i in range(K):
-            out = step(i, from_host)
-            recs.append(shard.pack_record(rank + world * i, out["H"][0] if len(out["H"]) else None, status=0 if len(out["H"]) else 1))
-        allr = shard.gather_records(recs, K * world, world, dev)                    # the one collective: per-pair records
+            outs = step(i, from_host)
+            for k, out in enumerate(outs):
+                recs.append(shard.pack_record(rank + world * (i * lanes + k), out["H"][0] if len(out["H"]) else None,
+                                              status=0 if len(out["H"]) else 1))
+        allr = shard.gather_records(recs, K * lanes * world, world, dev)            # the one collective: per-pair records
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
-        launches = rf._lib.launch_count() + (aligner.replayed_kernels if aligner is not None else 0) - l0
+        launches = rf._lib.launch_count() + replayed() - l0
         if world > 1:
             tmax = torch.tensor([ms], device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
-        return ms, launches, out, allr
+        return ms, launches, outs[-1], allr
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -210,7 +229,7 @@ def run_b200(args, rank, world, local):
     ms_dev, launches, out, _ = timed(False, args.steps, args.warmup)
     ms_e2e, _, out, allr = timed(True, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
-    assert allr.shape[0] == args.steps * world
+    assert allr.shape[0] == args.steps * lanes * world
 
     # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, mean of 5 pairs) ----
     def stage_breakdown():
@@ -249,7 +268,9 @@ def run_b200(args, rank, world, local):
             acc += np.array([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
                              evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
         return {n: round(float(v / reps), 4) for n, v in zip(names, acc)}
-    stages = stage_breakdown() if rank == 0 else None
+    if rank != 0:
+        return                                       # the per-kernel sections below are rank 0's (no collective inside)
+    stages = stage_breakdown()
 
     # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----
     fa, ft = coarse._feats_rows, coarse._featt_rows
@@ -266,7 +287,7 @@ def run_b200(args, rank, world, local):
     torch.cuda.synchronize()
     corr_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     # RANSAC alone (latency-bound: reported as us/call)
-    nm = int(out.get("nbMatch", len(coarse.match1)))
+    nm = int(coarse._match_count.item())             # matches of the pair `coarse` holds (set by stage_breakdown)
     m1, m2 = coarse.match1[:nm].contiguous(), coarse.match2[:nm].contiguous()
     smp = torch.randint(len(m1), (1000, 4), device=dev)
     for _ in range(3):
@@ -282,16 +303,18 @@ def run_b200(args, rank, world, local):
     abytes = 4.0 * CFEAT * (NA + NB) + 16.0 * len(m1)
     tf = flops / (corr_ms * 1e-3) / 1e12
     tensor_peak = pk["bf16_tflops"]
+    prec = rf.outil.corr_precision
+    v2 = prec == 2 and rf._lib.lib.rf_corr_mutual_nn_launches(2) == 3
     traffic = None
     try:                                   # dram__bytes_read+write of the dominant launch, from the committed ncu --set full capture
-        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_f16_ncu.json"}[rf.outil.corr_precision]
+        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_pipe_ncu.json" if v2 else "r1_corr_f16_ncu.json"}[rf.outil.corr_precision]
         prof = json.load(open(os.path.join(ROOT, "profiles", pf)))
-        traffic = [l for l in prof["launches"] if "tc_kernel" in l["kernel"]][0]["dram_traffic_bytes"]
+        traffic = [l for l in prof["launches"] if "tc_kernel" in l["kernel"] or "tc_corr_pipe" in l["kernel"]][0]["dram_traffic_bytes"]
     except Exception:  # noqa: BLE001
         pass
-    prec = rf.outil.corr_precision
     kname = {0: "corr_argmax_kernel (fp32 SIMT)", 1: "tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)",
-             2: "tc_kernel<128,MODE_CORR,f16> (fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
+             2: ("tc_corr_pipe_kernel (persistent, two TMEM accumulator pairs; " if v2 else "tc_kernel<128,MODE_CORR,f16> (")
+                + "fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
     # tensor work actually issued per algorithmic MAC: 3 MMAs either way; kind::tf32 runs at half the bf16/f16 rate
     executed = {0: None, 1: (3 * tf) / (tensor_peak / 2), 2: (3 * tf) / tensor_peak}[prec]
     roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % kname,
@@ -320,16 +343,17 @@ def run_b200(args, rank, world, local):
     if rank == 0:
         d2h = int(480 * 640 * 4 + out["flowDown8"].nbytes + out["matchDown8"].nbytes + 9 * 4 + 64)
         line = {
-            "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": world * lanes * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 (conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; 3xTF32 correlation; fp32/fp64 RANSAC)",
                       "f16-trunk": "f16 trunk + tf32 fine-flow nets"}[args.engine], "data": "synthetic",
-            "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": 1, "parallelism": "pairs sharded i %% %d" % world,
+            "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": lanes, "parallelism": "pairs sharded i %% %d" % world,
                        "l2": "256 MiB buffer written between steps (L2 flush); activations per step also exceed the 126 MB L2",
                        "preprocessing": "7-scale LANCZOS pyramid on the GPU (bit-exact PIL emulation)",
-                       "launch": "one CUDA graph per pair" if args.graph else "stream launches"},
-            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 2 * 480 * 640 * 3,
-                    "d2h_bytes_per_step": d2h},
+                       "launch": ("one CUDA graph per pair" + (", %d independent pairs in flight on %d streams" % (lanes, lanes) if lanes > 1 else ""))
+                                 if args.graph else "stream launches"},
+            "e2e": {"value": world * lanes * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": lanes * 2 * 480 * 640 * 3,
+                    "d2h_bytes_per_step": lanes * d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages_ms": stages,
         }
         print(json.dumps(line))
@@ -344,6 +368,8 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "f16"), choices=["fp32", "tf32", "f16", "f16-trunk"],
                     help="f16: tcgen05 convs with fp16 activations (default); tf32: tcgen05 convs with fp32 activations / TF32 operands; f16-trunk: fp16 trunk + tf32 fine-flow nets; fp32: exact-FMA SIMT engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("RF_LANES", "1")),
+                    help="independent pairs in flight per GPU and step (each with its own CUDA graph, models' activation buffers and stream)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the ~140 kernels of a pair one by one instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)

@@ -51,8 +51,14 @@ uint64_t rf_launch_count(void);
  * Outputs: idx1/idx2 (int64, capacity >= min(NA,NB)) sorted by idx1, *count.
  * precision: 0 = exact fp32 FMA (SIMT); 1 = 3xTF32 on tcgen05 tensor cores (hi*hi + lo*hi + hi*lo, C % 32 == 0);
  * 2 = fp16 split on tcgen05 (x = hi + lo * 2^-11 in fp16, cross terms in a second TMEM accumulator, C % 64 == 0): the
- * same 22 significand bits with half the MMAs per channel. */
+ * same 22 significand bits with half the MMAs per channel.
+ * Precision 2 has two kernel sequences with identical outputs (environment RF_CORR_V2, read per call): the persistent
+ * correlation kernel (one CTA per SM, two TMEM accumulator pairs, arg-max epilogue overlapped with the next tile's
+ * MMAs) between a fused split / key-zeroing launch and a fused mutual-test + compaction launch (3 launches), or the
+ * one-tile-per-CTA kernel with separate helpers (6 launches).  rf_corr_mutual_nn_launches() (host only) tells which
+ * one a call with this precision would run now: it returns the number of launches. */
 size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precision);
+int rf_corr_mutual_nn_launches(int precision);
 int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
                       int64_t* idx1_out, int64_t* idx2_out, int* count_out,
                       void* ws, size_t ws_bytes, int precision, void* stream);
@@ -149,6 +155,12 @@ int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mas
  * round_tf32_out = 2 stores fp16 (out then holds N*h*w*ldo halves: the operand of the engine-2 heads) */
 int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
                        float* out, void* stream);
+/* CorrNeigh(x, y) -> out_xy AND CorrNeigh(y, x) -> out_yx in one launch: the two volumes every PredFlowMask computes
+ * (evaluation/evalHpatch/evaluation.py:29-30; evalCorr/evaluation.py:36-37) hold the same dot products,
+ * out_yx[p][d] = out_xy[p+d][-d], so each product is computed once and stored twice (bit-identical to two
+ * rf_corr_neigh_nhwc calls). */
+int rf_corr_neigh_pair_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
+                            float* out_xy, float* out_yx, void* stream);
 /* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */
 int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream);
 /* model/model.py:306: sigmoid, NHWC [P][1] -> [P] */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "rf_launch_count": (C.c_uint64, []),
     "rf_l2norm_f16_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),
     "rf_corr_mutual_nn_workspace": (sz, [i32, i32, i32, i32]),
+    "rf_corr_mutual_nn_launches": (i32, [i32]),
     "rf_corr_mutual_nn": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, i32, vp]),
     "rf_ransac_workspace": (sz, [i32]),
     "rf_ransac_homography": (i32, [vp, vp, i32, vp, vp, i32, f32, i32, vp, vp, vp, vp, vp, sz, vp]),
@@ -31,6 +32,7 @@ SIGNATURES = {
     "rf_blur_downsample_nhwc": (i32, [vp, i32, vp, i32, i32, vp, vp]),
     "rf_l2norm_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),
     "rf_corr_neigh_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "rf_corr_neigh_pair_nhwc": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "rf_run_layers": (i32, [vp, i32, vp, i32, vp, i32, vp]),
     "rf_softmax_flow": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "rf_sigmoid": (i32, [vp, i64, vp, vp]),

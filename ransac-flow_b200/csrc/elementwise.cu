@@ -285,8 +285,12 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, long long P, int
 // model/model.py:129-160 CorrNeigh: out[n,r,c,i*k+j] = sum_ch x[n,r,c,ch] * y[n,r+i-k/2,c+j-k/2,ch]
 // one warp per output pixel, lanes over channels, k*k shuffled reductions
 // ---------------------------------------------------------------------------
+// `out2` (nullable): ALSO write CorrNeigh(y, x) there.  corr21[p][d] = <y_p, x_(p+d)> = <x_(p+d), y_p> = corr12[p+d][-d], the
+// same dot product (fmaf(a, b, acc) with a and b swapped is the same operation, so the bits are equal): the warp of
+// pixel p scatters every in-image tap to corr21[p+d][-d] and writes the zero of its own out-of-image taps, which covers
+// every entry of corr21 exactly once.  One launch instead of two (evaluation/evalHpatch/evaluation.py:29-30).
 __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k, int ldo, int round_out,
-                                  float* __restrict__ out) {
+                                  float* __restrict__ out, float* __restrict__ out2) {
     long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     long long P = (long long)N * h * w;
@@ -320,13 +324,27 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
             if (lane == 0) {
                 if (round_out == 2) reinterpret_cast<__half*>(out)[pix * ldo + i * k + j] = __float2half_rn(acc);
                 else out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
+                if (out2 != nullptr) {
+                    const bool inside = yr >= 0 && yr < h && yc >= 0 && yc < w;
+                    // inside: entry (p + d, -d) of the swapped volume; outside: this pixel's own (zero) entry (p, d)
+                    const long long q = inside ? (((long long)n * h + yr) * w + yc) : pix;
+                    const int e = inside ? (k - 1 - i) * k + (k - 1 - j) : i * k + j;
+                    if (round_out == 2) reinterpret_cast<__half*>(out2)[q * ldo + e] = __float2half_rn(acc);
+                    else out2[q * ldo + e] = round_out ? round_tf32(acc) : acc;
+                }
             }
         }
     }
     if (round_out == 2) {
-        for (int c = k * k + lane; c < ldo; c += 32) reinterpret_cast<__half*>(out)[pix * ldo + c] = __float2half_rn(0.f);
+        for (int c = k * k + lane; c < ldo; c += 32) {
+            reinterpret_cast<__half*>(out)[pix * ldo + c] = __float2half_rn(0.f);
+            if (out2 != nullptr) reinterpret_cast<__half*>(out2)[pix * ldo + c] = __float2half_rn(0.f);
+        }
     } else {
-        for (int c = k * k + lane; c < ldo; c += 32) out[pix * ldo + c] = 0.f;
+        for (int c = k * k + lane; c < ldo; c += 32) {
+            out[pix * ldo + c] = 0.f;
+            if (out2 != nullptr) out2[pix * ldo + c] = 0.f;
+        }
     }
 }
 
@@ -790,7 +808,18 @@ extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, 
     RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out);
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out, nullptr);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_corr_neigh_pair_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
+                                       float* out_xy, float* out_yx, void* stream) {
+    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_pair_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
+    RF_REQUIRE(out_xy != nullptr && out_yx != nullptr && out_xy != out_yx, "rf_corr_neigh_pair_nhwc: two distinct outputs");
+    long long P = (long long)N * h * w;
+    if (P == 0) return 0;
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out_xy, out_yx);
     RF_LAUNCHED();
     return 0;
 }

@@ -209,6 +209,55 @@ mutual_compact_kernel(const unsigned long long* __restrict__ flagged, int NA, lo
     if (tid == 0) *count = s_off;
 }
 
+// mutual test + order-preserving compaction in ONE single-CTA kernel (the two kernels above fused; used behind the
+// persistent correlation kernel).  Warp w owns a contiguous block of rows; pass 1 counts its mutual pairs with coalesced
+// loads and ballots, the 32 warp totals are scanned, pass 2 recomputes the flags (L1 / L2 hits) and writes the pairs in
+// row order.  rowbest / colbest are left untouched.
+__device__ __forceinline__ bool mutual_pair(const unsigned long long* __restrict__ rowbest, const unsigned long long* __restrict__ colbest,
+                                            int i, int NA, uint32_t& j) {
+    if (i >= NA) return false;
+    const unsigned long long rk = __ldg(rowbest + i);
+    if (rk == 0ull) return false;
+    j = key_index(rk);
+    const float v = key_value(rk);
+    const unsigned long long ck = __ldg(colbest + j);
+    return key_index(ck) == (uint32_t)i && (__fmul_rn(v, v) > 0.f);              // keepMax > 0 (utils/outil.py:41-42)
+}
+
+__global__ void __launch_bounds__(1024)
+mutual_flag_compact_kernel(const unsigned long long* __restrict__ rowbest, const unsigned long long* __restrict__ colbest, int NA,
+                           long long* __restrict__ idx1, long long* __restrict__ idx2, int* __restrict__ count) {
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (((NA + 31) / 32) + 31) / 32 * 32;          // rows per warp, a multiple of 32
+    const int begin = warp * chunk;
+    int cnt = 0;
+#pragma unroll 4
+    for (int b = 0; b < chunk; b += 32) {
+        uint32_t j = 0;
+        const bool f = mutual_pair(rowbest, colbest, begin + b + lane, NA, j);
+        cnt += __popc(__ballot_sync(0xffffffffu, f));
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int v = s_cnt[w]; off += (w < warp) ? v : 0; total += v; }
+#pragma unroll 4
+    for (int b = 0; b < chunk; b += 32) {
+        uint32_t j = 0;
+        const int i = begin + b + lane;
+        const bool f = mutual_pair(rowbest, colbest, i, NA, j);
+        const uint32_t bal = __ballot_sync(0xffffffffu, f);
+        if (f) {
+            const int o = off + __popc(bal & ((1u << lane) - 1u));
+            idx1[o] = i;
+            idx2[o] = (long long)j;
+        }
+        off += __popc(bal);
+    }
+    if (tid == 0) *count = total;
+}
+
 // ---------------------------------------------------------------------------
 // implicit-GEMM convolution
 // ---------------------------------------------------------------------------
@@ -396,7 +445,8 @@ using namespace rf;
 
 // tensor-core engines live in gemm_tc.cu
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision);
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2);
+int rf_corr_v2_mode();
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
 bool rf_conv2d_tc_supported(const ConvParams& p);
@@ -411,6 +461,11 @@ extern "C" size_t rf_corr_mutual_nn_workspace(int NA, int NB, int C, int precisi
     return b;
 }
 
+extern "C" int rf_corr_mutual_nn_launches(int precision) {
+    if (precision == 2 && rf_corr_v2_mode() != 0) return 3;          // split+zero, persistent correlation, flag+compact
+    return precision == 0 ? 4 : 6;                                   // memset, [split, split,] correlation, flag, compact
+}
+
 extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, int C,
                                  int64_t* idx1_out, int64_t* idx2_out, int* count_out,
                                  void* ws, size_t ws_bytes, int precision, void* stream) {
@@ -420,17 +475,25 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
     cudaStream_t st = as_stream(stream);
     unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(ws);
     unsigned long long* colbest = rowbest + NA;
-    RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
+    // precision 2 with RF_CORR_V2: persistent correlation kernel; its split launch zeroes the keys, and the mutual test
+    // and the compaction are one kernel (3 launches instead of 6)
+    const bool v2 = precision == 2 && NA > 0 && NB > 0 && rf_corr_v2_mode() != 0;
+    if (!v2) RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
     if (NA > 0 && NB > 0) {
         RF_REQUIRE(precision >= 0 && precision <= 2, "rf_corr_mutual_nn: precision is 0 (fp32 SIMT), 1 (3xTF32) or 2 (fp16 split)");
         if (precision >= 1) {
-            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, static_cast<unsigned char*>(ws) + keys_bytes(NA, NB), st, precision);
+            int rc = rf_corr_argmax_tc(featA, NA, featB, NB, C, rowbest, colbest, static_cast<unsigned char*>(ws) + keys_bytes(NA, NB), st, precision, v2);
             if (rc) return rc;
         } else {
             dim3 grid((NB + 127) / 128, (NA + BM - 1) / BM);
             corr_argmax_kernel<<<grid, 256, 0, st>>>(featA, NA, featB, NB, C, rowbest, colbest);
             RF_LAUNCHED();
         }
+    }
+    if (v2) {
+        mutual_flag_compact_kernel<<<1, 1024, 0, st>>>(rowbest, colbest, NA, (long long*)idx1_out, (long long*)idx2_out, count_out);
+        RF_LAUNCHED();
+        return 0;
     }
     if (NA > 0) {
         mutual_flag_kernel<<<(NA + 255) / 256, 256, 0, st>>>(rowbest, colbest, NA);

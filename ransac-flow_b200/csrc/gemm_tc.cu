@@ -1248,6 +1248,196 @@ tc_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// PERSISTENT correlation + mutual-NN kernel (utils/outil.py:34-37, precision 2 = fp16 split).  ncu on the
+// one-tile-per-CTA kernel (profiles/r1_corr_f16_ncu.json): 17.8 us per 128 x 128 score tile for 6.3 us of MMAs - one
+// CTA per SM (192 KB of stages), so TMEM allocation, the first TMA round trip and the whole arg-max epilogue are
+// serial with the K loop.  Here one CTA per SM walks its tiles (N-tiles fastest: the CTAs sharing a featA slab run
+// together) with the three roles decoupled:
+//   warp 0    : TMA producer, 3-stage ring of (A hi, A lo, B hi, B lo) K blocks, runs ahead into the next tile;
+//   warp 1    : MMA issuer, TWO accumulator pairs (hi*hi | cross terms) x 128 columns = all 512 TMEM columns: tile
+//               i+1 multiplies while tile i drains;
+//   warps 2-5 : epilogue.  Row arg-max thread-local straight from TMEM; column arg-max 32 columns at a time through
+//               a 128 x 33 float transposition buffer of its own (the stages are busy), four row quarters combined
+//               through 1 KB of keys, one atomicMax per column and per row of the tile as before.
+// Same arithmetic per score as tc_kernel<128, MODE_CORR, false, true> (same MMAs in the same order, same fma of the
+// cross-term accumulator), same (score, smallest index) ordering => identical match lists.
+// ------------------------------------------------------------------------------------------------------------
+struct CorrPipeCfg {
+    static constexpr int BN = 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * (TC_A_BYTES + B_BYTES);            // 64 KB
+    static constexpr int NS = 3;
+    static constexpr int LD = 33;                                             // transposition pitch: conflict-free both ways
+    static constexpr int OFF_T = NS * STAGE_BYTES;
+    static constexpr int T_BYTES = 128 * LD * 4;
+    static constexpr int OFF_P = OFF_T + T_BYTES;
+    static constexpr int P_BYTES = 4 * 32 * 8;
+    static constexpr int DATA_BYTES = OFF_P + P_BYTES;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 256;
+    static constexpr int TMEM_COLS = 512;
+};
+static_assert(CorrPipeCfg::SMEM_BYTES <= 227 * 1024, "shared memory");
+static_assert((CorrPipeCfg::OFF_P % 8) == 0 && (CorrPipeCfg::DATA_BYTES % 8) == 0, "alignment");
+
+// two 32-column TMEM loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t t0, uint32_t (&a)[32], uint32_t t1, uint32_t (&b)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+          "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+          "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+        : "r"(t0) : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+          "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]),
+          "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]),
+          "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(t1) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ unsigned long long pack_ord(uint32_t ord, uint32_t idx) {
+    return ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_corr_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) {
+    using Cfg = CorrPipeCfg;
+    constexpr int NS = Cfg::NS, BN = Cfg::BN, BK = TC_BK_F16, LD = Cfg::LD;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sT = reinterpret_cast<float*>(smem + Cfg::OFF_T);
+    unsigned long long* sP = reinterpret_cast<unsigned long long*>(smem + Cfg::OFF_P);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* empty = full + NS;
+    uint64_t* tmem_full = empty + NS;           // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = tiles_m * tiles_n;
+    const int KI = p.Cin / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapAlo); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapBlo);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int mt = t / tiles_n, nt = t - mt * tiles_n;
+                const int row0 = mt * 128, n0 = nt * BN;
+                for (int it = 0; it < KI; ++it, ++cnt) {
+                    const int st = cnt % NS;
+                    mbar_wait(&empty[st], ((cnt / NS) & 1) ^ 1);
+                    uint8_t* sbase = smem + st * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full[st], Cfg::STAGE_BYTES);
+                    const int c0 = it * BK;
+                    tma_load_3d(sbase, &p.mapA[0], &full[st], c0, row0, 0);
+                    tma_load_2d(sbase + 2 * TC_A_BYTES, &p.mapB, &full[st], c0, n0);
+                    tma_load_3d(sbase + TC_A_BYTES, &p.mapAlo, &full[st], c0, row0, 0);
+                    tma_load_2d(sbase + 2 * TC_A_BYTES + Cfg::B_BYTES, &p.mapBlo, &full[st], c0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (whole warp, warp-uniform) ===============================
+        constexpr uint32_t idesc = make_idesc_f16(BN);
+        uint32_t cnt = 0, ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator pair
+            tc_fence_after();
+            const uint32_t td = tmem_base + buf * (2 * BN), tx = td + BN;
+            for (int it = 0; it < KI; ++it, ++cnt) {
+                const int st = cnt % NS;
+                mbar_wait(&full[st], (cnt / NS) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + 2 * TC_A_BYTES;
+                umma_f16split_x4(td, tx, make_desc_sw128(sa), make_desc_sw128(sa + TC_A_BYTES), make_desc_sw128(sb),
+                                 make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(&tmem_full[buf]);
+        }
+    } else {
+        // =============================== epilogue (warps 2..5) ===============================
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                // accumulator row = featA row inside the tile
+        const int tid = (warp - 2) * 32 + lane;     // 0..127 for the column pass
+        const int cj = tid & 31, qq = tid >> 5;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            const int mt = t / tiles_n, nt = t - mt * tiles_n;
+            const int row0 = mt * 128, n0 = nt * BN;
+            const int rmax = min(128, p.NA - row0);
+            mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + buf * (2 * BN) + ((uint32_t)(q * 32) << 16);
+            uint32_t rbo = 0u, rbi = 0u;            // row best: ordered score (0 = none yet), column
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32], x[32];
+                tmem_ld32x2(trow + c * 32, v, trow + BN + c * 32, x);
+                if (c == BN / 32 - 1) {             // last TMEM read of this tile: hand the accumulators back
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[buf]);
+                }
+                const int colbase = n0 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = fmaf(__uint_as_float(x[j]), 0.00048828125f, __uint_as_float(v[j]));     // + cross terms * 2^-11
+                    sT[m * LD + j] = s;
+                    const uint32_t o = f2ord(s);
+                    if (colbase + j < p.NB && o > rbo) { rbo = o; rbi = (uint32_t)(colbase + j); }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // column arg-max of this 128 x 32 block: thread (qq, cj) scans rows qq*32 .. +31 of column cj
+                uint32_t cbo = 0u, cbi = 0u;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int r = qq * 32 + rr;
+                    const uint32_t o = f2ord(sT[r * LD + cj]);
+                    if (r < rmax && o > cbo) { cbo = o; cbi = (uint32_t)(row0 + r); }
+                }
+                sP[qq * 32 + cj] = cbo ? pack_ord(cbo, cbi) : 0ull;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid < 32) {
+                    unsigned long long k0 = sP[tid], k1 = sP[32 + tid], k2 = sP[64 + tid], k3 = sP[96 + tid];
+                    k0 = k1 > k0 ? k1 : k0;
+                    k2 = k3 > k2 ? k3 : k2;
+                    k0 = k2 > k0 ? k2 : k0;
+                    if (colbase + tid < p.NB && k0 != 0ull) atomicMax(p.colbest + colbase + tid, k0);
+                }
+            }
+            if (m < rmax && rbo != 0u) atomicMax(p.rowbest + row0 + m, pack_ord(rbo, rbi));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // ResNet-50 stem, fused (engine 2): conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
 // fp16 NHWC, without materialising the im2col matrix (350 MB written and read back per pair at 480x640 x 8 images).
 // One CTA = 16 x 8 output pixels x 64 channels:
@@ -1417,6 +1607,29 @@ __global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict
     lo2.x = *reinterpret_cast<const uint32_t*>(&l0); lo2.y = *reinterpret_cast<const uint32_t*>(&l1);
     hi[i] = ho;
     lo[i] = lo2;
+}
+
+// Both feature matrices in ONE launch (fp16 split as above; hi/lo of A then hi/lo of B are consecutive in the workspace),
+// and the arg-max keys zeroed by the first threads: replaces a memset node and two split launches in front of the
+// persistent correlation kernel.
+__global__ void split_f16_all_kernel(const float4* __restrict__ A, const float4* __restrict__ B, uint2* __restrict__ Ahi, uint2* __restrict__ Alo,
+                                     uint2* __restrict__ Bhi, uint2* __restrict__ Blo, long long na4, long long nb4,
+                                     unsigned long long* __restrict__ keys, long long nkeys) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nkeys) keys[i] = 0ull;
+    if (i >= na4 + nb4) return;
+    const bool isA = i < na4;
+    const long long k = isA ? i : i - na4;
+    const float4 v = __ldg((isA ? A : B) + k);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * 2048.f, (v.y - f0.y) * 2048.f);
+    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * 2048.f, (v.w - f1.y) * 2048.f);
+    uint2 ho, lo2;
+    ho.x = *reinterpret_cast<const uint32_t*>(&h0); ho.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo2.x = *reinterpret_cast<const uint32_t*>(&l0); lo2.y = *reinterpret_cast<const uint32_t*>(&l1);
+    (isA ? Ahi : Bhi)[k] = ho;
+    (isA ? Alo : Blo)[k] = lo2;
 }
 
 // ------------------------------------------------------------------ host side: tensor maps
@@ -1759,9 +1972,35 @@ int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* 
 
 size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }
 
+// RF_CORR_V2 (read per call): 1 = precision 2 runs the persistent correlation kernel with the fused split /
+// key-zeroing launch in front and the fused flag + compaction kernel behind (3 launches); 0 = the one-tile-per-CTA
+// kernel with separate memset / split / split / flag / compact launches (6).  Identical outputs.
+constexpr int RF_CORR_V2_DEFAULT = 0;
+int rf_corr_v2_mode() {
+    const char* e = getenv("RF_CORR_V2");
+    return e ? atoi(e) : RF_CORR_V2_DEFAULT;
+}
+
+static int launch_corr_pipe(const TcParams& p, int tiles_m, int tiles_n, cudaStream_t st) {
+    using Cfg = CorrPipeCfg;
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        RF_CUDA(cudaFuncSetAttribute(tc_corr_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr[dev] = true;
+    }
+    const long long total = (long long)tiles_m * tiles_n;
+    const int grid = total < num_sms() ? (int)total : num_sms();
+    tc_corr_pipe_kernel<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles_m, tiles_n);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// v2 (precision 2 only): the caller has NOT zeroed rowbest / colbest (contiguous, NA + NB keys): the split launch does it
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision) {
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2) {
     const bool f16 = precision == 2;
+    RF_REQUIRE(!v2 || f16, "rf_corr_mutual_nn: the persistent correlation kernel is the fp16-split one (precision 2)");
     RF_REQUIRE((C % (f16 ? TC_BK_F16 : TC_BK)) == 0, "rf_corr_mutual_nn: precision 1 needs C % 32 == 0, precision 2 C % 64 == 0");
     uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
     const size_t esz = f16 ? 2 : 4;
@@ -1770,7 +2009,13 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     char* Bhi = Alo + (size_t)NA * C * esz;
     char* Blo = Bhi + (size_t)NB * C * esz;
     long long na4 = (long long)NA * C / 4, nb4 = (long long)NB * C / 4;
-    if (f16) {
+    if (v2) {
+        RF_REQUIRE(colbest == rowbest + NA, "rf_corr_mutual_nn: arg-max keys must be contiguous");
+        const long long nkeys = (long long)NA + NB, n = na4 + nb4 > nkeys ? na4 + nb4 : nkeys;
+        split_f16_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)featA, (const float4*)featB, (uint2*)Ahi, (uint2*)Alo,
+                                                                            (uint2*)Bhi, (uint2*)Blo, na4, nb4, rowbest, nkeys);
+        RF_LAUNCHED();
+    } else if (f16) {
         split_f16_kernel<<<(unsigned)((na4 + 255) / 256), 256, 0, st>>>((const float4*)featA, (uint2*)Ahi, (uint2*)Alo, na4);
         RF_LAUNCHED();
         split_f16_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>((const float4*)featB, (uint2*)Bhi, (uint2*)Blo, nb4);
@@ -1800,6 +2045,7 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     if (rc) return rc;
     p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
+    if (v2) return launch_corr_pipe(p, p.tiles_x[0], (NB + 127) / 128, st);
     if (f16) return launch_tc<128, MODE_CORR, false, true>(p, p.tiles_x[0], (NB + 127) / 128, st);
     if (wide) return launch_tc<256, MODE_CORR, false>(p, p.tiles_x[0], (NB + 255) / 256, st);
     return launch_tc<128, MODE_CORR, false>(p, p.tiles_x[0], (NB + 127) / 128, st);

@@ -120,6 +120,20 @@ def corr_neigh(x, y, k, ldo=None, round_tf32=False):
     return Ragged(out, x.hw)
 
 
+def corr_neigh_pair(x, y, k, ldo=None, round_tf32=False):
+    """``corr_neigh(x, y)`` and ``corr_neigh(y, x)`` from ONE launch (each dot product computed once, stored in both
+    volumes).  Returns (corr_xy, corr_yx, both): ``both`` is the [2P, ldo] buffer the two halves live in, i.e. the
+    two-image batch the matchability head runs on, without a concatenation copy."""
+    need_cuda(x.data, y.data)
+    assert x.data.dtype == torch.float32 and y.data.dtype == torch.float32 and x.hw == y.hw
+    h, w = x.hw[0]
+    ldo = k * k if ldo is None else int(ldo)
+    P = x.data.shape[0]
+    buf = torch.empty((2 * P, ldo), device=x.data.device, dtype=torch.float16 if int(round_tf32) == 2 else torch.float32)
+    check(lib.rf_corr_neigh_pair_nhwc(ptr(x.data), ptr(y.data), x.n, h, w, x.C, k, ldo, int(round_tf32), ptr(buf[:P]), ptr(buf[P:]), stream()))
+    return Ragged(buf[:P], x.hw), Ragged(buf[P:], x.hw), Ragged(buf, x.hw + x.hw)
+
+
 def softmax_flow(logits, k):
     need_cuda(logits.data)
     h, w = logits.hw[0]

@@ -6,6 +6,8 @@ restated on the library's kernels (no file IO, no metrics: those stay in the dri
   align_pair   : evaluation/evalHpatch/evaluation.py:172-243
   getFlow_all  : evaluation/evalHpatch/getResults.py:16-63 (after the np.load calls)
 """
+import os
+
 import numpy as np
 import torch
 
@@ -19,6 +21,15 @@ def base_grid(h, w, device="cuda"):
     gy = torch.linspace(-1, 1, steps=h, device=device).view(1, -1, 1, 1).expand(1, h, w, 1)
     gx = torch.linspace(-1, 1, steps=w, device=device).view(1, 1, -1, 1).expand(1, h, w, 1)
     return torch.cat((gx, gy), dim=3).contiguous()
+
+
+CORR_NEIGH_PAIR_DEFAULT = "0"
+
+
+def _corr_neigh_pair():
+    """RF_CORR_NEIGH_PAIR=1: PredFlowMask computes corr12 and corr21 with one launch (``ops.corr_neigh_pair``) instead of two
+    launches and a concatenation.  Bit-identical volumes (tests/test_gpu_ops.py)."""
+    return os.environ.get("RF_CORR_NEIGH_PAIR", CORR_NEIGH_PAIR_DEFAULT) != "0"
 
 
 def fine_features(netFeatCoarse, img):
@@ -37,10 +48,13 @@ def PredFlowMask_device(IsTensor, featt, flowCoarse, size, network, with_match21
         k = network["netCorr"].kernelSize
         ld = network["netFlowCoarse"].CORR_LD
         tc = model.fine_engine()            # 0 plain fp32, 1 TF32-rounded, 2 fp16: the operand type of the heads
-        corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
-        corr21 = ops.corr_neigh(fs, ft, k, ld, tc)
+        if _corr_neigh_pair():                  # both volumes from one launch, already laid out as the two-image batch
+            corr12, corr21, both = ops.corr_neigh_pair(ft, fs, k, ld, tc)
+        else:
+            corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
+            corr21 = ops.corr_neigh(fs, ft, k, ld, tc)
+            both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
-        both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
         mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch
         flow12, match, _ = ops.compose_fine(flowDown8, mboth[0:1], mboth[1:2] if with_match21 else None, flowCoarse,
                                             clamp=True, align_corners=align_corners)
@@ -161,19 +175,85 @@ class GraphedAligner:
             packed, flow12, size, f8shape = _single_device(self.coarse, self.net, s_in, t_in, self.m21)
         return dict(n_kernels=_lib.launch_count() - n0, graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape)
 
-    def __call__(self, Is, It):
-        """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
+    def prepare(self, Is, It):
+        """Capture (once) the graph for this pair of input sizes; returns its record."""
         if isinstance(Is, np.ndarray):
             Is, It = torch.from_numpy(Is), torch.from_numpy(It)
         key = (tuple(Is.shape), tuple(It.shape))
         if key not in self.graphs:
             self.graphs[key] = self._build(Is, It)
-        c = self.graphs[key]
+        return self.graphs[key]
+
+    def enqueue(self, Is, It):
+        """Queue one pair on the CURRENT stream without waiting for it: input copies (H2D when the images are pinned host
+        tensors), one graph replay, one D2H of the packed results into this aligner's own pinned buffer.  Returns a
+        ticket for ``fetch``.  The ticket's buffers are reused by the next ``enqueue`` with the same sizes."""
+        if isinstance(Is, np.ndarray):
+            Is, It = torch.from_numpy(Is), torch.from_numpy(It)
+        c = self.prepare(Is, It)
         c["s_in"].copy_(Is, non_blocking=True)
         c["t_in"].copy_(It, non_blocking=True)
         c["graph"].replay()
         self.replayed_kernels += c["n_kernels"]
-        return _unpack_single(_to_host(c["packed"]).copy(), c["flow12"], c["size"], c["f8shape"])
+        if "host" not in c:
+            c["host"] = torch.empty(c["packed"].numel(), dtype=c["packed"].dtype).pin_memory()
+        c["host"].copy_(c["packed"].reshape(-1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return (c, done)
+
+    def fetch(self, ticket):
+        """Wait for a ticket and unpack it (same dict as ``align_pair_single``)."""
+        c, done = ticket
+        done.synchronize()
+        return _unpack_single(c["host"].numpy().copy(), c["flow12"], c["size"], c["f8shape"])
+
+    def __call__(self, Is, It):
+        """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
+        return self.fetch(self.enqueue(Is, It))
+
+
+class ConcurrentAligner:
+    """``lanes`` independent GraphedAligners (each with its OWN CoarseAlign state, network activations, graph memory,
+    pinned result buffer and stream) replayed side by side: pairs are independent, and a single pair leaves
+    SMs idle in its small layers (the /16 grids of the trunk's late layers, the 60 x 80 heads, RANSAC), which the other
+    lanes' kernels fill.  ``make_models()`` must return a fresh ``(coarseModel, network)`` per lane (layer programs cache
+    their activation buffers per module, so lanes cannot share modules).  Results are per pair and identical to what a
+    single GraphedAligner returns for it."""
+
+    def __init__(self, make_models, lanes=2, with_match21=False):
+        self.lanes = [GraphedAligner(*make_models(), with_match21=with_match21) for _ in range(lanes)]
+        self.streams = [torch.cuda.Stream() for _ in range(lanes)]
+
+    @property
+    def replayed_kernels(self):
+        return sum(a.replayed_kernels for a in self.lanes)
+
+    def prepare(self, Is, It):
+        for a in self.lanes:                      # graph capture is serial
+            a.prepare(Is, It)
+        torch.cuda.synchronize()
+
+    def enqueue(self, pairs):
+        """pairs: up to ``lanes`` (Is, It) tuples -> tickets; lane k runs on its own stream, ordered after the work
+        already queued on the current stream."""
+        assert len(pairs) <= len(self.lanes)
+        main = torch.cuda.current_stream()
+        tickets = []
+        for a, s, (Is, It) in zip(self.lanes, self.streams, pairs):
+            a.prepare(Is, It)
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                tickets.append(a.enqueue(Is, It))
+        for s in self.streams[:len(pairs)]:
+            main.wait_stream(s)                   # later work on the current stream (e.g. the next batch) follows all lanes
+        return tickets
+
+    def fetch(self, tickets):
+        return [a.fetch(t) for a, t in zip(self.lanes, tickets)]
+
+    def __call__(self, pairs):
+        return self.fetch(self.enqueue(pairs))
 
 
 def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):

@@ -1,5 +1,5 @@
 """Stand-alone launches of the hot kernels at config-2 shapes (for ncu captures and CUDA-event timing).
-Usage: python scripts/kernel_bench.py {corr|ransac|conv} [reps]"""
+Usage: python scripts/kernel_bench.py {corr|corr2|corr2v|ransac|conv|c64} [reps]"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ransac_flow_b200 as rf  # noqa: E402
-from oracle import synth  # noqa: E402
+import synthdata as synth  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "corr"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -39,6 +39,22 @@ if which == "corr":
     for prec in (2, 1, 0):
         m, mn = timed(lambda: rf.ops.corr_mutual_nn(A, B, prec))
         print("corr_mutual_nn precision=%d: mean %.1f us, min %.1f us -> %.1f TFLOP/s algorithmic" % (prec, m * 1e3, mn * 1e3, 32.108544 / m))
+elif which in ("corr2", "corr2v"):
+    # precision 2 only: the one-tile-per-CTA kernel sequence (RF_CORR_V2=0) against the persistent one (RF_CORR_V2=1);
+    # corr2v runs only the persistent one (for ncu captures)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    A = torch.nn.functional.normalize(torch.rand(13065, 1024, generator=g), dim=1).to(dev)
+    B = torch.nn.functional.normalize(torch.rand(1200, 1024, generator=g), dim=1).to(dev)
+    res = {}
+    for v2 in (("1",) if which == "corr2v" else ("0", "1", "0", "1")):
+        os.environ["RF_CORR_V2"] = v2
+        m, mn = timed(lambda: rf.ops.corr_mutual_nn(A, B, 2))
+        i1, i2, n = rf.ops.corr_mutual_nn(A, B, 2)
+        res[v2] = (i1[:int(n)].cpu(), i2[:int(n)].cpu())
+        print("corr_mutual_nn precision=2 RF_CORR_V2=%s (%d launches): mean %.1f us, min %.1f us -> %.1f TFLOP/s algorithmic, %d pairs"
+              % (v2, rf._lib.lib.rf_corr_mutual_nn_launches(2), m * 1e3, mn * 1e3, 32.108544 / m, int(n)))
+    if len(res) == 2:
+        print("identical pair lists:", bool(torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])))
 elif which == "ransac":
     m1, m2, _ = synth.make_matches(1, 636, 0.6)
     t1, t2 = torch.from_numpy(m1).to(dev), torch.from_numpy(m2).to(dev)

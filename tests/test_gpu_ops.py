@@ -83,6 +83,22 @@ def test_corr_neigh_and_heads_epilogues(rf):
     close(rf.ops.sigmoid(x.cuda()).cpu(), torch.sigmoid(x), 1e-6)
 
 
+@pytest.mark.parametrize("n,c,h,w,k,ldo,mode", [(1, 256, 60, 80, 7, 64, 2), (2, 256, 6, 8, 7, 49, 0), (1, 64, 5, 3, 7, 64, 1),
+                                                (3, 128, 9, 11, 3, 16, 2), (1, 256, 1, 1, 7, 64, 0)])
+def test_corr_neigh_pair_is_bit_identical_to_two_calls(rf, n, c, h, w, k, ldo, mode):
+    """rf_corr_neigh_pair_nhwc: CorrNeigh(x, y) and CorrNeigh(y, x) from one launch (yx[p][d] = xy[p+d][-d], each dot
+    product stored twice) == two rf_corr_neigh_nhwc launches, bit for bit, for fp32 / TF32-rounded / fp16 outputs."""
+    g = torch.Generator().manual_seed(n * 100 + h)
+    a = rf.ops.Ragged.from_nchw(F.normalize(torch.randn(n, c, h, w, generator=g)).cuda())
+    b = rf.ops.Ragged.from_nchw(F.normalize(torch.randn(n, c, h, w, generator=g)).cuda())
+    xy, yx = rf.ops.corr_neigh(a, b, k, ldo, mode), rf.ops.corr_neigh(b, a, k, ldo, mode)
+    pxy, pyx, both = rf.ops.corr_neigh_pair(a, b, k, ldo, mode)
+    torch.cuda.synchronize()
+    assert pxy.data.dtype == xy.data.dtype and both.data.shape == (2 * n * h * w, ldo) and both.hw == xy.hw + yx.hw
+    assert torch.equal(pxy.data, xy.data) and torch.equal(pyx.data, yx.data)
+    assert torch.equal(both.data[:n * h * w], xy.data) and torch.equal(both.data[n * h * w:], yx.data)
+
+
 def test_preproc_bit_exact(rf):
     rs = np.random.RandomState(0)
     img = rs.randint(0, 256, (33, 47, 3)).astype(np.uint8)

@@ -315,3 +315,38 @@ def test_kitti_shaped_pair_runs(rf):
     assert out["flowDown8"].shape == (1, 2, h // 8, w // 8)
     Hn = out["H"][0] / out["H"][0][2, 2]
     print("KITTI-shaped pair: %d matches, %d inliers, |H - Hgt|max = %.3f" % (out["nbMatch"], out["nbInlier"], np.abs(Hn - Hgt / Hgt[2, 2]).max()))
+
+
+def test_concurrent_aligner_equals_graphed_aligner(rf):
+    """ConcurrentAligner: two pairs in flight on two streams (own models / graphs / pinned buffers per lane) return, pair
+    by pair, what a single GraphedAligner returns.  The deterministic stages (pyramid, trunk, correlation -> match count)
+    must be identical - they would not be if the lanes shared a buffer; RANSAC draws its samples inside the graphs, so
+    H / flow are only checked for being a valid result of the same shape."""
+    rf.model.set_engine("f16")
+    rf.outil.corr_precision = 2
+    try:
+        rsd = synth.resnet50_conv4_state(0)
+
+        def make_models():
+            c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+            return c, networks(rf)
+        pairs = [tuple(torch.from_numpy(a).pin_memory() for a in synth.make_pair(30 + i, 96, 128)[:2]) for i in range(4)]
+        single = rf.pipeline.GraphedAligner(*make_models())
+        ref = [single(s, t) for s, t in pairs]
+        multi = rf.pipeline.ConcurrentAligner(make_models, lanes=2)
+        outs = multi(pairs[:2]) + multi(pairs[2:])
+        outs2 = multi(pairs[:2]) + multi(pairs[2:3])          # buffers are reused; a short batch is fine
+        assert len(outs) == 4 and len(outs2) == 3
+        for o, r in list(zip(outs, ref)) + list(zip(outs2, ref[:3])):
+            assert o["nbMatch"] == r["nbMatch"] and o["nbMatch"] >= 4
+            assert len(o["H"]) == len(r["H"])
+            if len(o["H"]):
+                assert o["H"].shape == (1, 3, 3) and np.isfinite(o["H"]).all() and o["nbInlier"] >= 4
+                assert o["flowDown8"].shape == r["flowDown8"].shape and np.isfinite(o["flowDown8"]).all()
+                assert o["match"][0].shape == r["match"][0].shape
+            print("pair: matches %d, inliers single %d / concurrent %d" % (o["nbMatch"], r["nbInlier"], o["nbInlier"]))
+        g0 = multi.lanes[0].graphs[next(iter(multi.lanes[0].graphs))]
+        assert multi.replayed_kernels == 7 * g0["n_kernels"] and g0["n_kernels"] > 50
+    finally:
+        rf.model.set_engine("fp32")
+        rf.outil.corr_precision = 0

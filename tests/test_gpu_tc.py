@@ -171,3 +171,35 @@ def test_corr_kitti_shape_both_engines_agree(rf):
         a = set(zip(i1[:n1].tolist(), i2[:n1].tolist()))
         print("KITTI-shaped correlation, precision %d: %d / %d pairs, %d differ" % (precision, n1, n2, len(a ^ b)))
         assert n1 >= 3000 and len(a ^ b) <= 2          # arg-max ties below fp32 accumulation noise only
+
+
+@pytest.mark.parametrize("C,NA,NB,seed", [(1024, 13065, 1200, 0), (1024, 2107, 300, 1), (64, 129, 127, 2), (256, 1, 1, 4),
+                                           (1024, 300, 1200, 5), (128, 5000, 130, 6), (64, 128, 128, 7), (192, 40000, 257, 8)])
+def test_corr_persistent_kernel_identical_to_one_tile_kernel(rf, monkeypatch, C, NA, NB, seed):
+    """Precision 2 has two kernel sequences (RF_CORR_V2, read per call): the persistent correlation kernel (two TMEM
+    accumulator pairs, arg-max epilogue overlapped with the next tile's MMAs, fused split / zeroing and fused mutual test +
+    compaction) must return exactly the pairs of the one-tile-per-CTA kernel - same MMAs, same (score, smallest index)
+    order - and both agree with the fp32 oracle up to arg-max ties below fp32 accumulation noise."""
+    rs = np.random.RandomState(seed)
+    A = np.abs(rs.randn(C, NA)).astype(np.float32)
+    B = np.abs(rs.randn(C, NB)).astype(np.float32)
+    n = min(NA, NB) // 2
+    B[:, :n] = A[:, rs.permutation(NA)[:n]] + 0.1 * np.abs(rs.randn(C, n)).astype(np.float32)
+    A /= np.linalg.norm(A, axis=0, keepdims=True)
+    B /= np.linalg.norm(B, axis=0, keepdims=True)
+    if NB > 2:
+        B[:, 1] = 0                              # masked target cell: never matches
+    fa, fb = torch.from_numpy(A.T.copy()).cuda(), torch.from_numpy(B.T.copy()).cuda()
+    got = {}
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("RF_CORR_V2", v2)
+        assert rf._lib.lib.rf_corr_mutual_nn_launches(2) == (3 if v2 == "1" else 6)
+        for rep in range(2):                     # twice: the workspace keys must be re-zeroed by the call itself
+            i1, i2, cnt = rf.ops.corr_mutual_nn(fa, fb, 2)
+        k = int(cnt.item())
+        got[v2] = (i1[:k].cpu().numpy(), i2[:k].cpu().numpy())
+    assert np.array_equal(got["0"][0], got["1"][0]) and np.array_equal(got["0"][1], got["1"][1])
+    assert np.all(np.diff(got["1"][0]) > 0)
+    if NA * NB <= 13065 * 1200:
+        o1, o2, score = OO.mutualMatching(A, B, return_score=True)
+        check_same(got["1"][0], got["1"][1], o1, o2, score)
