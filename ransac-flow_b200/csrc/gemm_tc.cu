@@ -1972,10 +1972,10 @@ int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* 
 
 size_t rf_corr_tc_workspace(int NA, int NB, int C) { return 2ull * ((size_t)NA + NB) * C * sizeof(float) + 1024; }
 
-// RF_CORR_V2 (read per call): 1 = precision 2 runs the persistent correlation kernel with the fused split /
+// RF_CORR_V2 (read per call): 1 (default) = precision 2 runs the persistent correlation kernel with the fused split /
 // key-zeroing launch in front and the fused flag + compaction kernel behind (3 launches); 0 = the one-tile-per-CTA
 // kernel with separate memset / split / split / flag / compact launches (6).  Identical outputs.
-constexpr int RF_CORR_V2_DEFAULT = 0;
+constexpr int RF_CORR_V2_DEFAULT = 1;      // measured on B200: 178 -> 112 us per call at config 2 (profiles/README.md)
 int rf_corr_v2_mode() {
     const char* e = getenv("RF_CORR_V2");
     return e ? atoi(e) : RF_CORR_V2_DEFAULT;

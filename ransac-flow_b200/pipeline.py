@@ -23,11 +23,11 @@ def base_grid(h, w, device="cuda"):
     return torch.cat((gx, gy), dim=3).contiguous()
 
 
-CORR_NEIGH_PAIR_DEFAULT = "0"
+CORR_NEIGH_PAIR_DEFAULT = "1"
 
 
 def _corr_neigh_pair():
-    """RF_CORR_NEIGH_PAIR=1: PredFlowMask computes corr12 and corr21 with one launch (``ops.corr_neigh_pair``) instead of two
+    """RF_CORR_NEIGH_PAIR=1 (default): PredFlowMask computes corr12 and corr21 with one launch (``ops.corr_neigh_pair``) instead of two
     launches and a concatenation.  Bit-identical volumes (tests/test_gpu_ops.py)."""
     return os.environ.get("RF_CORR_NEIGH_PAIR", CORR_NEIGH_PAIR_DEFAULT) != "0"
 

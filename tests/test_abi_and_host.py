@@ -129,6 +129,26 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
 
 
+def test_bench_product_arm_never_touches_oracle():
+    """bench.py may execute oracle/ only on its CPU-baseline / --impl reference leg: every `oracle` import must sit inside
+    run_reference(); the B200 arm gets its synthetic inputs from synthdata.py (no reference arithmetic)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            if any(m.split(".")[0] == "oracle" for m in mods):
+                assert fn.name == "run_reference", "oracle imported in bench.%s" % fn.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any("oracle" in ast.dump(n) for n in top)
+    src = open(os.path.join(ROOT, "synthdata.py")).read()
+    assert "import oracle" not in src and "from oracle" not in src and "ransac_flow_b200" not in src
+
+
 def test_dropin_installs_the_reference_module_names(rf, tmp_path):
     """The names the reference's drivers import by bare name resolve to this package."""
     import runpy
