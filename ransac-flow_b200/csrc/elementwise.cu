@@ -394,6 +394,29 @@ __global__ void preproc_kernel(const unsigned char* __restrict__ img, long long 
     out[i] = v;
 }
 
+// the same arithmetic, 12 bytes (4 RGB pixels) per thread: three 32-bit loads, three float4 stores
+__device__ __forceinline__ float preproc_one(unsigned int byte, int c, int normalize) {
+    float v = __fdiv_rn((float)byte, 255.f);
+    if (normalize) {
+        const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float sd = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        v = __fdiv_rn(__fsub_rn(v, mean), sd);
+    }
+    return v;
+}
+__global__ void preproc_vec_kernel(const unsigned int* __restrict__ img, long long ngroups, int normalize, float4* __restrict__ out) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const unsigned int w0 = __ldg(img + 3 * g), w1 = __ldg(img + 3 * g + 1), w2 = __ldg(img + 3 * g + 2);
+    // bytes 0..11 of the group: channel = byte index % 3 (a group starts on a pixel boundary)
+    out[3 * g] = make_float4(preproc_one(w0 & 255u, 0, normalize), preproc_one((w0 >> 8) & 255u, 1, normalize),
+                             preproc_one((w0 >> 16) & 255u, 2, normalize), preproc_one(w0 >> 24, 0, normalize));
+    out[3 * g + 1] = make_float4(preproc_one(w1 & 255u, 1, normalize), preproc_one((w1 >> 8) & 255u, 2, normalize),
+                                 preproc_one((w1 >> 16) & 255u, 0, normalize), preproc_one(w1 >> 24, 1, normalize));
+    out[3 * g + 2] = make_float4(preproc_one(w2 & 255u, 2, normalize), preproc_one((w2 >> 8) & 255u, 0, normalize),
+                                 preproc_one((w2 >> 16) & 255u, 1, normalize), preproc_one(w2 >> 24, 2, normalize));
+}
+
 // ---------------------------------------------------------------------------
 // PIL ImagingResample (8 bits per channel, fixed point, one pass)
 // ---------------------------------------------------------------------------
@@ -841,7 +864,19 @@ extern "C" int rf_sigmoid(const float* x, long long n, float* y, void* stream) {
 
 extern "C" int rf_preproc_u8(const uint8_t* img, long long npix, int normalize, float* out_nhwc, void* stream) {
     if (npix <= 0) return 0;
-    preproc_kernel<<<blocks_for(npix * 3, 256), 256, 0, as_stream(stream)>>>(img, npix * 3, normalize, out_nhwc);
+    const long long n = npix * 3;
+    if (((uintptr_t)img & 3) == 0 && ((uintptr_t)out_nhwc & 15) == 0 && n >= 12) {
+        const long long groups = n / 12, tail = n - groups * 12;                 // the tail starts on a pixel boundary too
+        preproc_vec_kernel<<<blocks_for(groups, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned int*>(img), groups, normalize,
+                                                                                   reinterpret_cast<float4*>(out_nhwc));
+        RF_LAUNCHED();
+        if (tail > 0) {
+            preproc_kernel<<<1, 32, 0, as_stream(stream)>>>(img + groups * 12, tail, normalize, out_nhwc + groups * 12);
+            RF_LAUNCHED();
+        }
+        return 0;
+    }
+    preproc_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(img, n, normalize, out_nhwc);
     RF_LAUNCHED();
     return 0;
 }

@@ -99,16 +99,20 @@ def test_corr_neigh_pair_is_bit_identical_to_two_calls(rf, n, c, h, w, k, ldo, m
     assert torch.equal(both.data[:n * h * w], xy.data) and torch.equal(both.data[n * h * w:], yx.data)
 
 
-def test_preproc_bit_exact(rf):
-    rs = np.random.RandomState(0)
-    img = rs.randint(0, 256, (33, 47, 3)).astype(np.uint8)
-    t = torch.from_numpy(img).permute(2, 0, 1).float().div(255)
-    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
-    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
-    got = rf.ops.preproc_u8(torch.from_numpy(img).cuda().reshape(-1, 3), True).view(33, 47, 3).permute(2, 0, 1).cpu()
-    assert torch.equal(got, (t - mean) / std)
-    got = rf.ops.preproc_u8(torch.from_numpy(img).cuda().reshape(-1, 3), False).view(33, 47, 3).permute(2, 0, 1).cpu()
-    assert torch.equal(got, t)
+@pytest.mark.parametrize("h,w,skip", [(33, 47, 0), (16, 16, 0), (1, 3, 0), (33, 47, 1), (480, 640, 0), (7, 4, 4)])
+def test_preproc_bit_exact(rf, h, w, skip):
+    """ToTensor (+ Normalize) in torchvision's op order, bit exact.  Covers the 12-bytes-per-thread kernel with and without a
+    tail, inputs shorter than one group, and a view that starts `skip` pixels into the buffer (3 * skip bytes: the
+    vector kernel needs 4-byte alignment, odd offsets take the byte kernel)."""
+    rs = np.random.RandomState(h * w + skip)
+    img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    flat = torch.from_numpy(img).reshape(-1, 3)
+    t = flat[skip:].float().div(255)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3)
+    dev = flat.cuda()[skip:]
+    assert torch.equal(rf.ops.preproc_u8(dev, True).cpu(), (t - mean) / std)
+    assert torch.equal(rf.ops.preproc_u8(dev, False).cpu(), t)
 
 
 @pytest.mark.parametrize("size", [(96, 64), (20, 11), (53, 80), (1280, 960), (320, 240)])
