@@ -347,7 +347,7 @@ def run_b200(args, rank, world, local):
         line = {
             "metric": METRIC, "value": world * lanes * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 (conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; 3xTF32 correlation; fp32/fp64 RANSAC)",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 (conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; fp16-split correlation = 22 significand bits; fp32/fp64 RANSAC)",
                       "f16-trunk": "f16 trunk + tf32 fine-flow nets"}[args.engine], "data": "synthetic",
             "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": lanes, "parallelism": "pairs sharded i %% %d" % world,
                        "l2": "256 MiB buffer written between steps (L2 flush); activations per step also exceed the 126 MB L2",
