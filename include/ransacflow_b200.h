@@ -192,6 +192,17 @@ int rf_upsample_bilinear(const float* in, int NC, int h, int w, int H, int W, fl
 int rf_compose_fine(const float* flowDown8, const float* match12, const float* match21, int h8, int w8,
                     const float* coarse, int H, int W, int clamp, int align_corners,
                     float* flow12_out, float* match_out, float* flowUp_out, void* stream);
+/* The same with a coarse grid of its own size, coarse [Hc][Wc][2] sampled at the (H, W) output positions: the second
+ * level of the KITTI flow (evaluation/evalKITTI/evaluation.py:296-302: PredFlowMask with the resized image's flow and
+ * the original image's grid) and the two-level recomposition of evaluation/evalKITTI/getResults.py:104-113. */
+int rf_compose_fine_ex(const float* flowDown8, const float* match12, const float* match21, int h8, int w8,
+                       const float* coarse, int Hc, int Wc, int H, int W, int clamp, int align_corners,
+                       float* flow12_out, float* match_out, float* flowUp_out, void* stream);
+/* remove_small_cc, evaluation/evalKITTI/evaluation.py:85-100 and evalKITTI/getResults.py:66-83, in place on
+ * match [N][H][W]: every 8-connected component (skimage.measure.label's default for 2-D) of (match > match_th) whose
+ * area fraction count / (H*W) is <= cc_th gets its matchability zeroed; cc_th == 0 leaves the map untouched. */
+size_t rf_remove_small_cc_workspace(int H, int W);
+int rf_remove_small_cc(float* match, int N, int H, int W, float match_th, double cc_th, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -320,6 +320,109 @@ def gen_coarse_align():
         torchvision.models.resnet50 = real_resnet50
 
 
+class _LabelShim:
+    """skimage is not installed: ``measure.label(binary, background=0)`` (8-connected components of a 2-D array, the
+    skimage default) is served by ``scipy.ndimage.label`` with a full 3x3 structure.  Harness-side stand-in for an absent
+    third-party dependency: the component NUMBERING may differ from skimage's, the components do not."""
+
+    @staticmethod
+    def label(binary, background=0):
+        import scipy.ndimage as nd
+        return nd.label(binary, structure=np.ones((3, 3), dtype=np.int32))[0]
+
+
+def gen_kitti():
+    """The KITTI-only pieces as written in evaluation/evalKITTI: PredFlowMask with a coarse flow of another size than the
+    output grid (the second level, evaluation.py:296-302), remove_small_cc (:85-100) and getResults.py's two-level
+    getFlow_all (:95-141, with and without the EDT hole filling)."""
+    import scipy.ndimage as nd
+    model = ref_model()
+    net = _ref_networks(model)
+    src, tgt, Hgt = synth.make_pair(4, 48, 64)
+    Is = torch.from_numpy(src).permute(2, 0, 1)[None].float() / 255
+    It = torch.from_numpy(tgt).permute(2, 0, 1)[None].float() / 255
+    Hm = torch.tensor(Hgt / np.linalg.norm(Hgt), dtype=torch.float32)[None]
+    ev = os.path.join(REF, "evaluation/evalKITTI/evaluation.py")
+    with cpu_as_cuda(), torch.no_grad():
+        fn = extract_function(ev, "PredFlowMask", {"torch": torch, "F": F})
+        # level-2 shapes: images at 48x64 (the "resized" target), coarse flow on that grid, outputs on a 56x80 "original" grid
+        flowCoarse = WO.warp_grid(Hm, 48, 64)
+        IsSample = F.grid_sample(Is, flowCoarse)
+        grid_org = WO.base_grid(56, 80)
+        flow12, match, f8, m8 = fn(IsSample, It, flowCoarse, grid_org, net)
+        save("kitti_pred_flow_mask", Is=Is.numpy(), It=It.numpy(), H=Hm.numpy(), IsSample=IsSample.numpy(), flow12=flow12.numpy(),
+             match=match, flowDown8=f8.numpy(), matchDown8=m8.numpy())
+    # remove_small_cc on a blobby map
+    rs = np.random.RandomState(9)
+    raw = nd.gaussian_filter(rs.rand(60, 96), 2.0)
+    m = ((raw - raw.min()) / (raw.max() - raw.min())).astype(np.float32)
+    m = np.where(m > 0.55, 1.0, m).astype(np.float32)
+    m[3:5, 90:93] = 1.0
+    m[40, 2] = 1.0
+    rcc = extract_function(ev, "remove_small_cc", {"np": np, "measure": _LabelShim})
+    outs = {}
+    for cc_th in (0.0, 0.01, 0.05, 1.0):
+        outs["out_%g" % cc_th] = rcc(m.copy(), 0.99, cc_th)
+    save("kitti_remove_small_cc", match=m, match_th=np.float64(0.99), **outs)
+    # getResults.getFlow_all (two levels, files on disk)
+    gr = os.path.join(REF, "evaluation/evalKITTI/getResults.py")
+    tmp = "/tmp/rf_golden_kitti"
+    os.makedirs(tmp, exist_ok=True)
+    nH = 2
+    Hs = np.stack([np.eye(3) + rs.uniform(-0.04, 0.04, (3, 3)) for _ in range(nH)]).astype(np.float32)
+    flowd2 = (rs.randn(nH, 2, 3, 5) * 0.02).astype(np.float32)
+    flow = (rs.randn(nH, 2, 6, 10) * 0.01).astype(np.float32)
+    mask = np.clip(nd.gaussian_filter(rs.rand(nH, 2, 6, 10), (0, 0, 1, 1)) * 2.2, 0, 1).astype(np.float32)
+    np.save(tmp + "/Homograpy_7_2.npy", Hs)
+    np.save(tmp + "/Finetune_D2_7_2.npy", flowd2)
+    np.save(tmp + "/Finetune_7_2.npy", flow)
+    np.save(tmp + "/Finetune_Mask_7_2.npy", mask)
+    np.save(tmp + "/BG_7_2H.npy", np.ones((48, 80), bool))
+
+    class Warper:                      # kornia is absent: the oracle's restatement stands in
+        def __init__(self, h, w):
+            self.h, self.w = h, w
+
+        def warp_grid(self, H):
+            return WO.warp_grid(H, self.h, self.w)
+    ns = {"torch": torch, "F": F, "np": np, "os": os, "nd": nd, "measure": _LabelShim}
+    ns["remove_small_cc"] = extract_function(gr, "remove_small_cc", ns)
+    ns["interpolate_flow_match"] = extract_function(gr, "interpolate_flow_match", ns)
+    gfa = extract_function(gr, "getFlow_all", ns)
+    h, w = 48, 80
+    grid = WO.base_grid(h, w)
+    res = {}
+    for interp in (False, True):
+        fg = gfa("7", tmp, 2, "Finetune", Warper(h, w), True, grid, 0.6, 0.01, interp)
+        res["flowGlobal_interp%d" % int(interp)] = fg.numpy()
+    save("kitti_get_flow_all", H=Hs, flowd2=flowd2, flow=flow, mask=mask, th=np.float64(0.6), cc_th=np.float64(0.01), **res)
+
+
+def gen_metrics():
+    """The two metric FUNCTIONS the getResults scripts define (the rest of their metric code is inline in the scripts):
+    ``epe`` (evaluation/evalHpatch/getResults.py:147-157) and ``alignmentError`` (evaluation/evalCorr/getResults.py:15-38)."""
+    rs = np.random.RandomState(21)
+    epe = extract_function(os.path.join(REF, "evaluation/evalHpatch/getResults.py"), "epe", {"torch": torch})
+    a = torch.from_numpy(rs.rand(500, 2).astype(np.float32) * 239)
+    b = a + torch.from_numpy(rs.randn(500, 2).astype(np.float32))
+    ae = extract_function(os.path.join(REF, "evaluation/evalCorr/getResults.py"), "alignmentError", {"torch": torch, "np": np})
+    hB, wB, hA, wA = 48, 64, 40, 72
+    flow = torch.from_numpy(rs.uniform(-1, 1, (1, hB, wB, 2)).astype(np.float32))
+    match2 = torch.from_numpy((rs.rand(1, hB, wB, 1) > 0.4).astype(np.float32))
+    n = 60
+    XB, YB = rs.uniform(0, wB - 1, n).astype(np.float32), rs.uniform(0, hB - 1, n).astype(np.float32)
+    XA, YA = rs.uniform(0, wA - 1, n).astype(np.float32), rs.uniform(0, hA - 1, n).astype(np.float32)
+    # make a third of the keypoints agree with the flow so that the counts are not all zero
+    xb, yb = XB.astype(np.int64), YB.astype(np.int64)
+    for k in range(0, n, 3):
+        XA[k] = (flow[0, yb[k], xb[k], 0].item() + 1) * 0.5 * (wA - 1) + rs.uniform(-2, 2)
+        YA[k] = (flow[0, yb[k], xb[k], 1].item() + 1) * 0.5 * (hA - 1) + rs.uniform(-2, 2)
+    pixelGrid = np.around(np.logspace(0, np.log10(36), 8).reshape(-1, 8))
+    cnt, nb = ae(wB, hB, wA, hA, XA, YA, XB, YB, flow, match2, pixelGrid)
+    save("metrics", epe_in=a.numpy(), epe_tgt=b.numpy(), epe=np.float64(epe(a, b).item()), flow=flow.numpy(), match2=match2.numpy(),
+         XA=XA, YA=YA, XB=XB, YB=YB, pixelGrid=pixelGrid, dims=np.array([wB, hB, wA, hA]), counts=np.asarray(cnt), nbAlign=np.int64(nb))
+
+
 def main():
     assert os.path.isdir(REF), "reference checkout not found at %s" % REF
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -327,6 +430,8 @@ def main():
     gen_models()
     gen_pred_flow_mask()
     gen_get_flow()
+    gen_kitti()
+    gen_metrics()
     gen_coarse_align()
 
 

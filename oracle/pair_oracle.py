@@ -225,3 +225,82 @@ def align2images(coarse, net, img1, img2):
     img1_fine = WO.grid_sample(coarse.IsTensor, flow12)
     return dict(bestPrm=bestPrm, inlierMask=inlierMask, flowCoarse=flowCoarse, img1_coarse=img1_coarse, flowDown=flowDown,
                 flow12=flow12, img1_fine=img1_fine)
+
+
+# --------------------------------------------------------------------------------------------------
+# KITTI: two-level fine flow (evaluation/evalKITTI/evaluation.py)
+# --------------------------------------------------------------------------------------------------
+def resize_img(I, strideNet, minSize):
+    """utils/outil.py:6-19 ``resizeImg`` (rounds to the nearest multiple of strideNet, unlike ResizeMinSize)."""
+    w, h = I.size
+    ratio = min(w / minSize, h / minSize)
+    w, h = w / ratio, h / ratio
+    return I.resize((round(w / strideNet) * strideNet, round(h / strideNet) * strideNet), resample=Image.LANCZOS)
+
+
+def pred_flow_mask_kitti(IsSample, ItSample, flowCoarse, grid, net):
+    """evaluation/evalKITTI/evaluation.py:49-81: both images' fine features computed inside, matchability always
+    ``match12 * grid_sample(match21)`` * inside; ``flowCoarse`` may have another size than ``grid`` (second level)."""
+    featsSample = F.normalize(MO.feature_extractor(IsSample, net["netFeatCoarse"]))
+    featt = F.normalize(MO.feature_extractor(ItSample, net["netFeatCoarse"]))
+    corr12 = MO.corr_neigh(featt, featsSample)
+    flowDown8 = MO.net_flow_coarse(corr12, net["netFlowCoarse"])
+    match12Down8 = MO.net_matchability(corr12, net["netMatch"])
+    corr21 = MO.corr_neigh(featsSample, featt)
+    match21Down8 = MO.net_matchability(corr21, net["netMatch"])
+    size = (grid.shape[1], grid.shape[2])
+    match12 = WO.interpolate_bilinear(match12Down8, size)
+    match21 = WO.interpolate_bilinear(match21Down8, size)
+    flow12, flowUp = WO.compose_fine(flowDown8, flowCoarse, grid, clamp=True)
+    match = match12 * WO.grid_sample(match21, flowUp) * WO.inside_mask(flow12)
+    return flow12, match[0, 0].numpy(), flowDown8, torch.cat((match12Down8, match21Down8), dim=1)
+
+
+def align_pair_kitti(coarse, net, Is, It, fineSize=650, cc_th=0.01, maskRegionTh=0.005, maxH=None):
+    """One pair through evaluation/evalKITTI/evaluation.py:216-336 (no segNet): coarse homography on the full-size pair,
+    first fine level on the half-size target, second level on the resized target sampled on the ORIGINAL image's grid,
+    small connected components of the matchability removed, multi-hypothesis mask update.  ``maxH`` caps the
+    reference's ``while True`` (BASELINE config 5 caps it at 5).  Returns dict(H (nH,3,3), flow_d2 (nH,2,.,.),
+    flow (nH,2,.,.), mask (nH,2,.,.)) - the four tensors the script saves (:338-344) - plus the per-hypothesis maps."""
+    strideNet = 8
+    It_resize = resize_img(It, strideNet, fineSize)
+    It_d2 = resize_img(It, strideNet, fineSize // 2)
+    w_org, h_org = It.size
+    tensor_org, tensor_s = to_tensor(It).unsqueeze(0), to_tensor(Is).unsqueeze(0)
+    grid_org = WO.base_grid(h_org, w_org)
+    w_r, h_r = It_resize.size
+    tensor_resize, grid_resize = to_tensor(It_resize).unsqueeze(0), WO.base_grid(h_r, w_r)
+    w_d2, h_d2 = It_d2.size
+    tensor_d2, grid_d2 = to_tensor(It_d2).unsqueeze(0), WO.base_grid(h_d2, w_d2)
+    coarse.setPair(Is, It)
+    It_bg = np.ones((h_org, w_org), dtype=np.float32)
+    Mask = np.zeros((h_org, w_org), dtype=np.float32)
+    Hs, D2, Msk, Fin, maps = [], [], [], [], []
+    nbCoarse = 0
+    while maxH is None or nbCoarse < maxH:
+        fgMask = ((Mask + (1 - It_bg)) > 0.5).astype(np.float32)
+        bestPara = coarse.getCoarse(fgMask)
+        if bestPara is None:
+            break
+        bp = torch.from_numpy(bestPara).unsqueeze(0)
+        homography_d2 = WO.warp_grid(bp, h_d2, w_d2)
+        homography_resize = WO.warp_grid(bp, h_r, w_r)
+        IsSample_d2 = WO.grid_sample(tensor_s, homography_d2)
+        _, _, flowFine_d2, _ = pred_flow_mask_kitti(IsSample_d2, tensor_d2, homography_d2, grid_d2, net)
+        flowCoarse, _ = WO.compose_fine(flowFine_d2, homography_resize, grid_resize, clamp=True)
+        IsSample = WO.grid_sample(tensor_s, flowCoarse)
+        flowFine_org, matchFine_org, f8, m8 = pred_flow_mask_kitti(IsSample, tensor_resize, flowCoarse, grid_org, net)
+        matchFine = WO.remove_small_cc(matchFine_org, 0.99, cc_th)
+        if ((matchFine > 0.9999) * (1 - fgMask)).mean() > maskRegionTh or nbCoarse == 0:
+            Hs.append(bp.numpy())
+            D2.append(flowFine_d2.numpy())
+            Msk.append(m8.numpy())
+            Fin.append(f8.numpy())
+            maps.append((flowFine_org, matchFine.copy()))
+            nbCoarse += 1
+            mf = matchFine if len(Msk) == 0 else matchFine * (1 - fgMask)
+            Mask = ((Mask + mf) > 0.9999).astype(np.float32)
+        else:
+            break
+    cat = lambda l: np.concatenate(l, axis=0) if l else np.zeros((0,))
+    return dict(H=cat(Hs), flow_d2=cat(D2), mask=cat(Msk), flow=cat(Fin), maps=maps, size=(h_org, w_org))

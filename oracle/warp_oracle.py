@@ -92,3 +92,69 @@ def get_flow_all(flow, param, match, h, w, th=0.95, multiH=True, with_match21=Fa
             tmp = tmp.expand_as(flowGlobal)
             flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
     return flowGlobal, m12
+
+
+# --------------------------------------------------------------------------------------------------
+# KITTI extras (evaluation/evalKITTI)
+# --------------------------------------------------------------------------------------------------
+def remove_small_cc(match, match_th, cc_th):
+    """evaluation/evalKITTI/evaluation.py:85-100 on one (H, W) float array (a copy is returned).
+    ``skimage.measure.label(binary, background=0)`` labels 8-connected components of a 2-D array (default
+    connectivity = ndim); skimage is not installed here, ``scipy.ndimage.label`` with a full 3x3 structure gives the
+    same components (their numbering is irrelevant: only each component's area fraction is used)."""
+    import scipy.ndimage as nd
+    match = np.array(match, dtype=np.float32, copy=True)
+    if cc_th == 0:
+        return match
+    labels, n = nd.label(match > match_th, structure=np.ones((3, 3), dtype=np.int32))
+    if n == 0:                                                   # len(np.unique(all_labels)) == 1
+        return match
+    for i in range(1, n + 1):
+        comp = labels == i
+        if np.mean(comp) <= cc_th:
+            match[comp] = 0
+    return match
+
+
+def interpolate_flow_match(flowGlobal, match_binary):
+    """evaluation/evalKITTI/getResults.py:87-93: fill the unmatched pixels with the flow of the nearest matched pixel
+    (scipy's exact EDT with indices, as the reference)."""
+    import scipy.ndimage as nd
+    mb = (~match_binary).squeeze().numpy()
+    idx = nd.distance_transform_edt(mb, return_distances=False, return_indices=True)
+    f = flowGlobal.squeeze().numpy()
+    return torch.from_numpy(f[tuple(idx)]).unsqueeze(0)
+
+
+def get_flow_all_kitti(param, flowd2, flow, match, h, w, th=1.0, cc_th=0.01, multiH=True, interpolate=False):
+    """evaluation/evalKITTI/getResults.py:95-141 ``getFlow_all`` after the np.load calls: param (nH,3,3), flowd2
+    (nH,2,hd,wd) the /8 flow of the half-size level, flow (nH,2,h8,w8) the /8 flow of the second level, match
+    (nH,2,h8,w8) -> flowGlobal (1,h,w,2) (and the binary match map)."""
+    param = torch.as_tensor(param, dtype=torch.float32)
+    flowd2 = torch.as_tensor(flowd2, dtype=torch.float32)
+    flow = torch.as_tensor(flow, dtype=torch.float32)
+    match = torch.as_tensor(match, dtype=torch.float32)
+    grid = base_grid(h, w)
+    homography_org = warp_grid(param, h, w)
+    fd2 = interpolate_bilinear(flowd2, (h, w)).permute(0, 2, 3, 1)
+    fd2 = torch.clamp(fd2 + grid, min=-1, max=1)
+    fd2 = grid_sample(homography_org.permute(0, 3, 1, 2), fd2).permute(0, 2, 3, 1).contiguous()
+    f = interpolate_bilinear(flow, (h, w)).permute(0, 2, 3, 1)
+    flowUp = torch.clamp(f + grid, min=-1, max=1)
+    f = grid_sample(fd2.permute(0, 3, 1, 2), flowUp).permute(0, 2, 3, 1).contiguous()
+    m = interpolate_bilinear(match, (h, w))
+    m = m.narrow(1, 0, 1) * grid_sample(m.narrow(1, 1, 1), flowUp) * inside_mask(f)
+    m = torch.from_numpy(np.stack([remove_small_cc(m[j, 0].numpy(), 0.99, cc_th) for j in range(m.shape[0])]))[:, None]
+    m = m.permute(0, 2, 3, 1)
+    f = torch.clamp(f, min=-1, max=1)
+    flowGlobal = f[:1].clone()
+    mb = m[:1] >= th
+    if multiH:
+        for i in range(1, len(m)):
+            tmp = (m.narrow(0, i, 1) >= th) * (~mb)
+            mb = mb + tmp
+            tmp = tmp.expand_as(flowGlobal)
+            flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    if interpolate:
+        flowGlobal = interpolate_flow_match(flowGlobal, mb)
+    return flowGlobal, mb

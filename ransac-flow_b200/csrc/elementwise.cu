@@ -582,9 +582,11 @@ __global__ void upsample_kernel(const float* __restrict__ in, int NC, int h, int
     out[t] = up_sample(in + (long long)nc * h * w, h, w, H, W, Y, X);
 }
 
-// evaluation/evalHpatch/evaluation.py:37-51 (and evalCorr :50-55) in one pass over the full-res grid
+// evaluation/evalHpatch/evaluation.py:37-51 (and evalCorr :50-55) in one pass over the full-res grid.  The coarse grid
+// may have its own size (Hc, Wc) != (H, W): evaluation/evalKITTI/evaluation.py:296-299 samples the flow of the resized
+// image at the original image's positions, and evalKITTI/getResults.py:104-113 composes two levels that way.
 __global__ void compose_fine_kernel(const float* __restrict__ flow8, const float* __restrict__ m12, const float* __restrict__ m21,
-                                    int h8, int w8, const float* __restrict__ coarse, int H, int W, int clamp, int align_corners,
+                                    int h8, int w8, const float* __restrict__ coarse, int Hc, int Wc, int H, int W, int clamp, int align_corners,
                                     float* __restrict__ flow12, float* __restrict__ match, float* __restrict__ flowUp_out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)H * W) return;
@@ -596,18 +598,32 @@ __global__ void compose_fine_kernel(const float* __restrict__ flow8, const float
         fy = fminf(fmaxf(fy, -1.f), 1.f);
     }
     if (flowUp_out) reinterpret_cast<float2*>(flowUp_out)[t] = make_float2(fx, fy);
-    float ix = unnormalize(fx, W, align_corners), iy = unnormalize(fy, H, align_corners);
-    float flx = floorf(ix), fly = floorf(iy);
-    int x0 = (int)flx, y0 = (int)fly, x1 = x0 + 1, y1 = y0 + 1;
-    float nw = (flx + 1.f - ix) * (fly + 1.f - iy), ne = (ix - flx) * (fly + 1.f - iy);
-    float sw = (flx + 1.f - ix) * (iy - fly), se = (ix - flx) * (iy - fly);
-    bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
     const float2* cg = reinterpret_cast<const float2*>(coarse);
     float ox = 0.f, oy = 0.f, mm = 0.f;
-    if (vy0 && vx0) { float2 v = __ldg(cg + (long long)y0 * W + x0); ox += v.x * nw; oy += v.y * nw; if (m21) mm += up_sample(m21, h8, w8, H, W, y0, x0) * nw; }
-    if (vy0 && vx1) { float2 v = __ldg(cg + (long long)y0 * W + x1); ox += v.x * ne; oy += v.y * ne; if (m21) mm += up_sample(m21, h8, w8, H, W, y0, x1) * ne; }
-    if (vy1 && vx0) { float2 v = __ldg(cg + (long long)y1 * W + x0); ox += v.x * sw; oy += v.y * sw; if (m21) mm += up_sample(m21, h8, w8, H, W, y1, x0) * sw; }
-    if (vy1 && vx1) { float2 v = __ldg(cg + (long long)y1 * W + x1); ox += v.x * se; oy += v.y * se; if (m21) mm += up_sample(m21, h8, w8, H, W, y1, x1) * se; }
+    {   // grid_sample(coarse, flowUp): bilinear, zero padding, in the coarse grid's own pixel coordinates
+        float ix = unnormalize(fx, Wc, align_corners), iy = unnormalize(fy, Hc, align_corners);
+        float flx = floorf(ix), fly = floorf(iy);
+        int x0 = (int)flx, y0 = (int)fly, x1 = x0 + 1, y1 = y0 + 1;
+        float nw = (flx + 1.f - ix) * (fly + 1.f - iy), ne = (ix - flx) * (fly + 1.f - iy);
+        float sw = (flx + 1.f - ix) * (iy - fly), se = (ix - flx) * (iy - fly);
+        bool vx0 = x0 >= 0 && x0 < Wc, vx1 = x1 >= 0 && x1 < Wc, vy0 = y0 >= 0 && y0 < Hc, vy1 = y1 >= 0 && y1 < Hc;
+        if (vy0 && vx0) { float2 v = __ldg(cg + (long long)y0 * Wc + x0); ox += v.x * nw; oy += v.y * nw; }
+        if (vy0 && vx1) { float2 v = __ldg(cg + (long long)y0 * Wc + x1); ox += v.x * ne; oy += v.y * ne; }
+        if (vy1 && vx0) { float2 v = __ldg(cg + (long long)y1 * Wc + x0); ox += v.x * sw; oy += v.y * sw; }
+        if (vy1 && vx1) { float2 v = __ldg(cg + (long long)y1 * Wc + x1); ox += v.x * se; oy += v.y * se; }
+    }
+    if (m21) {   // grid_sample(interpolate(match21, (H, W)), flowUp): the sampled map lives on the OUTPUT grid
+        float ix = unnormalize(fx, W, align_corners), iy = unnormalize(fy, H, align_corners);
+        float flx = floorf(ix), fly = floorf(iy);
+        int x0 = (int)flx, y0 = (int)fly, x1 = x0 + 1, y1 = y0 + 1;
+        float nw = (flx + 1.f - ix) * (fly + 1.f - iy), ne = (ix - flx) * (fly + 1.f - iy);
+        float sw = (flx + 1.f - ix) * (iy - fly), se = (ix - flx) * (iy - fly);
+        bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+        if (vy0 && vx0) mm += up_sample(m21, h8, w8, H, W, y0, x0) * nw;
+        if (vy0 && vx1) mm += up_sample(m21, h8, w8, H, W, y0, x1) * ne;
+        if (vy1 && vx0) mm += up_sample(m21, h8, w8, H, W, y1, x0) * sw;
+        if (vy1 && vx1) mm += up_sample(m21, h8, w8, H, W, y1, x1) * se;
+    }
     reinterpret_cast<float2*>(flow12)[t] = make_float2(ox, oy);
     if (match) {
         float m = up_sample(m12, h8, w8, H, W, Y, X);
@@ -615,6 +631,58 @@ __global__ void compose_fine_kernel(const float* __restrict__ flow8, const float
         float inside = ((ox >= -1.f && ox <= 1.f) ? 1.f : 0.f) * ((oy >= -1.f && oy <= 1.f) ? 1.f : 0.f);
         match[t] = m * inside;
     }
+}
+
+// ---------------------------------------------------------------------------
+// remove_small_cc (evaluation/evalKITTI/evaluation.py:85-100, evalKITTI/getResults.py:66-83): zero the matchability of
+// every 8-connected component of (match > match_th) whose area fraction is <= cc_th.  skimage.measure.label's default
+// connectivity for a 2-D array is 2 (8 neighbours).  Label-equivalence union-find (one pass over the four "backward"
+// neighbours, atomicMin roots), then flatten, count, filter.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int cc_find(const int* L, int i) {
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+__device__ __forceinline__ void cc_union(int* L, int a, int b) {
+    bool done = false;
+    while (!done) {
+        a = cc_find(L, a);
+        b = cc_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    }
+}
+__global__ void cc_init_kernel(const float* __restrict__ match, float th, int n, int* __restrict__ L, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    L[i] = (match[i] > th) ? i : -1;
+    cnt[i] = 0;
+}
+__global__ void cc_merge_kernel(int* __restrict__ L, int H, int W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W || L[i] < 0) return;
+    const int y = i / W, x = i - y * W;
+    if (x > 0 && L[i - 1] >= 0) cc_union(L, i, i - 1);
+    if (y > 0) {
+        if (L[i - W] >= 0) cc_union(L, i, i - W);
+        if (x > 0 && L[i - W - 1] >= 0) cc_union(L, i, i - W - 1);
+        if (x + 1 < W && L[i - W + 1] >= 0) cc_union(L, i, i - W + 1);
+    }
+}
+__global__ void cc_flatten_count_kernel(int* __restrict__ L, int n, int* __restrict__ cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    const int r = cc_find(L, i);
+    atomicAdd(&cnt[r], 1);
+    // L[i] is rewritten in the next kernel (roots must stay intact while other threads still walk to them)
+}
+__global__ void cc_filter_kernel(float* __restrict__ match, const int* __restrict__ L, const int* __restrict__ cnt, int n, double cc_th) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || L[i] < 0) return;
+    const int r = cc_find(L, i);
+    if ((double)cnt[r] / (double)n <= cc_th) match[i] = 0.f;         // np.mean(all_labels == i) <= cc_th
 }
 
 }  // namespace rf
@@ -986,8 +1054,45 @@ extern "C" int rf_compose_fine(const float* flowDown8, const float* match12, con
     long long total = (long long)H * W;
     if (total <= 0) return 0;
     RF_REQUIRE(match_out == nullptr || match12 != nullptr, "rf_compose_fine: match_out needs match12");
-    compose_fine_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(flowDown8, match12, match21, h8, w8, coarse, H, W, clamp,
+    compose_fine_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(flowDown8, match12, match21, h8, w8, coarse, H, W, H, W, clamp,
                                                                               align_corners, flow12_out, match_out, flowUp_out);
     RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_compose_fine_ex(const float* flowDown8, const float* match12, const float* match21, int h8, int w8,
+                                  const float* coarse, int Hc, int Wc, int H, int W, int clamp, int align_corners,
+                                  float* flow12_out, float* match_out, float* flowUp_out, void* stream) {
+    long long total = (long long)H * W;
+    if (total <= 0) return 0;
+    RF_REQUIRE(Hc >= 1 && Wc >= 1, "rf_compose_fine_ex: empty coarse grid");
+    RF_REQUIRE(match_out == nullptr || match12 != nullptr, "rf_compose_fine_ex: match_out needs match12");
+    compose_fine_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(flowDown8, match12, match21, h8, w8, coarse, Hc, Wc, H, W, clamp,
+                                                                              align_corners, flow12_out, match_out, flowUp_out);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" size_t rf_remove_small_cc_workspace(int H, int W) { return 2ull * (size_t)(H > 0 ? H : 0) * (size_t)(W > 0 ? W : 0) * sizeof(int) + 256; }
+
+extern "C" int rf_remove_small_cc(float* match, int N, int H, int W, float match_th, double cc_th, void* ws, size_t ws_bytes, void* stream) {
+    if (cc_th == 0.0 || N <= 0 || H <= 0 || W <= 0) return 0;         // evaluation.py:87-88
+    RF_REQUIRE((long long)H * W < (1ll << 31), "rf_remove_small_cc: image too large");
+    RF_REQUIRE(ws != nullptr && ws_bytes >= rf_remove_small_cc_workspace(H, W), "rf_remove_small_cc: workspace too small");
+    const int n = H * W;
+    int* L = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    int* cnt = L + n;
+    cudaStream_t st = as_stream(stream);
+    for (int j = 0; j < N; ++j) {                                     // getResults.py:71 loops over the hypotheses
+        float* m = match + (long long)j * n;
+        cc_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(m, match_th, n, L, cnt);
+        RF_LAUNCHED();
+        cc_merge_kernel<<<blocks_for(n, 256), 256, 0, st>>>(L, H, W);
+        RF_LAUNCHED();
+        cc_flatten_count_kernel<<<blocks_for(n, 256), 256, 0, st>>>(L, n, cnt);
+        RF_LAUNCHED();
+        cc_filter_kernel<<<blocks_for(n, 256), 256, 0, st>>>(m, L, cnt, n, cc_th);
+        RF_LAUNCHED();
+    }
     return 0;
 }

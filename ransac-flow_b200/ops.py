@@ -256,19 +256,34 @@ def upsample_bilinear(x, size):
     return out
 
 
-def compose_fine(flowDown8, match12, match21, coarse, clamp=True, align_corners=False, want_match=True, want_flowUp=False):
-    """Fused tail of PredFlowMask.  flowDown8 (1,2,h8,w8); match12/match21 (1,1,h8,w8) or None; coarse (1,H,W,2)."""
+def compose_fine(flowDown8, match12, match21, coarse, clamp=True, align_corners=False, want_match=True, want_flowUp=False, size=None):
+    """Fused tail of PredFlowMask.  flowDown8 (1,2,h8,w8); match12/match21 (1,1,h8,w8) or None; coarse (1,Hc,Wc,2).
+    ``size`` = (H, W) of the outputs when it differs from the coarse grid's (the KITTI two-level flow)."""
     need_cuda(flowDown8, match12, match21, coarse)
     _, _, h8, w8 = flowDown8.shape
-    _, H, W, _ = coarse.shape
+    _, Hc, Wc, _ = coarse.shape
+    H, W = (Hc, Wc) if size is None else (int(size[0]), int(size[1]))
     dev = coarse.device
     flow12 = torch.empty((1, H, W, 2), device=dev, dtype=torch.float32)
     match = torch.empty((1, 1, H, W), device=dev, dtype=torch.float32) if (want_match and match12 is not None) else None
     flowUp = torch.empty((1, H, W, 2), device=dev, dtype=torch.float32) if want_flowUp else None
-    check(lib.rf_compose_fine(ptr(flowDown8.contiguous()), ptr(match12.contiguous()) if match12 is not None else None,
-                              ptr(match21.contiguous()) if match21 is not None else None, h8, w8, ptr(coarse.contiguous()),
-                              H, W, int(clamp), int(align_corners), ptr(flow12), ptr(match), ptr(flowUp), stream()))
+    check(lib.rf_compose_fine_ex(ptr(flowDown8.contiguous()), ptr(match12.contiguous()) if match12 is not None else None,
+                                 ptr(match21.contiguous()) if match21 is not None else None, h8, w8, ptr(coarse.contiguous()),
+                                 Hc, Wc, H, W, int(clamp), int(align_corners), ptr(flow12), ptr(match), ptr(flowUp), stream()))
     return flow12, match, flowUp
+
+
+def remove_small_cc(match, match_th, cc_th):
+    """evaluation/evalKITTI/evaluation.py:85-100 on the device, in place: match (N,1,H,W) / (N,H,W) / (H,W) fp32 CUDA.
+    Returns ``match``."""
+    need_cuda(match)
+    assert match.dtype == torch.float32 and match.is_contiguous()
+    H, W = int(match.shape[-2]), int(match.shape[-1])
+    N = match.numel() // max(1, H * W)
+    wsz = lib.rf_remove_small_cc_workspace(H, W)
+    ws = torch.empty(wsz, device=match.device, dtype=torch.uint8)
+    check(lib.rf_remove_small_cc(ptr(match), N, H, W, float(match_th), float(cc_th), ptr(ws), wsz, stream()))
+    return match
 
 
 # --------------------------------------------------------------------------- PIL LANCZOS on device

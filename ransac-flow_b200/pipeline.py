@@ -5,6 +5,8 @@ restated on the library's kernels (no file IO, no metrics: those stay in the dri
   PredFlowMask : evaluation/evalHpatch/evaluation.py:23-55, evaluation/evalCorr/evaluation.py:29-59
   align_pair   : evaluation/evalHpatch/evaluation.py:172-243
   getFlow_all  : evaluation/evalHpatch/getResults.py:16-63 (after the np.load calls)
+  KITTI        : evaluation/evalKITTI/evaluation.py:49-100,216-344 (two-level flow, small connected components),
+                 evaluation/evalKITTI/getResults.py:95-141 (two-level recomposition)
 """
 import os
 
@@ -360,6 +362,124 @@ def align2images(coarseModel, network, img1, img2, align_corners=False):
         img1_fine = ops.grid_sample(coarseModel.IsTensor, flow12, align_corners)
         return dict(bestPrm=bestPrm, inlierMask=inlierMask, flowCoarse=flowCoarse, img1_coarse=img1_coarse, flowDown=flowDown,
                     flow12=flow12, img1_fine=img1_fine)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# KITTI: two-level fine flow (evaluation/evalKITTI/evaluation.py) and its recomposition (evalKITTI/getResults.py)
+# ------------------------------------------------------------------------------------------------------------------
+def PredFlowMask_kitti_device(IsSample, ItSample, flowCoarse, size, network, align_corners=False):
+    """evaluation/evalKITTI/evaluation.py:49-81 without the device->host copy: both images' fine features are computed
+    here (one ragged batch of two images), the matchability is always ``match12 * grid_sample(match21) * inside``, and
+    ``flowCoarse`` (1,Hc,Wc,2) may live on another grid than the ``size`` = (H, W) outputs (the second level, :296-302).
+    Returns CUDA tensors (flow12 (1,H,W,2), match (1,1,H,W), flowDown8 (1,2,h8,w8), matchDown8 (1,2,h8,w8))."""
+    with torch.no_grad():
+        f = fine_features(network["netFeatCoarse"], torch.cat([IsSample, ItSample], dim=0))
+        n = f.data.shape[0] // 2
+        fs, ft = Ragged(f.data[:n], f.hw[:1]), Ragged(f.data[n:], f.hw[1:])
+        k, ld, tc = network["netCorr"].kernelSize, network["netFlowCoarse"].CORR_LD, model.fine_engine()
+        corr12, _, both = ops.corr_neigh_pair(ft, fs, k, ld, tc)
+        flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
+        mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21
+        flow12, match, _ = ops.compose_fine(flowDown8, mboth[0:1], mboth[1:2], flowCoarse, clamp=True, align_corners=align_corners,
+                                            size=size)
+        return flow12, match, flowDown8, mboth.permute(1, 0, 2, 3).contiguous()
+
+
+def PredFlowMask_kitti(IsSample, ItSample, flowCoarse, grid, network):
+    """Same inputs / outputs as evaluation/evalKITTI/evaluation.py:49-81 (``match`` as a numpy (H, W) array, the /8
+    tensors on the device)."""
+    flow12, match, f8, m8 = PredFlowMask_kitti_device(IsSample, ItSample, flowCoarse, (grid.size()[1], grid.size()[2]), network)
+    return flow12, match[0, 0].cpu().numpy(), f8, m8
+
+
+def remove_small_cc(matchFine, match_th, cc_th):
+    """evaluation/evalKITTI/evaluation.py:85-100 for a numpy (H, W) map, on the device (connected components by union-find)."""
+    m = torch.from_numpy(np.ascontiguousarray(matchFine, dtype=np.float32)).cuda()
+    return ops.remove_small_cc(m, match_th, cc_th).cpu().numpy()
+
+
+def align_pair_kitti(coarseModel, network, Is, It, fineSize=650, cc_th=0.01, maskRegionTh=0.005, maxH=None):
+    """One pair through evaluation/evalKITTI/evaluation.py:216-344 (no segNet, no file output): per hypothesis the coarse
+    homography from ``coarseModel`` (variant A at ``coarseSize``), the first fine level on the half-size target, the
+    second level on the ``fineSize`` target sampled on the ORIGINAL image's grid, small connected components of the
+    matchability removed on the device, and the reference's mask update on the host.  ``Is`` / ``It``: PIL images.
+    ``maxH`` caps the reference's ``while True``.  Returns the four arrays the script saves (H (nH,3,3) 'Homograpy',
+    flow_d2 'Finetune_D2', mask 'Finetune_Mask', flow 'Finetune') plus the per-hypothesis full-resolution maps."""
+    from . import outil
+    strideNet = 8
+    to_t = lambda I: coarseModel._to_tensor01(coarseModel._to_device_u8(I))          # transforms.ToTensor()(I)[None].cuda()
+    It_resize = outil.resizeImg(It, strideNet, fineSize)
+    It_d2 = outil.resizeImg(It, strideNet, fineSize // 2)
+    w_org, h_org = It.size
+    tensor_s = to_t(Is)
+    (w_r, h_r), tensor_resize = It_resize.size, to_t(It_resize)
+    (w_d2, h_d2), tensor_d2 = It_d2.size, to_t(It_d2)
+    coarseModel.setPair(Is, It)
+    It_bg = np.ones((h_org, w_org), dtype=np.float32)
+    Mask = np.zeros((h_org, w_org), dtype=np.float32)
+    Hs, D2, Msk, Fin, maps = [], [], [], [], []
+    nbCoarse = 0
+    while maxH is None or nbCoarse < maxH:
+        fgMask = ((Mask + (1 - It_bg)) > 0.5).astype(np.float32)
+        bestPara = coarseModel.getCoarse(fgMask)
+        if bestPara is None:
+            break
+        with torch.no_grad():
+            bp = torch.from_numpy(bestPara).unsqueeze(0).cuda()
+            homography_d2 = ops.warp_grid(bp, h_d2, w_d2)
+            homography_resize = ops.warp_grid(bp, h_r, w_r)
+            IsSample_d2 = ops.grid_sample(tensor_s, homography_d2)
+            _, _, flowFine_d2, _ = PredFlowMask_kitti_device(IsSample_d2, tensor_d2, homography_d2, (h_d2, w_d2), network)
+            flowCoarse, _, _ = ops.compose_fine(flowFine_d2, None, None, homography_resize, clamp=True, want_match=False)     # :291-294
+            IsSample = ops.grid_sample(tensor_s, flowCoarse)
+            flowFine_org, match_org, f8, m8 = PredFlowMask_kitti_device(IsSample, tensor_resize, flowCoarse, (h_org, w_org), network)
+            ops.remove_small_cc(match_org, 0.99, cc_th)                                                                        # :311
+            matchFine = match_org[0, 0].cpu().numpy()
+        if ((matchFine > 0.9999) * (1 - fgMask)).mean() > maskRegionTh or nbCoarse == 0:
+            Hs.append(bestPara[None])
+            D2.append(flowFine_d2.cpu().numpy())
+            Msk.append(m8.cpu().numpy())
+            Fin.append(f8.cpu().numpy())
+            maps.append((flowFine_org, matchFine.copy()))
+            nbCoarse += 1
+            matchFine = matchFine * (1 - fgMask)              # :324 (len(Finetune_Mask) is never 0 here)
+            Mask = ((Mask + matchFine) > 0.9999).astype(np.float32)
+        else:
+            break
+    cat = lambda l: np.concatenate(l, axis=0) if l else np.zeros((0,))
+    return dict(H=cat(Hs), flow_d2=cat(D2), mask=cat(Msk), flow=cat(Fin), maps=maps, size=(h_org, w_org))
+
+
+def getFlow_all_kitti(param, flowd2, flow, match, outH, outW, th=1.0, cc_th=0.01, multiH=True, interpolate=False):
+    """evaluation/evalKITTI/getResults.py:95-141 after its np.load calls: param (nH,3,3) 'Homograpy', flowd2 (nH,2,.,.)
+    'Finetune_D2', flow (nH,2,.,.) 'Finetune', match (nH,2,.,.) 'Finetune_Mask' -> (flowGlobal (1,outH,outW,2), binary match
+    map), both CUDA.  The two levels are composed with the fused kernel, small connected components are removed on the
+    device, the first-hypothesis-wins merge is elementwise torch.  ``interpolate`` (EDT hole filling, :87-93) is not
+    implemented on the device: there is no CPU fallback, it raises."""
+    if interpolate:
+        raise NotImplementedError("getFlow_all_kitti(interpolate=True): the EDT hole filling of evalKITTI/getResults.py:87-93 is out of scope")
+    param = torch.as_tensor(param, dtype=torch.float32).cuda()
+    flowd2 = torch.as_tensor(flowd2, dtype=torch.float32).cuda()
+    flow = torch.as_tensor(flow, dtype=torch.float32).cuda()
+    match = torch.as_tensor(match, dtype=torch.float32).cuda()
+    homography_org = ops.warp_grid(param, outH, outW)
+    fl, ms = [], []
+    for i in range(flow.shape[0]):
+        fd2, _, _ = ops.compose_fine(flowd2[i:i + 1], None, None, homography_org[i:i + 1], clamp=True, want_match=False)     # :104-107
+        f12, m, _ = ops.compose_fine(flow[i:i + 1], match[i:i + 1, 0:1], match[i:i + 1, 1:2], fd2, clamp=True)              # :110-123
+        fl.append(f12)
+        ms.append(m)
+    m = ops.remove_small_cc(torch.cat(ms, dim=0).contiguous(), 0.99, cc_th).permute(0, 2, 3, 1)
+    f = torch.clamp(torch.cat(fl, dim=0), min=-1, max=1)
+    flowGlobal = f[:1].clone()
+    mb = m[:1] >= th
+    if multiH:
+        for i in range(1, len(m)):
+            tmp = (m.narrow(0, i, 1) >= th) * (~mb)
+            mb = mb + tmp
+            tmp = tmp.expand_as(flowGlobal)
+            flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    return flowGlobal, mb
 
 
 def getFlow_all(flow, param, match, outH, outW, th=0.95, multiH=True, with_match21=False):

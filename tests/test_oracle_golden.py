@@ -156,3 +156,34 @@ def test_coarse_align_variant_A():
             torch.randint = real
         np.testing.assert_allclose(H, g[key_h], atol=1e-5)
     assert len(c.match1) == int(g["nbMatch1"])
+
+
+# ---- KITTI extras (evaluation/evalKITTI): golden outputs of the unmodified reference functions --------------------
+def test_kitti_remove_small_cc():
+    g = golden("kitti_remove_small_cc")
+    for key in ("out_0", "out_0.01", "out_0.05", "out_1"):
+        got = WO.remove_small_cc(g["match"], float(g["match_th"]), float(key.split("_")[1]))
+        assert np.array_equal(got, g[key]), key
+    assert (g["out_0.01"] != g["match"]).sum() > 0 and (g["out_0.05"] != g["out_0.01"]).sum() > 0      # the fixture bites
+
+
+def test_kitti_pred_flow_mask_second_level():
+    """evaluation/evalKITTI/evaluation.py:49-81 with the coarse flow on a 48x64 grid and the outputs on a 56x80 grid."""
+    g = golden("kitti_pred_flow_mask")
+    net = {"netFeatCoarse": synth.feature_extractor_state(0), "netFlowCoarse": synth.net_flow_coarse_state(1),
+           "netMatch": synth.net_matchability_state(2)}
+    flowCoarse = WO.warp_grid(g["H"], 48, 64)
+    flow12, match, f8, m8 = PO.pred_flow_mask_kitti(torch.from_numpy(g["IsSample"]), torch.from_numpy(g["It"]), flowCoarse,
+                                                    WO.base_grid(56, 80), net)
+    np.testing.assert_allclose(f8.numpy(), g["flowDown8"], atol=1e-6)
+    np.testing.assert_allclose(m8.numpy(), g["matchDown8"], atol=1e-6)
+    np.testing.assert_allclose(flow12.numpy(), g["flow12"], atol=1e-6)
+    np.testing.assert_allclose(match, g["match"], atol=1e-6)
+
+
+@pytest.mark.parametrize("interp", [False, True])
+def test_kitti_get_flow_all(interp):
+    g = golden("kitti_get_flow_all")
+    fg, _ = WO.get_flow_all_kitti(g["H"], g["flowd2"], g["flow"], g["mask"], 48, 80, th=float(g["th"]), cc_th=float(g["cc_th"]),
+                                  multiH=True, interpolate=interp)
+    np.testing.assert_allclose(fg.numpy(), g["flowGlobal_interp%d" % int(interp)], atol=1e-6)
