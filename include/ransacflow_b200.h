@@ -204,6 +204,14 @@ int rf_compose_fine_ex(const float* flowDown8, const float* match12, const float
 size_t rf_remove_small_cc_workspace(int H, int W);
 int rf_remove_small_cc(float* match, int N, int H, int W, float match_th, double cc_th, void* ws, size_t ws_bytes, void* stream);
 
+/* interpolate_flow_match, evaluation/evalKITTI/getResults.py:87-93: flow_out[p] = flow[nearest matched pixel of p]
+ * (exact Euclidean distance; a matched pixel keeps its own flow).  flow / flow_out [H][W][2] (distinct buffers), matched
+ * u8 [H][W] (non-zero = matched), index_out (nullable) int32 [H][W][2] = (row, col) of the chosen pixel.  Between
+ * equidistant matched pixels the choice is this library's (documented at the kernel), not scipy's. */
+size_t rf_fill_nearest_matched_workspace(int H, int W);
+int rf_fill_nearest_matched(const float* flow, const uint8_t* matched, int H, int W, float* flow_out, int* index_out,
+                            void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ SIGNATURES = {
     "rf_upsample_bilinear": (i32, [vp, i32, i32, i32, i32, i32, vp, vp]),
     "rf_compose_fine": (i32, [vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "rf_compose_fine_ex": (i32, [vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "rf_fill_nearest_matched_workspace": (sz, [i32, i32]),
+    "rf_fill_nearest_matched": (i32, [vp, vp, i32, i32, vp, vp, vp, sz, vp]),
     "rf_remove_small_cc_workspace": (sz, [i32, i32]),
     "rf_remove_small_cc": (i32, [vp, i32, i32, i32, f32, C.c_double, vp, sz, vp]),
 }

@@ -685,6 +685,69 @@ __global__ void cc_filter_kernel(float* __restrict__ match, const int* __restric
     if ((double)cnt[r] / (double)n <= cc_th) match[i] = 0.f;         // np.mean(all_labels == i) <= cc_th
 }
 
+// ---------------------------------------------------------------------------
+// interpolate_flow_match (evaluation/evalKITTI/getResults.py:87-93): every unmatched pixel takes the flow of its nearest
+// matched pixel (exact Euclidean distance; scipy.ndimage.distance_transform_edt(return_indices=True) in the reference).
+// Exact two-pass feature transform in integer arithmetic: (1) per column, the nearest matched row above / below;
+// (2) per row, the lower envelope of the parabolas (x - x')^2 + dy(x')^2 (Felzenszwalb & Huttenlocher), then the gather.
+// Between equidistant matched pixels the choice is: smaller |dy| column-wise first (ties -> the row above), then the
+// envelope's left-most parabola; scipy resolves such ties in its own order, so outputs can differ there (and only there).
+// ---------------------------------------------------------------------------
+__global__ void edt_cols_kernel(const unsigned char* __restrict__ matched, int H, int W, int* __restrict__ gy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    int last = -1;
+    for (int y = 0; y < H; ++y) {
+        if (matched[(long long)y * W + x]) last = y;
+        gy[(long long)y * W + x] = last;
+    }
+    last = -1;
+    for (int y = H - 1; y >= 0; --y) {
+        if (matched[(long long)y * W + x]) last = y;
+        const int a = gy[(long long)y * W + x];
+        int pick = a;
+        if (a < 0) pick = last;
+        else if (last >= 0 && (last - y) < (y - a)) pick = last;
+        gy[(long long)y * W + x] = pick;
+    }
+}
+__global__ void edt_rows_fill_kernel(const int* __restrict__ gy, int H, int W, int* __restrict__ v, double* __restrict__ z,
+                                     const float2* __restrict__ flow, float2* __restrict__ out, int* __restrict__ idx_out) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= H) return;
+    const int* g = gy + (long long)y * W;
+    int* vv = v + (long long)y * W;
+    double* zz = z + (long long)y * (W + 1);
+    int k = -1;
+    for (int q = 0; q < W; ++q) {
+        if (g[q] < 0) continue;
+        const long long dq = (long long)(y - g[q]) * (y - g[q]);
+        double sx = -1e300;
+        while (k >= 0) {
+            const int p = vv[k];
+            const long long dp = (long long)(y - g[p]) * (y - g[p]);
+            sx = (double)((dq + (long long)q * q) - (dp + (long long)p * p)) / (double)(2 * (q - p));
+            if (sx <= zz[k]) --k; else break;
+        }
+        if (k < 0) sx = -1e300;
+        ++k;
+        vv[k] = q;
+        zz[k] = sx;
+    }
+    if (k < 0) {                                   // no matched pixel at all: leave the row as it is
+        for (int x = 0; x < W; ++x) { out[(long long)y * W + x] = flow[(long long)y * W + x]; if (idx_out) { idx_out[2 * ((long long)y * W + x)] = y; idx_out[2 * ((long long)y * W + x) + 1] = x; } }
+        return;
+    }
+    const int kmax = k;
+    k = 0;
+    for (int x = 0; x < W; ++x) {
+        while (k < kmax && zz[k + 1] < (double)x) ++k;
+        const int xs = vv[k], ys = g[xs];
+        out[(long long)y * W + x] = flow[(long long)ys * W + xs];
+        if (idx_out) { idx_out[2 * ((long long)y * W + x)] = ys; idx_out[2 * ((long long)y * W + x) + 1] = xs; }
+    }
+}
+
 }  // namespace rf
 
 using namespace rf;
@@ -1094,5 +1157,28 @@ extern "C" int rf_remove_small_cc(float* match, int N, int H, int W, float match
         cc_filter_kernel<<<blocks_for(n, 256), 256, 0, st>>>(m, L, cnt, n, cc_th);
         RF_LAUNCHED();
     }
+    return 0;
+}
+
+extern "C" size_t rf_fill_nearest_matched_workspace(int H, int W) {
+    const size_t h = H > 0 ? H : 0, w = W > 0 ? W : 0;
+    return 2 * h * w * sizeof(int) + h * (w + 1) * sizeof(double) + 512;
+}
+
+extern "C" int rf_fill_nearest_matched(const float* flow, const uint8_t* matched, int H, int W, float* flow_out, int* index_out,
+                                       void* ws, size_t ws_bytes, void* stream) {
+    if (H <= 0 || W <= 0) return 0;
+    RF_REQUIRE(flow != flow_out, "rf_fill_nearest_matched: in-place is not supported");
+    RF_REQUIRE(ws != nullptr && ws_bytes >= rf_fill_nearest_matched_workspace(H, W), "rf_fill_nearest_matched: workspace too small");
+    const size_t n = (size_t)H * W;
+    double* z = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    int* gy = reinterpret_cast<int*>(z + (size_t)H * (W + 1));
+    int* v = gy + n;
+    cudaStream_t st = as_stream(stream);
+    edt_cols_kernel<<<blocks_for(W, 64), 64, 0, st>>>(matched, H, W, gy);
+    RF_LAUNCHED();
+    edt_rows_fill_kernel<<<blocks_for(H, 32), 32, 0, st>>>(gy, H, W, v, z, reinterpret_cast<const float2*>(flow),
+                                                          reinterpret_cast<float2*>(flow_out), index_out);
+    RF_LAUNCHED();
     return 0;
 }

@@ -286,6 +286,21 @@ def remove_small_cc(match, match_th, cc_th):
     return match
 
 
+def fill_nearest_matched(flow, matched, want_index=False):
+    """evaluation/evalKITTI/getResults.py:87-93 on the device: flow (1,H,W,2) fp32, matched (H,W) / (1,H,W,1) bool ->
+    flow with every unmatched pixel replaced by the flow of its nearest matched pixel (exact EDT) [, (H,W,2) int32 indices]."""
+    need_cuda(flow, matched)
+    flow = flow.contiguous().float()
+    H, W = int(flow.shape[1]), int(flow.shape[2])
+    m = matched.reshape(H, W).to(torch.uint8).contiguous()
+    out = torch.empty_like(flow)
+    idx = torch.empty((H, W, 2), device=flow.device, dtype=torch.int32) if want_index else None
+    wsz = lib.rf_fill_nearest_matched_workspace(H, W)
+    ws = torch.empty(wsz, device=flow.device, dtype=torch.uint8)
+    check(lib.rf_fill_nearest_matched(ptr(flow), ptr(m), H, W, ptr(out), ptr(idx), ptr(ws), wsz, stream()))
+    return (out, idx) if want_index else out
+
+
 # --------------------------------------------------------------------------- PIL LANCZOS on device
 _coeff_cache = {}
 

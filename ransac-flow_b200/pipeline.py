@@ -454,10 +454,8 @@ def getFlow_all_kitti(param, flowd2, flow, match, outH, outW, th=1.0, cc_th=0.01
     """evaluation/evalKITTI/getResults.py:95-141 after its np.load calls: param (nH,3,3) 'Homograpy', flowd2 (nH,2,.,.)
     'Finetune_D2', flow (nH,2,.,.) 'Finetune', match (nH,2,.,.) 'Finetune_Mask' -> (flowGlobal (1,outH,outW,2), binary match
     map), both CUDA.  The two levels are composed with the fused kernel, small connected components are removed on the
-    device, the first-hypothesis-wins merge is elementwise torch.  ``interpolate`` (EDT hole filling, :87-93) is not
-    implemented on the device: there is no CPU fallback, it raises."""
-    if interpolate:
-        raise NotImplementedError("getFlow_all_kitti(interpolate=True): the EDT hole filling of evalKITTI/getResults.py:87-93 is out of scope")
+    device, the first-hypothesis-wins merge is elementwise torch.  ``interpolate``: the EDT hole filling of :87-93
+    (``ops.fill_nearest_matched``: exact nearest matched pixel; between equidistant ones the choice may differ from scipy's)."""
     param = torch.as_tensor(param, dtype=torch.float32).cuda()
     flowd2 = torch.as_tensor(flowd2, dtype=torch.float32).cuda()
     flow = torch.as_tensor(flow, dtype=torch.float32).cuda()
@@ -479,6 +477,8 @@ def getFlow_all_kitti(param, flowd2, flow, match, outH, outW, th=1.0, cc_th=0.01
             mb = mb + tmp
             tmp = tmp.expand_as(flowGlobal)
             flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    if interpolate:
+        flowGlobal = ops.fill_nearest_matched(flowGlobal, mb)
     return flowGlobal, mb
 
 

@@ -92,8 +92,22 @@ def test_kitti_get_flow_all_vs_reference(rf):
     same = (mb.cpu() == rmb).all(-1)[0]                      # the merge flips only where a matchability sits on the threshold
     assert same.float().mean() > 0.99
     assert np.abs(fg.cpu().numpy() - g["flowGlobal_interp0"])[0][same.numpy()].max() < 1e-5
-    with pytest.raises(NotImplementedError):
-        rf.pipeline.getFlow_all_kitti(g["H"], g["flowd2"], g["flow"], g["mask"], 48, 80, interpolate=True)
+    # interpolate=True (evalKITTI/getResults.py:87-93): holes take the flow of the nearest matched pixel.  Exact distances;
+    # the filled value equals the reference's wherever scipy picked the same (or the unique) nearest pixel
+    import scipy.ndimage as nd
+    fi, mbi = rf.pipeline.getFlow_all_kitti(g["H"], g["flowd2"], g["flow"], g["mask"], 48, 80, th=float(g["th"]), cc_th=float(g["cc_th"]),
+                                            multiH=True, interpolate=True)
+    assert torch.equal(mbi, mb)
+    holes = ~mb.cpu().numpy()[0, :, :, 0]
+    assert holes.any() and (~holes).any()
+    d_ref, idx_ref = nd.distance_transform_edt(holes, return_distances=True, return_indices=True)
+    _, idx = rf.ops.fill_nearest_matched(fg, mb, want_index=True)
+    idx = idx.cpu().numpy()
+    yy, xx = np.mgrid[0:48, 0:80]
+    assert np.array_equal((idx[..., 0] - yy) ** 2 + (idx[..., 1] - xx) ** 2, np.round(d_ref ** 2).astype(np.int64))
+    agree = (idx[..., 0] == idx_ref[0]) & (idx[..., 1] == idx_ref[1]) & same.numpy()
+    assert agree.mean() > 0.9
+    assert np.abs(fi.cpu().numpy() - g["flowGlobal_interp1"])[0][agree].max() < 1e-5
 
 
 def test_kitti_two_level_pair_vs_oracle(rf):
@@ -150,3 +164,26 @@ def test_get_flow_from_the_drivers_files(rf, tmp_path):
     fk = rf.results.getFlow_all_kitti_from_files(pid, str(kd), nbH, "Finetune", 48, 80, True, float(k["th"]), float(k["cc_th"]))
     d = np.abs(fk.cpu().numpy() - k["flowGlobal_interp0"])[0].max(-1)
     assert (d < 1e-5).mean() > 0.99                       # merge picks flip only where a matchability sits on the threshold
+
+
+@pytest.mark.parametrize("h,w,p,seed", [(376, 1241, 0.3, 0), (376, 1241, 0.001, 1), (60, 96, 0.05, 2), (1, 40, 0.2, 3), (37, 1, 0.3, 4),
+                                        (64, 64, 0.9, 5), (20, 30, 0.0, 6)])
+def test_fill_nearest_matched_is_exact(rf, h, w, p, seed):
+    """rf_fill_nearest_matched vs scipy's exact EDT: every pixel is filled from a MATCHED pixel at exactly the EDT distance
+    (ties between equidistant pixels may be resolved differently), matched pixels keep their own flow; p = 0 (nothing
+    matched) leaves the flow unchanged."""
+    import scipy.ndimage as nd
+    rs = np.random.RandomState(seed)
+    m = rs.rand(h, w) < p
+    flow = torch.from_numpy(rs.randn(1, h, w, 2).astype(np.float32)).cuda()
+    out, idx = rf.ops.fill_nearest_matched(flow, torch.from_numpy(m).cuda(), want_index=True)
+    out, idx, f = out.cpu().numpy(), idx.cpu().numpy().astype(np.int64), flow.cpu().numpy()
+    if not m.any():
+        assert np.array_equal(out, f)
+        return
+    d = nd.distance_transform_edt(~m)
+    yy, xx = np.mgrid[0:h, 0:w]
+    assert m[idx[..., 0], idx[..., 1]].all()
+    assert np.array_equal((idx[..., 0] - yy) ** 2 + (idx[..., 1] - xx) ** 2, np.round(d ** 2).astype(np.int64))
+    assert np.array_equal(out[0], f[0][idx[..., 0], idx[..., 1]])
+    assert np.array_equal(out[0][m], f[0][m])
