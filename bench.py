@@ -71,6 +71,49 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_facts(precision, v2):
+    """What the committed `ncu --set full` capture of the correlation kernel says (profiles/*.json, one launch at config 2):
+    DRAM bytes read + written, duration and tensor-pipe activity of the dominant launch.  {} when there is no capture."""
+    try:
+        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_pipe_ncu.json" if v2 else "r1_corr_f16_ncu.json"}[int(precision)]
+        prof = json.load(open(os.path.join(ROOT, "profiles", pf)))
+        l = [l for l in prof["launches"] if "tc_kernel" in l["kernel"] or "tc_corr_pipe" in l["kernel"]][0]
+        dur = l["gpu__time_duration.sum"]
+        us = float(dur["value"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(dur["unit"], 1.0)
+        return {"file": "profiles/" + pf, "traffic": l["dram_traffic_bytes"], "kernel_us": us,
+                "tensor_pct": float(l["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"])}
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def roofline_record(prec, v2, corr_ms, ransac_ms, n_matches, pk):
+    """The `roofline` object of the JSON line for the kernel BASELINE.json names (correlation + mutual NN, plus RANSAC as
+    us/call): algorithmic flops / bytes of config 2 over the call's measured time, against the measured peaks.
+    Pure arithmetic (tests/test_abi_and_host.py runs it without a GPU)."""
+    flops = 2.0 * NA * NB * CFEAT
+    abytes = 4.0 * CFEAT * (NA + NB) + 16.0 * n_matches
+    tf = flops / (corr_ms * 1e-3) / 1e12
+    tensor_peak = pk["bf16_tflops"]
+    ncu = ncu_facts(prec, v2)              # DRAM traffic etc. of the dominant launch, from the committed ncu --set full capture
+    kname = {0: "corr_argmax_kernel (fp32 SIMT)", 1: "tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)",
+             2: ("tc_corr_pipe_kernel (persistent, two TMEM accumulator pairs; " if v2 else "tc_kernel<128,MODE_CORR,f16> (")
+                + "fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
+    # tensor work actually issued per algorithmic MAC: 3 MMAs either way; kind::tf32 runs at half the bf16/f16 rate
+    rate = {0: None, 1: tensor_peak / 2, 2: tensor_peak}[prec]
+    return {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % kname,
+            "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": ncu.get("traffic"),
+            "peak_source": pk["src"] + " bf16 dense GEMM (burst); fp32-grade scores need 3 tensor MMAs per algorithmic MAC (split operands), "
+                           "so the executed tensor fraction is 3 x frac for the fp16 split (6 x for 3xTF32, whose MMAs run at half rate)",
+            "executed_tensor_frac": (3 * tf) / rate if rate else None,
+            "ms_per_launch": corr_ms, "algorithmic_gflop": flops / 1e9, "algorithmic_mb": abytes / 1e6,
+            "hbm_gbs_achieved": abytes / (corr_ms * 1e-3) / 1e9, "hbm_frac": abytes / (corr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+            # the dominant kernel alone, from the committed capture (the live number above times the whole 3-launch call)
+            "ncu_capture": ncu.get("file"), "kernel_us_ncu": ncu.get("kernel_us"), "tensor_pipe_active_pct_ncu": ncu.get("tensor_pct"),
+            "executed_tensor_frac_kernel_ncu": (3 * flops / (ncu["kernel_us"] * 1e-6) / 1e12 / rate) if (rate and ncu.get("kernel_us")) else None,
+            "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": n_matches,
+            "corr_plus_ransac_gbs": (abytes + 61e3) / ((corr_ms + ransac_ms) * 1e-3) / 1e9}
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
     try:
@@ -300,34 +343,9 @@ def run_b200(args, rank, world, local):
         b.record(st)
     torch.cuda.synchronize()
     ransac_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    pk = peaks()
-    flops = 2.0 * NA * NB * CFEAT
-    abytes = 4.0 * CFEAT * (NA + NB) + 16.0 * len(m1)
-    tf = flops / (corr_ms * 1e-3) / 1e12
-    tensor_peak = pk["bf16_tflops"]
     prec = rf.outil.corr_precision
     v2 = prec == 2 and rf._lib.lib.rf_corr_mutual_nn_launches(2) == 3
-    traffic = None
-    try:                                   # dram__bytes_read+write of the dominant launch, from the committed ncu --set full capture
-        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_pipe_ncu.json" if v2 else "r1_corr_f16_ncu.json"}[rf.outil.corr_precision]
-        prof = json.load(open(os.path.join(ROOT, "profiles", pf)))
-        traffic = [l for l in prof["launches"] if "tc_kernel" in l["kernel"] or "tc_corr_pipe" in l["kernel"]][0]["dram_traffic_bytes"]
-    except Exception:  # noqa: BLE001
-        pass
-    kname = {0: "corr_argmax_kernel (fp32 SIMT)", 1: "tc_kernel<128,MODE_CORR> (3xTF32 tcgen05)",
-             2: ("tc_corr_pipe_kernel (persistent, two TMEM accumulator pairs; " if v2 else "tc_kernel<128,MODE_CORR,f16> (")
-                + "fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
-    # tensor work actually issued per algorithmic MAC: 3 MMAs either way; kind::tf32 runs at half the bf16/f16 rate
-    executed = {0: None, 1: (3 * tf) / (tensor_peak / 2), 2: (3 * tf) / tensor_peak}[prec]
-    roofline = {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % kname,
-                "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": traffic,
-                "peak_source": pk["src"] + " bf16 dense GEMM (burst); fp32-grade scores need 3 tensor MMAs per algorithmic MAC (split operands), "
-                               "so the executed tensor fraction is 3 x frac for the fp16 split (6 x for 3xTF32, whose MMAs run at half rate)",
-                "executed_tensor_frac": executed,
-                "ms_per_launch": corr_ms, "algorithmic_gflop": flops / 1e9, "algorithmic_mb": abytes / 1e6,
-                "hbm_gbs_achieved": abytes / (corr_ms * 1e-3) / 1e9, "hbm_frac": abytes / (corr_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                "ransac_us_per_call": 1e3 * ransac_ms, "ransac_matches": int(len(m1)),
-                "corr_plus_ransac_gbs": (abytes + 61e3) / ((corr_ms + ransac_ms) * 1e-3) / 1e9}
+    roofline = roofline_record(prec, v2, corr_ms, ransac_ms, int(len(m1)), peaks())
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores,
     # run as `bench.py --impl reference` in a child process so that it can be cut off ----

@@ -149,6 +149,26 @@ def test_bench_product_arm_never_touches_oracle():
     assert "import oracle" not in src and "from oracle" not in src and "ransac_flow_b200" not in src
 
 
+def test_bench_roofline_record_is_complete():
+    """bench.py's `roofline` object (pure arithmetic over the measured times): the keys the bench contract names, algorithmic work
+    of config 2 (32.1 GFLOP, 58.4 MB) and the facts of the committed ncu capture."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pk = dict(hbm_gbs=6575.1, bf16_tflops=1703.4, bf16_tflops_sustained=1450.6, src="measured")
+    r = bench.roofline_record(2, True, 0.112, 0.039, 662, pk)
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["algorithmic_gflop"] - 2 * 13065 * 1200 * 1024 / 1e9) < 1e-9 and abs(r["algorithmic_mb"] - 58.44) < 0.01
+    assert abs(r["achieved"] - 32.108544 / 0.112) < 1e-6 and abs(r["executed_tensor_frac"] - 3 * r["frac"]) < 1e-12
+    assert r["traffic"] == bench.ncu_facts(2, True)["traffic"] and 55e6 < r["traffic"] < 70e6          # ~ the algorithmic bytes
+    assert r["ncu_capture"] == "profiles/r1_corr_pipe_ncu.json" and 0.5 < r["executed_tensor_frac_kernel_ncu"] < 1.0
+    assert bench.roofline_record(0, False, 1.0, 0.04, 10, pk)["executed_tensor_frac"] is None and bench.ncu_facts(0, False) == {}
+    assert abs(bench.roofline_record(1, False, 0.24, 0.04, 10, pk)["executed_tensor_frac"] - 6 * (32.108544 / 0.24) / 1703.4) < 1e-9
+
+
 def test_dropin_installs_the_reference_module_names(rf, tmp_path):
     """The names the reference's drivers import by bare name resolve to this package."""
     import runpy
