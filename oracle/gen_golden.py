@@ -398,6 +398,34 @@ def gen_kitti():
     save("kitti_get_flow_all", H=Hs, flowd2=flowd2, flow=flow, mask=mask, th=np.float64(0.6), cc_th=np.float64(0.01), **res)
 
 
+def gen_get_flow_corr(tmpdir="/tmp/rf_golden_getflow_corr"):
+    """evaluation/evalCorr/getResults.py:78-134 ``getFlow`` (flowGlobal AND matchGlobal) on three hypotheses."""
+    import scipy.ndimage as nd
+    for d in ("fine", "coarse"):
+        os.makedirs(os.path.join(tmpdir, d), exist_ok=True)
+    rs = np.random.RandomState(8)
+    nH = 3
+    flow = (rs.randn(nH, 2, 5, 7) * 0.02).astype(np.float32)
+    mask = np.clip(nd.gaussian_filter(rs.rand(nH, 2, 5, 7), (0, 0, 1, 1)) * 2.0, 0, 1).astype(np.float32)
+    Hs = np.stack([np.eye(3) + rs.uniform(-0.05, 0.05, (3, 3)) for _ in range(nH)]).astype(np.float32)
+    np.save(tmpdir + "/fine/flow_4_3H.npy", flow)
+    np.save(tmpdir + "/fine/mask_4_3H.npy", mask)
+    np.save(tmpdir + "/fine/maskBG_4_3H.npy", np.ones((40, 56), bool))
+    np.save(tmpdir + "/coarse/flow_4_3H.npy", Hs)
+
+    class Warper:                      # kornia is absent: the oracle's restatement stands in
+        def __init__(self, h, w):
+            self.h, self.w = h, w
+
+        def warp_grid(self, H):
+            return WO.warp_grid(H, self.h, self.w)
+    tgm = types.SimpleNamespace(HomographyWarper=Warper)
+    fn = extract_function(os.path.join(REF, "evaluation/evalCorr/getResults.py"), "getFlow",
+                          {"torch": torch, "F": F, "np": np, "os": os, "tgm": tgm})
+    fg, mg = fn(4, tmpdir + "/fine", ["flow_4_3H.npy"], tmpdir + "/coarse", tmpdir + "/fine", True, 0.55)
+    save("get_flow_corr", flow=flow, mask=mask, H=Hs, flowGlobal=fg.numpy(), matchGlobal=mg.numpy(), th=np.float64(0.55))
+
+
 def gen_metrics():
     """The two metric FUNCTIONS the getResults scripts define (the rest of their metric code is inline in the scripts):
     ``epe`` (evaluation/evalHpatch/getResults.py:147-157) and ``alignmentError`` (evaluation/evalCorr/getResults.py:15-38)."""
@@ -431,6 +459,7 @@ def main():
     gen_pred_flow_mask()
     gen_get_flow()
     gen_kitti()
+    gen_get_flow_corr()
     gen_metrics()
     gen_coarse_align()
 

@@ -94,6 +94,33 @@ def get_flow_all(flow, param, match, h, w, th=0.95, multiH=True, with_match21=Fa
     return flowGlobal, m12
 
 
+def get_flow_corr(flow, param, match, th=0.95, multiH=True):
+    """evaluation/evalCorr/getResults.py:78-134 ``getFlow`` after the np.load calls (evalYFCC/getResults.py:150-190 is the
+    same): flow (nH,2,h8,w8), param (nH,3,3), match (nH,2,h8,w8) -> (flowGlobal (1,8h8,8w8,2), matchGlobal (1,8h8,8w8,1)):
+    x8 upsampling, ``match12 * grid_sample(match21) * inside``, first-hypothesis-wins merge of flow AND matchability."""
+    flow = torch.as_tensor(flow, dtype=torch.float32)
+    match = torch.as_tensor(match, dtype=torch.float32)
+    h, w = flow.shape[2] * 8, flow.shape[3] * 8
+    grid = base_grid(h, w)
+    coarse = warp_grid(param, h, w)
+    f = F.interpolate(flow, scale_factor=8, mode="bilinear").permute(0, 2, 3, 1)
+    flowUp = torch.clamp(f + grid, min=-1, max=1)
+    f = grid_sample(coarse.permute(0, 3, 1, 2), flowUp).permute(0, 2, 3, 1).contiguous()
+    m = F.interpolate(match, scale_factor=8, mode="bilinear")
+    m = (m.narrow(1, 0, 1) * grid_sample(m.narrow(1, 1, 1), flowUp) * inside_mask(f)).permute(0, 2, 3, 1)
+    f = torch.clamp(f, min=-1, max=1)
+    flowGlobal, matchGlobal = f[:1].clone(), m[:1].clone()
+    mb = m[:1] >= th
+    if multiH:
+        for i in range(1, len(m)):
+            tmp = (m.narrow(0, i, 1) >= th) * (~mb)
+            matchGlobal[tmp] = m.narrow(0, i, 1)[tmp]
+            mb = mb + tmp
+            tmp = tmp.expand_as(flowGlobal)
+            flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    return flowGlobal, matchGlobal
+
+
 # --------------------------------------------------------------------------------------------------
 # KITTI extras (evaluation/evalKITTI)
 # --------------------------------------------------------------------------------------------------

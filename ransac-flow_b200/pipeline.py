@@ -482,6 +482,42 @@ def getFlow_all_kitti(param, flowd2, flow, match, outH, outW, th=1.0, cc_th=0.01
     return flowGlobal, mb
 
 
+def merge_first_wins(f, m, th, multiH=True):
+    """The first-hypothesis-wins merge every getResults script ends with (evaluation/evalCorr/getResults.py:121-134):
+    f (nH,H,W,2) clamped flows, m (nH,H,W,1) matchabilities -> (flowGlobal (1,H,W,2), matchGlobal (1,H,W,1), binary map).
+    Elementwise torch on the tensors' device."""
+    flowGlobal, matchGlobal = f[:1].clone(), m[:1].clone()
+    mb = m[:1] >= th
+    if multiH:
+        for i in range(1, len(m)):
+            tmp = (m.narrow(0, i, 1) >= th) * (~mb)
+            matchGlobal[tmp] = m.narrow(0, i, 1)[tmp]
+            mb = mb + tmp
+            tmp = tmp.expand_as(flowGlobal)
+            flowGlobal[tmp] = f.narrow(0, i, 1)[tmp]
+    return flowGlobal, matchGlobal, mb
+
+
+def getFlow_corr(flow, param, match, th=0.95, multiH=True):
+    """evaluation/evalCorr/getResults.py:78-134 ``getFlow`` (= evalYFCC/getResults.py:150-190 ``_getFlow``) after its np.load
+    calls: flow (nH,2,h8,w8), param (nH,3,3), match (nH,2,h8,w8) -> (flowGlobal (1,8h8,8w8,2), matchGlobal (1,8h8,8w8,1)), CUDA:
+    x8 upsampling, ``match12 * grid_sample(match21) * inside`` from the fused composition kernel, then ``merge_first_wins``."""
+    flow = torch.as_tensor(flow, dtype=torch.float32).cuda()
+    param = torch.as_tensor(param, dtype=torch.float32).cuda()
+    match = torch.as_tensor(match, dtype=torch.float32).cuda()
+    H, W = int(flow.shape[2]) * 8, int(flow.shape[3]) * 8
+    coarse = ops.warp_grid(param, H, W)
+    fl, ms = [], []
+    for i in range(flow.shape[0]):
+        f12, m, _ = ops.compose_fine(flow[i:i + 1], match[i:i + 1, 0:1], match[i:i + 1, 1:2], coarse[i:i + 1], clamp=True)
+        fl.append(f12)
+        ms.append(m)
+    f = torch.clamp(torch.cat(fl, dim=0), min=-1, max=1)
+    m = torch.cat(ms, dim=0).permute(0, 2, 3, 1)
+    flowGlobal, matchGlobal, _ = merge_first_wins(f, m, th, multiH)
+    return flowGlobal, matchGlobal
+
+
 def getFlow_all(flow, param, match, outH, outW, th=0.95, multiH=True, with_match21=False):
     """evaluation/evalHpatch/getResults.py:16-63 on device tensors: flow (nH,2,h8,w8), param (nH,3,3),
     match (nH,2,h8,w8) -> flowGlobal (1,outH,outW,2).  The reference runs this on CPU tensors; the

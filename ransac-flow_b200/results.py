@@ -3,6 +3,7 @@ that results written here are read by the reference's ``getResults.py`` and vice
 
   save_pair / load_pair            : evaluation/evalHpatch/evaluation.py:244-260 (identical in evalCorr :244-260)
   getFlow_all_from_files           : evaluation/evalHpatch/getResults.py:16-63 (file lookup + np.load + composition)
+  getFlow_from_files               : evaluation/evalCorr/getResults.py:78-134 / evalYFCC/getResults.py:132-190 (flow AND matchability)
   save_pair_kitti / kitti_pairs    : evaluation/evalKITTI/evaluation.py:43-47,338-344; evalKITTI/getResults.py:190-193
   getFlow_all_kitti_from_files     : evaluation/evalKITTI/getResults.py:95-141
   epe_hpatches                     : evaluation/evalHpatch/getResults.py:147-157,224-250
@@ -69,6 +70,16 @@ def getFlow_all_from_files(pairID, finePath, coarsePath, flowList, multiH, th, o
         return []
     flow, param, match = t
     return pipeline.getFlow_all(flow, param, match, outH, outW, th=th, multiH=multiH, with_match21=with_match21)
+
+
+def getFlow_from_files(pairID, finePath, flowList, coarsePath, maskPath, multiH, th):
+    """evaluation/evalCorr/getResults.py:78-134 ``getFlow`` with its own argument order (``maskPath`` only serves the
+    reference's unused ``maskBG`` load): (flowGlobal, matchGlobal) CUDA at 8x the saved resolution, or ([], [])."""
+    t = load_pair(pairID, finePath, coarsePath, flowList)
+    if t is None:
+        return [], []
+    flow, param, match = t
+    return pipeline.getFlow_corr(flow, param, match, th=th, multiH=multiH)
 
 
 # --------------------------------------------------------------------------- evalKITTI

@@ -187,3 +187,11 @@ def test_kitti_get_flow_all(interp):
     fg, _ = WO.get_flow_all_kitti(g["H"], g["flowd2"], g["flow"], g["mask"], 48, 80, th=float(g["th"]), cc_th=float(g["cc_th"]),
                                   multiH=True, interpolate=interp)
     np.testing.assert_allclose(fg.numpy(), g["flowGlobal_interp%d" % int(interp)], atol=1e-6)
+
+
+def test_get_flow_corr():
+    """evaluation/evalCorr/getResults.py:78-134 (flowGlobal and matchGlobal, three hypotheses)."""
+    g = golden("get_flow_corr")
+    fg, mg = WO.get_flow_corr(g["flow"], g["H"], g["mask"], th=float(g["th"]), multiH=True)
+    np.testing.assert_allclose(fg.numpy(), g["flowGlobal"], atol=1e-6)
+    np.testing.assert_allclose(mg.numpy(), g["matchGlobal"], atol=1e-6)

@@ -79,3 +79,23 @@ def test_dense_epe_metrics(rf):
     err = np.sqrt((f[0, :, :, 0] * (W - 1) / 2 - u) ** 2 + (f[0, :, :, 1] * (H - 1) / 2 - v) ** 2)
     ref = (err * valid).sum() / valid.sum()
     assert abs(rf.results.epe_kitti(torch.from_numpy(flow), u, v, valid) - ref) < 1e-6
+
+
+def test_merge_first_wins_equals_the_reference_merge(rf):
+    """pipeline.merge_first_wins is elementwise torch (device agnostic): on the CPU, fed with the oracle's per-hypothesis flows
+    and matchabilities, it must reproduce the reference's golden flowGlobal / matchGlobal (evalCorr/getResults.py:121-134)."""
+    import torch.nn.functional as F
+    from oracle import warp_oracle as WO
+    g = golden("get_flow_corr")
+    flow, match = torch.from_numpy(g["flow"]), torch.from_numpy(g["mask"])
+    h, w = flow.shape[2] * 8, flow.shape[3] * 8
+    grid, coarse = WO.base_grid(h, w), WO.warp_grid(g["H"], h, w)
+    flowUp = torch.clamp(F.interpolate(flow, scale_factor=8, mode="bilinear").permute(0, 2, 3, 1) + grid, min=-1, max=1)
+    f = WO.grid_sample(coarse.permute(0, 3, 1, 2), flowUp).permute(0, 2, 3, 1).contiguous()
+    m = F.interpolate(match, scale_factor=8, mode="bilinear")
+    m = (m.narrow(1, 0, 1) * WO.grid_sample(m.narrow(1, 1, 1), flowUp) * WO.inside_mask(f)).permute(0, 2, 3, 1)
+    fg, mg, mb = rf.pipeline.merge_first_wins(torch.clamp(f, min=-1, max=1), m, float(g["th"]), True)
+    assert np.abs(fg.numpy() - g["flowGlobal"]).max() < 1e-6 and np.abs(mg.numpy() - g["matchGlobal"]).max() < 1e-6
+    assert mb.dtype == torch.bool and 0.5 < mb.float().mean() < 1.0
+    fg1, mg1, _ = rf.pipeline.merge_first_wins(torch.clamp(f, min=-1, max=1), m, float(g["th"]), False)
+    assert torch.equal(fg1, torch.clamp(f, min=-1, max=1)[:1]) and torch.equal(mg1, m[:1])
