@@ -298,6 +298,21 @@ def gen_coarse_align():
                  featt=cC.featt.numpy(), feats_sum=cC.featsMultiScale.sum(0).numpy(),
                  WMulti=cC.WMultiScale.numpy(), HMulti=cC.HMultiScale.numpy(),
                  Is=np.asarray(cC.Is), It=np.asarray(cC.It))
+            # variant B (evalYFCC): variant C's API with ResizeMinSize and a use_cuda switch
+            modB = _coarse_align_common(os.path.join(REF, "evaluation/evalYFCC/coarseAlignFeatMatch.py"), "ref_coarse_B",
+                                        {"segEval": seg, "resnet50": res, "scipy.misc": misc})
+            cB = modB.CoarseAlign(3, 500, 0.05, "Homography", 96, 1, True, False, True, False, 1.5)
+            cB.setSource(Is)
+            cB.setTarget(It)
+            MtB = np.zeros((cB.It.size[1], cB.It.size[0]), dtype=np.float32)
+            MtB[: cB.It.size[1] // 5] = 1            # mask out the top fifth of the target
+            rec = []
+            with replay_randint(None, rec):
+                torch.manual_seed(1000)
+                HB, maskB = cB.getCoarse(MtB)
+            assert HB is not None
+            save("coarse_align_B", src=src, tgt=tgt, Mt=MtB, H=HB, inlierMask=maskB, samples=rec[0][1], nbMatch=np.int64(rec[0][0]),
+                 WMulti=cB.WMultiScale.numpy(), HMulti=cB.HMultiScale.numpy(), Is=np.asarray(cB.Is), It=np.asarray(cB.It))
             # variant A
             modA = _coarse_align_common(os.path.join(REF, "evaluation/evalHpatch/coarseAlignFeatMatch.py"), "ref_coarse_A",
                                         {"segEval": seg, "resnet50": res, "scipy.misc": misc})

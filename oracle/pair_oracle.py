@@ -60,14 +60,15 @@ def preproc(I):
 
 class CoarseAlignOracle:
     """Variant A when ``variant='A'`` (setPair / getCoarse(Mt) -> H | None),
-    variant C when ``variant='C'`` (setSource / setTarget / getCoarse(Mt) -> (H, mask))."""
+    variant C when ``variant='C'`` (setSource / setTarget / getCoarse(Mt) -> (H, mask)),
+    variant B (evaluation/evalYFCC/coarseAlignFeatMatch.py:35-196) = C's API with ResizeMinSize."""
 
     def __init__(self, resnet_sd, nbScale=7, nbIter=1000, tolerance=0.05, minSize=480, scaleR=2,
                  variant="A", seed=None, trunk=MO.resnet50_conv4):
         self.sd = resnet_sd
         self.nbIter, self.tolerance, self.minSize = nbIter, tolerance, minSize
         self.scaleList = scale_list(nbScale, scaleR)
-        self.mode = "min" if variant == "A" else "max"
+        self.mode = "max" if variant == "C" else "min"      # B (evalYFCC) = C's API with ResizeMinSize
         self.variant = variant
         self.seed = seed
         self.trunk = trunk

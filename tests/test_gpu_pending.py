@@ -29,3 +29,23 @@ def test_get_flow_corr_vs_reference(rf, tmp_path):
     fg2, mg2 = rf.results.getFlow_from_files(4, str(fine), sorted(p.name for p in fine.iterdir()), str(coarse), str(fine), True, float(g["th"]))
     assert np.array_equal(fg2.cpu().numpy(), fg.cpu().numpy()) and np.array_equal(mg2.cpu().numpy(), mg.cpu().numpy())
     assert rf.results.getFlow_from_files(5, str(fine), sorted(p.name for p in fine.iterdir()), str(coarse), str(fine), True, 0.5) == ([], [])
+
+
+def test_coarse_align_variant_B_vs_reference(rf):
+    """CoarseAlignB (evaluation/evalYFCC/coarseAlignFeatMatch.py:35-196) vs the reference's golden H / inlier mask / match
+    count with a masked target and the same samples."""
+    import PIL.Image as Image
+    import torch
+    from oracle import synth
+    from test_gpu_pair import fixed_randint
+    g = golden("coarse_align_B")
+    c = rf.CoarseAlignB(3, 500, 0.05, "Homography", 96, 1, True, True, True, False, 1.5, resnet_state_dict=synth.resnet50_conv4_state(0), verbose=False)
+    c.setSource(Image.fromarray(g["src"]))
+    c.setTarget(Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.Is), g["Is"]) and np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale.cpu().numpy(), g["WMulti"]) and np.array_equal(c.HMultiScale.cpu().numpy(), g["HMulti"])
+    with fixed_randint([g["samples"]]):
+        H, mask = c.getCoarse(g["Mt"])
+    assert len(c.match1) == int(g["nbMatch"])
+    np.testing.assert_allclose(H, g["H"], atol=1e-5)
+    assert np.array_equal(mask, g["inlierMask"])

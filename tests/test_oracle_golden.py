@@ -195,3 +195,23 @@ def test_get_flow_corr():
     fg, mg = WO.get_flow_corr(g["flow"], g["H"], g["mask"], th=float(g["th"]), multiH=True)
     np.testing.assert_allclose(fg.numpy(), g["flowGlobal"], atol=1e-6)
     np.testing.assert_allclose(mg.numpy(), g["matchGlobal"], atol=1e-6)
+
+
+def test_coarse_align_variant_B():
+    """evaluation/evalYFCC/coarseAlignFeatMatch.py:35-196 (variant C's API with ResizeMinSize) with a masked target."""
+    g = golden("coarse_align_B")
+    c = PO.CoarseAlignOracle(synth.resnet50_conv4_state(0), nbScale=3, nbIter=500, tolerance=0.05, minSize=96,
+                             scaleR=1.5, variant="B")
+    c.setSource(Image.fromarray(g["src"]))
+    c.setTarget(Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.Is), g["Is"]) and np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale, g["WMulti"]) and np.array_equal(c.HMultiScale, g["HMulti"])
+    real = torch.randint
+    torch.randint = lambda high, size, **k: torch.from_numpy(g["samples"]).clone()
+    try:
+        H, mask = c.getCoarse(g["Mt"])
+    finally:
+        torch.randint = real
+    assert len(c.match1) == int(g["nbMatch"])
+    np.testing.assert_allclose(H, g["H"], atol=1e-5)
+    assert np.array_equal(mask, g["inlierMask"]) and mask[0].sum() == 0          # the masked top rows hold no inlier
