@@ -1,0 +1,96 @@
+"""Host logic of the layer programs (program.py): the buffer-slot assignment that lets one C call run a whole network.
+Compiled on the CPU (no kernel is launched): every layer's destination slot must be distinct from every tensor that is still
+live (its own source / residual included), slots must be large enough, and the fp16 engine's element sizes must follow the
+hand-over rules (fp32 only for the image, OUT_F32 outputs and TF32 layers)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+
+
+def _programs(rf):
+    from ransac_flow_b200.coarseAlignFeatMatch import ResNet50Conv4
+    net = ResNet50Conv4(synth.resnet50_conv4_state(0), device="cpu")
+    yield "resnet50 fp32", net.program, False, 3
+    yield "resnet50 f16", net._build(64), True, 3
+    fe = rf.model.FeatureExtractor()
+    fe.load_state_dict(synth.feature_extractor_state(0))
+    fe.eval()
+    yield "FeatureExtractor fp32", fe._fold_build(False), False, 3
+    yield "FeatureExtractor f16", fe._fold_build(True), True, 3
+    nf = rf.model.NetFlowCoarse(7)
+    nf.load_state_dict(synth.net_flow_coarse_state(1))
+    yield "NetFlowCoarse fp32", nf._fold_build(False), False, 64
+    yield "NetFlowCoarse f16", nf._fold_build(True), True, 64
+    nm = rf.model.NetMatchability(7)
+    nm.load_state_dict(synth.net_matchability_state(2))
+    yield "NetMatchability f16", nm._fold_build(True), True, 64
+
+
+@pytest.mark.parametrize("hw", [[(96, 128)], [(192, 256), (96, 128), (48, 64), (96, 128)], [(33, 47), (480, 640)]])
+def test_slot_assignment_never_aliases_live_tensors(rf, hw):
+    for name, P, f16, cin in _programs(rf):
+        if "Net" in name:
+            hw_in = [(h // 8, w // 8) for h, w in hw]
+        else:
+            hw_in = hw
+        c = P._compile(hw_in, torch.device("cpu"), f16)
+        n_ops = len(P.ops)
+        layers = c["layers"]
+        # symbolic tensor -> slot, replayed in execution order with liveness from the topology
+        last_use = {}
+        for i, o in enumerate(P.ops):
+            last_use[o[1]] = i
+            if o[2] >= 0:
+                last_use[o[2]] = i
+        last_use[n_ops] = n_ops                                  # the output outlives the program
+        slot_of = {0: 0}
+        for i, o in enumerate(P.ops):
+            L = layers[i]
+            assert L.src == slot_of[o[1]] and (L.res == -1) == (o[2] < 0), name
+            if o[2] >= 0:
+                assert L.res == slot_of[o[2]], name
+            live = {t for t, s in slot_of.items() if last_use.get(t, -1) >= i}
+            for t in live:                                       # the destination must not overwrite anything still needed
+                assert slot_of[t] != L.dst, (name, i, t)
+            assert L.dst != 0, name                              # slot 0 is the caller's input
+            slot_of[i + 1] = L.dst
+        assert c["out_slot"] == slot_of[n_ops] and c["nslots"] <= 32
+        # every slot holds its largest tenant
+        for t, s in slot_of.items():
+            if s == 0:
+                continue
+            px = sum(h * w for h, w in _hw_of(P, hw_in, t))
+            esz = _esize(P, t, f16)
+            assert c["bufs"][s].numel() >= px * P.chan[t] * esz, (name, t)
+        assert c["out_dtype"] == (torch.float16 if (f16 and "Net" not in name) else torch.float32), name
+        assert c["in_dtype"] == (torch.float16 if (f16 and "Net" in name) else torch.float32), name
+
+
+def _hw_of(P, hw, t):
+    hws = [list(hw)]
+    for o in P.ops:
+        k, s, p = o[5], o[6], o[7]
+        hws.append([((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1) for h, w in hws[o[1]]])
+    return hws[t]
+
+
+def _esize(P, t, f16):
+    if not f16:
+        return 4
+    if t == 0:
+        return 4 if P.ops[0][0] in (3, 5) else 2                 # RF_OP_IM2COL / RF_OP_STEM7 read the fp32 image
+    return 4 if P.flags.get(t - 1, 0) else 2
+
+
+def test_fp16_handover_flags(rf):
+    """Heads under the fp16 engine: conv3 writes fp32 (OUT_F32) for the TF32 conv4; everything before is fp16."""
+    nf = rf.model.NetFlowCoarse(7)
+    P = nf._fold_build(True)
+    assert [P.flags.get(i, 0) for i in range(len(P.ops))] == [0, 0, 1, 2]
+    assert [o[4] for o in P.ops] == [512, 256, 128, 49] and P.chan[0] == 64
+    fe = rf.model.FeatureExtractor()
+    Pf = fe._fold_build(True)
+    assert all(Pf.flags.get(i, 0) == 0 for i in range(len(Pf.ops))) and Pf.chan[-1] == 256
+    assert np.prod([o[6] for o in Pf.ops if o[0] in (0, 4) and o[6] > 1]) == 8      # total stride of the main path
