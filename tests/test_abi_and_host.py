@@ -105,6 +105,24 @@ def test_scale_list_and_sizes_match_oracle(rf):
     assert sum((w // 16) * (h // 16) for w, h in sizes) == 13065
 
 
+def test_host_helpers_match_reference(rf):
+    """The two helpers of ``outil`` that are host arithmetic in the product too: getWHTensor(_Int) (exact IEEE division on
+    the host, cached) against the reference's golden output, and resizeImg (PIL) against the oracle's restatement."""
+    import PIL.Image as Image
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wh_tensor.npz"))
+    feat = torch.zeros(1, 4, int(g["h"]), int(g["w"]))
+    W, H = rf.outil.getWHTensor(feat)
+    Wi, Hi = rf.outil.getWHTensor_Int(feat)
+    assert np.array_equal(W.numpy(), g["W"]) and np.array_equal(H.numpy(), g["H"])
+    assert np.array_equal(Wi.numpy(), g["Wi"]) and np.array_equal(Hi.numpy(), g["Hi"])
+    rs = np.random.RandomState(0)
+    for (w, h, stride, ms) in [(1241, 376, 8, 650), (1241, 376, 8, 325), (640, 480, 16, 400), (123, 457, 8, 96)]:
+        I = Image.fromarray(rs.randint(0, 256, (h, w, 3)).astype(np.uint8))
+        a, b = rf.outil.resizeImg(I, stride, ms), PO.resize_img(I, stride, ms)
+        assert a.size == b.size and a.size[0] % stride == 0 and a.size[1] % stride == 0
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
 def test_no_cpu_fallback(rf):
     x = torch.zeros(4, 8)
     with pytest.raises(rf._lib.RFError):
