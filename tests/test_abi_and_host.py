@@ -187,6 +187,29 @@ def test_bench_roofline_record_is_complete():
     assert abs(bench.roofline_record(1, False, 0.24, 0.04, 10, pk)["executed_tensor_frac"] - 6 * (32.108544 / 0.24) / 1703.4) < 1e-9
 
 
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores; rank 0 only under torchrun) prints ONE JSON line with
+    the contract's keys; a non-zero rank prints nothing and exits 0."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RF_CPU_THREADS="8")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["metric"].startswith("image-pairs/sec at 480x640") and d["config"]["workload"].startswith("config2")
+    assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                        capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
 def test_dropin_installs_the_reference_module_names(rf, tmp_path):
     """The names the reference's drivers import by bare name resolve to this package."""
     import runpy
