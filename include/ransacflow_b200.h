@@ -106,6 +106,15 @@ int rf_build_matches(const int64_t* idx1, const int64_t* idx2, const int* count_
 #define RF_ENGINE_F16 2
 #define RF_ENGINE_F16_OUT32 3   /* engine 2 operands, fp32 output rounded to TF32 after ReLU (3x3 / stride 1 / no residual):
                                    the layer that hands over from fp16 activations to a TF32 layer */
+/* 4 = fp32-GRADE tcgen05 implicit GEMM ("f16x3"): every activation / weight element is carried as two fp16 values,
+ * v = hi + lo * 2^-11 (hi = fp16(v), lo = fp16((v - hi) * 2^11): 22 significand bits), and every MAC is three kind::f16 MMAs
+ * (hi*hi | hi*lo + lo*hi in a second TMEM accumulator).  x, residual and y are SPLIT tensors behind the same pointers:
+ * [2][sum HW][C] fp16, plane 0 = hi, plane 1 = lo * 2^11 (4 bytes per element like fp32); w_tc = [2][Cout][R*S*Cin] fp16,
+ * split the same way.  fp32 accumulation, bias, residual add and ReLU; needs Cin % 64 == 0, Cout % 8 == 0, 1x1 / 3x3,
+ * stride 1 / 2 (no fallback).  This is the engine whose features reproduce the reference's fp32 arg-max (match set).
+ * 5 = engine 4 operands with a plain fp32 [sum HoWo][Cout] output (any Cout, no residual): the heads' 49- / 1-channel layers. */
+#define RF_ENGINE_SPLIT 4
+#define RF_ENGINE_SPLIT_OUT32 5
 int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,
@@ -120,8 +129,9 @@ int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
 #define RF_OP_BLUR 2      /* model/downsample.py: reflect-pad 1 + [1 2 1]^2/16, stride */
 #define RF_OP_IM2COL 3    /* k x k x Cin patches (r, s, c order) zero-padded to Cout floats per output pixel: few-channel stems */
 #define RF_OP_POOLBLUR 4  /* MaxPool2d(2, stride 1) + blur stride 2 fused (model/model.py:71-72) */
-#define RF_OP_STEM7 5     /* engine 2 only: ResNet-50 stem fused (7x7 / stride 2 / pad 3 on the 3-channel fp32 image + bias + ReLU ->
-                             fp16, 64 channels) without the im2col matrix; w_f16 = [64][192] in (r, s, c) order, zero padded */
+#define RF_OP_STEM7 5     /* engines 2 / 4 only: ResNet-50 stem fused (7x7 / stride 2 / pad 3 on the 3-channel fp32 image + bias + ReLU ->
+                             fp16 / split, 64 channels) without the im2col matrix; w_f16 = [64][192] ([2][64][192] for engine 4) in
+                             (r, s, c) order, zero padded */
 #define RF_MAX_SLOTS 32
 typedef struct rf_layer {
     int op;
@@ -130,13 +140,15 @@ typedef struct rf_layer {
     const float* w;                 /* [k*k*Cin][Cout] */
     const float* w_tc;              /* [Cout][k*k*Cin] */
     const float* bias;              /* [Cout] or NULL */
-    const void* w_f16;              /* [Cout][k*k*Cin] fp16, engine 2 only (NULL otherwise) */
-    int flags;                      /* engine 2 only: RF_LAYER_* */
+    const void* w_f16;              /* engine 2: [Cout][k*k*Cin] fp16; engine 4: [2][Cout][k*k*Cin] fp16 hi / lo planes (NULL otherwise) */
+    int flags;                      /* engines 2 / 4: RF_LAYER_* */
 } rf_layer_t;
-#define RF_LAYER_OUT_F32 1          /* conv: fp16 operands, fp32 output (RF_ENGINE_F16_OUT32) */
+#define RF_LAYER_OUT_F32 1          /* conv: fp16 operands, fp32 output (RF_ENGINE_F16_OUT32; engine 4: RF_ENGINE_SPLIT_OUT32) */
 #define RF_LAYER_TF32 2             /* conv: fp32 input and output on the TF32 engine (e.g. a 49-channel head after an OUT_F32 layer) */
 /* engine 2: slots hold fp16 except the input of an RF_OP_IM2COL (the fp32 image; row length = Cout % 64 == 0), the
  * output of an RF_LAYER_OUT_F32 conv and the input / output of an RF_LAYER_TF32 conv; pooling and blur run in fp16. */
+/* engine 4: slots hold split tensors ([2][P][C] fp16) except the fp32 input image of an RF_OP_IM2COL / RF_OP_STEM7 and the fp32
+ * output of an RF_LAYER_OUT_F32 conv; pooling and blur rebuild the fp32 values and split their results again. */
 int rf_run_layers(const rf_layer_t* layers_host, int n, void* const* slots_host, int nimg, const int* hw_host,
                   int engine, void* stream);
 /* max pooling k x k / stride / zero-free padding: nn.MaxPool2d (model/model.py:71; torchvision resnet maxpool) */
@@ -147,6 +159,9 @@ int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C,
 /* F.normalize(x, dim=1): y = x / max(||x||_2, 1e-12) per pixel over C (P = total pixels).
  * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
 int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
+/* same with a split input (engine 4: [2][P][C] fp16), fp32 output; y_hi / y_lo (nullable, together): ALSO write the normalised rows
+ * as fp16 hi / lo * 2^11 planes [P][C] - the operands of rf_corr_mutual_nn_presplit; C % 8 == 0 */
+int rf_l2norm_split_nhwc(const void* x_split, long long P, int C, const uint8_t* mask, float* y, void* y_hi, void* y_lo, void* stream);
 /* same with fp16 input (the engine-2 trunk's output), fp32 output; C % 8 == 0 */
 int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mask, float* y, void* stream);
 /* model/model.py:129-160 CorrNeigh: x,y NHWC [N][h][w][C] -> out NHWC [N][h][w][ldo], channels >= k*k are
@@ -161,6 +176,11 @@ int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, int w, int 
  * rf_corr_neigh_nhwc calls). */
 int rf_corr_neigh_pair_nhwc(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, int round_tf32_out,
                             float* out_xy, float* out_yx, void* stream);
+/* engine 4 form of the pair call: split outputs (fp16 hi / lo * 2^11 planes).  out12_split = CorrNeigh(x, y) as [2][P][ldo] (the
+ * flow head's input), both_split = the two-image tensor [2][2P][ldo] = [CorrNeigh(x, y) ; CorrNeigh(y, x)] the matchability head
+ * runs on (P = N*h*w; also usable with both_split = NULL for a single volume). */
+int rf_corr_neigh_pair_split(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, void* out12_split, void* both_split,
+                             void* stream);
 /* model/model.py:226-233: softmax over k*k logits + expected offset -> flow NCHW [N][2][h][w] */
 int rf_softmax_flow(const float* logits, int N, int h, int w, int k, float* flow_nchw, void* stream);
 /* model/model.py:306: sigmoid, NHWC [P][1] -> [P] */

@@ -19,6 +19,8 @@ SIGNATURES = {
     "rf_last_error_string": (C.c_char_p, []),
     "rf_launch_count": (C.c_uint64, []),
     "rf_l2norm_f16_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),
+    "rf_l2norm_split_nhwc": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
+    "rf_corr_neigh_pair_split": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "rf_corr_mutual_nn_workspace": (sz, [i32, i32, i32, i32]),
     "rf_corr_mutual_nn_launches": (i32, [i32]),
     "rf_corr_mutual_nn": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, i32, vp]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libransacflow_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
-SOURCES = ["api.cu", "ransac.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "runner.cu"]
+SOURCES = ["api.cu", "ransac.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_split.cu", "elementwise.cu", "runner.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -48,6 +48,7 @@ class ResNet50Conv4:
                     if torch.is_tensor(v) and v.dtype.is_floating_point}
         self.program = self._build(32)            # fp32 activations: 'fp32' / 'tf32' engines
         self._program_f16 = None                  # fp16 activations ('f16' engine), built on first use
+        self._program_split = None                # split activations ('f16x3' engine), built on first use
         self.out_channels = self.program.chan[-1]
 
     def _build(self, kalign):
@@ -71,11 +72,15 @@ class ResNet50Conv4:
         return P
 
     def __call__(self, x):
-        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU; fp16 rows under the 'f16' engine,
-        which ``ops.l2norm`` turns into fp32).  One library call for the whole trunk; the output buffer belongs to the
+        """x: Ragged [P, 3] normalised images -> Ragged [P/256, 1024] (post-ReLU; fp16 rows under the 'f16' engine, split
+        planes under 'f16x3', which ``ops.l2norm`` turns into fp32).  One library call for the whole trunk; the output buffer belongs to the
         program (valid until the next call with these sizes)."""
         eng = rfmodel.get_engine()
-        if eng == ops.ENGINE_F16:
+        if eng == ops.ENGINE_SPLIT:
+            if self._program_split is None:
+                self._program_split = self._build(64)    # same topology as the fp16 program; the weights are read as hi / lo planes
+            out, ohw = self._program_split.run(x, eng)
+        elif eng == ops.ENGINE_F16:
             if self._program_f16 is None:
                 self._program_f16 = self._build(64)      # stem patches padded to a multiple of 64 halves
             out, ohw = self._program_f16.run(x, eng)

@@ -5,6 +5,8 @@
 // (float4) where the channel count allows.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rf {
@@ -119,26 +121,28 @@ __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >
 // 16-byte vectors of the activation type: 4 floats or 8 halves; arithmetic is always fp32
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
+    typedef float elem;
     static constexpr int N = 4;
-    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    static __device__ __forceinline__ void load(const float* p, long long, float (&v)[4]) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
-    static __device__ __forceinline__ void store(float* p, const float (&v)[4], int round_out) {
+    static __device__ __forceinline__ void store(float* p, long long, const float (&v)[4], int round_out) {
         float4 t = make_float4(v[0], v[1], v[2], v[3]);
         if (round_out) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
         *reinterpret_cast<float4*>(p) = t;
     }
 };
 template <> struct Vec16<__half> {
+    typedef __half elem;
     static constexpr int N = 8;
-    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    static __device__ __forceinline__ void load(const __half* p, long long, float (&v)[8]) {
         const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
         const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
     }
-    static __device__ __forceinline__ void store(__half* p, const float (&v)[8], int) {
+    static __device__ __forceinline__ void store(__half* p, long long, const float (&v)[8], int) {
         uint4 t;
         __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
@@ -146,9 +150,44 @@ template <> struct Vec16<__half> {
         *reinterpret_cast<uint4*>(p) = t;
     }
 };
+// engine 4: split tensors, two fp16 planes `plane` elements apart (x = hi + lo * 2^-11); values are rebuilt exactly in fp32,
+// results are split again (gemm_split.cu)
+struct SplitH {};
+__device__ __forceinline__ void split_store8(__half* p, long long plane, const float (&v)[8]) {
+    uint4 th, tl;
+    __half2* h = reinterpret_cast<__half2*>(&th);
+    __half2* l = reinterpret_cast<__half2*>(&tl);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float a = fminf(fmaxf(v[2 * e], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f);
+        h[e] = __floats2half2_rn(a, b);
+        const float2 f = __half22float2(h[e]);
+        l[e] = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
+    }
+    *reinterpret_cast<uint4*>(p) = th;
+    *reinterpret_cast<uint4*>(p + plane) = tl;
+}
+__device__ __forceinline__ void split_load8(const __half* p, long long plane, float (&v)[8]) {
+    const uint4 th = __ldg(reinterpret_cast<const uint4*>(p)), tl = __ldg(reinterpret_cast<const uint4*>(p + plane));
+    const __half2* h = reinterpret_cast<const __half2*>(&th);
+    const __half2* l = reinterpret_cast<const __half2*>(&tl);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 fh = __half22float2(h[e]), fl = __half22float2(l[e]);
+        v[2 * e] = fmaf(fl.x, 0.00048828125f, fh.x);
+        v[2 * e + 1] = fmaf(fl.y, 0.00048828125f, fh.y);
+    }
+}
+template <> struct Vec16<SplitH> {
+    typedef __half elem;
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __half* p, long long plane, float (&v)[8]) { split_load8(p, plane, v); }
+    static __device__ __forceinline__ void store(__half* p, long long plane, const float (&v)[8], int) { split_store8(p, plane, v); }
+};
 
 template <typename T>
-__global__ void blur_kernel(const __grid_constant__ ImgSet set, const T* __restrict__ x, T* __restrict__ y, int C, int stride, int round_out) {
+__global__ void blur_kernel(const __grid_constant__ ImgSet set, const typename Vec16<T>::elem* __restrict__ x, typename Vec16<T>::elem* __restrict__ y,
+                            int C, int stride, int round_out, long long pin = 0, long long pout = 0) {
     constexpr int VN = Vec16<T>::N;
     const int cvn = C / VN;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,12 +210,12 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const T* __restr
             int ix = reflect1(ox * stride - 1 + s, W);
             float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
             float v[VN];
-            Vec16<T>::load(x + (set.in_pix[im] + (long long)iy * W + ix) * C + cv * VN, v);
+            Vec16<T>::load(x + (set.in_pix[im] + (long long)iy * W + ix) * C + cv * VN, pin, v);
 #pragma unroll
             for (int e = 0; e < VN; ++e) acc[e] = fmaf(wgt, v[e], acc[e]);
         }
     }
-    Vec16<T>::store(y + pm * C + cv * VN, acc, round_out);
+    Vec16<T>::store(y + pm * C + cv * VN, pout, acc, round_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -186,7 +225,8 @@ __global__ void blur_kernel(const __grid_constant__ ImgSet set, const T* __restr
 // 78.6 + 78.6 + 78.6 + 19.7).
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const T* __restrict__ x, T* __restrict__ y, int C, int round_out) {
+__global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const typename Vec16<T>::elem* __restrict__ x, typename Vec16<T>::elem* __restrict__ y,
+                                int C, int round_out, long long pin = 0, long long pout = 0) {
     constexpr int VN = Vec16<T>::N;
     const int cvn = C / VN;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,7 +239,7 @@ __global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const T* __r
     int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
     const int H = set.H[im], W = set.W[im];
     const int Hp = H - 1, Wp = W - 1;                       // pooled map size
-    const T* base = x + set.in_pix[im] * C + cv * VN;
+    const typename Vec16<T>::elem* base = x + set.in_pix[im] * C + cv * VN;
     float acc[VN];
 #pragma unroll
     for (int e = 0; e < VN; ++e) acc[e] = 0.f;
@@ -211,15 +251,46 @@ __global__ void poolblur_kernel(const __grid_constant__ ImgSet set, const T* __r
             const int px = reflect1(ox * 2 - 1 + s, Wp);
             const float wgt = ((r == 1) ? 2.f : 1.f) * ((s == 1) ? 2.f : 1.f) * 0.0625f;
             float a[VN], b[VN], c[VN], d[VN];
-            Vec16<T>::load(base + ((long long)py * W + px) * C, a);
-            Vec16<T>::load(base + ((long long)py * W + px + 1) * C, b);
-            Vec16<T>::load(base + ((long long)(py + 1) * W + px) * C, c);
-            Vec16<T>::load(base + ((long long)(py + 1) * W + px + 1) * C, d);
+            Vec16<T>::load(base + ((long long)py * W + px) * C, pin, a);
+            Vec16<T>::load(base + ((long long)py * W + px + 1) * C, pin, b);
+            Vec16<T>::load(base + ((long long)(py + 1) * W + px) * C, pin, c);
+            Vec16<T>::load(base + ((long long)(py + 1) * W + px + 1) * C, pin, d);
 #pragma unroll
             for (int e = 0; e < VN; ++e) acc[e] = fmaf(wgt, fmaxf(fmaxf(a[e], b[e]), fmaxf(c[e], d[e])), acc[e]);
         }
     }
-    Vec16<T>::store(y + pm * C + cv * VN, acc, round_out);
+    Vec16<T>::store(y + pm * C + cv * VN, pout, acc, round_out);
+}
+
+// engine 4: max pooling on split tensors (values rebuilt in fp32, the maximum split again); one thread per (pixel, 8 channels)
+__global__ void maxpool_split_kernel(const __grid_constant__ ImgSet set, const __half* __restrict__ x, __half* __restrict__ y,
+                                     int C, int k, int stride, int pad, long long pin, long long pout) {
+    const int c8n = C >> 3;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = set.out_pix[set.n] * c8n;
+    if (t >= total) return;
+    long long pm = t / c8n;
+    int c8 = (int)(t - pm * c8n);
+    int im = find_img(set, pm);
+    int local = (int)(pm - set.out_pix[im]);
+    int oy = local / set.Wo[im], ox = local - oy * set.Wo[im];
+    const int H = set.H[im], W = set.W[im];
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+        int iy = oy * stride - pad + r;
+        if (iy < 0 || iy >= H) continue;
+        for (int s = 0; s < k; ++s) {
+            int ix = ox * stride - pad + s;
+            if (ix < 0 || ix >= W) continue;
+            float v[8];
+            split_load8(x + (set.in_pix[im] + (long long)iy * W + ix) * C + c8 * 8, pin, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+        }
+    }
+    split_store8(y + pm * C + c8 * 8, pout, m);
 }
 
 // ---------------------------------------------------------------------------
@@ -281,6 +352,47 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, long long P, int
     }
 }
 
+// engine 4: split input (planes `plane` elements apart), fp32 arithmetic and output.  `yhi` / `ylo` (nullable): ALSO write
+// the normalised rows as the fp16 hi / lo * 2^11 planes the fp16-split correlation kernel reads (rf_corr_mutual_nn with
+// presplit operands), which saves its split pass.
+__global__ void l2norm_split_kernel(const __half* __restrict__ x, long long plane, long long P, int C, const unsigned char* __restrict__ mask,
+                                    float* __restrict__ y, __half* __restrict__ yhi, __half* __restrict__ ylo) {
+    long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (pix >= P) return;
+    const __half* src = x + pix * C;
+    float4* dst = reinterpret_cast<float4*>(y + pix * C);
+    const int c8n = C >> 3;
+    if (mask != nullptr && mask[pix] == 0) {
+        for (int c = lane; c < 2 * c8n; c += 32) dst[c] = make_float4(0, 0, 0, 0);
+        if (yhi != nullptr)
+            for (int c = lane; c < c8n; c += 32) {
+                reinterpret_cast<uint4*>(yhi + pix * C)[c] = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(ylo + pix * C)[c] = make_uint4(0, 0, 0, 0);
+            }
+        return;
+    }
+    float ss = 0.f;
+    for (int c = lane; c < c8n; c += 32) {
+        float v[8];
+        split_load8(src + c * 8, plane, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[e], v[e], ss);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < c8n; c += 32) {
+        float v[8];
+        split_load8(src + c * 8, plane, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __fdiv_rn(v[e], denom);
+        dst[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (yhi != nullptr) split_store8(yhi + pix * C + c * 8, (ylo - yhi), v);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // model/model.py:129-160 CorrNeigh: out[n,r,c,i*k+j] = sum_ch x[n,r,c,ch] * y[n,r+i-k/2,c+j-k/2,ch]
 // one warp per output pixel, lanes over channels, k*k shuffled reductions
@@ -289,6 +401,22 @@ __global__ void l2norm_f16_kernel(const __half* __restrict__ x, long long P, int
 // same dot product (fmaf(a, b, acc) with a and b swapped is the same operation, so the bits are equal): the warp of
 // pixel p scatters every in-image tap to corr21[p+d][-d] and writes the zero of its own out-of-image taps, which covers
 // every entry of corr21 exactly once.  One launch instead of two (evaluation/evalHpatch/evaluation.py:29-30).
+// round_out: 0 fp32, 1 fp32 rounded to TF32, 2 fp16, 3 split (engine 4: [2][rows][ldo] fp16 planes).  Mode 3 with `out2`: `out` is
+// the standalone corr12 tensor (planes P * ldo apart) and `out2` the two-image tensor [corr12 ; corr21] (2P rows, planes
+// 2P * ldo apart) the matchability head runs on - corr12 is written to both.
+__device__ __forceinline__ void corr_store(float* out, long long idx, float v, int round_out, long long plane) {
+    if (round_out == 3) {
+        const float a = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(a);
+        reinterpret_cast<__half*>(out)[idx] = h;
+        reinterpret_cast<__half*>(out)[idx + plane] = __float2half_rn((a - __half2float(h)) * 2048.f);
+    } else if (round_out == 2) {
+        reinterpret_cast<__half*>(out)[idx] = __float2half_rn(v);
+    } else {
+        out[idx] = round_out ? round_tf32(v) : v;
+    }
+}
+
 __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int k, int ldo, int round_out,
                                   float* __restrict__ out, float* __restrict__ out2) {
     long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -299,6 +427,8 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
     int rem = (int)(pix - (long long)n * h * w);
     int r = rem / w, c = rem - r * w;
     const int pad = k / 2, c4n = C >> 2;
+    const bool split = round_out == 3;
+    const long long plane1 = P * ldo, plane2 = 2 * P * ldo;                  // split planes of `out` / of the two-image `out2`
     const float4* xs = reinterpret_cast<const float4*>(x + pix * C);
     // C <= 1024: up to 8 float4 per lane kept in registers
     float4 xv[8];
@@ -322,28 +452,24 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
             if (lane == 0) {
-                if (round_out == 2) reinterpret_cast<__half*>(out)[pix * ldo + i * k + j] = __float2half_rn(acc);
-                else out[pix * ldo + i * k + j] = round_out ? round_tf32(acc) : acc;
+                corr_store(out, pix * ldo + i * k + j, acc, round_out, plane1);
                 if (out2 != nullptr) {
+                    if (split) corr_store(out2, pix * ldo + i * k + j, acc, 3, plane2);
                     const bool inside = yr >= 0 && yr < h && yc >= 0 && yc < w;
                     // inside: entry (p + d, -d) of the swapped volume; outside: this pixel's own (zero) entry (p, d)
                     const long long q = inside ? (((long long)n * h + yr) * w + yc) : pix;
                     const int e = inside ? (k - 1 - i) * k + (k - 1 - j) : i * k + j;
-                    if (round_out == 2) reinterpret_cast<__half*>(out2)[q * ldo + e] = __float2half_rn(acc);
-                    else out2[q * ldo + e] = round_out ? round_tf32(acc) : acc;
+                    if (split) corr_store(out2, (P + q) * ldo + e, acc, 3, plane2);
+                    else corr_store(out2, q * ldo + e, acc, round_out, 0);
                 }
             }
         }
     }
-    if (round_out == 2) {
-        for (int c = k * k + lane; c < ldo; c += 32) {
-            reinterpret_cast<__half*>(out)[pix * ldo + c] = __float2half_rn(0.f);
-            if (out2 != nullptr) reinterpret_cast<__half*>(out2)[pix * ldo + c] = __float2half_rn(0.f);
-        }
-    } else {
-        for (int c = k * k + lane; c < ldo; c += 32) {
-            out[pix * ldo + c] = 0.f;
-            if (out2 != nullptr) out2[pix * ldo + c] = 0.f;
+    for (int cz = k * k + lane; cz < ldo; cz += 32) {
+        corr_store(out, pix * ldo + cz, 0.f, round_out, plane1);
+        if (out2 != nullptr) {
+            if (split) { corr_store(out2, pix * ldo + cz, 0.f, 3, plane2); corr_store(out2, (P + pix) * ldo + cz, 0.f, 3, plane2); }
+            else corr_store(out2, pix * ldo + cz, 0.f, round_out, 0);
         }
     }
 }
@@ -793,9 +919,13 @@ extern "C" int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_h
 
 // Stem-specialised im2col: one CTA = one output row segment of TPX pixels.  The K input rows it needs are staged in
 // shared memory with coalesced loads, then the (r, s, c)-ordered patches are written as contiguous float4 rows.
+template <typename T> struct OutElem { typedef T type; };
+template <> struct OutElem<SplitH> { typedef __half type; };
+
 template <int K, int C, int KPAD, int STRIDE, int PAD, int TPX, typename OutT = float>
 __global__ void __launch_bounds__(256)
-im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, OutT* __restrict__ y, int round_out) {
+im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__ x, typename OutElem<OutT>::type* __restrict__ y, int round_out,
+                   long long plane = 0) {
     constexpr int INW = ((TPX - 1) * STRIDE + K) * C;          // floats of one staged input row
     constexpr int Q4 = KPAD / 4;
     __shared__ float sIn[K][INW + 1];
@@ -823,7 +953,22 @@ im2col_smem_kernel(const __grid_constant__ ImgSet set, const float* __restrict__
     }
     __syncthreads();
     const int npx = min(TPX, Wo - ox0);
-    if constexpr (sizeof(OutT) == 2) {
+    if constexpr (std::is_same<OutT, SplitH>::value) {
+        // engine 4: rows of KPAD values as hi / lo planes
+        constexpr int Q8 = KPAD / 8;
+        __half* dsts = y + (set.out_pix[im] + (long long)oy * Wo + ox0) * KPAD;
+        for (int f = threadIdx.x; f < npx * Q8; f += 256) {
+            const int px = f / Q8, e0 = (f - px * Q8) * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = e0 + j;
+                v[j] = (e < K * K * C) ? sIn[e / (K * C)][px * STRIDE * C + e % (K * C)] : 0.f;
+            }
+            split_store8(dsts + (long long)f * 8, plane, v);
+        }
+        return;
+    } else if constexpr (sizeof(OutT) == 2) {
         // engine 2: rows of KPAD halves, eight per 16-byte store
         constexpr int Q8 = KPAD / 8;
         uint4* dst8 = reinterpret_cast<uint4*>(y + (set.out_pix[im] + (long long)oy * Wo + ox0) * KPAD);
@@ -946,6 +1091,79 @@ extern "C" int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const u
     RF_REQUIRE(((uintptr_t)x_f16 % 16) == 0 && ((uintptr_t)y % 16) == 0, "rf_l2norm_f16_nhwc: pointers must be 16-byte aligned");
     if (P == 0) return 0;
     l2norm_f16_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x_f16), P, C, mask, y);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// ---- engine 4 (split tensors: [2][P][C] fp16 planes) ----
+int rf_blur_split_impl(const void* x, int nimg, const int* hw_host, int C, int stride, void* y, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && stride >= 1, "rf_blur (engine 4): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 3, stride, 1) == 0, "rf_blur: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 2 && set.W[i] >= 2, "rf_blur: reflect padding needs H, W >= 2");
+    long long total = set.out_pix[nimg] * (C / 8);
+    blur_kernel<SplitH><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x), static_cast<__half*>(y), C, stride, 0,
+                                                                              set.in_pix[nimg] * C, set.out_pix[nimg] * C);
+    RF_LAUNCHED();
+    return 0;
+}
+
+int rf_poolblur_split_impl(const void* x, int nimg, const int* hw_host, int C, void* y, void* stream) {
+    RF_REQUIRE((C % 8) == 0, "rf_poolblur (engine 4): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 4, 2, 1) == 0, "rf_poolblur: bad image set");
+    for (int i = 0; i < nimg; ++i) RF_REQUIRE(set.H[i] >= 3 && set.W[i] >= 3, "rf_poolblur: needs H, W >= 3");
+    long long total = set.out_pix[nimg] * (C / 8);
+    poolblur_kernel<SplitH><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x), static_cast<__half*>(y), C, 0,
+                                                                                  set.in_pix[nimg] * C, set.out_pix[nimg] * C);
+    RF_LAUNCHED();
+    return 0;
+}
+
+int rf_maxpool_split_impl(const void* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, void* y, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && k >= 1 && stride >= 1, "rf_maxpool (engine 4): C must be a multiple of 8");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_maxpool: bad image set");
+    long long total = set.out_pix[nimg] * (C / 8);
+    maxpool_split_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(set, static_cast<const __half*>(x), static_cast<__half*>(y), C, k, stride, pad,
+                                                                               set.in_pix[nimg] * C, set.out_pix[nimg] * C);
+    RF_LAUNCHED();
+    return 0;
+}
+
+// FeatureExtractor stem patches (3x3 / 1 / pad 1, 27 -> 64 columns) as a split tensor
+int rf_im2col_split_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y, void* stream) {
+    RF_REQUIRE(k == 3 && C == 3 && Kpad == 64 && stride == 1 && pad == 1, "rf_im2col (engine 4): only the FeatureExtractor stem (3x3/1, Kpad 64)");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, k, stride, pad) == 0, "rf_im2col: bad image set");
+    int maxHo = 0, maxWo = 0;
+    for (int i = 0; i < nimg; ++i) { maxHo = set.Ho[i] > maxHo ? set.Ho[i] : maxHo; maxWo = set.Wo[i] > maxWo ? set.Wo[i] : maxWo; }
+    im2col_smem_kernel<3, 3, 64, 1, 1, 128, SplitH><<<dim3((maxWo + 127) / 128, maxHo, nimg), 256, 0, as_stream(stream)>>>(
+        set, x, static_cast<__half*>(y), 0, set.out_pix[nimg] * 64);
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_l2norm_split_nhwc(const void* x_split, long long P, int C, const uint8_t* mask, float* y, void* y_hi, void* y_lo, void* stream) {
+    RF_REQUIRE((C % 8) == 0 && P >= 0, "rf_l2norm_split_nhwc: C must be a multiple of 8");
+    RF_REQUIRE(((uintptr_t)x_split % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)y_hi % 16) == 0 && ((uintptr_t)y_lo % 16) == 0,
+               "rf_l2norm_split_nhwc: pointers must be 16-byte aligned");
+    RF_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "rf_l2norm_split_nhwc: y_hi and y_lo go together");
+    if (P == 0) return 0;
+    l2norm_split_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x_split), P * C, P, C, mask, y,
+                                                                               static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
+    RF_LAUNCHED();
+    return 0;
+}
+
+extern "C" int rf_corr_neigh_pair_split(const float* x, const float* y, int N, int h, int w, int C, int k, int ldo, void* out12_split, void* both_split,
+                                        void* stream) {
+    RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_pair_split: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
+    RF_REQUIRE(out12_split != nullptr && out12_split != both_split, "rf_corr_neigh_pair_split: outputs");
+    long long P = (long long)N * h * w;
+    if (P == 0) return 0;
+    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, 3, static_cast<float*>(out12_split),
+                                                                             static_cast<float*>(both_split));
     RF_LAUNCHED();
     return 0;
 }

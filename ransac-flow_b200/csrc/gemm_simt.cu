@@ -450,6 +450,7 @@ int rf_corr_v2_mode();
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
 bool rf_conv2d_tc_supported(const ConvParams& p);
+int rf_conv2d_split(const ImgSet& set, const ConvParams& p, const void* w_split, cudaStream_t st, bool out32);
 
 static size_t keys_bytes(int NA, int NB) {
     return (((size_t)(NA > 0 ? NA : 0) + (size_t)(NB > 0 ? NB : 0)) * sizeof(unsigned long long) + 255) / 256 * 256;
@@ -520,11 +521,15 @@ extern "C" int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int 
     // (the MMA truncates), which removes the truncation bias.  The fp32 engine never rounds.
     p.round_out = ((engine == RF_ENGINE_TF32 || engine == RF_ENGINE_F16_OUT32) && relu) ? 1 : 0;
     cudaStream_t st = as_stream(stream);
-    RF_REQUIRE(engine >= RF_ENGINE_FP32 && engine <= RF_ENGINE_F16_OUT32, "rf_conv2d_nhwc: unknown engine");
+    RF_REQUIRE(engine >= RF_ENGINE_FP32 && engine <= RF_ENGINE_SPLIT_OUT32, "rf_conv2d_nhwc: unknown engine");
     // engine 2 = tcgen05 with fp16 activations and weights (x, residual, y, w_tc hold IEEE halves); no SIMT fallback.
     // engine 3 = the same with an fp32 (TF32-rounded after ReLU) output: the hand-over to a TF32 layer
     if (engine == RF_ENGINE_F16) return rf_conv2d_tc(set, p, w_tc, st, true, false);
     if (engine == RF_ENGINE_F16_OUT32) return rf_conv2d_tc(set, p, w_tc, st, true, true);
+    // engine 4 = tcgen05 with fp16 hi / lo split operands (fp32-grade, gemm_split.cu): x, residual, y are split tensors
+    // ([2][P][C] fp16), w_tc = [2][Cout][K] fp16.  engine 5 = the same with an fp32 [P][Cout] output (no residual)
+    if (engine == RF_ENGINE_SPLIT) return rf_conv2d_split(set, p, w_tc, st, false);
+    if (engine == RF_ENGINE_SPLIT_OUT32) return rf_conv2d_split(set, p, w_tc, st, true);
     // engine 1 = tcgen05 TF32 where the layer shape allows it (stride 1, Cin % 32 == 0); other layers
     // (3-channel stems, stride-2 convs, 49-channel heads) run on the exact-fp32 SIMT engine below
     if (engine == 1 && w_tc != nullptr && rf_conv2d_tc_supported(p)) return rf_conv2d_tc(set, p, w_tc, st, false, false);

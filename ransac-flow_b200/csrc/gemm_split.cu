@@ -1,0 +1,596 @@
+// Engine 4 ("f16x3"): fp32-GRADE convolutions on the tcgen05 tensor cores.
+//
+// The reference runs its networks in fp32 (quick_start/coarseAlignFeatMatch.py:34-52,106; model/model.py:59-125,167-322)
+// and the mutual-nearest-neighbour arg-max of utils/outil.py:34-43 is decided by score gaps of a few 1e-7, so 10-bit
+// tensor-core operands (TF32 / fp16 activations) do not reproduce its match set.  Here every activation and weight is
+// carried as TWO fp16 planes, x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11) (22 significand bits), and
+// every MAC is three kind::f16 MMAs: hi*hi into one TMEM accumulator, hi*lo + lo*hi (at 2^11 scale) into a second one; the
+// epilogue adds them with one fma, applies folded-BN bias / residual / ReLU in fp32 and writes the result split again.
+//
+// Data layout: a split tensor is [2][P][C] fp16 (plane 0 = hi, plane 1 = lo * 2^11; 4 bytes per element like fp32).  Every
+// TMA tensor map is 4-D (C, W, H, plane) with a box of 2 planes, so ONE bulk copy brings the hi and the lo tile of a K block
+// into consecutive shared memory ([hi tile | lo tile], both 128-byte swizzled), one copy stores both output planes, one
+// loads both residual planes.  Weights are (K, Cout, plane) with a 3-D box.
+//
+// One persistent kernel, one CTA per SM, 320 threads:
+//   warp 0    : TMA producer.  Tap streaming (1x1 of any stride, 3x3 / stride 2): A = (64 ch, tw, th, 2) box at the tap's
+//               offset (zero padding by out-of-bounds fill), B = (64 k, 64 rows, 2) box.  HALO (3x3 / stride 1): A = the
+//               (8+2) x (16+2) halo of one 64-channel block once, the nine taps are nine UMMA descriptors into it (see
+//               tc_halo_kernel in gemm_tc.cu), B = nine weight boxes.  Runs ahead across tiles; prefetches the residual
+//               tile of tile i into epilogue staging buffer i & 1.
+//   warp 1    : MMA issuer.  Two accumulator PAIRS (main | cross) x 64 columns x 2 buffers = 256 TMEM columns: tile i+1
+//               multiplies while tile i drains.
+//   warps 2-5 : epilogue group 0 (even tiles), warps 6-9: group 1 (odd tiles): TMEM -> main + cross * 2^-11 + bias
+//               (+ residual hi + lo * 2^-11) -> ReLU -> split -> swizzled staging [hi box | lo box] -> one TMA store.
+//               `out32`: fp32 rows straight to global memory instead (the 49- / 1-channel outputs of the heads).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rf {
+
+constexpr int SP_BN = 64;
+constexpr int SP_THREADS = 320;
+constexpr int SP_HALO_TW = 8, SP_HALO_TH = 16, SP_HALO_LD = SP_HALO_TW + 2;
+constexpr int SP_HALO_PLANE = SP_HALO_LD * (SP_HALO_TH + 2) * 128;          // 23040 B: one plane of a halo block
+
+struct alignas(64) SplitParams {
+    CUtensorMap mapA[RF_MAX_IMGS];        // per image: input (Cin, W, H, 2) fp16
+    CUtensorMap mapY[RF_MAX_IMGS];        // per image: output (Cout, Wo, Ho, 2), box (64, tw, th, 2)
+    CUtensorMap mapR[RF_MAX_IMGS];        // per image: residual, same geometry
+    CUtensorMap mapB;                     // weights (K, Cout, 2), box (64, 64, 2)
+    int nimg;
+    int tile_start[RF_MAX_IMGS + 1];
+    int tiles_x[RF_MAX_IMGS];
+    int tw[RF_MAX_IMGS];
+    int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
+    long long out_pix[RF_MAX_IMGS + 1];
+    int R, S, pad, stride, Cin, Cout, relu, has_res, out32;
+    int tiles_m, tiles_n;
+    const float* bias;
+    float* y32;                           // out32: fp32 [P][Cout]
+};
+
+template <bool HALO>
+struct SplitCfg {
+    static constexpr int BN = SP_BN;
+    static constexpr int B_PLANE = BN * 128;                                  // 8 KB
+    static constexpr int B_TILE = 2 * B_PLANE;                                // hi + lo planes of one weight tile
+    static constexpr int A_LO = HALO ? SP_HALO_PLANE : TC_A_BYTES;            // offset of the lo plane inside an A slot
+    static constexpr int A_TX = 2 * A_LO;
+    static constexpr int A_SLOT = HALO ? 46 * 1024 : 2 * TC_A_BYTES;          // 1024-byte aligned slots
+    static constexpr int NA = HALO ? 2 : 3;
+    static constexpr int NB = HALO ? 4 : 3;
+    static constexpr int TB = HALO ? 9 : 1;                                   // B tiles consumed per A slot
+    static constexpr int STG = 2 * TC_A_BYTES;                                // per epilogue group: [hi box | lo box]
+    static constexpr int OFF_B = NA * A_SLOT;
+    static constexpr int OFF_STG = OFF_B + NB * B_TILE;
+    static constexpr int DATA_BYTES = OFF_STG + 2 * STG;
+    static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
+    static constexpr int TMEM_COLS = 4 * BN;                                  // 2 buffers x (main | cross)
+};
+static_assert(SplitCfg<true>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false>::SMEM_BYTES <= 227 * 1024, "shared memory");
+static_assert(SplitCfg<true>::A_TX <= SplitCfg<true>::A_SLOT, "halo slot");
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// K-major, 128-byte swizzle, 8-row core groups one HALO row pitch (10 pixels = 1280 B) apart; base offset 0 (the
+// swizzle of tcgen05.mma is a function of the shared-memory address: gemm_tc.cu make_desc_halo, measured in round 1)
+__device__ __forceinline__ uint64_t sp_desc_halo(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)(saddr >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((SP_HALO_LD * 128) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct SpTile { int img, ox0, oy0, tw, n0; };
+
+template <bool HALO>
+__device__ __forceinline__ SpTile sp_decode(const SplitParams& p, int t) {
+    SpTile c;
+    const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;      // channel tiles fastest: co-running CTAs share the pixel tile
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mt >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = mt - p.tile_start[img];
+    c.img = img;
+    c.tw = HALO ? SP_HALO_TW : p.tw[img];
+    const int th = 128 / c.tw;
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    c.ox0 = txi * c.tw;
+    c.oy0 = tyi * th;
+    c.n0 = nt * SP_BN;
+    return c;
+}
+
+// split one fp32 value pair into (hi, lo * 2^11) half2 pairs, saturating like the fp16 engine
+__device__ __forceinline__ void sp_split2(float a, float b, __half2& hi, __half2& lo) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    hi = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(hi);
+    lo = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
+}
+
+template <bool HALO>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+tc_split_kernel(const __grid_constant__ SplitParams p) {
+    using Cfg = SplitCfg<HALO>;
+    constexpr int BN = Cfg::BN, NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB, BK = TC_BK_F16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::OFF_B;
+    uint8_t* sStg = smem + Cfg::OFF_STG;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+    uint64_t* emptyA = fullA + NA;
+    uint64_t* fullB = emptyA + NA;
+    uint64_t* emptyB = fullB + NB;
+    uint64_t* tmem_full = emptyB + NB;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
+    uint64_t* res_full = tmem_empty + 2;        // [2]
+    uint64_t* stg_free = res_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.tiles_m * p.tiles_n;
+    const int kc = p.Cin / BK;
+    const int NAI = HALO ? kc : p.R * p.S * kc;             // A slots per tile
+    const bool has_res = p.has_res != 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); mbar_init(&res_full[i], 1); mbar_init(&stg_free[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const SpTile c = sp_decode<HALO>(p, t);
+                if (has_res) {
+                    const uint32_t g = ti & 1;
+                    mbar_wait(&stg_free[g], ((ti >> 1) & 1) ^ 1);        // tile ti-2's store has read this buffer (passes at once for ti < 2)
+                    mbar_expect_tx(&res_full[g], Cfg::STG);
+                    tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0, c.ox0, c.oy0, 0);
+                }
+                for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
+                    const int sa = ia_cnt % NA;
+                    mbar_wait(&emptyA[sa], ((ia_cnt / NA) & 1) ^ 1);
+                    mbar_expect_tx(&fullA[sa], Cfg::A_TX);
+                    int tap = 0, cc = ia;
+                    if (HALO) {
+                        tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], ia * BK, c.ox0 - 1, c.oy0 - 1, 0);
+                    } else {
+                        tap = ia / kc;
+                        cc = ia - tap * kc;
+                        const int r = tap / p.S, sx = tap - r * p.S;
+                        tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], cc * BK, c.ox0 * p.stride + sx - p.pad,
+                                    c.oy0 * p.stride + r - p.pad, 0);
+                    }
+                    for (int jb = 0; jb < TB; ++jb, ++ib_cnt) {
+                        const int sb = ib_cnt % NB;
+                        mbar_wait(&emptyB[sb], ((ib_cnt / NB) & 1) ^ 1);
+                        mbar_expect_tx(&fullB[sb], Cfg::B_TILE);
+                        const int btap = HALO ? jb : tap;
+                        tma_load_3d(sB + sb * Cfg::B_TILE, &p.mapB, &fullB[sb], btap * p.Cin + cc * BK, c.n0, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (whole warp, warp-uniform) ===============================
+        constexpr uint32_t idesc = make_idesc_f16(BN);
+        uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator pair
+            tc_fence_after();
+            const uint32_t td = tmem_base + buf * (2 * BN), tx = td + BN;
+            for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
+                const int sa = ia_cnt % NA;
+                mbar_wait(&fullA[sa], (ia_cnt / NA) & 1);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(sA + sa * Cfg::A_SLOT);
+                for (int jb = 0; jb < TB; ++jb, ++ib_cnt) {
+                    const int sb = ib_cnt % NB;
+                    mbar_wait(&fullB[sb], (ib_cnt / NB) & 1);
+                    tc_fence_after();
+                    const uint32_t bb = smem_u32(sB + sb * Cfg::B_TILE);
+                    uint32_t aaddr = abase;
+                    if (HALO) { const int r = jb / 3, sx = jb - r * 3; aaddr += (uint32_t)((r * SP_HALO_LD + sx) * 128); }
+                    const uint64_t ahi = HALO ? sp_desc_halo(aaddr) : make_desc_sw128(aaddr);
+                    const uint64_t alo = HALO ? sp_desc_halo(aaddr + Cfg::A_LO) : make_desc_sw128(aaddr + Cfg::A_LO);
+                    umma_f16split_x4(td, tx, ahi, alo, make_desc_sw128(bb), make_desc_sw128(bb + Cfg::B_PLANE), idesc, (ia | jb) != 0 ? 1u : 0u);
+                    umma_commit(&emptyB[sb]);
+                }
+                umma_commit(&emptyA[sa]);
+            }
+            umma_commit(&tmem_full[buf]);
+        }
+    } else {
+        // =============================== epilogue groups ===============================
+        const uint32_t g = (uint32_t)(warp - 2) >> 2;                       // 0: warps 2-5, 1: warps 6-9
+        const int q = warp & 3;                                             // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+        uint8_t* stg = sStg + g * Cfg::STG;
+        uint32_t k = 0;                                                     // this group's tile counter
+        for (int t = blockIdx.x + (int)g * (int)gridDim.x; t < total; t += 2 * gridDim.x, ++k) {
+            const SpTile c = sp_decode<HALO>(p, t);
+            // the leader comes here only after the previous store has read the staging buffer
+            if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            mbar_wait(&tmem_full[g], k & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(&res_full[g], k & 1);
+            const uint32_t trow = tmem_base + g * (2 * BN) + ((uint32_t)(q * 32) << 16);
+            const int py = m / c.tw, px = m - py * c.tw;
+            const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
+            float* yrow = p.out32 ? p.y32 + (p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px)) * p.Cout : nullptr;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32], x[32];
+                tmem_ld32x2(trow + cb * 32, v, trow + BN + cb * 32, x);
+                const int n = c.n0 + cb * 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (n + 8 * j + e < p.Cout) o[e] += __ldg(p.bias + n + 8 * j + e);
+                    }
+                    if (p.out32) {
+                        if (pvalid) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (n + 8 * j + e < p.Cout) yrow[n + 8 * j + e] = p.relu ? fmaxf(o[e], 0.f) : o[e];
+                        }
+                        continue;
+                    }
+                    const int chunk = cb * 4 + j;
+                    uint4* hp = reinterpret_cast<uint4*>(stg + m * 128 + ((chunk ^ (m & 7)) << 4));
+                    uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hp) + TC_A_BYTES);
+                    if (has_res) {
+                        const uint4 rh = *hp, rl = *lp;
+                        const __half2* h = reinterpret_cast<const __half2*>(&rh);
+                        const __half2* l = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 fh = __half22float2(h[e]), fl = __half22float2(l[e]);
+                            o[2 * e] += fmaf(fl.x, 0.00048828125f, fh.x);
+                            o[2 * e + 1] += fmaf(fl.y, 0.00048828125f, fh.y);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+                    }
+                    uint4 oh, ol;
+                    __half2* ph = reinterpret_cast<__half2*>(&oh);
+                    __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sp_split2(o[2 * e], o[2 * e + 1], ph[e], pl[e]);
+                    *hp = oh;
+                    *lp = ol;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[g]);                                    // accumulator pair drained (128 arrivals)
+            if (!p.out32) {
+                fence_proxy_async();
+                if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (leader) {
+                    tma_store_4d(&p.mapY[c.img], stg, c.n0, c.ox0, c.oy0, 0);
+                    tma_store_commit_and_wait_read();
+                    if (has_res) mbar_arrive(&stg_free[g]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ResNet-50 stem, fused, split operands: conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
+// split NHWC.  Same structure as stem7_f16_kernel (gemm_tc.cu): the 147-long patches are built in shared memory straight
+// in the swizzled K-major layout, here as hi and lo planes (3 + 3 K blocks), and each K block is three MMA groups.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SS_TW = 16, SS_TH = 8, SS_K = 7, SS_C = 3, SS_KK = 147, SS_KB = 3;
+constexpr int SS_IN_W = ((SS_TW - 1) * 2 + SS_K) * SS_C;                  // 111 floats per staged input row
+constexpr int SS_IN_H = (SS_TH - 1) * 2 + SS_K;                           // 21 rows
+constexpr int SS_IN_LD = 112;
+constexpr int SS_B_TILE = 2 * 64 * 128;                                   // [hi | lo] weights of one K block: 16 KB
+constexpr int SS_OFF_ALO = SS_KB * TC_A_BYTES;                            // 48 KB: lo planes of the patches
+constexpr int SS_OFF_B = 2 * SS_KB * TC_A_BYTES;                          // 96 KB
+constexpr int SS_OFF_IN = SS_OFF_B + SS_KB * SS_B_TILE;                   // 144 KB
+constexpr int SS_OFF_BAR = SS_OFF_IN + SS_IN_H * SS_IN_LD * 4;
+constexpr int SS_SMEM = SS_OFF_BAR + 64 + 1024;
+constexpr int SS_THREADS = 160;
+
+struct alignas(64) StemSplitParams {
+    CUtensorMap mapB;                     // weights (192, 64, 2) fp16, box (64, 64, 2)
+    CUtensorMap mapY[RF_MAX_IMGS];        // output (64, Wo, Ho, 2), box (64, 16, 8, 2)
+    int nimg;
+    int tile_start[RF_MAX_IMGS + 1];
+    int tiles_x[RF_MAX_IMGS];
+    int H[RF_MAX_IMGS], W[RF_MAX_IMGS];
+    long long in_pix[RF_MAX_IMGS];
+    const float* x;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(SS_THREADS, 1)
+stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + SS_OFF_B;
+    float* sIn = reinterpret_cast<float*>(smem + SS_OFF_IN);
+    uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + SS_OFF_BAR);
+    uint64_t* bar_a = bar_b + 1;
+    uint64_t* bar_mma = bar_a + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = blockIdx.x - p.tile_start[img];
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    const int ox0 = txi * SS_TW, oy0 = tyi * SS_TH;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_a, 128);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[img]); }
+        tmem_alloc(tmem_slot, 128);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_b, SS_KB * SS_B_TILE);
+#pragma unroll
+            for (int kb = 0; kb < SS_KB; ++kb) tma_load_3d(sB + kb * SS_B_TILE, &p.mapB, bar_b, kb * 64, 0, 0);
+        }
+        mbar_wait(bar_b, 0);
+        mbar_wait(bar_a, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_f16(64);
+#pragma unroll
+        for (int kb = 0; kb < SS_KB; ++kb) {
+            const uint32_t a = smem_u32(sA + kb * TC_A_BYTES), b = smem_u32(sB + kb * SS_B_TILE);
+            umma_f16split_x4(tmem_base, tmem_base + 64, make_desc_sw128(a), make_desc_sw128(a + SS_OFF_ALO), make_desc_sw128(b),
+                             make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_mma);
+    } else {
+        const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = accumulator row
+        const int H = p.H[img], WC = p.W[img] * SS_C;
+        const float* src = p.x + p.in_pix[img] * SS_C;
+        const int iy0 = oy0 * 2 - 3, col0 = (ox0 * 2 - 3) * SS_C;
+        constexpr int NLD = (SS_IN_H * SS_IN_W + 127) / 128;
+        float stage[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int idx = m + i * 128;
+            const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
+            const int iy = iy0 + r, col = col0 + j;
+            stage[i] = (idx < SS_IN_H * SS_IN_W && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+            const int idx = m + i * 128;
+            const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
+            if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int py = m >> 4, px = m & 15;
+        const float* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
+#pragma unroll
+        for (int kb = 0; kb < SS_KB; ++kb) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 oh, ol;
+                __half2* ph = reinterpret_cast<__half2*>(&oh);
+                __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
+                    const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
+                    const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
+                    sp_split2(a, b, ph[e], pl[e]);
+                }
+                uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = oh;
+                *reinterpret_cast<uint4*>(dst + SS_OFF_ALO) = ol;
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_a);
+        // ---- epilogue: [hi box | lo box] staged over the first two patch blocks (the MMAs are done), one TMA store ----
+        mbar_wait(bar_mma, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < 2; ++cb) {
+            uint32_t v[32], x[32];
+            tmem_ld32x2(trow + cb * 32, v, trow + 64 + cb * 32, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
+                    if (p.bias != nullptr) o[e] += __ldg(p.bias + cb * 32 + 8 * j + e);
+                    o[e] = fmaxf(o[e], 0.f);
+                }
+                uint4 oh, ol;
+                __half2* ph = reinterpret_cast<__half2*>(&oh);
+                __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sp_split2(o[2 * e], o[2 * e + 1], ph[e], pl[e]);
+                const int chunk = cb * 4 + j;
+                uint8_t* dst = sA + m * 128 + ((chunk ^ (m & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = oh;
+                *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
+            }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (m == 0) {
+            tma_store_4d(&p.mapY[img], sA, 0, ox0, oy0, 0);
+            tma_store_commit_and_wait_read();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace rf
+
+using namespace rf;
+
+bool rf_conv2d_split_supported(const ConvParams& p) {
+    return (p.stride == 1 || p.stride == 2) && (p.Cin % TC_BK_F16) == 0 && p.Cout >= 1 && p.R == p.S && (p.R == 1 || p.R == 3);
+}
+
+// x / residual / y: split tensors ([2][P][C] fp16, planes `P * C` elements apart); w_split: [2][Cout][K] fp16; out32: y is
+// fp32 [P][Cout] (no residual).
+int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split, cudaStream_t st, bool out32) {
+    RF_REQUIRE(w_split != nullptr, "rf_conv2d_nhwc: engine 4 needs the split weights ([2][Cout][R*S*Cin] fp16)");
+    RF_REQUIRE(rf_conv2d_split_supported(cp), "rf_conv2d_nhwc: engine 4 needs stride 1 or 2, 1x1 or 3x3, Cin % 64 == 0");
+    RF_REQUIRE(out32 || (cp.Cout % 8) == 0, "rf_conv2d_nhwc: engine 4 needs Cout % 8 == 0 for split outputs");
+    RF_REQUIRE(!out32 || cp.residual == nullptr, "rf_conv2d_nhwc: engine 4 fp32 outputs take no residual");
+    RF_REQUIRE(((uintptr_t)cp.x % 16) == 0 && ((uintptr_t)cp.y % 16) == 0 && ((uintptr_t)cp.residual % 16) == 0 && ((uintptr_t)w_split % 16) == 0,
+               "rf_conv2d_nhwc: engine 4 needs 16-byte aligned pointers");
+    SplitParams p;
+    memset(&p, 0, sizeof(p));
+    const bool halo = (cp.R == 3 && cp.stride == 1 && cp.pad == 1);
+    const char* xb = reinterpret_cast<const char*>(cp.x);
+    const char* rb = reinterpret_cast<const char*>(cp.residual);
+    char* yb = reinterpret_cast<char*>(cp.y);
+    const unsigned long long in_plane = (unsigned long long)set.in_pix[set.n] * cp.Cin * 2ull;
+    const unsigned long long out_plane = (unsigned long long)set.out_pix[set.n] * cp.Cout * 2ull;
+    p.nimg = set.n;
+    int tiles = 0;
+    for (int i = 0; i < set.n; ++i) {
+        const int tw = halo ? SP_HALO_TW : pick_tw(set.Ho[i], set.Wo[i]), th = 128 / tw;
+        p.tw[i] = tw;
+        p.tiles_x[i] = (set.Wo[i] + tw - 1) / tw;
+        p.tile_start[i] = tiles;
+        tiles += p.tiles_x[i] * ((set.Ho[i] + th - 1) / th);
+        p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
+        p.out_pix[i] = set.out_pix[i];
+        int rc = get_map4(&p.mapA[i], xb + set.in_pix[i] * cp.Cin * 2, (unsigned long long)cp.Cin, (unsigned long long)set.W[i], (unsigned long long)set.H[i], 2,
+                          in_plane, TC_BK_F16, (unsigned)(halo ? tw + 2 : tw), (unsigned)(halo ? th + 2 : th), 2, (unsigned)cp.stride, 2);
+        if (rc) return rc;
+        if (!out32) {
+            rc = get_map4(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
+                          out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
+            if (!rc && cp.residual)
+                rc = get_map4(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
+                              out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
+            if (rc) return rc;
+        }
+    }
+    for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
+    p.out_pix[set.n] = set.out_pix[set.n];
+    int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, SP_BN, 2, 1, 2);
+    if (rc) return rc;
+    p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
+    p.has_res = cp.residual != nullptr ? 1 : 0;
+    p.out32 = out32 ? 1 : 0;
+    p.bias = cp.bias;
+    p.y32 = out32 ? cp.y : nullptr;
+    p.tiles_m = tiles;
+    p.tiles_n = (cp.Cout + SP_BN - 1) / SP_BN;
+    const long long total = (long long)p.tiles_m * p.tiles_n;
+    RF_REQUIRE(total < (1ll << 30), "rf_conv2d_nhwc: too many tiles");
+    const int grid = total < num_sms() ? (int)total : num_sms();
+    static bool attr[64][2] = {{false}};
+    const int dev = current_device();
+    if (halo) {
+        if (!attr[dev][1]) {
+            RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true>::SMEM_BYTES));
+            attr[dev][1] = true;
+        }
+        tc_split_kernel<true><<<grid, SP_THREADS, SplitCfg<true>::SMEM_BYTES, st>>>(p);
+    } else {
+        if (!attr[dev][0]) {
+            RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false>::SMEM_BYTES));
+            attr[dev][0] = true;
+        }
+        tc_split_kernel<false><<<grid, SP_THREADS, SplitCfg<false>::SMEM_BYTES, st>>>(p);
+    }
+    RF_LAUNCHED();
+    return 0;
+}
+
+// engine 4: fused ResNet-50 stem.  x fp32 [sum HW][3], w_split [2][64][192] fp16 ((r, s, c) order, zero padded), bias fp32 [64],
+// y split [2][sum HoWo][64]
+int rf_stem7_split_impl(const float* x, int nimg, const int* hw_host, const void* w_split, const float* bias, void* y_split, void* stream) {
+    RF_REQUIRE(x != nullptr && w_split != nullptr && y_split != nullptr, "rf_stem7: null pointer");
+    RF_REQUIRE(((uintptr_t)y_split % 16) == 0 && ((uintptr_t)w_split % 16) == 0, "rf_stem7: pointers must be 16-byte aligned");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw_host, 7, 2, 3) == 0, "rf_stem7: bad image set");
+    StemSplitParams p;
+    memset(&p, 0, sizeof(p));
+    p.nimg = nimg;
+    const unsigned long long out_plane = (unsigned long long)set.out_pix[nimg] * 64ull * 2ull;
+    int tiles = 0;
+    for (int i = 0; i < nimg; ++i) {
+        p.tiles_x[i] = (set.Wo[i] + SS_TW - 1) / SS_TW;
+        p.tile_start[i] = tiles;
+        tiles += p.tiles_x[i] * ((set.Ho[i] + SS_TH - 1) / SS_TH);
+        p.H[i] = set.H[i]; p.W[i] = set.W[i];
+        p.in_pix[i] = set.in_pix[i];
+        int rc = get_map4(&p.mapY[i], static_cast<char*>(y_split) + set.out_pix[i] * 64 * 2, 64ull, (unsigned long long)set.Wo[i],
+                          (unsigned long long)set.Ho[i], 2, out_plane, 64, SS_TW, SS_TH, 2, 1, 2);
+        if (rc) return rc;
+    }
+    for (int i = nimg; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
+    int rc = get_map(&p.mapB, w_split, 192ull, 64ull, 2, 64, 64, 2, 1, 2);
+    if (rc) return rc;
+    p.x = x; p.bias = bias;
+    static bool attr[64] = {false};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        RF_CUDA(cudaFuncSetAttribute(stem7_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
+        attr[dev] = true;
+    }
+    stem7_split_kernel<<<tiles, SS_THREADS, SS_SMEM, as_stream(stream)>>>(p);
+    RF_LAUNCHED();
+    return 0;
+}

@@ -13,6 +13,11 @@ int rf_maxpool_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, 
 int rf_stem7_f16_impl(const float* x, int nimg, const int* hw_host, const void* w_f16, const float* bias, void* y_f16, void* stream);
 int rf_blur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, int stride, void* y_f16, void* stream);
 int rf_poolblur_f16_impl(const void* x_f16, int nimg, const int* hw_host, int C, void* y_f16, void* stream);
+int rf_stem7_split_impl(const float* x, int nimg, const int* hw_host, const void* w_split, const float* bias, void* y_split, void* stream);
+int rf_blur_split_impl(const void* x, int nimg, const int* hw_host, int C, int stride, void* y, void* stream);
+int rf_poolblur_split_impl(const void* x, int nimg, const int* hw_host, int C, void* y, void* stream);
+int rf_maxpool_split_impl(const void* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, void* y, void* stream);
+int rf_im2col_split_impl(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, int Kpad, void* y, void* stream);
 int rf_blur_downsample_impl(const float* x, int nimg, const int* hw_host, int C, int stride, int round_out, float* y, void* stream);
 
 extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int nimg, const int* hw_host, int engine, void* stream) {
@@ -32,7 +37,31 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
         float* y = static_cast<float*>(slots[l.dst]);
         int rc = 0;
         int k = l.k, stride = l.stride, pad = l.pad;
-        if (engine == RF_ENGINE_F16) {
+        if (engine == RF_ENGINE_SPLIT) {
+            // split activations ([2][P][C] fp16): the fp32 input image may only feed the stem; RF_LAYER_OUT_F32 convs write fp32
+            if (l.op == RF_OP_CONV) {
+                const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;
+                rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, static_cast<const float*>(l.w_f16), l.bias, res, l.Cout, k, k, stride, pad, l.relu,
+                                    (l.flags & RF_LAYER_OUT_F32) ? RF_ENGINE_SPLIT_OUT32 : RF_ENGINE_SPLIT, y, stream);
+            } else if (l.op == RF_OP_MAXPOOL) {
+                rc = rf_maxpool_split_impl(x, nimg, shw, l.Cin, k, stride, pad, y, stream);
+            } else if (l.op == RF_OP_BLUR) {
+                k = 3; pad = 1;
+                rc = rf_blur_split_impl(x, nimg, shw, l.Cin, stride, y, stream);
+            } else if (l.op == RF_OP_POOLBLUR) {
+                k = 4; stride = 2; pad = 1;
+                rc = rf_poolblur_split_impl(x, nimg, shw, l.Cin, y, stream);
+            } else if (l.op == RF_OP_STEM7) {
+                RF_REQUIRE(l.src == L[0].src && l.Cin == 3 && l.Cout == 64 && k == 7 && stride == 2 && pad == 3 && l.relu,
+                           "rf_run_layers: RF_OP_STEM7 is the ResNet-50 stem on the fp32 input slot");
+                rc = rf_stem7_split_impl(x, nimg, shw, l.w_f16, l.bias, y, stream);
+            } else if (l.op == RF_OP_IM2COL) {
+                RF_REQUIRE(l.src == L[0].src, "rf_run_layers (engine 4): im2col reads the fp32 input slot");
+                rc = rf_im2col_split_impl(x, nimg, shw, l.Cin, k, stride, pad, l.Cout, y, stream);
+            } else {
+                return fail_msg("rf_run_layers: unknown op");
+            }
+        } else if (engine == RF_ENGINE_F16) {
             // fp16 activations: the (fp32) input image may only feed the stem's im2col; everything after it is fp16
             if (l.op == RF_OP_CONV) {
                 const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;

@@ -18,13 +18,14 @@ _engine = ops.ENGINE_FP32
 
 
 def set_engine(engine):
-    """'fp32' (exact FMA, SIMT), 'tf32' (tcgen05 tensor cores, fp32 activations), 'f16' (tcgen05 with fp16
-    activations: ResNet-50 trunk, FeatureExtractor and the 3x3 body of the heads; the 49- / 1-channel head outputs
-    stay TF32 / fp32) or 'f16-trunk' (fp16 trunk only, fine-flow networks on 'tf32')."""
+    """'fp32' (exact FMA, SIMT), 'f16x3' (tcgen05 tensor cores with fp16 hi / lo split operands and activations: fp32-GRADE,
+    22 significand bits, three MMAs per MAC - the engine that reproduces the reference's fp32 match set), 'tf32' (tcgen05,
+    fp32 activations, 10-bit operands), 'f16' (tcgen05 with fp16 activations: the fast, reduced-precision mode; the 49- /
+    1-channel head outputs stay TF32 / fp32) or 'f16-trunk' (fp16 trunk only, fine-flow networks on 'tf32')."""
     global _engine, _fine_f16
     _fine_f16 = engine != "f16-trunk"
-    _engine = ({"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32, "f16": ops.ENGINE_F16, "f16-trunk": ops.ENGINE_F16}[engine]
-               if isinstance(engine, str) else int(engine))
+    _engine = ({"fp32": ops.ENGINE_FP32, "tf32": ops.ENGINE_TF32, "f16": ops.ENGINE_F16, "f16-trunk": ops.ENGINE_F16,
+                "f16x3": ops.ENGINE_SPLIT}[engine] if isinstance(engine, str) else int(engine))
 
 
 def get_engine():
@@ -36,7 +37,7 @@ _fine_f16 = True
 
 def fine_engine():
     """Engine of FeatureExtractor / NetFlowCoarse / NetMatchability ('f16-trunk' keeps them on 'tf32')."""
-    return _engine if (_engine < ops.ENGINE_F16 or _fine_f16) else ops.ENGINE_TF32
+    return _engine if (_engine != ops.ENGINE_F16 or _fine_f16) else ops.ENGINE_TF32
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -84,6 +85,15 @@ class FoldedConv:
         self.pad = (k // 2) if pad is None else pad
 
     @property
+    def w_split(self):
+        """[2][Cout][R*S*Cin] fp16: hi = fp16(w), lo = fp16((w - hi) * 2^11) - the engine-4 operand; built on first use."""
+        if getattr(self, "_w_split", None) is None:
+            hi = self._wt.to(torch.float16)
+            lo = ((self._wt - hi.float()) * 2048.0).to(torch.float16)
+            self._w_split = torch.stack([hi, lo]).contiguous()
+        return self._w_split
+
+    @property
     def w_f16(self):
         """[Cout][R*S*Cin] fp16 (round to nearest), the engine-2 operand; built on first use."""
         if self._w_f16 is None:
@@ -92,6 +102,8 @@ class FoldedConv:
 
     def __call__(self, x, relu, residual=None, engine=None):
         eng = min(fine_engine(), ops.ENGINE_TF32) if engine is None else engine     # fp32 activations here; the library keeps unsupported shapes on the FMA engine
+        if int(eng) == ops.ENGINE_SPLIT:
+            return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_split)
         return ops.conv2d(x, self.w, self.bias, self.cout, self.k, self.stride, self.pad, relu, residual, eng, self.w_tc)
 
 
@@ -99,7 +111,8 @@ class _Engine(nn.Module):
     """Caches folded weights; rebuilt whenever parameters change or move."""
 
     def _folded(self, f16=False):
-        """The layer program for fp32 activations (f16 = False) or for the fp16 engine."""
+        """The layer program for fp32 activations (False / 0), the fp16 engine (True / 2) or the split engine (4)."""
+        f16 = 2 if f16 is True else (int(f16) if int(f16) in (ops.ENGINE_F16, ops.ENGINE_SPLIT) else 0)
         ver = tuple((p._version, p.data_ptr()) for p in list(self.parameters()) + list(self.buffers()))
         if getattr(self, "_fold_ver", None) != ver:
             self._fold = {}
@@ -170,7 +183,7 @@ class FeatureExtractor(_Engine):
     def _fold_build(self, f16=False):
         """The whole network as one layer program (model/model.py:106-114 do_forward)."""
         P = LayerProgram(3)
-        x = P.stem(0, self.conv1.weight, self.bn1, 1, 1, 64 if f16 else 32)          # conv1 + bn1 + relu (im2col + 1x1)
+        x = P.stem(0, self.conv1.weight, self.bn1, 1, 1, 64 if f16 else 32)          # conv1 + bn1 + relu (im2col + 1x1; 64-wide rows for fp16 / split)
         x = P.poolblur(x)                                                            # MaxPool2d(2, 1) + anti-aliased stride 2, fused
         for layer in (self.layer1, self.layer2, self.layer3):
             for b in layer:
@@ -188,13 +201,16 @@ class FeatureExtractor(_Engine):
         """Ragged [P, 3] -> Ragged [P/64, 256].  The returned buffer is owned by the program and valid until
         the next forward with the same image sizes; callers normalise / copy it right away."""
         eng = fine_engine()
-        out, ohw = self._folded(eng == ops.ENGINE_F16).run(x, eng)
-        return Ragged(out, ohw)                 # fp16 rows under the fp16 engine (ops.l2norm returns fp32 either way)
+        out, ohw = self._folded(eng).run(x, eng)
+        return Ragged(out, ohw)                 # fp16 rows / split planes under the tensor-core engines (ops.l2norm returns fp32 either way)
 
     def forward(self, x):
         self._check(x)
         with torch.no_grad():
-            return self.forward_ragged(Ragged.from_nchw(x)).to_nchw().float().clone(memory_format=torch.channels_last)
+            r = self.forward_ragged(Ragged.from_nchw(x))
+            if r.split:
+                r = Ragged(ops.from_split(r.data), r.hw)
+            return r.to_nchw().float().clone(memory_format=torch.channels_last)
 
 
 class CorrNeigh(nn.Module):
@@ -230,27 +246,35 @@ class _Head(_Engine):
     CORR_LD = 64      # the k*k = 49-channel correlation volume is carried with 64 channels (15 zeros)
 
     def _fold_build(self, f16=False):
-        # under the fp16 engine conv1..conv3 read fp16; conv3 writes fp32 and the 49- / 1-channel conv4 stays on TF32
+        # under the fp16 engine conv1..conv3 read fp16; conv3 writes fp32 and the 49- / 1-channel conv4 stays on TF32.  Under the
+        # split engine all four layers are split-operand convolutions and conv4 writes plain fp32 rows
         P = LayerProgram(self.CORR_LD)
+        split = f16 == 4
         x = P.conv(0, FoldedConv(self.conv1.weight, self.bn1, cin_pad=self.CORR_LD), relu=True)
         x = P.conv(x, FoldedConv(self.conv2.weight, self.bn2), relu=True)
-        x = P.conv(x, FoldedConv(self.conv3.weight, self.bn3), relu=True, out_f32=True)
-        P.conv(x, FoldedConv(self.conv4.weight, None), relu=False, tf32=True)
+        x = P.conv(x, FoldedConv(self.conv3.weight, self.bn3), relu=True, out_f32=not split)
+        P.conv(x, FoldedConv(self.conv4.weight, None), relu=False, tf32=not split, out_f32=split)
         return P
 
-    def _padded(self, corr, dtype):
-        """Accept the reference's 49-channel volume or the library's 64-channel one (fp32, or fp16 for the fp16 engine)."""
-        if corr.C == self.CORR_LD and corr.data.dtype == dtype:
+    def _padded(self, corr, dtype, split=False):
+        """Accept the reference's 49-channel volume or the library's 64-channel one (fp32, fp16 for the fp16 engine, split
+        planes for the split engine)."""
+        if corr.C == self.CORR_LD and corr.data.dtype == dtype and corr.split == split:
             return corr
+        if split:
+            src = ops.from_split(corr.data) if corr.split else corr.data.float()
+            d = torch.zeros((src.shape[0], self.CORR_LD), device=src.device, dtype=torch.float32)
+            d[:, :min(src.shape[1], self.kernelSize ** 2)] = src[:, :self.kernelSize ** 2]
+            return Ragged(ops.to_split(d), corr.hw)
         d = torch.zeros((corr.data.shape[0], self.CORR_LD), device=corr.data.device, dtype=dtype)
         d[:, :min(corr.C, self.kernelSize ** 2)] = corr.data[:, :self.kernelSize ** 2].to(dtype)
         return Ragged(d, corr.hw)
 
     def trunk(self, corr):
         eng = fine_engine()
-        f16 = eng == ops.ENGINE_F16
-        corr = self._padded(corr, torch.float16 if f16 else torch.float32)
-        out, ohw = self._folded(f16).run(corr, eng)
+        f16, split = eng == ops.ENGINE_F16, eng == ops.ENGINE_SPLIT
+        corr = self._padded(corr, torch.float16 if (f16 or split) else torch.float32, split)
+        out, ohw = self._folded(eng).run(corr, eng)
         return Ragged(out, ohw)
 
 

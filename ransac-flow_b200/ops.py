@@ -16,6 +16,21 @@ from ._lib import check, lib, need_cuda, ptr, stream
 ENGINE_FP32 = 0      # exact fp32 FMA (SIMT)
 ENGINE_TF32 = 1      # tcgen05 tensor cores, TF32 operands, fp32 accumulate
 ENGINE_F16 = 2       # tcgen05 tensor cores, fp16 activations + weights in HBM, fp32 accumulate (ResNet-50 trunk)
+ENGINE_SPLIT = 4     # tcgen05 tensor cores, fp16 hi / lo split activations + weights (22 significand bits, 3 MMAs per MAC): fp32-grade
+
+
+def to_split(x):
+    """fp32 [P, C] -> split tensor [2, P, C] fp16 (hi = fp16(x), lo = fp16((x - hi) * 2^11)): the engine-4 layout.  Torch
+    elementwise ops: a conversion helper for tests and API edges, not on the pair path."""
+    x = x.float().clamp(-65504.0, 65504.0)
+    hi = x.to(torch.float16)
+    lo = ((x - hi.float()) * 2048.0).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def from_split(s):
+    """split tensor [2, P, C] -> fp32 [P, C] (exact)."""
+    return s[0].float() + s[1].float() * (1.0 / 2048.0)
 
 
 class Ragged:
@@ -28,7 +43,12 @@ class Ragged:
 
     @property
     def C(self):
-        return self.data.shape[1]
+        return self.data.shape[-1]
+
+    @property
+    def split(self):
+        """True for an engine-4 split tensor ([2, P, C] fp16 planes)."""
+        return self.data.dim() == 3
 
     @property
     def n(self):
@@ -44,6 +64,7 @@ class Ragged:
         """(1, C, H, W) view (channels_last memory) of image i - no copy."""
         o = self.offsets()
         h, w = self.hw[i]
+        assert not self.split
         return self.data[o[i]:o[i + 1]].view(1, h, w, self.C).permute(0, 3, 1, 2)
 
     def to_nchw(self):
@@ -71,8 +92,14 @@ def conv2d(x, w_packed, bias, Cout, k, stride, pad, relu, residual=None, engine=
     if int(engine) == ENGINE_F16:      # x, residual, w_tc fp16 -> y fp16
         assert x.data.dtype == torch.float16 and w_tc is not None and w_tc.dtype == torch.float16
         assert residual is None or residual.data.dtype == torch.float16
-    y = torch.empty((sum(h * w for h, w in ohw), Cout), device=x.data.device,
-                    dtype=torch.float16 if int(engine) == ENGINE_F16 else torch.float32)
+    if int(engine) in (ENGINE_SPLIT, ENGINE_SPLIT + 1):      # split x / residual / weights -> split y (engine 5: fp32 y)
+        assert x.split and x.data.is_contiguous() and w_tc is not None and w_tc.dim() == 3 and w_tc.dtype == torch.float16
+        assert residual is None or (residual.split and residual.data.is_contiguous())
+    P_out = sum(h * w for h, w in ohw)
+    if int(engine) == ENGINE_SPLIT:
+        y = torch.empty((2, P_out, Cout), device=x.data.device, dtype=torch.float16)
+    else:
+        y = torch.empty((P_out, Cout), device=x.data.device, dtype=torch.float16 if int(engine) == ENGINE_F16 else torch.float32)
     check(lib.rf_conv2d_nhwc(ptr(x.data), x.n, x._c, x.C, ptr(w_packed), ptr(w_tc), ptr(bias),
                              ptr(residual.data) if residual is not None else None,
                              Cout, k, k, stride, pad, int(relu), int(engine), ptr(y), stream()))
@@ -98,6 +125,11 @@ def blur_downsample(x, stride):
 def l2norm(x2d, mask=None):
     """x2d [P, C] -> x / max(||x||, 1e-12) per row; rows with mask == 0 become zeros."""
     need_cuda(x2d, mask)
+    if x2d.dim() == 3:                  # engine-4 output: split planes in, fp32 out
+        assert x2d.dtype == torch.float16 and x2d.is_contiguous()
+        y = torch.empty(x2d.shape[1:], device=x2d.device, dtype=torch.float32)
+        check(lib.rf_l2norm_split_nhwc(ptr(x2d), x2d.shape[1], x2d.shape[2], ptr(mask), ptr(y), None, None, stream()))
+        return y
     if x2d.dtype == torch.float16:      # engine-2 trunk output: fp16 in, fp32 out
         y = torch.empty(x2d.shape, device=x2d.device, dtype=torch.float32)
         check(lib.rf_l2norm_f16_nhwc(ptr(x2d), x2d.shape[0], x2d.shape[1], ptr(mask), ptr(y), stream()))
@@ -132,6 +164,19 @@ def corr_neigh_pair(x, y, k, ldo=None, round_tf32=False):
     buf = torch.empty((2 * P, ldo), device=x.data.device, dtype=torch.float16 if int(round_tf32) == 2 else torch.float32)
     check(lib.rf_corr_neigh_pair_nhwc(ptr(x.data), ptr(y.data), x.n, h, w, x.C, k, ldo, int(round_tf32), ptr(buf[:P]), ptr(buf[P:]), stream()))
     return Ragged(buf[:P], x.hw), Ragged(buf[P:], x.hw), Ragged(buf, x.hw + x.hw)
+
+
+def corr_neigh_pair_split(x, y, k, ldo, want_both=True):
+    """Engine-4 form: CorrNeigh(x, y) as a split tensor [2, P, ldo] (the flow head's input) and, with ``want_both``, the
+    two-image split tensor [2, 2P, ldo] = [CorrNeigh(x, y) ; CorrNeigh(y, x)] of the matchability head, from ONE launch."""
+    need_cuda(x.data, y.data)
+    assert x.data.dtype == torch.float32 and y.data.dtype == torch.float32 and x.hw == y.hw
+    h, w = x.hw[0]
+    P = x.data.shape[0]
+    c12 = torch.empty((2, P, ldo), device=x.data.device, dtype=torch.float16)
+    both = torch.empty((2, 2 * P, ldo), device=x.data.device, dtype=torch.float16) if want_both else None
+    check(lib.rf_corr_neigh_pair_split(ptr(x.data), ptr(y.data), x.n, h, w, x.C, k, int(ldo), ptr(c12), ptr(both), stream()))
+    return Ragged(c12, x.hw), (Ragged(both, x.hw + x.hw) if want_both else None)
 
 
 def softmax_flow(logits, k):

@@ -49,8 +49,10 @@ def PredFlowMask_device(IsTensor, featt, flowCoarse, size, network, with_match21
         ft = featt if isinstance(featt, Ragged) else Ragged.from_nchw(featt)
         k = network["netCorr"].kernelSize
         ld = network["netFlowCoarse"].CORR_LD
-        tc = model.fine_engine()            # 0 plain fp32, 1 TF32-rounded, 2 fp16: the operand type of the heads
-        if _corr_neigh_pair():                  # both volumes from one launch, already laid out as the two-image batch
+        tc = model.fine_engine()            # 0 plain fp32, 1 TF32-rounded, 2 fp16, 4 split planes: the operand type of the heads
+        if tc == ops.ENGINE_SPLIT:              # one launch: corr12 standalone + the two-image [corr12 ; corr21] tensor, split planes
+            corr12, both = ops.corr_neigh_pair_split(ft, fs, k, ld)
+        elif _corr_neigh_pair():                # both volumes from one launch, already laid out as the two-image batch
             corr12, corr21, both = ops.corr_neigh_pair(ft, fs, k, ld, tc)
         else:
             corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
@@ -356,7 +358,10 @@ def align2images(coarseModel, network, img1, img2, align_corners=False):
         feat1 = fine_features(network["netFeatCoarse"], img1_coarse)
         feat2 = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
         k = network["netCorr"].kernelSize
-        corr12 = ops.corr_neigh(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, model.fine_engine())
+        if model.fine_engine() == ops.ENGINE_SPLIT:
+            corr12, _ = ops.corr_neigh_pair_split(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, want_both=False)
+        else:
+            corr12 = ops.corr_neigh(feat1, feat2, k, network["netFlowCoarse"].CORR_LD, model.fine_engine())
         flowDown = network["netFlowCoarse"].forward_ragged(corr12)
         flow12, _, _ = ops.compose_fine(flowDown, None, None, flowCoarse, clamp=False, align_corners=align_corners, want_match=False)
         img1_fine = ops.grid_sample(coarseModel.IsTensor, flow12, align_corners)
@@ -377,7 +382,10 @@ def PredFlowMask_kitti_device(IsSample, ItSample, flowCoarse, size, network, ali
         n = f.data.shape[0] // 2
         fs, ft = Ragged(f.data[:n], f.hw[:1]), Ragged(f.data[n:], f.hw[1:])
         k, ld, tc = network["netCorr"].kernelSize, network["netFlowCoarse"].CORR_LD, model.fine_engine()
-        corr12, _, both = ops.corr_neigh_pair(ft, fs, k, ld, tc)
+        if tc == ops.ENGINE_SPLIT:
+            corr12, both = ops.corr_neigh_pair_split(ft, fs, k, ld)
+        else:
+            corr12, _, both = ops.corr_neigh_pair(ft, fs, k, ld, tc)
         flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
         mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21
         flow12, match, _ = ops.compose_fine(flowDown8, mboth[0:1], mboth[1:2], flowCoarse, clamp=True, align_corners=align_corners,

@@ -101,7 +101,7 @@ class LayerProgram:
         return len(self.chan) - 1
 
     # -- compilation for one image-set signature --------------------------------------------------
-    def _compile(self, hw, device, f16=False):
+    def _compile(self, hw, device, f16=False, split=False):
         n_t = len(self.chan)
         last_use = [0] * n_t
         for i, o in enumerate(self.ops):
@@ -116,7 +116,7 @@ class LayerProgram:
             hws.append([((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1) for h, w in hws[o[1]]])
         # element size per tensor: fp32 everywhere, except under the fp16 engine (fp32 only for the image an im2col
         # reads and around RF_LAYER_OUT_F32 / RF_LAYER_TF32 convs)
-        esize = [4] * n_t
+        esize = [4] * n_t          # engine 4: split tensors are 2 fp16 planes = 4 bytes per element, like the fp32 image / OUT_F32 outputs
         if f16:
             esize[0] = 4 if self.ops[0][0] in (RF_OP_IM2COL, RF_OP_STEM7) else 2
             for i, o in enumerate(self.ops):
@@ -148,8 +148,8 @@ class LayerProgram:
             fc = o[9]
             if fc is not None:
                 L.w, L.w_tc = fc.w.data_ptr(), fc.w_tc.data_ptr()
-                L.w_f16 = fc.w_f16.data_ptr() if f16 else None
-                L.flags = self.flags.get(i, 0) if f16 else 0
+                L.w_f16 = fc.w_f16.data_ptr() if f16 else (fc.w_split.data_ptr() if split else None)
+                L.flags = self.flags.get(i, 0) if (f16 or split) else 0
                 L.bias = fc.bias.data_ptr() if fc.bias is not None else None
             for t in {o[1], o[2]}:
                 if t > 0 and last_use[t] == i:
@@ -158,19 +158,23 @@ class LayerProgram:
         bufs = [None] + [torch.empty(max(16, e), device=device, dtype=torch.uint8) for e in slot_elems[1:]]       # bytes
         out_slot = slot_of[n_t - 1]
         chw = (C.c_int * (2 * len(hw)))(*[v for p in hw for v in p])
+        out_split = split and not (self.flags.get(len(self.ops) - 1, 0) & RF_LAYER_OUT_F32)
+        in_split = split and self.ops[0][0] not in (RF_OP_IM2COL, RF_OP_STEM7)
         return dict(layers=layers, bufs=bufs, out_slot=out_slot, out_hw=hws[-1], out_elems=elems[-1], chw=chw, nslots=len(slot_elems),
-                    out_dtype=torch.float16 if esize[-1] == 2 else torch.float32, in_dtype=torch.float16 if esize[0] == 2 else torch.float32)
+                    out_dtype=torch.float16 if (esize[-1] == 2 or out_split) else torch.float32, out_split=out_split,
+                    in_dtype=torch.float16 if (esize[0] == 2 or in_split) else torch.float32)
 
     def run(self, x, engine):
         """x: ops.Ragged input -> (output buffer view [P_out, C_out] valid until the next run, out_hw)."""
         need_cuda(x.data)
-        f16 = int(engine) == 2
-        assert f16 or not getattr(self, "f16_only", False), "this program uses fp16-engine-only layers"
-        key = (tuple(x.hw), str(x.data.device), f16)
+        f16, split = int(engine) == 2, int(engine) == 4
+        assert f16 or split or not getattr(self, "f16_only", False), "this program uses tensor-core-engine-only layers"
+        key = (tuple(x.hw), str(x.data.device), int(engine) if (f16 or split) else 0)
         if key not in self._compiled:
-            if len(self._compiled) > 16:
-                self._compiled.clear()
-            self._compiled[key] = self._compile(x.hw, x.data.device, f16)
+            # compiled entries own the activation buffers; captured CUDA graphs hold raw pointers into them, so entries are
+            # never evicted behind a live graph's back: the cache only grows (one entry per image-set signature; callers with
+            # many sizes bound it with `release()` once no graph / result refers to the buffers any more)
+            self._compiled[key] = self._compile(x.hw, x.data.device, f16, split)
         c = self._compiled[key]
         assert x.data.dtype == c["in_dtype"], (x.data.dtype, c["in_dtype"])
         slots = (C.c_void_p * c["nslots"])()
@@ -178,5 +182,12 @@ class LayerProgram:
         for i in range(1, c["nslots"]):
             slots[i] = c["bufs"][i].data_ptr()
         check(lib.rf_run_layers(c["layers"], len(self.ops), slots, len(x.hw), c["chw"], int(engine), stream()))
-        out = c["bufs"][c["out_slot"]][:c["out_elems"]].view(c["out_dtype"]).view(-1, self.chan[-1])
+        out = c["bufs"][c["out_slot"]][:c["out_elems"]].view(c["out_dtype"])
+        out = out.view(2, -1, self.chan[-1]) if c["out_split"] else out.view(-1, self.chan[-1])
         return out, c["out_hw"]
+
+    def release(self, keep=()):
+        """Drop the compiled entries (activation buffers) of every image-set signature except those in ``keep``.  Only safe
+        when no captured CUDA graph and no live result view refers to them (pipeline.GraphedAligner.release does both)."""
+        for k in [k for k in self._compiled if k not in keep]:
+            del self._compiled[k]
