@@ -71,9 +71,20 @@ int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, in
  * match1/match2 [M][3] fp32 (x, y, 1).  `M_dev` (nullable) overrides M with a
  * device-side count (<= M) so no host sync is needed after matching.
  * Outputs: H_out[9] fp32, nbInlier_out int64, mask_out[M] u8, status_out int. */
+/* `sample_mode`: how `samples` (nbIter x 4 int64) becomes match indices.
+ *   RF_SAMPLES_INDEX    the tensor torch.randint(M, (nbIter, 4)) returned (utils/outil.py:120), used as is;
+ *   RF_SAMPLES_MOD      arbitrary non-negative integers, reduced `% M` on the device (M = *M_dev);
+ *   RF_SAMPLES_PHILOX64 full-range 64-bit generator words (`Tensor.random_(-2**63, None)` on CUDA = (x << 32) | y of one
+ *                       curand4 call per element): index = x % M, which IS what torch.randint(M, (nbIter, 4), device='cuda')
+ *                       returns from the same generator state (ATen random_from_to_kernel, range < 2^28, nbIter * 4 <=
+ *                       256 * SMs * blocks-per-SM so that every element has its own Philox subsequence) - the reference's
+ *                       seeded sample stream without knowing M on the host, usable inside a CUDA graph. */
+#define RF_SAMPLES_INDEX 0
+#define RF_SAMPLES_MOD 1
+#define RF_SAMPLES_PHILOX64 2
 size_t rf_ransac_workspace(int nbIter);
 int rf_ransac_homography(const float* match1, const float* match2, int M, const int* M_dev,
-                         const int64_t* samples, int nbIter, float tolerance, int chunk,
+                         const int64_t* samples, int sample_mode, int nbIter, float tolerance, int chunk,
                          float* H_out, int64_t* nbInlier_out, uint8_t* mask_out, int* status_out,
                          void* ws, size_t ws_bytes, void* stream);
 /* utils/outil.py:68-87 Homography alone: X,Y [N][4][3] -> H [N][9] (for tests). */

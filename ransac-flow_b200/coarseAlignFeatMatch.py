@@ -282,12 +282,14 @@ class CoarseAlignA(_CoarseAlignBase):
     W2MutualMatchInt = property(lambda self: self._matched()["W2MutualMatchInt"])
     H2MutualMatchInt = property(lambda self: self._matched()["H2MutualMatchInt"])
 
-    def getCoarse_device(self, Mt=None):
+    def getCoarse_device(self, Mt=None, samples=None):
         """Device-resident ``getCoarse``: no host synchronisation.  Returns (H [9], nbInlier [1], mask [NB], status [1],
         match_count [1]) as CUDA tensors; ``status`` follows RF_RANSAC_* (0 = OK; 1/3 = the reference returns None).
-        The RANSAC samples are drawn as ``torch.randint(2**32 - 1) % M`` with M read on the device (the reference
-        draws ``torch.randint(M)`` on the host, which needs M there); callers that need the reference's exact
-        generator stream use ``getCoarse``."""
+        The RANSAC samples are the reference's own stream: ``ops.philox_words`` draws the generator words
+        ``torch.randint(M, (nbIter, 4), device='cuda')`` (utils/outil.py:120) would reduce modulo M, and the kernel reduces
+        them with M read on the device - under ``torch.manual_seed(s)`` this path returns what ``getCoarse`` returns, also
+        inside a replayed CUDA graph.  ``samples`` (optional, (nbIter, 4) int64 indices): injected sample table instead
+        (parity tests drive both paths with the oracle's ``last_samples``)."""
         with torch.no_grad():
             valid16 = None
             if torch.is_tensor(Mt):                          # device-resident mask (480x640 float, 1 = masked)
@@ -298,8 +300,11 @@ class CoarseAlignA(_CoarseAlignBase):
             match1, match2, _, cnt = ops.build_matches(self._idx1, self._idx2, self._count, self.WMultiScale, self.HMultiScale,
                                                        self.Wt, self.Ht, valid16)
             self.match1, self.match2, self._match_count = match1, match2, cnt
-            raw = torch.randint(2 ** 32 - 1, (self.nbIter, self.nbPoint), device=match1.device)
-            H, nb, mask, status = ops.ransac_homography(match1, match2, raw, self.tolerance, 100, cnt)
+            if samples is not None:
+                raw, mode = torch.as_tensor(samples, dtype=torch.int64).to(match1.device).contiguous(), ops.SAMPLES_MOD
+            else:
+                raw, mode = ops.philox_words(self.nbIter, self.nbPoint, match1.device), ops.SAMPLES_PHILOX64
+            H, nb, mask, status = ops.ransac_homography(match1, match2, raw, self.tolerance, 100, cnt, mode)
             return H, nb, mask, status, cnt
 
     def getCoarse(self, Mt):

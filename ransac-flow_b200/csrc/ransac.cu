@@ -185,7 +185,7 @@ __device__ __forceinline__ float reproj_error(const float* H, float x0, float x1
 // dynamic smem: float Hs[G][9] | int flags[G]
 __global__ void __launch_bounds__(RANSAC_THREADS)
 ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2, int M_host,
-              const int* __restrict__ M_dev, const long long* __restrict__ samples, int nbIter,
+              const int* __restrict__ M_dev, const long long* __restrict__ samples, int sample_mode, int nbIter,
               float tol, int chunk, int G,
               RansacHeader* hdr, int* counts, float* Hall, int* chunk_nz,
               float* H_out, long long* nbInlier_out, unsigned char* mask_out, int* status_out) {
@@ -197,8 +197,7 @@ ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = RANSAC_THREADS / 32;
-    const bool modM = (M_dev != nullptr);
-    const int M = modM ? min(*M_dev, M_host) : M_host;
+    const int M = (M_dev != nullptr) ? min(*M_dev, M_host) : M_host;
     const int nGroups = (nbIter + G - 1) / G;
 
     if (M >= 4) {
@@ -212,7 +211,10 @@ ransac_kernel(const float* __restrict__ match1, const float* __restrict__ match2
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         s[k] = samples[(long long)i * 4 + k];
-                        if (modM) s[k] = s[k] % M;
+                        // RF_SAMPLES_PHILOX64: the word is (x << 32) | y of curand4(); torch.randint(M) on CUDA returns x % M
+                        // for the same generator state (ATen DistributionTemplates.h, range < 2^28): take the high word
+                        if (sample_mode == RF_SAMPLES_PHILOX64) s[k] = (long long)((unsigned long long)s[k] >> 32);
+                        if (sample_mode != RF_SAMPLES_INDEX) s[k] = s[k] % M;
                     }
                     bool dup = (s[0] == s[1]) | (s[0] == s[2]) | (s[0] == s[3]) | (s[1] == s[2]) | (s[1] == s[3]) | (s[2] == s[3]);
                     bool bad = false;
@@ -440,10 +442,11 @@ extern "C" size_t rf_ransac_workspace(int nbIter) {
 }
 
 extern "C" int rf_ransac_homography(const float* match1, const float* match2, int M, const int* M_dev,
-                                    const int64_t* samples, int nbIter, float tolerance, int chunk,
+                                    const int64_t* samples, int sample_mode, int nbIter, float tolerance, int chunk,
                                     float* H_out, int64_t* nbInlier_out, uint8_t* mask_out, int* status_out,
                                     void* ws, size_t ws_bytes, void* stream) {
     RF_REQUIRE(M >= 0 && nbIter >= 0 && chunk >= 1, "rf_ransac_homography: bad sizes");
+    RF_REQUIRE(sample_mode >= RF_SAMPLES_INDEX && sample_mode <= RF_SAMPLES_PHILOX64, "rf_ransac_homography: unknown sample_mode");
     RF_REQUIRE(ws != nullptr && ws_bytes >= rf_ransac_workspace(nbIter), "rf_ransac_homography: workspace too small");
     cudaStream_t st = as_stream(stream);
     size_t n = (size_t)(nbIter > 0 ? nbIter : 1);
@@ -461,7 +464,7 @@ extern "C" int rf_ransac_homography(const float* match1, const float* match2, in
     int nGroups = (nbIter + G - 1) / G;
     int grid = nGroups < 1 ? 1 : (nGroups < 4 * sms ? nGroups : 4 * sms);
     size_t smem = (size_t)G * (9 * sizeof(float) + sizeof(int));
-    ransac_kernel<<<grid, RANSAC_THREADS, smem, st>>>(match1, match2, M, M_dev, (const long long*)samples, nbIter, tolerance,
+    ransac_kernel<<<grid, RANSAC_THREADS, smem, st>>>(match1, match2, M, M_dev, (const long long*)samples, sample_mode, nbIter, tolerance,
                                                       chunk, G, hdr, counts, Hall, chunk_nz, H_out,
                                                       (long long*)nbInlier_out, mask_out, status_out);
     RF_LAUNCHED();

@@ -220,8 +220,23 @@ def corr_mutual_nn(featA, featB, precision=0):
     return idx1, idx2, count
 
 
-def ransac_homography(match1, match2, samples, tolerance, chunk=100, M_dev=None):
-    """Returns device tensors (H [9] f32, nbInlier [1] i64, mask [M] u8, status [1] i32)."""
+SAMPLES_INDEX, SAMPLES_MOD, SAMPLES_PHILOX64 = 0, 1, 2
+
+
+def philox_words(nbIter, nbPoint, device):
+    """(nbIter, nbPoint) full-range 64-bit words from torch's CUDA generator: element i is (x << 32) | y of the curand4 call
+    whose x torch.randint(M, (nbIter, nbPoint), device='cuda') reduces modulo M from the same generator state (and the
+    generator advances by the same offset).  With ``SAMPLES_PHILOX64`` the RANSAC kernel therefore sees the reference's
+    seeded sample stream (utils/outil.py:120) with M read on the device; the draw is graph-capturable."""
+    assert nbIter * nbPoint <= 256 * 1024, "beyond this size ATen maps several elements to one Philox subsequence"
+    return torch.empty((nbIter, nbPoint), dtype=torch.int64, device=device).random_(-2 ** 63, None)
+
+
+def ransac_homography(match1, match2, samples, tolerance, chunk=100, M_dev=None, sample_mode=None):
+    """Returns device tensors (H [9] f32, nbInlier [1] i64, mask [M] u8, status [1] i32).  ``sample_mode``: SAMPLES_INDEX
+    (default without ``M_dev``), SAMPLES_MOD (default with ``M_dev``: ``samples % M`` on the device) or SAMPLES_PHILOX64."""
+    if sample_mode is None:
+        sample_mode = SAMPLES_INDEX if M_dev is None else SAMPLES_MOD
     need_cuda(match1, match2, samples, M_dev)
     M = match1.shape[0]
     nbIter = samples.shape[0]
@@ -232,7 +247,7 @@ def ransac_homography(match1, match2, samples, tolerance, chunk=100, M_dev=None)
     status = torch.empty(1, device=dev, dtype=torch.int32)
     wsz = lib.rf_ransac_workspace(nbIter)
     ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
-    check(lib.rf_ransac_homography(ptr(match1), ptr(match2), M, ptr(M_dev), ptr(samples), nbIter, float(tolerance), int(chunk),
+    check(lib.rf_ransac_homography(ptr(match1), ptr(match2), M, ptr(M_dev), ptr(samples), int(sample_mode), nbIter, float(tolerance), int(chunk),
                                    ptr(H), ptr(nb), ptr(mask), ptr(status), ptr(ws), wsz, stream()))
     return H, nb, mask[:M], status
 

@@ -100,7 +100,7 @@ def _to_host(t):
     return h.numpy()
 
 
-def _single_device(coarseModel, network, Is, It, with_match21):
+def _single_device(coarseModel, network, Is, It, with_match21, samples=None):
     """Device part of the single-hypothesis path: everything queued on the current stream, nothing read back."""
     # the target's fine features do not depend on the coarse stage: queue them on a second stream as soon as the resized
     # target exists, so they fill the SMs that the small late layers of the ResNet trunk, the matching and RANSAC leave idle
@@ -114,7 +114,7 @@ def _single_device(coarseModel, network, Is, It, with_match21):
             box["featt"] = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
     coarseModel.setPair(Is, It, after_preproc=start_target_features)
     Itw, Ith = coarseModel.target_size
-    Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(None)
+    Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(None, samples)
     flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
     main.wait_stream(side)
     featt = box["featt"]
@@ -139,12 +139,13 @@ def _unpack_single(host, flow12, size, f8shape):
                 flow12=[flow12], match=[host[o:o + n0].reshape(Ith, Itw)], nbInlier=int(host[2]), nbMatch=int(host[1]))
 
 
-def align_pair_single(coarseModel, network, Is, It, with_match21=False):
+def align_pair_single(coarseModel, network, Is, It, with_match21=False, samples=None):
     """The single-hypothesis case of the evaluation loop (maxCoarse = 0, no background mask) with NO host
     synchronisation until the results are fetched: matching, RANSAC (device-side match count), warp, fine flow and
     composition are queued back to back, then one pinned D2H brings back status, H, the matchability map and the /8
-    tensors.  Same outputs as ``align_pair``."""
-    packed, flow12, size, f8shape = _single_device(coarseModel, network, Is, It, with_match21)
+    tensors.  Same outputs as ``align_pair``; under ``torch.manual_seed(s)`` also the same RANSAC samples (the reference's
+    stream, ``ops.philox_words``).  ``samples``: an injected (nbIter, 4) index table instead."""
+    packed, flow12, size, f8shape = _single_device(coarseModel, network, Is, It, with_match21, samples)
     return _unpack_single(_to_host(packed).copy(), flow12, size, f8shape)
 
 
@@ -296,11 +297,12 @@ def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, wit
     return dict(H=cat(Hs), flowDown8=cat(flows8), matchDown8=cat(matches8), flow12=flows, match=matches)
 
 
-def align_pair_device(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):
+def align_pair_device(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None, samples=None):
     """The multi-hypothesis loop of evaluation/evalHpatch/evaluation.py:211-243 with the masks kept on the device:
     per hypothesis only the two scalars the host needs to steer the loop (RANSAC status, new-region matchability mean)
     cross the bus instead of the full-resolution matchability map, and the accepted results are fetched once at the
-    end.  Same outputs as ``align_pair`` (plus ``nbMatch`` per hypothesis)."""
+    end.  Same outputs as ``align_pair`` (plus ``nbMatch`` per hypothesis), and under a seed the same RANSAC samples per
+    hypothesis.  ``samples``: optional list of injected (nbIter, 4) index tables, one per ``getCoarse`` call."""
     coarseModel.setPair(Is, It)
     Itw, Ith = coarseModel.target_size
     dev = coarseModel.ItTensor.device
@@ -308,10 +310,14 @@ def align_pair_device(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.
     featt = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
     Mask = torch.zeros((Ith, Itw), device=dev)
     acc = []
-    nbCoarse = 0
+    nbCoarse = ncall = 0
     while nbCoarse <= maxCoarse:
         fgMask = ((Mask + (1 - bg)) > 0.5).float()
-        Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(fgMask if nbCoarse > 0 or It_bg is not None else None)
+        Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(fgMask if nbCoarse > 0 or It_bg is not None else None,
+                                                                 None if samples is None else samples[ncall])
+        ncall += 1
+        # the fine stage is queued before the status is known (no host round trip between RANSAC and the networks); a failed
+        # RANSAC leaves H = 0, whose warp grid is NaN: harmless (the results are dropped below) and finite work
         flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
         flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
         newreg = (match[0, 0] * (1 - fgMask)).mean()

@@ -31,8 +31,8 @@ def test_split_roundtrip(rf):
     s = rf.ops.to_split(x)
     back = rf.ops.from_split(s)
     assert s.shape == (2, 1000, 64) and s.dtype == torch.float16
-    rel = ((back - x).abs() / x.abs().clamp_min(1e-30)).max().item()
-    assert rel < 2.0 ** -21, rel
+    # 22 significand bits for normal fp16 hi parts (|x| >= 2^-14); an absolute floor of 2^-35 below (fp16 subnormals)
+    assert bool(((back - x).abs() <= torch.maximum(x.abs() * 2.0 ** -22, torch.tensor(2.0 ** -35, device="cuda"))).all())
 
 
 @pytest.mark.parametrize("cin,cout,k,sizes", [
