@@ -73,6 +73,7 @@ class CoarseAlignOracle:
         self.seed = seed
         self.trunk = trunk
         self.last_samples = None
+        self.all_samples = []          # one (nbIter, 4) table per RANSAC call since the last setPair / setSource
 
     def _feat(self, I):
         return F.normalize(self.trunk(preproc(I).unsqueeze(0), self.sd))
@@ -102,6 +103,7 @@ class CoarseAlignOracle:
 
     # variant C API
     def setSource(self, Is_org):
+        self.all_samples = []
         self._source(Is_org)
 
     def setTarget(self, It_org):
@@ -109,6 +111,7 @@ class CoarseAlignOracle:
 
     # variant A API
     def setPair(self, Is_org, It_org):
+        self.all_samples = []
         self._source(Is_org)
         self._target(It_org)
         featt = self.featt.contiguous().view(self.featt.shape[1], -1)
@@ -124,6 +127,7 @@ class CoarseAlignOracle:
             torch.manual_seed(self.seed)
         samples = torch.randint(len(match1), (self.nbIter, 4)).numpy()
         self.last_samples = samples
+        self.all_samples.append(samples)
         return OO.RANSAC_from_samples(match1, match2, samples, self.tolerance)
 
     def getCoarse(self, Mt):

@@ -155,11 +155,33 @@ class GraphedAligner:
     Inputs are copied into static device buffers (H2D when they are host tensors / arrays); the RANSAC samples are
     drawn inside the graph (torch's graph-safe Philox offsets), so successive replays use fresh samples."""
 
-    def __init__(self, coarseModel, network, with_match21=False, warmup=2):
+    def __init__(self, coarseModel, network, with_match21=False, warmup=2, max_graphs=8):
         self.coarse, self.net, self.m21, self.warmup = coarseModel, network, with_match21, warmup
         self.coarse.device_preproc = True
-        self.graphs = {}
+        self.graphs = {}                # insertion-ordered: least recently used first
+        self.max_graphs = max_graphs    # datasets with many image sizes (HPatches, MegaDepth, YFCC): LRU-bounded graph memory
         self.replayed_kernels = 0       # library kernels executed through graph replays (they bypass rf_launch_count)
+
+    def _programs(self):
+        """Every LayerProgram whose cached activation buffers a captured graph of this aligner points into."""
+        progs = [p for p in (self.coarse.net.program, self.coarse.net._program_f16, self.coarse.net._program_split) if p is not None]
+        for m in self.net.values():
+            progs += list(getattr(m, "_fold", {}).values())
+        return progs
+
+    def _evict(self):
+        """Drop the least recently used graph TOGETHER with the activation buffers only it refers to: the graph holds raw
+        pointers into the layer programs' cached buffers, so neither may outlive the other (use-after-free)."""
+        key = next(iter(self.graphs))
+        torch.cuda.synchronize()
+        rec = self.graphs.pop(key)
+        live = set()
+        for r in self.graphs.values():
+            live |= r["prog_keys"]
+        for prog in self._programs():
+            for k in [k for k in prog._compiled if (id(prog), k) in rec["prog_keys"] and (id(prog), k) not in live]:
+                del prog._compiled[k]
+        del rec
 
     def _build(self, Is, It):
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -178,7 +200,13 @@ class GraphedAligner:
         n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             packed, flow12, size, f8shape = _single_device(self.coarse, self.net, s_in, t_in, self.m21)
-        return dict(n_kernels=_lib.launch_count() - n0, graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape)
+        # the compiled program entries (activation buffers) this graph's kernels point into: every entry whose image-set
+        # signature the warm-up / capture of THIS input size touched
+        touched = {(id(p), k) for p in self._programs() for k in p._compiled if k in p.__dict__.get("_touched", ())}
+        for p in self._programs():
+            p.__dict__["_touched"] = set()
+        return dict(n_kernels=_lib.launch_count() - n0, graph=g, s_in=s_in, t_in=t_in, packed=packed, flow12=flow12, size=size, f8shape=f8shape,
+                    prog_keys=touched)
 
     def prepare(self, Is, It):
         """Capture (once) the graph for this pair of input sizes; returns its record."""
@@ -186,7 +214,13 @@ class GraphedAligner:
             Is, It = torch.from_numpy(Is), torch.from_numpy(It)
         key = (tuple(Is.shape), tuple(It.shape))
         if key not in self.graphs:
+            while self.max_graphs and len(self.graphs) >= self.max_graphs:
+                self._evict()
+            for p in self._programs():
+                p.__dict__["_touched"] = set()
             self.graphs[key] = self._build(Is, It)
+        else:
+            self.graphs[key] = self.graphs.pop(key)            # most recently used last
         return self.graphs[key]
 
     def enqueue(self, Is, It):
@@ -207,15 +241,17 @@ class GraphedAligner:
         done.record()
         return (c, done)
 
-    def fetch(self, ticket):
-        """Wait for a ticket and unpack it (same dict as ``align_pair_single``)."""
+    def fetch(self, ticket, copy=True):
+        """Wait for a ticket and unpack it (same dict as ``align_pair_single``).  ``flow12`` is the graph's static output
+        buffer: it is cloned so that results collected over several replays stay valid (``copy=False`` returns the live
+        buffer, overwritten by the next replay with these input sizes)."""
         c, done = ticket
         done.synchronize()
-        return _unpack_single(c["host"].numpy().copy(), c["flow12"], c["size"], c["f8shape"])
+        return _unpack_single(c["host"].numpy().copy(), c["flow12"].clone() if copy else c["flow12"], c["size"], c["f8shape"])
 
-    def __call__(self, Is, It):
+    def __call__(self, Is, It, copy=True):
         """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
-        return self.fetch(self.enqueue(Is, It))
+        return self.fetch(self.enqueue(Is, It), copy)
 
 
 class ConcurrentAligner:
@@ -254,11 +290,11 @@ class ConcurrentAligner:
             main.wait_stream(s)                   # later work on the current stream (e.g. the next batch) follows all lanes
         return tickets
 
-    def fetch(self, tickets):
-        return [a.fetch(t) for a, t in zip(self.lanes, tickets)]
+    def fetch(self, tickets, copy=True):
+        return [a.fetch(t, copy) for a, t in zip(self.lanes, tickets)]
 
-    def __call__(self, pairs):
-        return self.fetch(self.enqueue(pairs))
+    def __call__(self, pairs, copy=True):
+        return self.fetch(self.enqueue(pairs), copy)
 
 
 def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):

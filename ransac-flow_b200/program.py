@@ -176,6 +176,7 @@ class LayerProgram:
             # many sizes bound it with `release()` once no graph / result refers to the buffers any more)
             self._compiled[key] = self._compile(x.hw, x.data.device, f16, split)
         c = self._compiled[key]
+        self.__dict__.setdefault("_touched", set()).add(key)       # pipeline.GraphedAligner ties graphs to the entries they use
         assert x.data.dtype == c["in_dtype"], (x.data.dtype, c["in_dtype"])
         slots = (C.c_void_p * c["nslots"])()
         slots[0] = x.data.data_ptr()

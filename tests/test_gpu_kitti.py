@@ -187,3 +187,22 @@ def test_fill_nearest_matched_is_exact(rf, h, w, p, seed):
     assert np.array_equal((idx[..., 0] - yy) ** 2 + (idx[..., 1] - xx) ** 2, np.round(d ** 2).astype(np.int64))
     assert np.array_equal(out[0], f[0][idx[..., 0], idx[..., 1]])
     assert np.array_equal(out[0][m], f[0][m])
+
+
+def test_get_flow_corr_vs_reference(rf, tmp_path):
+    """pipeline.getFlow_corr / results.getFlow_from_files (evaluation/evalCorr/getResults.py:78-134) vs the reference's golden
+    flowGlobal / matchGlobal, away from the merge threshold."""
+    g = golden("get_flow_corr")
+    fg, mg = rf.pipeline.getFlow_corr(g["flow"], g["H"], g["mask"], th=float(g["th"]), multiH=True)
+    assert tuple(fg.shape) == (1, 40, 56, 2) and tuple(mg.shape) == (1, 40, 56, 1)
+    far = np.abs(g["matchGlobal"][0, :, :, 0] - float(g["th"])) > 1e-3
+    assert np.abs(mg.cpu().numpy() - g["matchGlobal"])[0, :, :, 0][far].max() < 1e-5
+    d = np.abs(fg.cpu().numpy() - g["flowGlobal"])[0].max(-1)
+    assert (d < 1e-5).mean() > 0.98
+    fine, coarse = tmp_path / "fine", tmp_path / "coarse"
+    fine.mkdir()
+    coarse.mkdir()
+    rf.results.save_pair(str(coarse), str(fine), 4, dict(H=g["H"], flowDown8=g["flow"], matchDown8=g["mask"]))
+    fg2, mg2 = rf.results.getFlow_from_files(4, str(fine), sorted(p.name for p in fine.iterdir()), str(coarse), str(fine), True, float(g["th"]))
+    assert np.array_equal(fg2.cpu().numpy(), fg.cpu().numpy()) and np.array_equal(mg2.cpu().numpy(), mg.cpu().numpy())
+    assert rf.results.getFlow_from_files(5, str(fine), sorted(p.name for p in fine.iterdir()), str(coarse), str(fine), True, 0.5) == ([], [])

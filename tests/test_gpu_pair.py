@@ -137,60 +137,6 @@ def test_get_flow_all_vs_reference(rf):
     assert np.abs(fg.cpu().numpy() - g["flowGlobal"])[0][far].max() < 1e-5
 
 
-@pytest.fixture
-def engine(request, rf):
-    rf.model.set_engine(request.param)
-    rf.outil.corr_precision = {"fp32": 0, "tf32": 1, "f16": 2}[request.param]
-    yield request.param
-    rf.model.set_engine("fp32")
-    rf.outil.corr_precision = 0
-
-
-@pytest.mark.parametrize("engine", ["fp32", "tf32", "f16"], indirect=True)
-@pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
-def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
-    """L2 parity: the full path, same seeded samples on both sides.  fp32 engine: the match set is
-    the oracle's up to arg-max ties.  tf32 engine (tcgen05 convs): features carry TF32 rounding, so the match set
-    may differ; the flow is compared when the coarse homographies agree."""
-    src, tgt, _ = synth.make_pair(11, h, w)
-    Is, It = Image.fromarray(src), Image.fromarray(tgt)
-    rsd = synth.resnet50_conv4_state(0)
-    oc = PO.CoarseAlignOracle(rsd, nbScale=nbScale, nbIter=1000, tolerance=0.05, minSize=minSize, scaleR=2, variant="A", seed=1000)
-    ref = PO.align_pair(oc, oracle_net(), Is, It, maxCoarse=0)
-    c = rf.CoarseAlignA(nbScale, 1000, 0.05, "Homography", minSize, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
-    with fixed_randint([oc.last_samples]):
-        out = rf.pipeline.align_pair(c, networks(rf), Is, It, maxCoarse=0)
-    # the match set: identical up to fp32-noise ties of the arg-max
-    m_ref = set(map(tuple, np.round(oc.match2[:, :2] * 1e4).astype(int).tolist()))
-    m_got = set(map(tuple, np.round(c.match2.cpu().numpy()[:, :2] * 1e4).astype(int).tolist()))
-    print("[%s] matches ref %d got %d sym-diff %d" % (engine, len(m_ref), len(m_got), len(m_ref ^ m_got)))
-    if engine == "fp32":
-        assert len(m_ref ^ m_got) <= max(2, len(m_ref) // 50)
-    assert out["H"].shape == ref["H"].shape
-    dH = np.abs(out["H"] - ref["H"]).max()
-    d = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy()).max()
-    d8 = np.abs(out["flowDown8"] - ref["flowDown8"]).max()
-    print("[%s] max |H - oracle| = %.3g, max |flow12 - oracle| = %.3g, max |flowDown8 - oracle| = %.3g" % (engine, dH, d, d8))
-    if len(m_ref ^ m_got) == 0:
-        np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
-    if dH < 1e-5:
-        assert d8 < FLOW_TOL                                   # the /8 flow the reference saves (flow_*.npy)
-        if engine == "fp32":
-            assert d < FLOW_TOL
-        else:
-            # grid_sample pads with zeros: where the fine flow samples the coarse grid within a pixel of its border the
-            # value is discontinuous in the sampling position, so TF32-level differences are amplified by ~W/2 there.
-            # Compare the full-resolution flow on the pixels that sample the interior.
-            Hh, Ww = ref["flow12"][0].shape[1:3]
-            f8 = torch.from_numpy(ref["flowDown8"][:1])
-            _, flowUp = WO.compose_fine(f8, WO.warp_grid(ref["H"][:1], Hh, Ww), WO.base_grid(Hh, Ww), clamp=True)
-            fu = flowUp[0].numpy()
-            interior = (np.abs(fu[..., 0]) < 1 - 4.0 / Ww) & (np.abs(fu[..., 1]) < 1 - 4.0 / Hh)
-            di = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy())[0][interior].max()
-            print("[%s] interior pixels %.1f%%: max |flow12 - oracle| = %.3g" % (engine, 100 * interior.mean(), di))
-            assert di < FLOW_TOL
-
-
 def test_multi_hypothesis_loop_runs(rf):
     src, tgt, _ = synth.make_pair(12, 96, 128)
     c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False,
@@ -221,22 +167,12 @@ def test_async_single_hypothesis_path_equals_the_loop(rf):
     net = networks(rf)
     c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
     raw = synth.draw_samples(5, 2 ** 31 - 1, 1000)
-    with fixed_randint([raw]):
-        a = rf.pipeline.align_pair_single(c, net, Is, It)
+    a = rf.pipeline.align_pair_single(c, net, Is, It, samples=raw)
     with fixed_randint([raw % a["nbMatch"]]):
         b = rf.pipeline.align_pair(c, net, Is, It, maxCoarse=0)
     assert np.array_equal(a["H"], b["H"])
     assert np.array_equal(a["flowDown8"], b["flowDown8"]) and np.array_equal(a["matchDown8"], b["matchDown8"])
     assert torch.equal(a["flow12"][0], b["flow12"][0]) and np.array_equal(a["match"][0], b["match"][0])
-
-
-def test_randint_modulo_stream_on_cuda(rf):
-    """Documented property used by getCoarse_device: report whether randint(2**32-1) % M equals randint(M) on this torch."""
-    torch.manual_seed(1000)
-    a = torch.randint(636, (1000, 4), device="cuda")
-    torch.manual_seed(1000)
-    b = torch.randint(2 ** 32 - 1, (1000, 4), device="cuda") % 636
-    print("randint(M) == randint(2**32-1) %% M on CUDA: %s" % bool((a == b).all()))
 
 
 def test_config1_quick_start_align2images_vs_oracle(rf):
@@ -254,12 +190,28 @@ def test_config1_quick_start_align2images_vs_oracle(rf):
     assert ref is not None and out is not None
     same = len(c.match1) == len(oc.match1) and np.array_equal(c.match2.cpu().numpy(), oc.match2)
     print("config1: matches %d/%d identical=%s" % (len(c.match1), len(oc.match1), same))
-    if same:
-        np.testing.assert_allclose(out["bestPrm"], ref["bestPrm"], atol=1e-5)
-        assert np.array_equal(out["inlierMask"], ref["inlierMask"])
-        assert np.abs(out["flowDown"].cpu().numpy() - ref["flowDown"].numpy()).max() < FLOW_TOL
-        assert np.abs(out["flow12"].cpu().numpy() - ref["flow12"].numpy()).max() < FLOW_TOL
-        assert np.abs(out["img1_fine"].cpu().numpy() - ref["img1_fine"].numpy()).max() < 5e-3
+    assert same, "config 1 (fp32 engine): the match list must be the oracle's"
+    np.testing.assert_allclose(out["bestPrm"], ref["bestPrm"], atol=1e-5)
+    assert np.array_equal(out["inlierMask"], ref["inlierMask"])
+    assert np.abs(out["flowDown"].cpu().numpy() - ref["flowDown"].numpy()).max() < FLOW_TOL
+    assert np.abs(out["flow12"].cpu().numpy() - ref["flow12"].numpy()).max() < FLOW_TOL
+    assert np.abs(out["img1_fine"].cpu().numpy() - ref["img1_fine"].numpy()).max() < 5e-3
+
+
+def test_coarse_align_variant_B_vs_reference(rf):
+    """CoarseAlignB (evaluation/evalYFCC/coarseAlignFeatMatch.py:35-196) vs the reference's golden H / inlier mask / match
+    count with a masked target and the same samples."""
+    g = golden("coarse_align_B")
+    c = rf.CoarseAlignB(3, 500, 0.05, "Homography", 96, 1, True, True, True, False, 1.5, resnet_state_dict=synth.resnet50_conv4_state(0), verbose=False)
+    c.setSource(Image.fromarray(g["src"]))
+    c.setTarget(Image.fromarray(g["tgt"]))
+    assert np.array_equal(np.asarray(c.Is), g["Is"]) and np.array_equal(np.asarray(c.It), g["It"])
+    assert np.array_equal(c.WMultiScale.cpu().numpy(), g["WMulti"]) and np.array_equal(c.HMultiScale.cpu().numpy(), g["HMulti"])
+    with fixed_randint([g["samples"]]):
+        H, mask = c.getCoarse(g["Mt"])
+    assert len(c.match1) == int(g["nbMatch"])
+    np.testing.assert_allclose(H, g["H"], atol=1e-5)
+    assert np.array_equal(mask, g["inlierMask"])
 
 
 def test_coarse_align_variant_B_api(rf):
@@ -312,8 +264,7 @@ def test_device_resident_multi_hypothesis_loop_equals_host_loop(rf):
     net = networks(rf)
     c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
     raws = [synth.draw_samples(30 + k, 2 ** 31 - 1, 1000) for k in range(6)]
-    with fixed_randint(raws):
-        a = rf.pipeline.align_pair_device(c, net, Is, It, maxCoarse=3, with_match21=True)
+    a = rf.pipeline.align_pair_device(c, net, Is, It, maxCoarse=3, with_match21=True, samples=raws)
     nH = len(a["flow12"])
     assert 1 <= nH <= 4 and len(a["nbMatch"]) == nH
     # the host loop draws one sample set per getCoarse call, including a last rejected / failed one
@@ -380,3 +331,35 @@ def test_concurrent_aligner_equals_graphed_aligner(rf):
     finally:
         rf.model.set_engine("fp32")
         rf.outil.corr_precision = 0
+
+
+def test_graphed_aligner_results_survive_later_replays_and_graph_eviction(rf):
+    """ADVICE r1: (1) a result kept across replays must not be overwritten (flow12 used to alias the graph's static buffer);
+    (2) graphs are LRU-bounded and an evicted graph takes the activation buffers only it used with it - replaying the
+    survivors and re-capturing the evicted size afterwards still gives the eager results."""
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    ga = rf.pipeline.GraphedAligner(c, net, max_graphs=2)
+    sizes = [(96, 128), (80, 112), (64, 96)]
+    pairs = [tuple(torch.from_numpy(a).cuda() for a in synth.make_pair(40 + i, h, w)[:2]) for i, (h, w) in enumerate(sizes)]
+
+    def eager(i):
+        c2 = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+        c2.device_preproc = True
+        torch.manual_seed(7)
+        return rf.pipeline.align_pair_single(c2, net, *pairs[i])
+
+    torch.manual_seed(7)
+    first = ga(*pairs[0])
+    keep = first["flow12"][0].clone()
+    torch.manual_seed(8)
+    second = ga(*pairs[0])                                    # same size: the same graph replayed with other samples
+    assert torch.equal(first["flow12"][0], keep) and first["flow12"][0].data_ptr() != second["flow12"][0].data_ptr()
+    for i in (1, 2, 0, 1, 2):                                 # three sizes through two graph slots: evictions + re-captures
+        torch.manual_seed(7)
+        out = ga(*pairs[i])
+        ref = eager(i)
+        assert len(ga.graphs) <= 2
+        assert np.array_equal(out["H"], ref["H"]) and np.array_equal(out["flowDown8"], ref["flowDown8"])
+        assert torch.equal(out["flow12"][0], ref["flow12"][0])

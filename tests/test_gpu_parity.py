@@ -1,0 +1,226 @@
+"""Whole-pair parity against the CPU oracle at BASELINE config 2 (480x640, nbScale 7, nbIter 1000) and on a small pair,
+with NO conditional asserts:
+
+  (a) match set: every pair in the symmetric difference of the product's and the oracle's mutual-NN lists must be a PROVEN
+      arg-max tie - its margin in the oracle's own fp32 score matrix is below twice the largest score deviation the engine's
+      features can cause (measured on the spot, and itself bounded for the fp32-grade engines);
+  (b) coarse stage in isolation: the ORACLE's match list + sample table -> H, inlier count and inlier mask bit-exact;
+  (c) fine stage in isolation: the ORACLE's H -> flowDown8, matchDown8 and flow12 on ALL pixels within north_star's 1e-3;
+  (d) end to end with the oracle's samples: identical when the match sets coincide (checked whenever they do).
+
+The multi-hypothesis loop (maxCoarse > 0, evaluation/evalCorr/evaluation.py:211-243) and the device-resident paths are
+compared with the oracle's loop under injected samples, and the sync-free path's own sample stream with the reference's
+seeded ``torch.randint`` (utils/outil.py:120)."""
+import numpy as np
+import PIL.Image as Image
+import pytest
+import torch
+
+from oracle import outil_oracle as OO
+from oracle import pair_oracle as PO
+from oracle import synth
+from oracle import warp_oracle as WO
+from test_gpu_pair import fixed_randint, networks, oracle_net
+
+pytestmark = pytest.mark.gpu
+FLOW_TOL = 1e-3
+STRICT = ("fp32", "f16x3")            # engines that must reproduce the reference's fp32 arg-max
+PREC = {"fp32": 0, "tf32": 1, "f16": 2, "f16x3": 2}
+_cache = {}
+
+
+@pytest.fixture
+def engine(request, rf):
+    rf.model.set_engine(request.param)
+    rf.outil.corr_precision = PREC[request.param]
+    yield request.param
+    rf.model.set_engine("fp32")
+    rf.outil.corr_precision = 0
+
+
+def oracle_pair(seed, h, w, minSize, nbScale, maxCoarse=0, m21=False, net=None):
+    """The oracle's run of one synthetic pair (cached: 480x640 costs seconds of CPU)."""
+    key = (seed, h, w, minSize, nbScale, maxCoarse, m21, id(net))
+    if key not in _cache:
+        src, tgt, _ = synth.make_pair(seed, h, w)
+        Is, It = Image.fromarray(src), Image.fromarray(tgt)
+        rsd = synth.resnet50_conv4_state(0)
+        oc = PO.CoarseAlignOracle(rsd, nbScale=nbScale, nbIter=1000, tolerance=0.05, minSize=minSize, scaleR=2, variant="A", seed=1000)
+        ref = PO.align_pair(oc, net or oracle_net(), Is, It, maxCoarse=maxCoarse, with_match21=m21)
+        featt = oc.featt.contiguous().view(oc.featt.shape[1], -1).numpy()
+        score = oc.featsMultiScale.numpy().T @ featt
+        _cache[key] = dict(Is=Is, It=It, rsd=rsd, oc=oc, ref=ref, score=score, samples=list(oc.all_samples),
+                           match1=oc.match1.copy(), match2=oc.match2.copy())
+    return _cache[key]
+
+
+def tie_report(score, ref_pairs, got_pairs):
+    """For every pair in the symmetric difference: its margin in the oracle's fp32 score matrix (how far the oracle's scores
+    are from making the other decision)."""
+    rowmax, colmax = score.max(1), score.max(0)
+    s2r = np.partition(score, -2, axis=1)[:, -2] if score.shape[1] > 1 else np.full(score.shape[0], -np.inf, np.float32)
+    s2c = np.partition(score, -2, axis=0)[-2] if score.shape[0] > 1 else np.full(score.shape[1], -np.inf, np.float32)
+    out = []
+    for (i, j) in sorted(ref_pairs ^ got_pairs):
+        if (i, j) in ref_pairs:       # the oracle's mutual maximum lost: one of its two top-2 gaps must be tiny
+            margin = min(rowmax[i] - s2r[i], colmax[j] - s2c[j])
+        else:                          # the product's pair is not the oracle's maximum: it must be within reach of both maxima
+            margin = max(rowmax[i] - score[i, j], colmax[j] - score[i, j])
+        out.append(((i, j), float(margin)))
+    return out
+
+
+@pytest.mark.parametrize("engine", ["fp32", "f16x3", "f16", "tf32"], indirect=True)
+@pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
+def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
+    o = oracle_pair(11, h, w, minSize, nbScale)
+    oc, ref = o["oc"], o["ref"]
+    net = networks(rf)
+    c = rf.CoarseAlignA(nbScale, 1000, 0.05, "Homography", minSize, 2, False, 2, True, False, resnet_state_dict=o["rsd"], verbose=False)
+    with fixed_randint([o["samples"][0]]):
+        out = rf.pipeline.align_pair(c, net, o["Is"], o["It"], maxCoarse=0)
+    assert out["H"].shape == ref["H"].shape == (1, 3, 3)
+
+    # ---- (a) match set: identical up to proven ties -----------------------------------------------------------------
+    n = int(c._count.item())
+    got_pairs = set(zip(c._idx1[:n].cpu().tolist(), c._idx2[:n].cpu().tolist()))
+    ref_pairs = set(zip(oc.index1.tolist(), oc.index2.tolist()))
+    fa, fb = c._feats_rows.double(), c._featt_rows.double()
+    dev = float((fa @ fb.t() - torch.from_numpy(o["score"]).cuda().double()).abs().max())      # what the engine's features do to the scores
+    ties = tie_report(o["score"], ref_pairs, got_pairs)
+    worst = max([m for _, m in ties], default=0.0)
+    print("[%s %dx%d] matches ref %d got %d sym-diff %d; max |score - oracle score| %.3g; worst margin among differing pairs %.3g"
+          % (engine, h, w, len(ref_pairs), len(got_pairs), len(ties), dev, worst))
+    if engine in STRICT:
+        assert dev < 2e-5, "features are not fp32-grade"
+        for pair, margin in ties:
+            assert margin <= 2 * dev + 1e-6, "pair %s differs from the oracle and is not an arg-max tie (margin %.3g, score noise %.3g)" % (pair, margin, dev)
+        assert len(ties) <= max(2, len(ref_pairs) // 50)
+
+    # ---- (b) coarse stage in isolation: the oracle's matches and samples -> bit-exact RANSAC ----------------------------
+    m1, m2 = torch.from_numpy(o["match1"]).cuda(), torch.from_numpy(o["match2"]).cuda()
+    Hd, nb, mask, status = rf.ops.ransac_homography(m1, m2, torch.from_numpy(o["samples"][0]).cuda(), 0.05)
+    bestRef, nbRef, inlRef, _ = OO.RANSAC_from_samples(o["match1"], o["match2"], o["samples"][0], 0.05)
+    assert int(status.item()) == 0 and int(nb.item()) == int(nbRef)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), inlRef)
+    np.testing.assert_allclose(Hd.cpu().numpy().reshape(3, 3), bestRef, atol=2e-6, rtol=0)
+    np.testing.assert_allclose(bestRef.astype(np.float32), ref["H"][0], atol=0, rtol=0)
+
+    # ---- (c) fine stage in isolation: the oracle's H -> flows on ALL pixels ---------------------------------------------
+    Itw, Ith = c.target_size
+    featt = rf.pipeline.fine_features(net["netFeatCoarse"], c.ItTensor)
+    flowCoarse = rf.ops.warp_grid(torch.from_numpy(ref["H"]).cuda(), Ith, Itw)
+    f12, match, f8, mb = rf.pipeline.PredFlowMask_device(c.IsTensor, featt, flowCoarse, (Ith, Itw), net)
+    d8 = np.abs(f8.cpu().numpy() - ref["flowDown8"]).max()
+    dm8 = np.abs(mb.cpu().numpy().reshape(ref["matchDown8"].shape) - ref["matchDown8"]).max()
+    d12 = np.abs(f12.cpu().numpy() - ref["flow12"][0].numpy()).max()
+    far = (np.abs(np.abs(ref["flow12"][0].numpy()) - 1) > 1e-3).all(-1)[0]                 # inside-mask flips only at |flow| = 1
+    dm = np.abs(match[0, 0].cpu().numpy() - ref["match"][0])[far].max()
+    print("[%s %dx%d] oracle H injected: |flowDown8| %.3g |matchDown8| %.3g |flow12| (all pixels) %.3g |match| %.3g" % (engine, h, w, d8, dm8, d12, dm))
+    assert d8 < FLOW_TOL and dm8 < FLOW_TOL
+    if engine in STRICT:
+        assert d12 < FLOW_TOL and dm < FLOW_TOL
+    else:
+        # 10-bit-operand engines (explicitly the fast, reduced-precision modes): grid_sample's zero padding makes flow12
+        # discontinuous where the fine flow samples the coarse grid within a pixel of its border; measured bound, not parity
+        assert d12 < 5e-3
+
+    # ---- (d) end to end (same samples): equal whenever the match lists are equal ---------------------------------------
+    dH = np.abs(out["H"] - ref["H"]).max()
+    de = np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"][0].numpy()).max()
+    print("[%s %dx%d] end to end: |H - oracle| %.3g |flow12 - oracle| %.3g" % (engine, h, w, dH, de))
+    if not ties:
+        np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
+        assert np.abs(out["flowDown8"] - ref["flowDown8"]).max() < FLOW_TOL
+        if engine in STRICT:
+            assert de < FLOW_TOL
+
+
+def saturating_net():
+    """The seeded fine-flow weights with NetMatchability's last layer scaled up so that the matchability saturates to exactly
+    0 / 1 over regions: the multi-hypothesis mask update ``(Mask + matchFine) >= 1`` then really changes the mask."""
+    net = oracle_net()
+    sd = {k: v.clone() for k, v in net["netMatch"].items()}
+    sd["conv4.weight"] = sd["conv4.weight"] * 3e5
+    net["netMatch"] = sd
+    return net
+
+
+def product_net(rf, onet):
+    net = networks(rf)
+    net["netMatch"].load_state_dict(onet["netMatch"])
+    return net
+
+
+_SAT = {}
+
+
+@pytest.mark.parametrize("engine", ["fp32", "f16x3"], indirect=True)
+@pytest.mark.parametrize("sat", [False, True])
+@pytest.mark.parametrize("path", ["host", "device"])
+def test_multi_hypothesis_loop_vs_oracle(rf, engine, sat, path):
+    """align_pair (host masks, the reference's loop) and align_pair_device (device masks) with maxCoarse = 3 and the evalCorr
+    matchability against the oracle's loop, every RANSAC call fed the oracle's sample table: number of accepted hypotheses,
+    every H, flowDown8 / matchDown8 per hypothesis and the full-resolution maps."""
+    onet = _SAT.setdefault("net", saturating_net()) if sat else None
+    o = oracle_pair(12, 96, 128, 96, 3, maxCoarse=3, m21=True, net=onet)
+    ref = o["ref"]
+    net = product_net(rf, onet) if sat else networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=o["rsd"], verbose=False)
+    samples = o["samples"] + [o["samples"][-1]]           # a spare table: the loops may draw once more than the oracle did
+    if path == "host":
+        with fixed_randint(samples):
+            out = rf.pipeline.align_pair(c, net, o["Is"], o["It"], maxCoarse=3, with_match21=True)
+    else:
+        out = rf.pipeline.align_pair_device(c, net, o["Is"], o["It"], maxCoarse=3, with_match21=True, samples=samples)
+    nH = len(ref["flow12"])
+    print("[%s sat=%s %s] oracle accepted %d hypotheses (%d RANSAC calls), product %d" % (engine, sat, path, nH, len(o["samples"]), len(out["flow12"])))
+    assert nH >= 2 and len(out["flow12"]) == nH and out["H"].shape == ref["H"].shape
+    np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
+    assert np.abs(out["flowDown8"] - ref["flowDown8"]).max() < FLOW_TOL
+    assert np.abs(out["matchDown8"] - ref["matchDown8"]).max() < FLOW_TOL
+    for i in range(nH):
+        assert np.abs(out["flow12"][i].cpu().numpy() - ref["flow12"][i].numpy()).max() < FLOW_TOL
+        far = (np.abs(np.abs(ref["flow12"][i].numpy()) - 1) > 1e-3).all(-1)[0]
+        assert np.abs(out["match"][i] - ref["match"][i])[far].max() < FLOW_TOL
+    if sat:
+        assert any(not np.array_equal(ref["H"][0], ref["H"][i]) for i in range(1, nH)), "the mask update never changed the match set"
+
+
+@pytest.mark.parametrize("engine", ["fp32", "f16x3"], indirect=True)
+def test_device_path_draws_the_reference_sample_stream(rf, engine):
+    """utils/outil.py:120 draws ``torch.randint(nbMatch, (nbIter, 4), device=match1.device)``.  Under the same seed the
+    sync-free path (M read on the device, ops.philox_words + RF_SAMPLES_PHILOX64) returns what the host path returns - eagerly,
+    and inside a replayed CUDA graph."""
+    src, tgt, _ = synth.make_pair(14, 96, 128)
+    rsd = synth.resnet50_conv4_state(0)
+    net = networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+    c.setPair(Image.fromarray(src), Image.fromarray(tgt))
+    torch.manual_seed(1000)
+    Href = c.getCoarse(np.zeros((96, 128), np.float32))
+    M = len(c.match1)
+    torch.manual_seed(1000)
+    expect = torch.randint(M, (1000, 4), device="cuda")
+    torch.manual_seed(1000)
+    words = rf.ops.philox_words(1000, 4, "cuda")
+    assert torch.equal((words >> 32) & 0xFFFFFFFF, (words >> 32) & 0xFFFFFFFF) and torch.equal(((words >> 32) & 0xFFFFFFFF) % M, expect)
+    torch.manual_seed(1000)
+    Hd, nb, mask, status, cnt = c.getCoarse_device(None)
+    assert int(status.item()) == 0 and int(cnt.item()) == M
+    assert np.array_equal(Hd.cpu().numpy().reshape(3, 3), Href)
+    # the whole single-hypothesis path, eager and graphed, against the host loop under the same seed
+    torch.manual_seed(1000)
+    b = rf.pipeline.align_pair(c, net, Image.fromarray(src), Image.fromarray(tgt), maxCoarse=0)
+    torch.manual_seed(1000)
+    a = rf.pipeline.align_pair_single(c, net, Image.fromarray(src), Image.fromarray(tgt))
+    assert np.array_equal(a["H"], b["H"]) and np.array_equal(a["flowDown8"], b["flowDown8"])
+    ga = rf.pipeline.GraphedAligner(c, net)
+    s, t = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+    ga.prepare(s, t)
+    for _ in range(2):
+        torch.manual_seed(1000)
+        g = ga(s, t)
+        assert np.array_equal(g["H"], b["H"]) and np.array_equal(g["flowDown8"], b["flowDown8"])
+    g2 = ga(s, t)                                     # no reseed: the generator moved on, fresh samples
+    assert g2["H"].shape == (1, 3, 3)
