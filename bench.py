@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py - image-pairs/sec on synthetic 480x640 pairs (BASELINE.json config 2).
+"""bench.py - image-pairs/sec on synthetic pairs (BASELINE.json configs 2-5; default config 2 = 480x640).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--engine fp32|tf32|f16] [--lanes L]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5]
+                    [--engine f16x3|fp32|f16|tf32] [--lanes L] [--pairs-per-step P]
 
-One "step" = one batch of L independent pairs (default 4, `config.pairs_per_gpu_per_step`), each through the
-whole hot path (variant-A CoarseAlign.setPair -> getCoarse -> warp_grid -> PredFlowMask), nbScale 7, scaleR 2,
-nbIter 1000, one hypothesis; the L pairs run as L CUDA graphs on L streams (pipeline.ConcurrentAligner) so that one
-pair's small layers overlap another's.  Prints ONE JSON line
-(rank 0).  `value` = pairs/s with the uint8 480x640 images already in HBM; `e2e` = the same
-through the public API from pinned HOST images (H2D of the inputs + D2H of the results inside the
-timed region).  `--impl reference` times the CPU oracle (oracle/pair_oracle.py: the reference's own
-PyTorch-CPU algorithm, all host threads) on the same workload.
+One "step" = P independent pairs per GPU (default 32, `config.pairs_per_gpu_per_step`), each through the whole hot path
+(variant-A CoarseAlign.setPair -> getCoarse -> warp_grid -> PredFlowMask).  Config 2: nbScale 7, scaleR 2, nbIter 1000, one
+hypothesis; L pairs at a time run as L CUDA graphs on L streams (pipeline.ConcurrentAligner).  Config 3 adds the
+getFlow_all recomposition at minSize 240 (evalHpatch/getResults.py), config 4 the multi-hypothesis loop with maxCoarse = 10
+and the evalCorr matchability (device-resident masks), config 5 the KITTI two-level flow on 376x1241 pairs capped at 5
+hypotheses.  Prints ONE JSON line (rank 0).  `value` = pairs/s with the uint8 images already in HBM; `e2e` = the same
+through the public API from pinned HOST images (H2D of the inputs + D2H of the results inside the timed region).  The default
+engine `f16x3` is the fp32-grade tensor-core engine (fp16 hi / lo split operands, 3 MMAs per MAC); `parity` reports how far
+that engine is from the CPU oracle on pair 0 of the workload (computed outside the timed region from the file the
+cpu_baseline child wrote).  `--impl reference` times the CPU oracle (oracle/pair_oracle.py: the reference's own PyTorch-CPU
+algorithm, all host threads) on the same workload.
 """
 import argparse
 import json
@@ -25,9 +29,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "config2: synthetic 480x640 pairs, variant-A CoarseAlign nbScale=7 scaleR=2 nbIter=1000 tol=0.05, 1 hypothesis, PredFlowMask"
+WORKLOADS = {
+    2: "config2: synthetic 480x640 pairs, variant-A CoarseAlign nbScale=7 scaleR=2 nbIter=1000 tol=0.05, 1 hypothesis, PredFlowMask",
+    3: "config3: HPatches-shaped synthetic 480x640 pairs, config-2 path + getFlow_all recomposition at minSize 240 (evalHpatch/getResults.py:171,191-194)",
+    4: "config4: MegaDepth/YFCC-shaped synthetic 480x640 pairs, multi-hypothesis loop maxCoarse=10, match12*grid_sample(match21) (evalCorr/evaluation.py:211-243)",
+    5: "config5: KITTI-shaped synthetic 376x1241 pairs, coarseSize 800 nbScale=3 scaleR=1.2, two-level fine flow, up to 5 hypotheses (evalKITTI/evaluation.py:270-336)",
+}
+WORKLOAD = WORKLOADS[2]
 METRIC = "image-pairs/sec at 480x640, nbIter=1k RANSAC"
 NA, NB, CFEAT = 13065, 1200, 1024
+PARITY_RAW_SEED = 1000            # the raw sample table both arms reduce modulo their match count for the parity pair
+DTYPES = {"fp32": "f32", "tf32": "tf32",
+          "f16x3": "f32-grade: fp16 hi/lo split operands and activations (22 significand bits), 3 tcgen05 MMAs per MAC, fp32 accumulate; fp16-split correlation; fp32/fp64 RANSAC",
+          "f16": "f16 (reduced precision fast mode: conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; fp16-split correlation; fp32/fp64 RANSAC)",
+          "f16-trunk": "f16 trunk + tf32 fine-flow nets (reduced precision)"}
 
 
 def peaks():
@@ -136,9 +151,19 @@ def usable_cores():
     return max(1, n)
 
 
-def make_pairs(n):
+def pair_size(config):
+    return (376, 1241) if config == 5 else (480, 640)
+
+
+def make_pairs(n, config=2):
     import synthdata as synth                        # workload generator (repo root); nothing under oracle/ on the B200 arm
-    return [synth.make_pair(i, 480, 640)[:2] for i in range(n)]
+    h, w = pair_size(config)
+    return [synth.make_pair(i, h, w)[:2] for i in range(n)]
+
+
+def raw_sample_table(nbIter=1000):
+    import synthdata as synth
+    return synth.draw_samples(PARITY_RAW_SEED, 2 ** 31 - 1, nbIter)
 
 
 def states():
@@ -149,21 +174,37 @@ def states():
 
 # ----------------------------------------------------------------------------- reference arm (CPU oracle)
 def run_reference(args, rank, world):
+    """The reference's own algorithm on the host cores (oracle/pair_oracle.py, torch-CPU fp32).  With --dump-parity FILE it
+    also runs pair 0 of the workload once more with the shared raw sample table and writes everything a parity check needs
+    (index lists, score matrix, matches, H, inlier mask, flows) to FILE: the B200 arm reads that FILE, never the oracle."""
     if rank != 0:
         return
     import PIL.Image as Image
     import torch
     from oracle import pair_oracle as PO
+    from oracle import warp_oracle as WO
     cores = int(os.environ.get("RF_CPU_THREADS", "0")) or min(usable_cores(), 64)
     torch.set_num_threads(cores)
     rsd, fe, nf, nm = states()
     net = {"netFeatCoarse": fe, "netFlowCoarse": nf, "netMatch": nm}
-    pairs = make_pairs(2)
-    oc = PO.CoarseAlignOracle(rsd, nbScale=7, nbIter=1000, tolerance=0.05, minSize=480, scaleR=2, variant="A", seed=1000)
+    cfg = args.config
+    pairs = make_pairs(2, cfg)
+    if cfg == 5:
+        oc = PO.CoarseAlignOracle(rsd, nbScale=3, nbIter=1000, tolerance=0.05, minSize=800, scaleR=1.2, variant="A", seed=1000)
+    else:
+        oc = PO.CoarseAlignOracle(rsd, nbScale=7, nbIter=1000, tolerance=0.05, minSize=480, scaleR=2, variant="A", seed=1000)
 
     def step(i):
         s, t = pairs[i % len(pairs)]
-        return PO.align_pair(oc, net, Image.fromarray(s), Image.fromarray(t), maxCoarse=0)
+        Is, It = Image.fromarray(s), Image.fromarray(t)
+        if cfg == 5:
+            return PO.align_pair_kitti(oc, net, Is, It, maxH=5)
+        if cfg == 4:
+            return PO.align_pair(oc, net, Is, It, maxCoarse=10, with_match21=True)
+        out = PO.align_pair(oc, net, Is, It, maxCoarse=0)
+        if cfg == 3:
+            out["flowGlobal"] = WO.get_flow_all(out["flowDown8"], out["H"], out["matchDown8"], 240, 240, th=0.95, multiH=True)[0]
+        return out
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
@@ -171,13 +212,71 @@ def run_reference(args, rank, world):
         step(i)
     dt = time.perf_counter() - t0
     v = args.steps / dt
+    if args.dump_parity and cfg in (2, 3):
+        oc.raw_samples = raw_sample_table()
+        s0, t0_ = pairs[0]
+        ref = PO.align_pair(oc, net, Image.fromarray(s0), Image.fromarray(t0_), maxCoarse=0)
+        featt = oc.featt.contiguous().view(oc.featt.shape[1], -1).numpy()
+        score = oc.featsMultiScale.numpy().T @ featt
+        _, nbInl, isInl, _ = __import__("oracle.outil_oracle", fromlist=["x"]).RANSAC_from_samples(oc.match1, oc.match2, oc.last_samples, 0.05)
+        np.savez(args.dump_parity, index1=oc.index1, index2=oc.index2, score=score, match1=oc.match1, match2=oc.match2,
+                 samples=oc.last_samples, H=ref["H"], nbInlier=np.int64(nbInl), isInlier=np.asarray(isInl, dtype=bool),
+                 flowDown8=ref["flowDown8"], matchDown8=ref["matchDown8"], flow12=ref["flow12"][0].numpy(), match=ref["match"][0])
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOADS[cfg]},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": "%d whole pairs through oracle/pair_oracle.py (torch-CPU fp32, %d threads)" % (args.steps, torch.get_num_threads())},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def parity_report(rf, torch, ref, coarse, net, pair, engine):
+    """How far the timed engine is from the CPU oracle on pair 0 (outside the timed region).  `ref` = the arrays the
+    cpu_baseline child wrote.  (a) match set and tie proofs, (b) the oracle's matches + samples through the RANSAC kernel,
+    (c) the oracle's H through the fine stage, (d) end to end with the shared sample table."""
+    import PIL.Image as Image
+    raw = raw_sample_table()
+    s, t = pair
+    out = rf.pipeline.align_pair_single(coarse, net, s, t, samples=raw)
+    n = int(coarse._count.item())
+    got = set(zip(coarse._idx1[:n].cpu().tolist(), coarse._idx2[:n].cpu().tolist()))
+    exp = set(zip(ref["index1"].tolist(), ref["index2"].tolist()))
+    score = ref["score"]
+    dev = float((coarse._feats_rows.double() @ coarse._featt_rows.double().t() - torch.from_numpy(score).cuda().double()).abs().max())
+    rowmax, colmax = score.max(1), score.max(0)
+    s2r, s2c = np.partition(score, -2, axis=1)[:, -2], np.partition(score, -2, axis=0)[-2]
+    margins = [float(min(rowmax[i] - s2r[i], colmax[j] - s2c[j])) if (i, j) in exp else float(max(rowmax[i] - score[i, j], colmax[j] - score[i, j]))
+               for (i, j) in sorted(got ^ exp)]
+    # (b) the oracle's match list and sample table through the RANSAC kernel
+    m1, m2 = torch.from_numpy(ref["match1"]).cuda(), torch.from_numpy(ref["match2"]).cuda()
+    Hd, nb, mask, status = rf.ops.ransac_homography(m1, m2, torch.from_numpy(ref["samples"]).cuda(), 0.05)
+    # (c) the oracle's H through warp_grid + PredFlowMask
+    Itw, Ith = coarse.target_size
+    featt = rf.pipeline.fine_features(net["netFeatCoarse"], coarse.ItTensor)
+    fc = rf.ops.warp_grid(torch.from_numpy(ref["H"]).cuda(), Ith, Itw)
+    f12, match, f8, mb = rf.pipeline.PredFlowMask_device(coarse.IsTensor, featt, fc, (Ith, Itw), net)
+    same = len(got ^ exp) == 0
+    rec = {
+        "engine": engine, "pair": "pair 0 of the workload, shared raw sample table %% match count, oracle = oracle/pair_oracle.py (CPU fp32)",
+        "matches_oracle": len(exp), "matches_b200": len(got), "match_symdiff": len(got ^ exp),
+        "max_abs_score_dev": dev, "symdiff_worst_margin": max(margins, default=0.0),
+        "symdiff_all_proven_ties": bool(all(m <= 2 * dev + 1e-6 for m in margins)),
+        "stage_ransac_on_oracle_matches": {"status": int(status.item()), "nb_inlier_equal": bool(int(nb.item()) == int(ref["nbInlier"])),
+                                           "inlier_mask_equal": bool(np.array_equal(mask.cpu().numpy().astype(bool), ref["isInlier"])),
+                                           "max_abs_H": float(np.abs(Hd.cpu().numpy().reshape(3, 3) - ref["H"][0]).max())},
+        "stage_fine_on_oracle_H": {"max_abs_flowDown8": float(np.abs(f8.cpu().numpy() - ref["flowDown8"]).max()),
+                                   "max_abs_matchDown8": float(np.abs(mb.cpu().numpy().reshape(ref["matchDown8"].shape) - ref["matchDown8"]).max()),
+                                   "max_abs_flow12": float(np.abs(f12.cpu().numpy() - ref["flow12"]).max())},
+        "end_to_end": {"max_abs_H": float(np.abs(out["H"] - ref["H"]).max()) if len(out["H"]) else None,
+                       "max_abs_flowDown8": float(np.abs(out["flowDown8"] - ref["flowDown8"]).max()) if len(out["H"]) else None,
+                       "max_abs_flow12": float(np.abs(out["flow12"][0].cpu().numpy() - ref["flow12"]).max()) if len(out["H"]) else None,
+                       "note": "meaningful as parity only when match_symdiff == 0: the samples index the match list, so one tie re-labels every hypothesis (the reference's own CPU and GPU runs differ the same way)" if not same else "match lists identical"},
+    }
+    fine = rec["stage_fine_on_oracle_H"]
+    rec["within_north_star"] = bool(rec["symdiff_all_proven_ties"] and rec["stage_ransac_on_oracle_matches"]["inlier_mask_equal"]
+                                    and max(fine.values()) < 1e-3 and (not same or rec["end_to_end"]["max_abs_flow12"] < 1e-3))
+    return rec
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -191,9 +290,11 @@ def run_b200(args, rank, world, local):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cfg = args.config
     rf.model.set_engine(args.engine)
     rf.outil.corr_precision = {"fp32": 0, "tf32": 1}.get(args.engine, 2)      # exact fp32 / 3xTF32 / fp16 split
     rsd, fe_sd, nf_sd, nm_sd = states()
+    H_img, W_img = pair_size(cfg)
 
     def make_models():
         """A fresh (CoarseAlign, networks) set: same weights, own activation buffers / pair state."""
@@ -205,17 +306,23 @@ def run_b200(args, rank, world, local):
         for m in net.values():
             m.cuda()
             m.eval()
-        c = rf.CoarseAlignA(7, 1000, 0.05, "Homography", 480, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
+        if cfg == 5:
+            c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 800, 2, False, 1.2, True, False, resnet_state_dict=rsd, verbose=False)
+        else:
+            c = rf.CoarseAlignA(7, 1000, 0.05, "Homography", 480, 2, False, 2, True, False, resnet_state_dict=rsd, verbose=False)
         c.device_preproc = True
         return c, net
     coarse, net = make_models()
-    lanes = max(1, args.lanes) if args.graph else 1
-    pairs = make_pairs(4)
+    graphed = args.graph and cfg in (2, 3)             # configs 4 / 5 steer their hypothesis loop from the host (12 bytes per hypothesis)
+    lanes = max(1, args.lanes) if graphed else 1
+    P = max(lanes, (args.pairs_per_step // lanes) * lanes) if cfg in (2, 3) else max(1, args.pairs_per_step)
+    pairs = make_pairs(4, cfg)
     host = [(torch.from_numpy(s).pin_memory(), torch.from_numpy(t).pin_memory()) for s, t in pairs]
     resident = [(s.to(dev), t.to(dev)) for s, t in host]
+    pil = [(Image.fromarray(s), Image.fromarray(t)) for s, t in pairs]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    aligner = rf.pipeline.GraphedAligner(coarse, net) if (args.graph and lanes == 1) else None
+    aligner = rf.pipeline.GraphedAligner(coarse, net) if (graphed and lanes == 1) else None
     multi = rf.pipeline.ConcurrentAligner(make_models, lanes) if lanes > 1 else None
     if multi is not None:
         multi.prepare(*resident[0])
@@ -223,20 +330,37 @@ def run_b200(args, rank, world, local):
     def replayed():
         return (aligner.replayed_kernels if aligner is not None else 0) + (multi.replayed_kernels if multi is not None else 0)
 
+    def one_pair(i, from_host):
+        """Configs 4 / 5 (and --no-graph): one pair through the eager API."""
+        s, t = (host if from_host else resident)[i % len(resident)]
+        if cfg == 5:
+            Is, It = pil[i % len(pil)]               # align_pair_kitti takes PIL images (resizeImg on the host, like the script)
+            torch.manual_seed(1000)                  # evalKITTI/evaluation.py:182
+            return rf.pipeline.align_pair_kitti(coarse, net, Is, It, maxH=5)
+        if from_host:
+            s, t = s.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
+        torch.manual_seed(1000)
+        if cfg == 4:
+            return rf.pipeline.align_pair_device(coarse, net, s, t, maxCoarse=10, with_match21=True)
+        return rf.pipeline.align_pair_single(coarse, net, s, t)
+
     def step(i, from_host):
-        """One step = `lanes` pairs (1 unless --lanes): returns the list of per-pair results."""
+        """One step = P pairs: returns the list of per-pair results."""
         src = host if from_host else resident                                       # pinned host (H2D inside) or HBM-resident
+        outs = []
         if multi is not None:
-            outs = multi([src[(i * lanes + k) % len(src)] for k in range(lanes)])    # lanes graphs side by side, one D2H each
+            for r in range(P // lanes):                                             # lanes graphs side by side, one D2H each
+                outs += multi([src[(i * P + r * lanes + k) % len(src)] for k in range(lanes)], copy=False)
+        elif aligner is not None:
+            for r in range(P):
+                outs.append(aligner(*src[(i * P + r) % len(src)], copy=False))      # one CUDA-graph launch + one pinned D2H
         else:
-            s, t = src[i % len(src)]
-            if aligner is not None:
-                outs = [aligner(s, t)]                                              # one CUDA-graph launch + one pinned D2H
-            else:
-                if from_host:
-                    s, t = s.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
-                torch.manual_seed(1000)                                             # evalKITTI/evaluation.py:182
-                outs = [rf.pipeline.align_pair_single(coarse, net, s, t)]           # results come back as numpy (one pinned D2H)
+            for r in range(P):
+                outs.append(one_pair(i * P + r, from_host))
+        if cfg == 3:                                                                # evalHpatch/getResults.py: recomposition at minSize 240
+            for o in outs:
+                if len(o["H"]):
+                    o["flowGlobal"] = rf.pipeline.getFlow_all(o["flowDown8"], o["H"], o["matchDown8"], 240, 240, th=0.95, multiH=True)
         flush.zero_()                                                               # L2 flush between steps
         return outs
 
@@ -253,11 +377,13 @@ def run_b200(args, rank, world, local):
         for i in range(K):
             outs = step(i, from_host)
             for k, out in enumerate(outs):
-                recs.append(shard.pack_record(rank + world * (i * lanes + k), out["H"][0] if len(out["H"]) else None,
+                recs.append(shard.pack_record(rank + world * (i * P + k), out["H"][0] if len(out["H"]) else None,
                                               status=0 if len(out["H"]) else 1))
-        allr = shard.gather_records(recs, K * lanes * world, world, dev)            # the one collective: per-pair records
+        g0 = time.perf_counter()
+        allr = shard.gather_records(recs, K * P * world, world, dev)                # the one collective: per-pair records
         e1.record()
         torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - g0)
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -266,115 +392,129 @@ def run_b200(args, rank, world, local):
             tmax = torch.tensor([ms], device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
-        return ms, launches, outs[-1], allr
+        return ms, launches, outs[-1], allr, gather_ms
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, out, _ = timed(False, args.steps, args.warmup)
-    ms_e2e, _, out, allr = timed(True, args.steps, max(1, args.warmup // 2))
+    ms_dev, launches, out, _, _ = timed(False, args.steps, args.warmup)
+    ms_e2e, _, out, allr, gather_ms = timed(True, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
-    assert allr.shape[0] == args.steps * lanes * world
-
-    # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, mean of 5 pairs) ----
-    def stage_breakdown():
-        names = ["pyramid+preproc+resnet50_conv4(8 imgs)+l2norm", "corr+mutual_nn", "fine_features(target)", "build_matches+ransac",
-                 "warp_grid+PredFlowMask"]
-        acc = np.zeros(len(names))
-        reps, skip = 5, 3                     # the first eager passes of these model objects build TMA maps / layer programs
-        for rep in range(reps + skip):
-            s_, t_ = resident[rep % len(resident)]
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-            saved = rf.ops.corr_mutual_nn
-            marks = {}
-
-            def corr_hook(*a, **k):                                  # setPair ends with the correlation: split it out
-                marks["pre"] = torch.cuda.Event(enable_timing=True)
-                marks["pre"].record()
-                return saved(*a, **k)
-            rf.ops.corr_mutual_nn = corr_hook
-            try:
-                evs[0].record()
-                coarse.setPair(s_, t_)
-            finally:
-                rf.ops.corr_mutual_nn = saved
-            evs[2].record()
-            Itw, Ith = coarse.target_size
-            featt = rf.pipeline.fine_features(net["netFeatCoarse"], coarse.ItTensor)
-            evs[3].record()
-            Hd, nb, mask, status, cnt = coarse.getCoarse_device(None)
-            evs[4].record()
-            fc = rf.ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
-            rf.pipeline.PredFlowMask_device(coarse.IsTensor, featt, fc, (Ith, Itw), net)
-            evs[5].record()
-            torch.cuda.synchronize()
-            if rep < skip:
-                continue
-            acc += np.array([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
-                             evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
-        return {n: round(float(v / reps), 4) for n, v in zip(names, acc)}
+    assert allr.shape[0] == args.steps * P * world
     if rank != 0:
         return                                       # the per-kernel sections below are rank 0's (no collective inside)
-    stages = stage_breakdown()
+    nH_mean = float(np.mean([len(o["H"]) for o in [out]]))
 
-    # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----
-    fa, ft = coarse._feats_rows, coarse._featt_rows
-    st = torch.cuda.current_stream()
-    reps = 20
-    for _ in range(3):
-        rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for a, b in ev:
-        flush.zero_()
-        a.record(st)
-        rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
-        b.record(st)
-    torch.cuda.synchronize()
-    corr_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    # RANSAC alone (latency-bound: reported as us/call)
-    nm = int(coarse._match_count.item())             # matches of the pair `coarse` holds (set by stage_breakdown)
-    m1, m2 = coarse.match1[:nm].contiguous(), coarse.match2[:nm].contiguous()
-    smp = torch.randint(len(m1), (1000, 4), device=dev)
-    for _ in range(3):
-        rf.ops.ransac_homography(m1, m2, smp, 0.05)
-    for a, b in ev:
-        a.record(st)
-        rf.ops.ransac_homography(m1, m2, smp, 0.05)
-        b.record(st)
-    torch.cuda.synchronize()
-    ransac_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    prec = rf.outil.corr_precision
-    v2 = prec == 2 and rf._lib.lib.rf_corr_mutual_nn_launches(2) == 3
-    roofline = roofline_record(prec, v2, corr_ms, ransac_ms, int(len(m1)), peaks())
+    stages = roofline = None
+    if cfg in (2, 3):
+        # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, mean of 5 pairs) ----
+        def stage_breakdown():
+            names = ["pyramid+preproc+resnet50_conv4(8 imgs)+l2norm", "corr+mutual_nn", "fine_features(target)", "build_matches+ransac",
+                     "warp_grid+PredFlowMask"]
+            acc = np.zeros(len(names))
+            reps, skip = 5, 3                     # the first eager passes of these model objects build TMA maps / layer programs
+            for rep in range(reps + skip):
+                s_, t_ = resident[rep % len(resident)]
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                saved = rf.ops.corr_mutual_nn
+                marks = {}
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores,
-    # run as `bench.py --impl reference` in a child process so that it can be cut off ----
-    cpu = None
+                def corr_hook(*a, **k):                                  # setPair ends with the correlation: split it out
+                    marks["pre"] = torch.cuda.Event(enable_timing=True)
+                    marks["pre"].record()
+                    return saved(*a, **k)
+                rf.ops.corr_mutual_nn = corr_hook
+                try:
+                    evs[0].record()
+                    coarse.setPair(s_, t_)
+                finally:
+                    rf.ops.corr_mutual_nn = saved
+                evs[2].record()
+                Itw, Ith = coarse.target_size
+                featt = rf.pipeline.fine_features(net["netFeatCoarse"], coarse.ItTensor)
+                evs[3].record()
+                Hd, nb, mask, status, cnt = coarse.getCoarse_device(None)
+                evs[4].record()
+                fc = rf.ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+                rf.pipeline.PredFlowMask_device(coarse.IsTensor, featt, fc, (Ith, Itw), net)
+                evs[5].record()
+                torch.cuda.synchronize()
+                if rep < skip:
+                    continue
+                acc += np.array([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
+                                 evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
+            return {n: round(float(v / reps), 4) for n, v in zip(names, acc)}
+        stages = stage_breakdown()
+
+        # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----
+        fa, ft = coarse._feats_rows, coarse._featt_rows
+        st = torch.cuda.current_stream()
+        reps = 20
+        for _ in range(3):
+            rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            flush.zero_()
+            a.record(st)
+            rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
+            b.record(st)
+        torch.cuda.synchronize()
+        corr_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        # RANSAC alone (latency-bound: reported as us/call)
+        nm = int(coarse._match_count.item())             # matches of the pair `coarse` holds (set by stage_breakdown)
+        m1, m2 = coarse.match1[:nm].contiguous(), coarse.match2[:nm].contiguous()
+        smp = torch.randint(len(m1), (1000, 4), device=dev)
+        for _ in range(3):
+            rf.ops.ransac_homography(m1, m2, smp, 0.05)
+        for a, b in ev:
+            a.record(st)
+            rf.ops.ransac_homography(m1, m2, smp, 0.05)
+            b.record(st)
+        torch.cuda.synchronize()
+        ransac_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        prec = rf.outil.corr_precision
+        v2 = prec == 2 and rf._lib.lib.rf_corr_mutual_nn_launches(2) == 3
+        roofline = roofline_record(prec, v2, corr_ms, ransac_ms, int(len(m1)), peaks())
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores, run as
+    # `bench.py --impl reference` in a child process so that it can be cut off.  The child also writes the oracle's
+    # outputs for pair 0 to a file; `parity` compares the timed engine with that file (outside every timed region) ----
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import tempfile
+        dump = os.path.join(tempfile.mkdtemp(prefix="rf_parity_"), "pair0.npz")
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
-                               capture_output=True, text=True, timeout=240)
+            nref = {2: 3, 3: 3, 4: 1, 5: 1}[cfg]
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(nref), "--warmup", "1",
+                                "--config", str(cfg), "--dump-parity", dump], capture_output=True, text=True, timeout=420)
             ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
             cpu = ref["cpu_baseline"]
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "pairs/s", "cores": usable_cores(), "kind": "port",
-                   "sample": "CPU oracle did not finish 1+3 pairs in 240 s (%s)" % type(e).__name__}
+                   "sample": "CPU oracle did not finish in 420 s (%s)" % type(e).__name__}
+        if cfg in (2, 3) and os.path.exists(dump):
+            try:
+                parity = parity_report(rf, torch, dict(np.load(dump)), coarse, net, resident[0], args.engine)
+            except Exception as e:  # noqa: BLE001
+                parity = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
-        d2h = int(480 * 640 * 4 + out["flowDown8"].nbytes + out["matchDown8"].nbytes + 9 * 4 + 64)
+        hw8 = (H_img // 8) * (W_img // 8)
+        d2h = int(H_img * W_img * 4 + 4 * hw8 * 4 + 9 * 4 + 64) if cfg in (2, 3) else None
         line = {
-            "metric": METRIC, "value": world * lanes * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": world * P * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16 (conv operands and activations fp16, fp32 accumulate; TF32 output convs of the heads; fp16-split correlation = 22 significand bits; fp32/fp64 RANSAC)",
-                      "f16-trunk": "f16 trunk + tf32 fine-flow nets"}[args.engine], "data": "synthetic",
-            "config": {"workload": WORKLOAD, "engine": args.engine, "pairs_per_gpu_per_step": lanes, "parallelism": "pairs sharded i %% %d" % world,
-                       "l2": "256 MiB buffer written between steps (L2 flush); activations per step also exceed the 126 MB L2",
-                       "preprocessing": "7-scale LANCZOS pyramid on the GPU (bit-exact PIL emulation)",
+            "dtype": DTYPES[args.engine], "data": "synthetic",
+            "config": {"workload": WORKLOADS[cfg], "engine": args.engine, "pairs_per_gpu_per_step": P, "pairs_in_flight": lanes,
+                       "parallelism": "pairs sharded i %% %d" % world,
+                       "l2": "256 MiB buffer written between steps (L2 flush); activations per pair also exceed the 126 MB L2",
+                       "preprocessing": "LANCZOS pyramid on the GPU (bit-exact PIL emulation)" if cfg != 5 else "coarse pyramid on the GPU; the two fine-level resizes with PIL on the host like the script",
                        "launch": ("one CUDA graph per pair" + (", %d independent pairs in flight on %d streams" % (lanes, lanes) if lanes > 1 else ""))
-                                 if args.graph else "stream launches"},
-            "e2e": {"value": world * lanes * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": lanes * 2 * 480 * 640 * 3,
-                    "d2h_bytes_per_step": lanes * d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages_ms": stages,
+                                 if graphed else "stream launches, hypothesis loop steered from the host (12 bytes per hypothesis)"},
+            "e2e": {"value": world * P * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * H_img * W_img * 3,
+                    "d2h_bytes_per_step": (P * d2h) if d2h else None},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "stages_ms": stages,
+            "all_gather_ms": round(gather_ms, 3), "hypotheses_last_pair": nH_mean,
         }
         print(json.dumps(line))
 
@@ -382,16 +522,23 @@ def run_b200(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "f16"), choices=["fp32", "tf32", "f16", "f16-trunk"],
-                    help="f16: tcgen05 convs with fp16 activations (default); tf32: tcgen05 convs with fp32 activations / TF32 operands; f16-trunk: fp16 trunk + tf32 fine-flow nets; fp32: exact-FMA SIMT engine")
+    ap.add_argument("--config", type=int, default=int(os.environ.get("RF_CONFIG", "2")), choices=[2, 3, 4, 5], help="BASELINE.json configs[N-1]")
+    ap.add_argument("--engine", default=os.environ.get("RF_ENGINE", "f16x3"), choices=["f16x3", "fp32", "tf32", "f16", "f16-trunk"],
+                    help="f16x3 (default): fp32-grade tcgen05 engine, fp16 hi/lo split operands, 3 MMAs per MAC; fp32: exact-FMA SIMT engine; "
+                         "f16 / tf32 / f16-trunk: reduced-precision fast modes (10-bit operands)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("RF_LANES", "4")),
-                    help="independent pairs in flight per GPU and step (each with its own CUDA graph, models' activation buffers and stream)")
-    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the ~140 kernels of a pair one by one instead of replaying a CUDA graph")
+                    help="independent pairs in flight per GPU (each with its own CUDA graph, models' activation buffers and stream)")
+    ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("RF_PAIRS_PER_STEP", "0")),
+                    help="pairs per GPU and step (default 32 for configs 2 / 3, 8 for config 4, 4 for config 5)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the kernels of a pair one by one instead of replaying a CUDA graph")
+    ap.add_argument("--dump-parity", default=None, help="(reference arm) write the oracle's outputs for pair 0 to this .npz")
     args = ap.parse_args()
+    if args.pairs_per_step <= 0:
+        args.pairs_per_step = {2: 32, 3: 32, 4: 8, 5: 4}[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

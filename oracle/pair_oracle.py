@@ -123,9 +123,14 @@ class CoarseAlignOracle:
         return (MtTensor > 0.5)[0, 0]
 
     def _ransac(self, match1, match2):
-        if self.seed is not None:
-            torch.manual_seed(self.seed)
-        samples = torch.randint(len(match1), (self.nbIter, 4)).numpy()
+        if getattr(self, "raw_samples", None) is not None:
+            # injected table of non-negative integers, reduced modulo the match count (what rf_ransac_homography's
+            # RF_SAMPLES_MOD does with the same table): lets a CPU run and a CUDA run share one sample stream
+            samples = (np.asarray(self.raw_samples, dtype=np.int64) % len(match1))
+        else:
+            if self.seed is not None:
+                torch.manual_seed(self.seed)
+            samples = torch.randint(len(match1), (self.nbIter, 4)).numpy()
         self.last_samples = samples
         self.all_samples.append(samples)
         return OO.RANSAC_from_samples(match1, match2, samples, self.tolerance)

@@ -5,6 +5,7 @@
 // (float4) where the channel count allows.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -474,6 +475,96 @@ __global__ void corr_neigh_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// k = 7 (every configuration of the reference): the 49 dot products of a pixel are accumulated per lane in registers and
+// reduced with ONE multi-value butterfly (62 shuffles instead of 49 x 5): at each step a lane keeps half of its values and
+// hands the other half to its partner, so lane L ends up with the complete sums 2L and 2L + 1 and the warp stores its 49
+// (64 with padding) outputs as one coalesced row.  Eight warps of a CTA take eight horizontally adjacent pixels, whose
+// 7 x 14 y-neighbourhood is mostly shared in L1.  Same products, same per-lane channel order and the same reduction tree for
+// every tap, so CorrNeigh(y, x) written from here is bit-identical to a separate launch (see corr_neigh_kernel).
+__global__ void __launch_bounds__(256)
+corr_neigh7_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int h, int w, int C, int ldo, int round_out,
+                   float* __restrict__ out, float* __restrict__ out2) {
+    constexpr int K = 7, KK = 49, PAD = 3;
+    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long P = (long long)N * h * w;
+    if (pix >= P) return;
+    const int n = (int)(pix / ((long long)h * w));
+    const int rem = (int)(pix - (long long)n * h * w);
+    const int r = rem / w, c = rem - r * w;
+    const int c4n = C >> 2;
+    const bool split = round_out == 3;
+    const long long plane1 = P * ldo, plane2 = 2 * P * ldo;
+    const float4* xs = reinterpret_cast<const float4*>(x + pix * C);
+    float4 xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xv[q] = (lane + 32 * q < c4n) ? __ldg(xs + lane + 32 * q) : make_float4(0, 0, 0, 0);
+    float a[64];
+#pragma unroll
+    for (int t = 0; t < 64; ++t) a[t] = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int yr = r + i - PAD;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int yc = c + j - PAD;
+            if (yr >= 0 && yr < h && yc >= 0 && yc < w) {
+                const float4* ys = reinterpret_cast<const float4*>(y + (((long long)n * h + yr) * w + yc) * C);
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (lane + 32 * q < c4n) {
+                        const float4 v = __ldg(ys + lane + 32 * q);
+                        acc = fmaf(xv[q].x, v.x, acc); acc = fmaf(xv[q].y, v.y, acc);
+                        acc = fmaf(xv[q].z, v.z, acc); acc = fmaf(xv[q].w, v.w, acc);
+                    }
+                a[i * K + j] = acc;
+            }
+        }
+    }
+    // multi-value butterfly: 64 -> 32 -> 16 -> 8 -> 4 -> 2 values per lane
+#pragma unroll
+    for (int s = 16, nv = 32; s >= 1; s >>= 1, nv >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int v = 0; v < nv; ++v) {
+            const float send = up ? a[v] : a[v + nv];
+            const float keep = up ? a[v + nv] : a[v];
+            a[v] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    // lane L holds taps 2L and 2L + 1 (taps >= 49 are the zero padding of a 64-wide row)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int t = 2 * lane + u;
+        if (t >= ldo) continue;
+        const float v = a[u];
+        corr_store(out, pix * ldo + t, v, round_out, plane1);
+        if (out2 != nullptr) {
+            if (split) corr_store(out2, pix * ldo + t, v, 3, plane2);
+            if (t < KK) {
+                const int i = t / K, j = t - i * K;
+                const int yr = r + i - PAD, yc = c + j - PAD;
+                const bool inside = yr >= 0 && yr < h && yc >= 0 && yc < w;
+                const long long q = inside ? (((long long)n * h + yr) * w + yc) : pix;
+                const int e = inside ? (KK - 1 - t) : t;
+                if (split) corr_store(out2, (P + q) * ldo + e, v, 3, plane2);
+                else corr_store(out2, q * ldo + e, v, round_out, 0);
+            } else {
+                if (split) corr_store(out2, (P + pix) * ldo + t, 0.f, 3, plane2);
+                else corr_store(out2, pix * ldo + t, 0.f, round_out, 0);
+            }
+        }
+    }
+    for (int t = 64 + lane; t < ldo; t += 32) {          // ldo > 64: remaining zero columns
+        corr_store(out, pix * ldo + t, 0.f, round_out, plane1);
+        if (out2 != nullptr) {
+            if (split) { corr_store(out2, pix * ldo + t, 0.f, 3, plane2); corr_store(out2, (P + pix) * ldo + t, 0.f, 3, plane2); }
+            else corr_store(out2, pix * ldo + t, 0.f, round_out, 0);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // model/model.py:226-233: softmax over k*k channels + expected offset.  logits NHWC [P][k*k]
 // ---------------------------------------------------------------------------
@@ -880,6 +971,13 @@ using namespace rf;
 
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// RF_CORR_NEIGH_V2 (read per call): 1 (default) = register-accumulating kernel with one multi-value butterfly per pixel
+// (k = 7); 0 = the one-reduction-per-tap kernel.  Same sums up to the order of the cross-lane additions.
+static int corr_neigh_v2() {
+    const char* e = getenv("RF_CORR_NEIGH_V2");
+    return e ? atoi(e) : 1;
+}
+
 extern "C" int rf_maxpool2d_nhwc(const float* x, int nimg, const int* hw_host, int C, int k, int stride, int pad, float* y, void* stream) {
     RF_REQUIRE((C % 4) == 0 && k >= 1 && stride >= 1, "rf_maxpool2d_nhwc: C must be a multiple of 4");
     ImgSet set;
@@ -1162,8 +1260,12 @@ extern "C" int rf_corr_neigh_pair_split(const float* x, const float* y, int N, i
     RF_REQUIRE(out12_split != nullptr && out12_split != both_split, "rf_corr_neigh_pair_split: outputs");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, 3, static_cast<float*>(out12_split),
-                                                                             static_cast<float*>(both_split));
+    if (k == 7 && corr_neigh_v2())
+        corr_neigh7_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, ldo, 3, static_cast<float*>(out12_split),
+                                                                                  static_cast<float*>(both_split));
+    else
+        corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, 3, static_cast<float*>(out12_split),
+                                                                                 static_cast<float*>(both_split));
     RF_LAUNCHED();
     return 0;
 }
@@ -1180,7 +1282,8 @@ extern "C" int rf_corr_neigh_nhwc(const float* x, const float* y, int N, int h, 
     RF_REQUIRE((C % 4) == 0 && C <= 1024 && (k % 2) == 1 && ldo >= k * k, "rf_corr_neigh_nhwc: need C % 4 == 0, C <= 1024, odd k, ldo >= k*k");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out, nullptr);
+    if (k == 7 && corr_neigh_v2()) corr_neigh7_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, ldo, round_tf32_out, out, nullptr);
+    else corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out, nullptr);
     RF_LAUNCHED();
     return 0;
 }
@@ -1191,7 +1294,8 @@ extern "C" int rf_corr_neigh_pair_nhwc(const float* x, const float* y, int N, in
     RF_REQUIRE(out_xy != nullptr && out_yx != nullptr && out_xy != out_yx, "rf_corr_neigh_pair_nhwc: two distinct outputs");
     long long P = (long long)N * h * w;
     if (P == 0) return 0;
-    corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out_xy, out_yx);
+    if (k == 7 && corr_neigh_v2()) corr_neigh7_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, ldo, round_tf32_out, out_xy, out_yx);
+    else corr_neigh_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(x, y, N, h, w, C, k, ldo, round_tf32_out, out_xy, out_yx);
     RF_LAUNCHED();
     return 0;
 }

@@ -99,6 +99,37 @@ def test_corr_neigh_pair_is_bit_identical_to_two_calls(rf, n, c, h, w, k, ldo, m
     assert torch.equal(both.data[:n * h * w], xy.data) and torch.equal(both.data[n * h * w:], yx.data)
 
 
+@pytest.mark.parametrize("n,c,h,w,ldo", [(1, 256, 60, 80, 64), (2, 256, 6, 8, 49), (1, 64, 5, 3, 64), (1, 1024, 4, 7, 64), (1, 256, 1, 1, 96)])
+def test_corr_neigh_register_kernel_equals_per_tap_kernel(rf, monkeypatch, n, c, h, w, ldo):
+    """corr_neigh7_kernel (49 sums in registers, one multi-value butterfly, coalesced row store; RF_CORR_NEIGH_V2=1, default)
+    == corr_neigh_kernel (one warp reduction per tap) bit for bit in every output mode, single and pair, and the split form
+    (engine 4) rebuilds the fp32 values to 2^-22."""
+    g = torch.Generator().manual_seed(n * 10 + h)
+    a = rf.ops.Ragged.from_nchw(F.normalize(torch.randn(n, c, h, w, generator=g)).cuda())
+    b = rf.ops.Ragged.from_nchw(F.normalize(torch.randn(n, c, h, w, generator=g)).cuda())
+    res = {}
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("RF_CORR_NEIGH_V2", v2)
+        r = []
+        for mode in (0, 1, 2):
+            r.append(rf.ops.corr_neigh(a, b, 7, ldo, mode).data)
+            r += [t.data for t in rf.ops.corr_neigh_pair(a, b, 7, ldo, mode)]
+        c12, both = rf.ops.corr_neigh_pair_split(a, b, 7, ldo)
+        r += [c12.data, both.data]
+        torch.cuda.synchronize()
+        res[v2] = r
+    for x0, x1 in zip(res["0"], res["1"]):
+        assert x0.shape == x1.shape and torch.equal(x0, x1)
+    P = n * h * w
+    full = res["1"][0]                                          # fp32 CorrNeigh(a, b)
+    c12, both = res["1"][-2], res["1"][-1]
+    assert c12.shape == (2, P, ldo) and both.shape == (2, 2 * P, ldo)
+    assert (rf.ops.from_split(c12) - full).abs().max().item() < 2.0 ** -21
+    assert torch.equal(both[:, :P], c12)
+    swapped = rf.ops.corr_neigh(b, a, 7, ldo, 0).data
+    assert (rf.ops.from_split(both[:, P:].contiguous()) - swapped).abs().max().item() < 2.0 ** -21
+
+
 @pytest.mark.parametrize("h,w,skip", [(33, 47, 0), (16, 16, 0), (1, 3, 0), (33, 47, 1), (480, 640, 0), (7, 4, 4)])
 def test_preproc_bit_exact(rf, h, w, skip):
     """ToTensor (+ Normalize) in torchvision's op order, bit exact.  Covers the 12-bytes-per-thread kernel with and without a

@@ -357,6 +357,7 @@ def test_graphed_aligner_results_survive_later_replays_and_graph_eviction(rf):
     second = ga(*pairs[0])                                    # same size: the same graph replayed with other samples
     assert torch.equal(first["flow12"][0], keep) and first["flow12"][0].data_ptr() != second["flow12"][0].data_ptr()
     for i in (1, 2, 0, 1, 2):                                 # three sizes through two graph slots: evictions + re-captures
+        ga.prepare(*pairs[i])                                 # (re-)capture first: its warm-up runs draw from the generator
         torch.manual_seed(7)
         out = ga(*pairs[i])
         ref = eager(i)

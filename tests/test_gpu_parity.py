@@ -141,7 +141,7 @@ def saturating_net():
     0 / 1 over regions: the multi-hypothesis mask update ``(Mask + matchFine) >= 1`` then really changes the mask."""
     net = oracle_net()
     sd = {k: v.clone() for k, v in net["netMatch"].items()}
-    sd["conv4.weight"] = sd["conv4.weight"] * 3e5
+    sd["conv4.weight"] = sd["conv4.weight"] * 30.0      # tuned on the CPU oracle: ~60 % of the first map saturates to 1.0f, 4 hypotheses accepted
     net["netMatch"] = sd
     return net
 
