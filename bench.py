@@ -101,7 +101,7 @@ def ncu_facts(precision, v2):
         return {}
 
 
-def roofline_record(prec, v2, corr_ms, ransac_ms, n_matches, pk):
+def roofline_record(prec, v2, corr_ms, ransac_ms, n_matches, pk, presplit=False):
     """The `roofline` object of the JSON line for the kernel BASELINE.json names (correlation + mutual NN, plus RANSAC as
     us/call): algorithmic flops / bytes of config 2 over the call's measured time, against the measured peaks.
     Pure arithmetic (tests/test_abi_and_host.py runs it without a GPU)."""
@@ -115,7 +115,9 @@ def roofline_record(prec, v2, corr_ms, ransac_ms, n_matches, pk):
                 + "fp16 split tcgen05: hi*hi + (hi*lo + lo*hi) * 2^-11)"}[prec]
     # tensor work actually issued per algorithmic MAC: 3 MMAs either way; kind::tf32 runs at half the bf16/f16 rate
     rate = {0: None, 1: tensor_peak / 2, 2: tensor_peak}[prec]
-    return {"kernel": "rf_corr_mutual_nn = %s + split/compaction helpers" % kname,
+    call = ("rf_corr_mutual_nn_presplit = key memset + %s + column-driven compaction (operand planes written by rf_l2norm_split_nhwc)" if presplit
+            else "rf_corr_mutual_nn = %s + split/compaction helpers")
+    return {"kernel": call % kname,
             "bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak, "traffic": ncu.get("traffic"),
             "peak_source": pk["src"] + " bf16 dense GEMM (burst); fp32-grade scores need 3 tensor MMAs per algorithmic MAC (split operands), "
                            "so the executed tensor fraction is 3 x frac for the fp16 split (6 x for 3xTF32, whose MMAs run at half rate)",
@@ -416,19 +418,21 @@ def run_b200(args, rank, world, local):
             for rep in range(reps + skip):
                 s_, t_ = resident[rep % len(resident)]
                 evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-                saved = rf.ops.corr_mutual_nn
+                saved, saved_p = rf.ops.corr_mutual_nn, rf.ops.corr_mutual_nn_presplit
                 marks = {}
 
-                def corr_hook(*a, **k):                                  # setPair ends with the correlation: split it out
-                    marks["pre"] = torch.cuda.Event(enable_timing=True)
-                    marks["pre"].record()
-                    return saved(*a, **k)
-                rf.ops.corr_mutual_nn = corr_hook
+                def hook(fn):                                            # setPair ends with the correlation: split it out
+                    def wrapped(*a, **k):
+                        marks["pre"] = torch.cuda.Event(enable_timing=True)
+                        marks["pre"].record()
+                        return fn(*a, **k)
+                    return wrapped
+                rf.ops.corr_mutual_nn, rf.ops.corr_mutual_nn_presplit = hook(saved), hook(saved_p)
                 try:
                     evs[0].record()
                     coarse.setPair(s_, t_)
                 finally:
-                    rf.ops.corr_mutual_nn = saved
+                    rf.ops.corr_mutual_nn, rf.ops.corr_mutual_nn_presplit = saved, saved_p
                 evs[2].record()
                 Itw, Ith = coarse.target_size
                 featt = rf.pipeline.fine_features(net["netFeatCoarse"], coarse.ItTensor)
@@ -447,16 +451,22 @@ def run_b200(args, rank, world, local):
         stages = stage_breakdown()
 
         # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----
-        fa, ft = coarse._feats_rows, coarse._featt_rows
+        presplit = "_src_planes" in coarse.__dict__      # engine f16x3: the normalisation wrote the correlation's hi / lo planes
+        if presplit:
+            sp, tp = coarse._src_planes, coarse._tgt_planes
+            corr_call = lambda: rf.ops.corr_mutual_nn_presplit(sp[0], sp[1], tp[0], tp[1])
+        else:
+            fa, ft = coarse._feats_rows, coarse._featt_rows
+            corr_call = lambda: rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
         st = torch.cuda.current_stream()
         reps = 20
         for _ in range(3):
-            rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
+            corr_call()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in ev:
             flush.zero_()
             a.record(st)
-            rf.ops.corr_mutual_nn(fa, ft, rf.outil.corr_precision)
+            corr_call()
             b.record(st)
         torch.cuda.synchronize()
         corr_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
@@ -474,7 +484,7 @@ def run_b200(args, rank, world, local):
         ransac_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         prec = rf.outil.corr_precision
         v2 = prec == 2 and rf._lib.lib.rf_corr_mutual_nn_launches(2) == 3
-        roofline = roofline_record(prec, v2, corr_ms, ransac_ms, int(len(m1)), peaks())
+        roofline = roofline_record(prec, v2, corr_ms, ransac_ms, int(len(m1)), peaks(), presplit)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores, run as
     # `bench.py --impl reference` in a child process so that it can be cut off.  The child also writes the oracle's

@@ -63,6 +63,14 @@ int rf_corr_mutual_nn(const float* featA, int NA, const float* featB, int NB, in
                       int64_t* idx1_out, int64_t* idx2_out, int* count_out,
                       void* ws, size_t ws_bytes, int precision, void* stream);
 
+/* The same with operands their producer already split (rf_l2norm_split_nhwc writes the normalised rows as fp16 hi / lo * 2^11
+ * planes): no split pass.  A_hi / A_lo [NA][C], B_hi / B_lo [NB][C] fp16, C % 64 == 0.  Three graph nodes: memset of the
+ * arg-max keys, the persistent fp16-split tcgen05 kernel (precision 2 of rf_corr_mutual_nn, identical arithmetic), the
+ * column-driven mutual test + compaction. */
+size_t rf_corr_mutual_nn_presplit_workspace(int NA, int NB);
+int rf_corr_mutual_nn_presplit(const void* A_hi, const void* A_lo, int NA, const void* B_hi, const void* B_lo, int NB, int C,
+                               int64_t* idx1_out, int64_t* idx2_out, int* count_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ RANSAC --
  * utils/outil.py:117-164 RANSAC + :102-113 ScoreRANSAC + :68-87 Homography +
  * :97-100 Prediction as ONE persistent kernel.  `samples` is the (nbIter,4)
@@ -170,8 +178,8 @@ int rf_blur_downsample_nhwc(const float* x, int nimg, const int* hw_host, int C,
 /* F.normalize(x, dim=1): y = x / max(||x||_2, 1e-12) per pixel over C (P = total pixels).
  * mask (nullable, u8 [P]): masked pixels are written as zeros (quick_start/coarseAlignFeatMatch.py:143). */
 int rf_l2norm_nhwc(const float* x, long long P, int C, const uint8_t* mask, float* y, void* stream);
-/* same with a split input (engine 4: [2][P][C] fp16), fp32 output; y_hi / y_lo (nullable, together): ALSO write the normalised rows
- * as fp16 hi / lo * 2^11 planes [P][C] - the operands of rf_corr_mutual_nn_presplit; C % 8 == 0 */
+/* same with a split input (engine 4: [2][P][C] fp16), fp32 output y (nullable); y_hi / y_lo (nullable, together): write the
+ * normalised rows as fp16 hi / lo * 2^11 planes [P][C] - the operands of rf_corr_mutual_nn_presplit; C % 8 == 0 */
 int rf_l2norm_split_nhwc(const void* x_split, long long P, int C, const uint8_t* mask, float* y, void* y_hi, void* y_lo, void* stream);
 /* same with fp16 input (the engine-2 trunk's output), fp32 output; C % 8 == 0 */
 int rf_l2norm_f16_nhwc(const void* x_f16, long long P, int C, const uint8_t* mask, float* y, void* stream);

@@ -24,6 +24,8 @@ SIGNATURES = {
     "rf_corr_mutual_nn_workspace": (sz, [i32, i32, i32, i32]),
     "rf_corr_mutual_nn_launches": (i32, [i32]),
     "rf_corr_mutual_nn": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, vp, sz, i32, vp]),
+    "rf_corr_mutual_nn_presplit_workspace": (sz, [i32, i32]),
+    "rf_corr_mutual_nn_presplit": (i32, [vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp, sz, vp]),
     "rf_ransac_workspace": (sz, [i32]),
     "rf_ransac_homography": (i32, [vp, vp, i32, vp, vp, i32, i32, f32, i32, vp, vp, vp, vp, vp, sz, vp]),
     "rf_homography_dlt": (i32, [vp, vp, i32, vp, vp]),

@@ -166,6 +166,10 @@ class _CoarseAlignBase:
         flat = torch.cat([t.reshape(-1, 3) for t in u8], dim=0) if len(u8) > 1 else u8[0].reshape(-1, 3)
         x = Ragged(ops.preproc_u8(flat, normalize=True), hw)
         f = self.net(x)
+        if f.split and outil.corr_precision == 2 and os.environ.get("RF_CORR_PRESPLIT", "1") != "0":
+            # engine 'f16x3' + fp16-split correlation: the normalisation writes the correlation's operand planes directly;
+            # the fp32 views the reference exposes (featsMultiScale, featt) are rebuilt on first access (__getattr__)
+            return Ragged(ops.l2norm_planes(f.data), f.hw), u8
         return Ragged(ops.l2norm(f.data), f.hw), u8
 
     def _pyramid(self, I_org, sizes):
@@ -203,25 +207,51 @@ class _CoarseAlignBase:
         h, w = int(u8.shape[0]), int(u8.shape[1])
         return ops.preproc_u8(u8.reshape(-1, 3), normalize=False).view(1, h, w, 3).permute(0, 3, 1, 2)
 
+    _LAZY = ("_feats_rows", "featsMultiScale", "_featt_rows", "featt")
+
+    def __getattr__(self, name):
+        """fp32 views of features held as fp16 hi / lo planes (engine 'f16x3'): rebuilt (exactly) on first access."""
+        if name in _CoarseAlignBase._LAZY:
+            d = self.__dict__
+            if name in ("_feats_rows", "featsMultiScale") and "_src_planes" in d:
+                d["_feats_rows"] = ops.from_split(d["_src_planes"])               # [NA, 1024] rows = feature vectors
+                d["featsMultiScale"] = d["_feats_rows"].t()                       # (1024, NA) view, the reference's layout
+                return d[name]
+            if name in ("_featt_rows", "featt") and "_tgt_planes" in d:
+                d["_featt_rows"] = ops.from_split(d["_tgt_planes"])
+                d["featt"] = d["_featt_rows"].view(1, self.W2, self.H2, -1).permute(0, 3, 1, 2)
+                return d[name]
+        raise AttributeError(name)
+
     def _set_source_feats(self, feats, nS):
         o = feats.offsets()
         self._srcN = o[nS]
-        self._feats_rows = feats.data[:o[nS]]                     # [NA, 1024] rows = feature vectors
-        self.featsMultiScale = self._feats_rows.t()               # (1024, NA) view, the reference's layout
+        for k in ("_feats_rows", "featsMultiScale", "_src_planes"):
+            self.__dict__.pop(k, None)
+        if feats.split:
+            self._src_planes = feats.data[:, :o[nS]]                  # (hi, lo) planes of the [NA, 1024] rows
+        else:
+            self._feats_rows = feats.data[:o[nS]]                     # [NA, 1024] rows = feature vectors
+            self.featsMultiScale = self._feats_rows.t()               # (1024, NA) view, the reference's layout
         Ws, Hs = [], []
         for i in range(nS):
-            W, H = outil.getWHTensor(feats.image(i))
+            _, _, W, H = outil._wh(feats.hw[i][0], feats.hw[i][1], feats.data.device)      # outil.getWHTensor of scale i
             Ws.append(W)
             Hs.append(H)
         self.WMultiScale = torch.cat(Ws)
         self.HMultiScale = torch.cat(Hs)
 
     def _set_target_feats(self, feats, i):
-        self.featt = feats.image(i)                               # (1, 1024, h16, w16) view
-        self._featt_rows = feats.data[feats.offsets()[i]:feats.offsets()[i + 1]]
-        self.Wt, self.Ht = outil.getWHTensor(self.featt)
-        self.WtInt, self.HtInt = outil.getWHTensor_Int(self.featt)
-        self.W2, self.H2 = self.featt.size()[2], self.featt.size()[3]
+        o = feats.offsets()
+        self.W2, self.H2 = feats.hw[i]
+        for k in ("_featt_rows", "featt", "_tgt_planes"):
+            self.__dict__.pop(k, None)
+        if feats.split:
+            self._tgt_planes = feats.data[:, o[i]:o[i + 1]]
+        else:
+            self.featt = feats.image(i)                               # (1, 1024, h16, w16) view
+            self._featt_rows = feats.data[o[i]:o[i + 1]]
+        self.WtInt, self.HtInt, self.Wt, self.Ht = outil._wh(self.W2, self.H2, feats.data.device)   # getWHTensor(_Int) of featt
 
     def _mask16(self, Mt):
         """coarseAlignFeatMatch.py (A) :158-162: 1 - Mt, bilinear to the feature grid, > 0.5."""
@@ -264,7 +294,11 @@ class CoarseAlignA(_CoarseAlignBase):
             self._set_target_feats(feats, nS)
             # mutual matching once per pair (:139-147), kept on the device; the matched-coordinate attributes the
             # reference caches (:140-147) are materialised lazily (they need the match count on the host)
-            self._idx1, self._idx2, self._count = ops.corr_mutual_nn(self._feats_rows, self._featt_rows, outil.corr_precision)
+            if feats.split:
+                sp, tp = self._src_planes, self._tgt_planes
+                self._idx1, self._idx2, self._count = ops.corr_mutual_nn_presplit(sp[0], sp[1], tp[0], tp[1])
+            else:
+                self._idx1, self._idx2, self._count = ops.corr_mutual_nn(self._feats_rows, self._featt_rows, outil.corr_precision)
             self._mm = None
 
     def _matched(self):

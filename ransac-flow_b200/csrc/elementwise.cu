@@ -362,10 +362,11 @@ __global__ void l2norm_split_kernel(const __half* __restrict__ x, long long plan
     int lane = threadIdx.x & 31;
     if (pix >= P) return;
     const __half* src = x + pix * C;
-    float4* dst = reinterpret_cast<float4*>(y + pix * C);
+    float4* dst = reinterpret_cast<float4*>(y + pix * C);       // y == nullptr: planes only
     const int c8n = C >> 3;
     if (mask != nullptr && mask[pix] == 0) {
-        for (int c = lane; c < 2 * c8n; c += 32) dst[c] = make_float4(0, 0, 0, 0);
+        if (y != nullptr)
+            for (int c = lane; c < 2 * c8n; c += 32) dst[c] = make_float4(0, 0, 0, 0);
         if (yhi != nullptr)
             for (int c = lane; c < c8n; c += 32) {
                 reinterpret_cast<uint4*>(yhi + pix * C)[c] = make_uint4(0, 0, 0, 0);
@@ -388,8 +389,10 @@ __global__ void l2norm_split_kernel(const __half* __restrict__ x, long long plan
         split_load8(src + c * 8, plane, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __fdiv_rn(v[e], denom);
-        dst[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        if (y != nullptr) {
+            dst[2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
         if (yhi != nullptr) split_store8(yhi + pix * C + c * 8, (ylo - yhi), v);
     }
 }
@@ -1247,6 +1250,7 @@ extern "C" int rf_l2norm_split_nhwc(const void* x_split, long long P, int C, con
     RF_REQUIRE(((uintptr_t)x_split % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)y_hi % 16) == 0 && ((uintptr_t)y_lo % 16) == 0,
                "rf_l2norm_split_nhwc: pointers must be 16-byte aligned");
     RF_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "rf_l2norm_split_nhwc: y_hi and y_lo go together");
+    RF_REQUIRE(y != nullptr || y_hi != nullptr, "rf_l2norm_split_nhwc: no output");
     if (P == 0) return 0;
     l2norm_split_kernel<<<blocks_for(P * 32, 256), 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x_split), P * C, P, C, mask, y,
                                                                                static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));

@@ -11,6 +11,8 @@
 // (transposed on the store so fragment reads are 128-bit and conflict free),
 // global loads of slice k+1 in flight while slice k is multiplied.
 // The tcgen05 tensor-core engine (gemm_tc.cu) replaces these where TF32 is allowed.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rf {
@@ -258,6 +260,72 @@ mutual_flag_compact_kernel(const unsigned long long* __restrict__ rowbest, const
     if (tid == 0) *count = total;
 }
 
+// Column-driven form of the kernel above: a mutual pair is one per COLUMN at most (<= NB of them), so the dependent
+// rowbest[i] -> colbest[j] chain is walked for the NB columns only (one or two independent loads per thread); the matches
+// are scattered into a row-indexed table in shared memory and compacted from there in row order (= the reference's
+// nonzero() order, utils/outil.py:43) with ballots.  dynamic smem: NA ints.  ~3 us instead of ~12 us at config 2.
+__global__ void __launch_bounds__(1024)
+mutual_cols_compact_kernel(const unsigned long long* __restrict__ rowbest, const unsigned long long* __restrict__ colbest, int NA, int NB,
+                           long long* __restrict__ idx1, long long* __restrict__ idx2, int* __restrict__ count) {
+    extern __shared__ int sRow[];                 // 0 = unmatched row, j + 1 = matched with column j
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NA; i += 1024) sRow[i] = 0;
+    __syncthreads();
+    for (int j = tid; j < NB; j += 1024) {
+        const unsigned long long ck = __ldg(colbest + j);
+        if (ck == 0ull) continue;
+        const uint32_t i = key_index(ck);
+        if (i >= (uint32_t)NA) continue;
+        const unsigned long long rk = __ldg(rowbest + i);
+        const float v = key_value(rk);
+        if (rk != 0ull && key_index(rk) == (uint32_t)j && (__fmul_rn(v, v) > 0.f)) sRow[i] = j + 1;     // keepMax > 0 (utils/outil.py:41-42)
+    }
+    __syncthreads();
+    const int chunk = (((NA + 31) / 32) + 31) / 32 * 32;          // rows per warp, a multiple of 32
+    const int begin = warp * chunk;
+    int cnt = 0;
+    for (int b = 0; b < chunk; b += 32) {
+        const int i = begin + b + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, i < NA && sRow[i] != 0));
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int v = s_cnt[w]; off += (w < warp) ? v : 0; total += v; }
+    for (int b = 0; b < chunk; b += 32) {
+        const int i = begin + b + lane;
+        const int f = (i < NA) ? sRow[i] : 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, f != 0);
+        if (f) {
+            const int o = off + __popc(bal & ((1u << lane) - 1u));
+            idx1[o] = i;
+            idx2[o] = (long long)(f - 1);
+        }
+        off += __popc(bal);
+    }
+    if (tid == 0) *count = total;
+}
+
+static int launch_mutual_compact(const unsigned long long* rowbest, const unsigned long long* colbest, int NA, int NB, long long* idx1, long long* idx2,
+                                 int* count, cudaStream_t st) {
+    const size_t smem = (size_t)NA * sizeof(int);
+    const char* e = getenv("RF_COMPACT_COLS");                    // 1 (default): column-driven compaction; 0: the row-driven kernel
+    if ((e ? atoi(e) : 1) && smem <= 200 * 1024) {
+        static bool attr[64] = {false};
+        const int dev = current_device();
+        if (!attr[dev]) {
+            RF_CUDA(cudaFuncSetAttribute(mutual_cols_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr[dev] = true;
+        }
+        mutual_cols_compact_kernel<<<1, 1024, smem, st>>>(rowbest, colbest, NA, NB, idx1, idx2, count);
+    } else {
+        mutual_flag_compact_kernel<<<1, 1024, 0, st>>>(rowbest, colbest, NA, idx1, idx2, count);
+    }
+    RF_LAUNCHED();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // implicit-GEMM convolution
 // ---------------------------------------------------------------------------
@@ -445,7 +513,8 @@ using namespace rf;
 
 // tensor-core engines live in gemm_tc.cu
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2);
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2,
+                      const void* const* presplit = nullptr);
 int rf_corr_v2_mode();
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
@@ -491,11 +560,7 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
             RF_LAUNCHED();
         }
     }
-    if (v2) {
-        mutual_flag_compact_kernel<<<1, 1024, 0, st>>>(rowbest, colbest, NA, (long long*)idx1_out, (long long*)idx2_out, count_out);
-        RF_LAUNCHED();
-        return 0;
-    }
+    if (v2) return launch_mutual_compact(rowbest, colbest, NA, NB, (long long*)idx1_out, (long long*)idx2_out, count_out, st);
     if (NA > 0) {
         mutual_flag_kernel<<<(NA + 255) / 256, 256, 0, st>>>(rowbest, colbest, NA);
         RF_LAUNCHED();
@@ -503,6 +568,28 @@ extern "C" int rf_corr_mutual_nn(const float* featA, int NA, const float* featB,
     mutual_compact_kernel<<<1, 1024, 0, st>>>(rowbest, NA, (long long*)idx1_out, (long long*)idx2_out, count_out);
     RF_LAUNCHED();
     return 0;
+}
+
+// utils/outil.py:32-45 with operands the producer already split (rf_l2norm_split_nhwc: hi = fp16(x), lo = fp16((x - hi) * 2^11)):
+// memset of the keys, the persistent fp16-split correlation kernel, the column-driven compaction.  ws: (NA + NB) keys.
+extern "C" size_t rf_corr_mutual_nn_presplit_workspace(int NA, int NB) { return keys_bytes(NA, NB) + 256; }
+
+extern "C" int rf_corr_mutual_nn_presplit(const void* A_hi, const void* A_lo, int NA, const void* B_hi, const void* B_lo, int NB, int C,
+                                          int64_t* idx1_out, int64_t* idx2_out, int* count_out, void* ws, size_t ws_bytes, void* stream) {
+    RF_REQUIRE(NA >= 0 && NB >= 0 && C > 0 && (C % 64) == 0, "rf_corr_mutual_nn_presplit: bad sizes (C must be a multiple of 64)");
+    RF_REQUIRE(ws != nullptr && ws_bytes >= rf_corr_mutual_nn_presplit_workspace(NA, NB), "rf_corr_mutual_nn_presplit: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(ws);
+    unsigned long long* colbest = rowbest + NA;
+    RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
+    if (NA == 0 || NB == 0) {
+        RF_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
+        return 0;
+    }
+    const void* planes[4] = {A_hi, A_lo, B_hi, B_lo};
+    int rc = rf_corr_argmax_tc(nullptr, NA, nullptr, NB, C, rowbest, colbest, nullptr, st, 2, true, planes);
+    if (rc) return rc;
+    return launch_mutual_compact(rowbest, colbest, NA, NB, (long long*)idx1_out, (long long*)idx2_out, count_out, st);
 }
 
 extern "C" int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,

@@ -1776,9 +1776,13 @@ static int launch_corr_pipe(const TcParams& p, int tiles_m, int tiles_n, cudaStr
 }
 
 // v2 (precision 2 only): the caller has NOT zeroed rowbest / colbest (contiguous, NA + NB keys): the split launch does it
+// presplit (precision 2, v2 only; nullable): {A hi, A lo, B hi, B lo} fp16 planes written by the producer of the features
+// (rf_l2norm_split_nhwc): no split launch; the caller has zeroed the keys.
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
-                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2) {
+                      unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2,
+                      const void* const* presplit) {
     const bool f16 = precision == 2;
+    RF_REQUIRE(presplit == nullptr || (v2 && f16), "rf_corr_mutual_nn: pre-split operands go with the persistent fp16-split kernel");
     RF_REQUIRE(!v2 || f16, "rf_corr_mutual_nn: the persistent correlation kernel is the fp16-split one (precision 2)");
     RF_REQUIRE((C % (f16 ? TC_BK_F16 : TC_BK)) == 0, "rf_corr_mutual_nn: precision 1 needs C % 32 == 0, precision 2 C % 64 == 0");
     uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
@@ -1788,7 +1792,13 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     char* Bhi = Alo + (size_t)NA * C * esz;
     char* Blo = Bhi + (size_t)NB * C * esz;
     long long na4 = (long long)NA * C / 4, nb4 = (long long)NB * C / 4;
-    if (v2) {
+    if (presplit != nullptr) {
+        Ahi = const_cast<char*>(static_cast<const char*>(presplit[0]));
+        Alo = const_cast<char*>(static_cast<const char*>(presplit[1]));
+        Bhi = const_cast<char*>(static_cast<const char*>(presplit[2]));
+        Blo = const_cast<char*>(static_cast<const char*>(presplit[3]));
+        for (int i = 0; i < 4; ++i) RF_REQUIRE(presplit[i] != nullptr && ((uintptr_t)presplit[i] % 16) == 0, "rf_corr_mutual_nn_presplit: planes must be 16-byte aligned");
+    } else if (v2) {
         RF_REQUIRE(colbest == rowbest + NA, "rf_corr_mutual_nn: arg-max keys must be contiguous");
         const long long nkeys = (long long)NA + NB, n = na4 + nb4 > nkeys ? na4 + nb4 : nkeys;
         split_f16_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)featA, (const float4*)featB, (uint2*)Ahi, (uint2*)Alo,

@@ -139,6 +139,16 @@ def l2norm(x2d, mask=None):
     return y
 
 
+def l2norm_planes(x_split, mask=None):
+    """Engine-4 features [2, P, C] -> their L2-normalised rows as fp16 planes [2, P, C] (hi, lo * 2^11): exactly what the
+    fp16-split correlation kernel reads, written by the normalisation itself (no fp32 copy, no split pass)."""
+    need_cuda(x_split, mask)
+    assert x_split.dim() == 3 and x_split.dtype == torch.float16 and x_split.is_contiguous()
+    out = torch.empty_like(x_split)
+    check(lib.rf_l2norm_split_nhwc(ptr(x_split), x_split.shape[1], x_split.shape[2], ptr(mask), None, ptr(out[0]), ptr(out[1]), stream()))
+    return out
+
+
 def corr_neigh(x, y, k, ldo=None, round_tf32=False):
     """x, y: Ragged with identical (h, w) per image -> Ragged with ``ldo`` (default k*k) channels; channels
     beyond k*k are zeros (ldo = 64 gives the heads a 128-byte aligned K-major operand).  ``round_tf32``: 0 / False =
@@ -230,6 +240,24 @@ def philox_words(nbIter, nbPoint, device):
     seeded sample stream (utils/outil.py:120) with M read on the device; the draw is graph-capturable."""
     assert nbIter * nbPoint <= 256 * 1024, "beyond this size ATen maps several elements to one Philox subsequence"
     return torch.empty((nbIter, nbPoint), dtype=torch.int64, device=device).random_(-2 ** 63, None)
+
+
+def corr_mutual_nn_presplit(A_hi, A_lo, B_hi, B_lo):
+    """``corr_mutual_nn`` at precision 2 on operands that are already fp16 hi / lo planes ([N, C] each, contiguous)."""
+    need_cuda(A_hi, A_lo, B_hi, B_lo)
+    NA, Cc = A_hi.shape
+    NB = B_hi.shape[0]
+    for t in (A_hi, A_lo, B_hi, B_lo):
+        assert t.dtype == torch.float16 and t.is_contiguous() and t.shape[1] == Cc
+    cap = max(1, min(NA, NB))
+    dev = A_hi.device
+    idx1 = torch.empty(cap, device=dev, dtype=torch.int64)
+    idx2 = torch.empty(cap, device=dev, dtype=torch.int64)
+    count = torch.zeros(1, device=dev, dtype=torch.int32)
+    wsz = lib.rf_corr_mutual_nn_presplit_workspace(NA, NB)
+    ws = torch.empty(wsz, device=dev, dtype=torch.uint8)
+    check(lib.rf_corr_mutual_nn_presplit(ptr(A_hi), ptr(A_lo), NA, ptr(B_hi), ptr(B_lo), NB, Cc, ptr(idx1), ptr(idx2), ptr(count), ptr(ws), wsz, stream()))
+    return idx1, idx2, count
 
 
 def ransac_homography(match1, match2, samples, tolerance, chunk=100, M_dev=None, sample_mode=None):
