@@ -315,25 +315,35 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
 
 // ------------------------------------------------------------------------------------------------------------
 // ResNet-50 stem, fused, split operands: conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
-// split NHWC.  Same structure as stem7_f16_kernel (gemm_tc.cu): the 147-long patches are built in shared memory straight
-// in the swizzled K-major layout, here as hi and lo planes (3 + 3 K blocks), and each K block is three MMA groups.
+// split NHWC, without an im2col matrix in HBM.  PERSISTENT, two CTAs per SM (92 KB each), 160 threads:
+//   warps 0-3 : stage the 37 x 21 x 3 input window of the tile in shared memory (the NEXT tile's window is already in
+//               flight in registers), then build the tile's 147-long (r, s, c) patches one 64-wide K block at a time,
+//               as hi / lo planes straight in the 128-byte-swizzled K-major layout (one 32 KB slot, reused per block);
+//               after the last block: epilogue TMEM -> + bias, ReLU, split -> [hi box | lo box] in the same slot -> one
+//               TMA store of both planes;
+//   warp 4    : loads the split weights ONCE per CTA (3 K blocks x [hi | lo] = 48 KB), then per K block three MMA
+//               groups (hi*hi | lo*hi + hi*lo) and a commit that hands the slot back.
+// The first version of this kernel (one tile per CTA, all three K blocks resident, 155 KB => one CTA per SM) ran 358 us
+// per pair at config 2: every tile paid the weight load, the window load, TMEM allocation and the store drain serially.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SS_TW = 16, SS_TH = 8, SS_K = 7, SS_C = 3, SS_KK = 147, SS_KB = 3;
 constexpr int SS_IN_W = ((SS_TW - 1) * 2 + SS_K) * SS_C;                  // 111 floats per staged input row
 constexpr int SS_IN_H = (SS_TH - 1) * 2 + SS_K;                           // 21 rows
 constexpr int SS_IN_LD = 112;
 constexpr int SS_B_TILE = 2 * 64 * 128;                                   // [hi | lo] weights of one K block: 16 KB
-constexpr int SS_OFF_ALO = SS_KB * TC_A_BYTES;                            // 48 KB: lo planes of the patches
-constexpr int SS_OFF_B = 2 * SS_KB * TC_A_BYTES;                          // 96 KB
-constexpr int SS_OFF_IN = SS_OFF_B + SS_KB * SS_B_TILE;                   // 144 KB
+constexpr int SS_A_SLOT = 2 * TC_A_BYTES;                                 // [hi | lo] patches of one K block: 32 KB
+constexpr int SS_OFF_B = SS_A_SLOT;
+constexpr int SS_OFF_IN = SS_OFF_B + SS_KB * SS_B_TILE;                   // 80 KB
 constexpr int SS_OFF_BAR = SS_OFF_IN + SS_IN_H * SS_IN_LD * 4;
 constexpr int SS_SMEM = SS_OFF_BAR + 64 + 1024;
 constexpr int SS_THREADS = 160;
+constexpr int SS_NLD = (SS_IN_H * SS_IN_W + 127) / 128;                   // window floats per builder thread
+static_assert(2 * (SS_SMEM + 1024) <= 227 * 1024, "two stem CTAs per SM");
 
 struct alignas(64) StemSplitParams {
     CUtensorMap mapB;                     // weights (192, 64, 2) fp16, box (64, 64, 2)
     CUtensorMap mapY[RF_MAX_IMGS];        // output (64, Wo, Ho, 2), box (64, 16, 8, 2)
-    int nimg;
+    int nimg, total;
     int tile_start[RF_MAX_IMGS + 1];
     int tiles_x[RF_MAX_IMGS];
     int H[RF_MAX_IMGS], W[RF_MAX_IMGS];
@@ -342,7 +352,34 @@ struct alignas(64) StemSplitParams {
     const float* bias;
 };
 
-__global__ void __launch_bounds__(SS_THREADS, 1)
+struct StemTile { int img, ox0, oy0; };
+__device__ __forceinline__ StemTile stem_decode(const StemSplitParams& p, int t) {
+    StemTile c;
+    int img = 0;
+#pragma unroll
+    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && t >= p.tile_start[j]) ? 1 : 0;
+    const int tloc = t - p.tile_start[img];
+    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    c.img = img;
+    c.ox0 = txi * SS_TW;
+    c.oy0 = tyi * SS_TH;
+    return c;
+}
+// the (zero padded) 21 x 111 input window of a tile, 128 threads x SS_NLD floats
+__device__ __forceinline__ void stem_load_window(const StemSplitParams& p, const StemTile& c, int m, float (&stage)[SS_NLD]) {
+    const int H = p.H[c.img], WC = p.W[c.img] * SS_C;
+    const float* src = p.x + p.in_pix[c.img] * SS_C;
+    const int iy0 = c.oy0 * 2 - 3, col0 = (c.ox0 * 2 - 3) * SS_C;
+#pragma unroll
+    for (int i = 0; i < SS_NLD; ++i) {
+        const int idx = m + i * 128;
+        const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
+        const int iy = iy0 + r, col = col0 + j;
+        stage[i] = (idx < SS_IN_H * SS_IN_W && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(SS_THREADS, 2)
 stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -350,26 +387,21 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     uint8_t* sB = smem + SS_OFF_B;
     float* sIn = reinterpret_cast<float*>(smem + SS_OFF_IN);
     uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + SS_OFF_BAR);
-    uint64_t* bar_a = bar_b + 1;
-    uint64_t* bar_mma = bar_a + 1;
+    uint64_t* bar_a = bar_b + 1;          // 128 arrivals: a K block of patches is in the slot
+    uint64_t* bar_free = bar_a + 1;       // commit: the MMAs reading the slot are done
+    uint64_t* bar_mma = bar_free + 1;     // commit: the tile's accumulators are complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    int img = 0;
-#pragma unroll
-    for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && (int)blockIdx.x >= p.tile_start[j]) ? 1 : 0;
-    const int tloc = blockIdx.x - p.tile_start[img];
-    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
-    const int ox0 = txi * SS_TW, oy0 = tyi * SS_TH;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_b, 1);
         mbar_init(bar_a, 128);
+        mbar_init(bar_free, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
     if (warp == 4) {
-        if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[img]); }
+        if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
         tmem_alloc(tmem_slot, 128);
     }
     tc_fence_before();
@@ -384,93 +416,102 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
             for (int kb = 0; kb < SS_KB; ++kb) tma_load_3d(sB + kb * SS_B_TILE, &p.mapB, bar_b, kb * 64, 0, 0);
         }
         mbar_wait(bar_b, 0);
-        mbar_wait(bar_a, 0);
-        tc_fence_after();
         constexpr uint32_t idesc = make_idesc_f16(64);
-#pragma unroll
-        for (int kb = 0; kb < SS_KB; ++kb) {
-            const uint32_t a = smem_u32(sA + kb * TC_A_BYTES), b = smem_u32(sB + kb * SS_B_TILE);
-            umma_f16split_x4(tmem_base, tmem_base + 64, make_desc_sw128(a), make_desc_sw128(a + SS_OFF_ALO), make_desc_sw128(b),
-                             make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
+        const uint32_t a = smem_u32(sA);
+        uint32_t n = 0;
+        for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
+#pragma unroll 1
+            for (int kb = 0; kb < SS_KB; ++kb, ++n) {
+                mbar_wait(bar_a, n & 1);                        // also: the builders have drained the previous tile's accumulators
+                tc_fence_after();
+                const uint32_t b = smem_u32(sB + kb * SS_B_TILE);
+                umma_f16split_x4(tmem_base, tmem_base + 64, make_desc_sw128(a), make_desc_sw128(a + TC_A_BYTES), make_desc_sw128(b),
+                                 make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
+                umma_commit(bar_free);
+            }
+            umma_commit(bar_mma);
         }
-        umma_commit(bar_mma);
     } else {
         const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = accumulator row
-        const int H = p.H[img], WC = p.W[img] * SS_C;
-        const float* src = p.x + p.in_pix[img] * SS_C;
-        const int iy0 = oy0 * 2 - 3, col0 = (ox0 * 2 - 3) * SS_C;
-        constexpr int NLD = (SS_IN_H * SS_IN_W + 127) / 128;
-        float stage[NLD];
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            const int idx = m + i * 128;
-            const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
-            const int iy = iy0 + r, col = col0 + j;
-            stage[i] = (idx < SS_IN_H * SS_IN_W && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-            const int idx = m + i * 128;
-            const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
-            if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         const int py = m >> 4, px = m & 15;
         const float* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
+        float stage[SS_NLD];
+        StemTile c = stem_decode(p, blockIdx.x < p.total ? blockIdx.x : 0);
+        if ((int)blockIdx.x < p.total) stem_load_window(p, c, m, stage);
+        uint32_t n = 0, ti = 0;
+        for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
 #pragma unroll
-        for (int kb = 0; kb < SS_KB; ++kb) {
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                uint4 oh, ol;
-                __half2* ph = reinterpret_cast<__half2*>(&oh);
-                __half2* pl = reinterpret_cast<__half2*>(&ol);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
-                    const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
-                    const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
-                    sp_split2(a, b, ph[e], pl[e]);
-                }
-                uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = oh;
-                *reinterpret_cast<uint4*>(dst + SS_OFF_ALO) = ol;
+            for (int i = 0; i < SS_NLD; ++i) {
+                const int idx = m + i * 128;
+                const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
+                if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
             }
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_a);
-        // ---- epilogue: [hi box | lo box] staged over the first two patch blocks (the MMAs are done), one TMA store ----
-        mbar_wait(bar_mma, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const StemTile cur = c;
+            if (t + (int)gridDim.x < p.total) {                 // next tile's window: in flight while this tile is built
+                c = stem_decode(p, t + gridDim.x);
+                stem_load_window(p, c, m, stage);
+            }
+            // ---- this pixel's patch, (r, s, c) order: element k = r*21 + s*3 + c sits at sIn[2*py + r][6*px + (k % 21)] ----
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
-            uint32_t v[32], x[32];
-            tmem_ld32x2(trow + cb * 32, v, trow + 64 + cb * 32, x);
+            for (int kb = 0; kb < SS_KB; ++kb, ++n) {
+                if (n > 0) mbar_wait(bar_free, (n - 1) & 1);    // the MMAs that read the slot's previous content are done
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float o[8];
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    uint4 oh, ol;
+                    __half2* ph = reinterpret_cast<__half2*>(&oh);
+                    __half2* pl = reinterpret_cast<__half2*>(&ol);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
-                    if (p.bias != nullptr) o[e] += __ldg(p.bias + cb * 32 + 8 * j + e);
-                    o[e] = fmaxf(o[e], 0.f);
+                    for (int e = 0; e < 4; ++e) {
+                        const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
+                        const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
+                        const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
+                        sp_split2(a, b, ph[e], pl[e]);
+                    }
+                    uint8_t* dst = sA + m * 128 + ((c8 ^ (m & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = oh;
+                    *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
                 }
-                uint4 oh, ol;
-                __half2* ph = reinterpret_cast<__half2*>(&oh);
-                __half2* pl = reinterpret_cast<__half2*>(&ol);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) sp_split2(o[2 * e], o[2 * e + 1], ph[e], pl[e]);
-                const int chunk = cb * 4 + j;
-                uint8_t* dst = sA + m * 128 + ((chunk ^ (m & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = oh;
-                *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
+                fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core (async proxy)
+                tc_fence_before();
+                mbar_arrive(bar_a);
             }
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (m == 0) {
-            tma_store_4d(&p.mapY[img], sA, 0, ox0, oy0, 0);
-            tma_store_commit_and_wait_read();
+            // ---- epilogue: [hi box | lo box] staged in the slot (the MMAs are done), one TMA store ----
+            mbar_wait(bar_mma, ti & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int cb = 0; cb < 2; ++cb) {
+                uint32_t v[32], x[32];
+                tmem_ld32x2(trow + cb * 32, v, trow + 64 + cb * 32, x);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
+                    if (p.bias != nullptr) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb * 32 + 8 * j));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb * 32 + 8 * j + 4));
+                        o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+                    }
+                    uint4 oh, ol;
+                    __half2* ph = reinterpret_cast<__half2*>(&oh);
+                    __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sp_split2(fmaxf(o[2 * e], 0.f), fmaxf(o[2 * e + 1], 0.f), ph[e], pl[e]);
+                    const int chunk = cb * 4 + j;
+                    uint8_t* dst = sA + m * 128 + ((chunk ^ (m & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = oh;
+                    *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
+                }
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (m == 0) {
+                tma_store_4d(&p.mapY[cur.img], sA, 0, cur.ox0, cur.oy0, 0);
+                tma_store_commit_and_wait_read();
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the slot and the window buffer are free again
         }
     }
     tc_fence_before();
@@ -590,7 +631,9 @@ int rf_stem7_split_impl(const float* x, int nimg, const int* hw_host, const void
         RF_CUDA(cudaFuncSetAttribute(stem7_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM));
         attr[dev] = true;
     }
-    stem7_split_kernel<<<tiles, SS_THREADS, SS_SMEM, as_stream(stream)>>>(p);
+    p.total = tiles;
+    const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+    stem7_split_kernel<<<grid, SS_THREADS, SS_SMEM, as_stream(stream)>>>(p);
     RF_LAUNCHED();
     return 0;
 }
