@@ -41,6 +41,9 @@ extern "C" {
 #define RF_RANSAC_TOO_FEW 3     /* fewer than 4 matches (callers return None before calling)      */
 
 int rf_version(void);
+/* sha256 of the sources (csrc/, this header, compiler flags) the library was built from; the Python binding refuses a library
+ * whose digest differs from the sources next to it */
+const char* rf_source_digest(void);
 const char* rf_last_error_string(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 uint64_t rf_launch_count(void);

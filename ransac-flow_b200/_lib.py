@@ -16,6 +16,7 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 # name -> (restype, argtypes); every symbol declared in include/ransacflow_b200.h
 SIGNATURES = {
     "rf_version": (i32, []),
+    "rf_source_digest": (C.c_char_p, []),
     "rf_last_error_string": (C.c_char_p, []),
     "rf_launch_count": (C.c_uint64, []),
     "rf_l2norm_f16_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),
@@ -56,17 +57,19 @@ SIGNATURES = {
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        # build in-tree if a compiler is present (build container); never fall back to anything else
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("_rf_build", os.path.join(_HERE, "build.py"))
-        b = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(b)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_rf_build", os.path.join(_HERE, "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    if not b.is_current():
+        # missing, or built from other sources than the ones next to it (a stale git-ignored .so after a pull would be called
+        # through newer ctypes signatures): rebuild in-tree if a compiler is present; never fall back to anything else
         try:
             b.build(verbose=False)
         except Exception as e:  # noqa: BLE001
-            raise RuntimeError("ransac_flow_b200: CUDA library %s is missing and could not be built (%s). "
-                               "There is no CPU fallback; run `python ransac-flow_b200/build.py`." % (LIB_PATH, e))
+            raise RuntimeError("ransac_flow_b200: CUDA library %s is %s and could not be built (%s). "
+                               "There is no CPU fallback; run `python ransac-flow_b200/build.py`."
+                               % (LIB_PATH, "stale" if os.path.exists(LIB_PATH) else "missing", e))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = header/library mismatch: fail loudly

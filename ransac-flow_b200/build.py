@@ -12,7 +12,6 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libransacflow_b200.so")
-STAMP = os.path.join(HERE, ".build_stamp")
 SOURCES = ["api.cu", "ransac.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_split.cu", "elementwise.cu", "runner.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -29,20 +28,35 @@ def _digest():
     return h.hexdigest()
 
 
+def lib_digest(path=LIB):
+    """The digest embedded in a built library (rf_source_digest), or None."""
+    if not os.path.exists(path):
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(path)
+        fn = lib.rf_source_digest
+        fn.restype = ctypes.c_char_p
+        return fn().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def is_current():
-    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == _digest()
+    return lib_digest() == _digest()
 
 
 def build(force=False, verbose=True):
     if not force and is_current():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    digest = _digest()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for s in SOURCES:
         o = os.path.join(objdir, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + (['-DRF_SOURCE_DIGEST="%s"' % digest] if s == "api.cu" else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     objs = []
     for s, o, p in procs:
@@ -54,7 +68,6 @@ def build(force=False, verbose=True):
         objs.append(o)
     cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    open(STAMP, "w").write(_digest())
     if verbose:
         print("built", LIB)
     return LIB

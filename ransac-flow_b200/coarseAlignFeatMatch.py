@@ -44,7 +44,8 @@ class ResNet50Conv4:
     variant model/resnet50.py:107-168 has the same trunk) on the library's conv kernels."""
 
     def __init__(self, state_dict, device="cuda"):
-        self._sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
+        self.device = torch.device(device)
+        self._sd = {k: v.detach().to(device="cpu", dtype=torch.float32) for k, v in state_dict.items()       # folded on the host
                     if torch.is_tensor(v) and v.dtype.is_floating_point}
         self.program = self._build(32)            # fp32 activations: 'fp32' / 'tf32' engines
         self._program_f16 = None                  # fp16 activations ('f16' engine), built on first use
@@ -52,8 +53,8 @@ class ResNet50Conv4:
         self.out_channels = self.program.chan[-1]
 
     def _build(self, kalign):
-        sd = self._sd
-        P = LayerProgram(3)
+        sd, dev = self._sd, self.device
+        P = LayerProgram(3, device=dev)
         if kalign == 64 and os.environ.get("RF_STEM_FUSED", "1") != "0":
             x = P.stem7_fused(0, sd["conv1.weight"], _BN(sd, "bn1"))                 # fp16 engine: patches built in shared memory
         else:
@@ -63,12 +64,12 @@ class ResNet50Conv4:
             for b in range(blocks):
                 p = "%s.%d" % (layer, b)
                 s = stride if b == 0 else 1
-                out = P.conv(x, FoldedConv(sd[p + ".conv1.weight"], _BN(sd, p + ".bn1"), 1, pad=0), relu=True)
-                out = P.conv(out, FoldedConv(sd[p + ".conv2.weight"], _BN(sd, p + ".bn2"), s, pad=1), relu=True)
+                out = P.conv(x, FoldedConv(sd[p + ".conv1.weight"], _BN(sd, p + ".bn1"), 1, pad=0, device=dev), relu=True)
+                out = P.conv(out, FoldedConv(sd[p + ".conv2.weight"], _BN(sd, p + ".bn2"), s, pad=1, device=dev), relu=True)
                 r = x
                 if (p + ".downsample.0.weight") in sd:
-                    r = P.conv(x, FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0), relu=False)
-                x = P.conv(out, FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0), relu=True, res=r)
+                    r = P.conv(x, FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0, device=dev), relu=False)
+                x = P.conv(out, FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0, device=dev), relu=True, res=r)
         return P
 
     def __call__(self, x):

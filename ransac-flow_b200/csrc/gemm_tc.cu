@@ -426,8 +426,8 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, int mode) {
     // The start address is NOT 1024-byte aligned and the groups are 1280 B apart.  Measured on B200 (round 1): the
     // 128-byte swizzle of tcgen05.mma is a pure function of the shared-memory address bits (it matches what the TMA
     // wrote for any row phase) and the descriptor's base-offset field must stay 0; setting it to (addr >> 7) & 7, as the
-    // PTX text suggests for unaligned starts, double-applies the phase and gives wrong results (mode 1, kept for the record).
-    if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+    // PTX text suggests for unaligned starts, double-applies the phase and gives wrong results.
+    (void)mode;
     d |= (uint64_t)2 << 61;
     return d;
 }
@@ -1487,8 +1487,8 @@ int pick_tw(int Ho, int Wo) {
 static int halo_mode() {
     static int m = -1;
     if (m < 0) {
-        const char* e = getenv("RF_TC_HALO");     // 0 = tap-streaming kernel, 2 = halo reuse (default), 1 = experiment (wrong)
-        m = e ? atoi(e) : 2;
+        const char* e = getenv("RF_TC_HALO");     // 0 = tap-streaming kernel, anything else = halo reuse (default)
+        m = (e && atoi(e) == 0) ? 0 : 2;
     }
     return m;
 }

@@ -61,25 +61,29 @@ def _init_like_reference(module):
 class FoldedConv:
     """conv weight (+ following eval-mode BatchNorm) packed for the kernels."""
 
-    def __init__(self, weight, bn=None, stride=1, pad=None, eps=None, cin_pad=None):
-        w = weight.detach().float()
+    def __init__(self, weight, bn=None, stride=1, pad=None, eps=None, cin_pad=None, device=None):
+        # folding and packing run on the HOST (a few hundred KB per layer, once per model): no swarm of tiny elementwise
+        # launches in front of the first pair, one H2D copy per packed tensor
+        dev = weight.device if device is None else torch.device(device)
+        w = weight.detach().float().cpu()
         if cin_pad is not None and cin_pad > w.shape[1]:          # zero input channels (49 -> 64 for the heads)
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))
         cout, cin, k, _ = w.shape
         if bn is not None:
             e = bn.eps if eps is None else eps
-            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + e)
-            self.bias = (bn.bias.detach().float() - bn.running_mean.detach().float() * scale).contiguous()
+            scale = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + e)
+            self.bias = (bn.bias.detach().float().cpu() - bn.running_mean.detach().float().cpu() * scale).contiguous().to(dev)
             w = w * scale.view(-1, 1, 1, 1)
         else:
             self.bias = None
-        self.w = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous()      # [R*S*Cin][Cout]
+        self.w = w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous().to(dev)      # [R*S*Cin][Cout]
         # tensor-core copy: [Cout][R*S*Cin], rounded to nearest-even TF32 once (the MMA would truncate)
         wt = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()
         bits = wt.view(torch.int32)
         bits = (bits + 0xFFF + ((bits >> 13) & 1)) & ~0x1FFF
-        self.w_tc = bits.view(torch.float32).contiguous()
-        self._wt = wt
+        self.w_tc = bits.view(torch.float32).contiguous().to(dev)
+        self._wt = wt                                                                        # host copy: source of the fp16 / split packings
+        self._dev = dev
         self._w_f16 = None
         self.cout, self.cin, self.k, self.stride = cout, cin, k, stride
         self.pad = (k // 2) if pad is None else pad
@@ -90,14 +94,14 @@ class FoldedConv:
         if getattr(self, "_w_split", None) is None:
             hi = self._wt.to(torch.float16)
             lo = ((self._wt - hi.float()) * 2048.0).to(torch.float16)
-            self._w_split = torch.stack([hi, lo]).contiguous()
+            self._w_split = torch.stack([hi, lo]).contiguous().to(self._dev)
         return self._w_split
 
     @property
     def w_f16(self):
         """[Cout][R*S*Cin] fp16 (round to nearest), the engine-2 operand; built on first use."""
         if self._w_f16 is None:
-            self._w_f16 = self._wt.to(torch.float16).contiguous()
+            self._w_f16 = self._wt.to(torch.float16).contiguous().to(self._dev)
         return self._w_f16
 
     def __call__(self, x, relu, residual=None, engine=None):

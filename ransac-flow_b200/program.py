@@ -29,7 +29,8 @@ lib.rf_run_layers.argtypes = [C.POINTER(rf_layer_t), C.c_int, C.POINTER(C.c_void
 class LayerProgram:
     """Symbolic tensors are integers; tensor 0 is the input."""
 
-    def __init__(self, cin):
+    def __init__(self, cin, device=None):
+        self.device = device     # where folded weights built by stem() / stem7_fused() go (default: the weight's own device)
         self.ops = []            # (op, src, res, cin, cout, k, stride, pad, relu, folded)
         self.chan = [cin]
         self._keep = []          # folded weights (keeps the device tensors alive)
@@ -74,10 +75,11 @@ class LayerProgram:
         from .model import FoldedConv
         cout, cin, k, _ = weight.shape
         kpad = (k * k * cin + kalign - 1) // kalign * kalign
-        w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k * cin)          # (r, s, c) order
+        dev = self.device or weight.device
+        w = weight.detach().float().cpu().permute(0, 2, 3, 1).reshape(cout, k * k * cin)    # (r, s, c) order
         w = torch.nn.functional.pad(w, (0, kpad - k * k * cin)).reshape(cout, kpad, 1, 1)
         x = self.im2col(src, k, stride, pad, kpad)
-        return self.conv(x, FoldedConv(w, bn, 1, pad=0), relu=True)
+        return self.conv(x, FoldedConv(w, bn, 1, pad=0, device=dev), relu=True)
 
     def stem7_fused(self, src, weight, bn):
         """fp16 engine only: the ResNet-50 stem (7x7 / 2 / pad 3, 3 -> 64, BN, ReLU) in one kernel that builds the patches
@@ -85,9 +87,10 @@ class LayerProgram:
         from .model import FoldedConv
         cout, cin, k, _ = weight.shape
         assert (cout, cin, k) == (64, 3, 7) and self.chan[src] == 3
-        w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+        dev = self.device or weight.device
+        w = weight.detach().float().cpu().permute(0, 2, 3, 1).reshape(cout, k * k * cin)
         w = torch.nn.functional.pad(w, (0, 192 - k * k * cin)).reshape(cout, 192, 1, 1)
-        fc = FoldedConv(w, bn, 1, pad=0)
+        fc = FoldedConv(w, bn, 1, pad=0, device=dev)
         self.ops.append((RF_OP_STEM7, src, -1, 3, 64, 7, 2, 3, 1, fc))
         self._keep.append(fc)
         self.chan.append(64)
