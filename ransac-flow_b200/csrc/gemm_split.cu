@@ -52,26 +52,31 @@ struct alignas(64) SplitParams {
     float* y32;                           // out32: fp32 [P][Cout]
 };
 
-template <bool HALO>
+// BN = 64: the two epilogue groups take alternate tiles.  BN = 128 (tap streaming only): each group takes one 64-channel half of
+// EVERY tile - twice the work per operand byte fetched from L2 (the tap-streaming layers are L2-bandwidth bound at BN = 64:
+// 48 KB per K block for 12 MMAs) and N = 128 MMAs, which the shared-memory read port can feed at the full tensor rate.
+template <bool HALO, int BN_>
 struct SplitCfg {
-    static constexpr int BN = SP_BN;
-    static constexpr int B_PLANE = BN * 128;                                  // 8 KB
+    static constexpr int BN = BN_;
+    static constexpr int B_PLANE = BN * 128;                                  // 8 / 16 KB
     static constexpr int B_TILE = 2 * B_PLANE;                                // hi + lo planes of one weight tile
     static constexpr int A_LO = HALO ? SP_HALO_PLANE : TC_A_BYTES;            // offset of the lo plane inside an A slot
     static constexpr int A_TX = 2 * A_LO;
     static constexpr int A_SLOT = HALO ? 46 * 1024 : 2 * TC_A_BYTES;          // 1024-byte aligned slots
-    static constexpr int NA = HALO ? 2 : 3;
+    static constexpr int NA = HALO ? 2 : (BN == 128 ? 2 : 3);
     static constexpr int NB = HALO ? 4 : 3;
     static constexpr int TB = HALO ? 9 : 1;                                   // B tiles consumed per A slot
-    static constexpr int STG = 2 * TC_A_BYTES;                                // per epilogue group: [hi box | lo box]
+    static constexpr int STG = 2 * TC_A_BYTES;                                // per epilogue group: [hi box | lo box] of 64 channels
     static constexpr int OFF_B = NA * A_SLOT;
     static constexpr int OFF_STG = OFF_B + NB * B_TILE;
     static constexpr int DATA_BYTES = OFF_STG + 2 * STG;
     static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
     static constexpr int TMEM_COLS = 4 * BN;                                  // 2 buffers x (main | cross)
+    static_assert(!(HALO && BN != 64), "halo reuse runs with 64-channel tiles");
 };
-static_assert(SplitCfg<true>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false>::SMEM_BYTES <= 227 * 1024, "shared memory");
-static_assert(SplitCfg<true>::A_TX <= SplitCfg<true>::A_SLOT, "halo slot");
+static_assert(SplitCfg<true, 64>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false, 64>::SMEM_BYTES <= 227 * 1024 &&
+              SplitCfg<false, 128>::SMEM_BYTES <= 227 * 1024, "shared memory");
+static_assert(SplitCfg<true, 64>::A_TX <= SplitCfg<true, 64>::A_SLOT, "halo slot");
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -96,7 +101,7 @@ __device__ __forceinline__ uint64_t sp_desc_halo(uint32_t saddr) {
 
 struct SpTile { int img, ox0, oy0, tw, n0; };
 
-template <bool HALO>
+template <bool HALO, int BN = SP_BN>
 __device__ __forceinline__ SpTile sp_decode(const SplitParams& p, int t) {
     SpTile c;
     const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;      // channel tiles fastest: co-running CTAs share the pixel tile
@@ -110,7 +115,7 @@ __device__ __forceinline__ SpTile sp_decode(const SplitParams& p, int t) {
     const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
     c.ox0 = txi * c.tw;
     c.oy0 = tyi * th;
-    c.n0 = nt * SP_BN;
+    c.n0 = nt * BN;
     return c;
 }
 
@@ -123,11 +128,12 @@ __device__ __forceinline__ void sp_split2(float a, float b, __half2& hi, __half2
     lo = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
 }
 
-template <bool HALO>
+template <bool HALO, int BN_>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 tc_split_kernel(const __grid_constant__ SplitParams p) {
-    using Cfg = SplitCfg<HALO>;
+    using Cfg = SplitCfg<HALO, BN_>;
     constexpr int BN = Cfg::BN, NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB, BK = TC_BK_F16;
+    constexpr bool WIDE = BN == 128;            // both epilogue groups work on every tile (one 64-channel half each)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -151,7 +157,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); mbar_init(&res_full[i], 1); mbar_init(&stg_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); mbar_init(&res_full[i], 1); mbar_init(&stg_free[i], 1); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
@@ -166,12 +172,21 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         if (lane == 0) {
             uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
-                const SpTile c = sp_decode<HALO>(p, t);
+                const SpTile c = sp_decode<HALO, BN>(p, t);
                 if (has_res) {
-                    const uint32_t g = ti & 1;
-                    mbar_wait(&stg_free[g], ((ti >> 1) & 1) ^ 1);        // tile ti-2's store has read this buffer (passes at once for ti < 2)
-                    mbar_expect_tx(&res_full[g], Cfg::STG);
-                    tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0, c.ox0, c.oy0, 0);
+                    if (WIDE) {                                          // one residual box per group and tile
+#pragma unroll
+                        for (uint32_t g = 0; g < 2; ++g) {
+                            mbar_wait(&stg_free[g], (ti & 1) ^ 1);       // tile ti-1's store has read this buffer (passes at once for ti = 0)
+                            mbar_expect_tx(&res_full[g], Cfg::STG);
+                            tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0 + 64 * g, c.ox0, c.oy0, 0);
+                        }
+                    } else {
+                        const uint32_t g = ti & 1;
+                        mbar_wait(&stg_free[g], ((ti >> 1) & 1) ^ 1);    // tile ti-2's store has read this buffer (passes at once for ti < 2)
+                        mbar_expect_tx(&res_full[g], Cfg::STG);
+                        tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0, c.ox0, c.oy0, 0);
+                    }
                 }
                 for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
                     const int sa = ia_cnt % NA;
@@ -235,30 +250,39 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
         uint8_t* stg = sStg + g * Cfg::STG;
         uint32_t k = 0;                                                     // this group's tile counter
-        for (int t = blockIdx.x + (int)g * (int)gridDim.x; t < total; t += 2 * gridDim.x, ++k) {
-            const SpTile c = sp_decode<HALO>(p, t);
+        for (int t = blockIdx.x + (WIDE ? 0 : (int)g * (int)gridDim.x); t < total; t += (WIDE ? 1 : 2) * gridDim.x, ++k) {
+            const SpTile c = sp_decode<HALO, BN>(p, t);
+            const uint32_t buf = WIDE ? (k & 1) : g;                        // accumulator pair of this tile
+            const uint32_t fph = WIDE ? ((k >> 1) & 1) : (k & 1);           // phase of its tmem_full barrier
+            const int nbase = c.n0 + (WIDE ? 64 * (int)g : 0);              // first output channel of this group's 64-wide slice
             // the leader comes here only after the previous store has read the staging buffer
             if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-            mbar_wait(&tmem_full[g], k & 1);
+            mbar_wait(&tmem_full[buf], fph);
             tc_fence_after();
             if (has_res) mbar_wait(&res_full[g], k & 1);
-            const uint32_t trow = tmem_base + g * (2 * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t trow = tmem_base + buf * (2 * BN) + (WIDE ? 64 * g : 0) + ((uint32_t)(q * 32) << 16);
             const int py = m / c.tw, px = m - py * c.tw;
             const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
             float* yrow = p.out32 ? p.y32 + (p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px)) * p.Cout : nullptr;
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
+            for (int cb = 0; cb < 2; ++cb) {
                 uint32_t v[32], x[32];
                 tmem_ld32x2(trow + cb * 32, v, trow + BN + cb * 32, x);
-                const int n = c.n0 + cb * 32;
+                const int n = nbase + cb * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
                     if (p.bias != nullptr) {
+                        if (n + 8 * j + 8 <= p.Cout && (p.Cout & 3) == 0) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * j + 4));
+                            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) if (n + 8 * j + e < p.Cout) o[e] += __ldg(p.bias + n + 8 * j + e);
+                            for (int e = 0; e < 8; ++e) if (n + 8 * j + e < p.Cout) o[e] += __ldg(p.bias + n + 8 * j + e);
+                        }
                     }
                     if (p.out32) {
                         if (pvalid) {
@@ -296,12 +320,12 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[g]);                                    // accumulator pair drained (128 arrivals)
+            mbar_arrive(&tmem_empty[buf]);                                  // accumulator pair drained (128 arrivals per group)
             if (!p.out32) {
                 fence_proxy_async();
                 if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (leader) {
-                    tma_store_4d(&p.mapY[c.img], stg, c.n0, c.ox0, c.oy0, 0);
+                    if (nbase < p.Cout) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
                     tma_store_commit_and_wait_read();
                     if (has_res) mbar_arrive(&stg_free[g]);
                 }
@@ -568,7 +592,11 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     }
     for (int i = set.n; i <= RF_MAX_IMGS; ++i) p.tile_start[i] = tiles;
     p.out_pix[set.n] = set.out_pix[set.n];
-    int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, SP_BN, 2, 1, 2);
+    // 128-channel tiles for the tap-streaming layers that have them (RF_SPLIT_BN=64 forces the narrow tile everywhere)
+    static int bn_env = -1;
+    if (bn_env < 0) { const char* e = getenv("RF_SPLIT_BN"); bn_env = e ? atoi(e) : 128; }
+    const int BN = (!halo && cp.Cout >= 128 && bn_env == 128) ? 128 : 64;
+    int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, (unsigned)BN, 2, 1, 2);
     if (rc) return rc;
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
     p.has_res = cp.residual != nullptr ? 1 : 0;
@@ -576,25 +604,22 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     p.bias = cp.bias;
     p.y32 = out32 ? cp.y : nullptr;
     p.tiles_m = tiles;
-    p.tiles_n = (cp.Cout + SP_BN - 1) / SP_BN;
+    p.tiles_n = (cp.Cout + BN - 1) / BN;
     const long long total = (long long)p.tiles_m * p.tiles_n;
     RF_REQUIRE(total < (1ll << 30), "rf_conv2d_nhwc: too many tiles");
     const int grid = total < num_sms() ? (int)total : num_sms();
-    static bool attr[64][2] = {{false}};
+    static bool attr[64][3] = {{false}};
     const int dev = current_device();
-    if (halo) {
-        if (!attr[dev][1]) {
-            RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true>::SMEM_BYTES));
-            attr[dev][1] = true;
-        }
-        tc_split_kernel<true><<<grid, SP_THREADS, SplitCfg<true>::SMEM_BYTES, st>>>(p);
-    } else {
-        if (!attr[dev][0]) {
-            RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false>::SMEM_BYTES));
-            attr[dev][0] = true;
-        }
-        tc_split_kernel<false><<<grid, SP_THREADS, SplitCfg<false>::SMEM_BYTES, st>>>(p);
+    const int which = halo ? 1 : (BN == 128 ? 2 : 0);
+    if (!attr[dev][which]) {
+        if (which == 1) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true, 64>::SMEM_BYTES));
+        else if (which == 2) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 128>::SMEM_BYTES));
+        else RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 64>::SMEM_BYTES));
+        attr[dev][which] = true;
     }
+    if (which == 1) tc_split_kernel<true, 64><<<grid, SP_THREADS, SplitCfg<true, 64>::SMEM_BYTES, st>>>(p);
+    else if (which == 2) tc_split_kernel<false, 128><<<grid, SP_THREADS, SplitCfg<false, 128>::SMEM_BYTES, st>>>(p);
+    else tc_split_kernel<false, 64><<<grid, SP_THREADS, SplitCfg<false, 64>::SMEM_BYTES, st>>>(p);
     RF_LAUNCHED();
     return 0;
 }
