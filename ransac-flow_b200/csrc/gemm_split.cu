@@ -339,30 +339,31 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
 
 // ------------------------------------------------------------------------------------------------------------
 // ResNet-50 stem, fused, split operands: conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
-// split NHWC, without an im2col matrix in HBM.  PERSISTENT, two CTAs per SM (92 KB each), 160 threads:
-//   warps 0-3 : stage the 37 x 21 x 3 input window of the tile in shared memory (the NEXT tile's window is already in
-//               flight in registers), then build the tile's 147-long (r, s, c) patches one 64-wide K block at a time,
-//               as hi / lo planes straight in the 128-byte-swizzled K-major layout (one 32 KB slot, reused per block);
-//               after the last block: epilogue TMEM -> + bias, ReLU, split -> [hi box | lo box] in the same slot -> one
-//               TMA store of both planes;
-//   warp 4    : loads the split weights ONCE per CTA (3 K blocks x [hi | lo] = 48 KB), then per K block three MMA
-//               groups (hi*hi | lo*hi + hi*lo) and a commit that hands the slot back.
-// The first version of this kernel (one tile per CTA, all three K blocks resident, 155 KB => one CTA per SM) ran 358 us
-// per pair at config 2: every tile paid the weight load, the window load, TMEM allocation and the store drain serially.
+// split NHWC, without an im2col matrix in HBM.  PERSISTENT and warp specialised, one CTA per SM, 288 threads:
+//   warps 0-3 : builders.  Stage the 37 x 21 x 3 input window of the tile in shared memory (the NEXT tile's window is
+//               already in flight in registers), then build the tile's 147-long (r, s, c) patches as hi / lo planes
+//               straight in the 128-byte-swizzled K-major layout (3 + 3 K blocks of 64), fence.proxy.async, arrive;
+//   warp 4    : loads the split weights ONCE per CTA (48 KB), then per tile nine MMA groups into accumulator pair
+//               (tile & 1); one commit hands the patch buffer back to the builders, one publishes the accumulators;
+//   warps 5-8 : epilogue.  TMEM -> + bias, ReLU, split -> [hi box | lo box] staging -> one TMA store of both planes,
+//               overlapped with the builders' next tile.
+// History (config 2, 7132 tiles): one tile per CTA, everything serial, 155 KB: 358 us; persistent with a single reused K-block
+// slot and two CTAs per SM: 408 us (three build -> MMA -> commit round trips per tile); this version: see profiles/.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SS_TW = 16, SS_TH = 8, SS_K = 7, SS_C = 3, SS_KK = 147, SS_KB = 3;
 constexpr int SS_IN_W = ((SS_TW - 1) * 2 + SS_K) * SS_C;                  // 111 floats per staged input row
 constexpr int SS_IN_H = (SS_TH - 1) * 2 + SS_K;                           // 21 rows
 constexpr int SS_IN_LD = 112;
 constexpr int SS_B_TILE = 2 * 64 * 128;                                   // [hi | lo] weights of one K block: 16 KB
-constexpr int SS_A_SLOT = 2 * TC_A_BYTES;                                 // [hi | lo] patches of one K block: 32 KB
-constexpr int SS_OFF_B = SS_A_SLOT;
-constexpr int SS_OFF_IN = SS_OFF_B + SS_KB * SS_B_TILE;                   // 80 KB
+constexpr int SS_OFF_ALO = SS_KB * TC_A_BYTES;                            // 48 KB: lo planes of the patches
+constexpr int SS_OFF_B = 2 * SS_KB * TC_A_BYTES;                          // 96 KB
+constexpr int SS_OFF_STG = SS_OFF_B + SS_KB * SS_B_TILE;                  // 144 KB
+constexpr int SS_OFF_IN = SS_OFF_STG + 2 * TC_A_BYTES;                    // 176 KB
 constexpr int SS_OFF_BAR = SS_OFF_IN + SS_IN_H * SS_IN_LD * 4;
-constexpr int SS_SMEM = SS_OFF_BAR + 64 + 1024;
-constexpr int SS_THREADS = 160;
+constexpr int SS_SMEM = SS_OFF_BAR + 128 + 1024;
+constexpr int SS_THREADS = 288;
 constexpr int SS_NLD = (SS_IN_H * SS_IN_W + 127) / 128;                   // window floats per builder thread
-static_assert(2 * (SS_SMEM + 1024) <= 227 * 1024, "two stem CTAs per SM");
+static_assert(SS_SMEM <= 227 * 1024, "stem shared memory");
 
 struct alignas(64) StemSplitParams {
     CUtensorMap mapB;                     // weights (192, 64, 2) fp16, box (64, 64, 2)
@@ -403,67 +404,49 @@ __device__ __forceinline__ void stem_load_window(const StemSplitParams& p, const
     }
 }
 
-__global__ void __launch_bounds__(SS_THREADS, 2)
+__global__ void __launch_bounds__(SS_THREADS, 1)
 stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + SS_OFF_B;
+    uint8_t* sStg = smem + SS_OFF_STG;
     float* sIn = reinterpret_cast<float*>(smem + SS_OFF_IN);
     uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + SS_OFF_BAR);
-    uint64_t* bar_a = bar_b + 1;          // 128 arrivals: a K block of patches is in the slot
-    uint64_t* bar_free = bar_a + 1;       // commit: the MMAs reading the slot are done
-    uint64_t* bar_mma = bar_free + 1;     // commit: the tile's accumulators are complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    uint64_t* bar_a = bar_b + 1;          // 128 arrivals: the tile's patches are in shared memory
+    uint64_t* bar_free = bar_a + 1;       // commit: the MMAs reading the patches are done
+    uint64_t* tmem_full = bar_free + 1;   // [2] commit: accumulator pair complete
+    uint64_t* tmem_empty = tmem_full + 2; // [2] 128 arrivals: the epilogue has drained it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_b, 1);
         mbar_init(bar_a, 128);
         mbar_init(bar_free, 1);
-        mbar_init(bar_mma, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
         fence_barrier_init();
     }
     if (warp == 4) {
         if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
-        tmem_alloc(tmem_slot, 128);
+        tmem_alloc(tmem_slot, 256);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
-        if (lane == 0) {
-            mbar_expect_tx(bar_b, SS_KB * SS_B_TILE);
-#pragma unroll
-            for (int kb = 0; kb < SS_KB; ++kb) tma_load_3d(sB + kb * SS_B_TILE, &p.mapB, bar_b, kb * 64, 0, 0);
-        }
-        mbar_wait(bar_b, 0);
-        constexpr uint32_t idesc = make_idesc_f16(64);
-        const uint32_t a = smem_u32(sA);
-        uint32_t n = 0;
-        for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
-#pragma unroll 1
-            for (int kb = 0; kb < SS_KB; ++kb, ++n) {
-                mbar_wait(bar_a, n & 1);                        // also: the builders have drained the previous tile's accumulators
-                tc_fence_after();
-                const uint32_t b = smem_u32(sB + kb * SS_B_TILE);
-                umma_f16split_x4(tmem_base, tmem_base + 64, make_desc_sw128(a), make_desc_sw128(a + TC_A_BYTES), make_desc_sw128(b),
-                                 make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
-                umma_commit(bar_free);
-            }
-            umma_commit(bar_mma);
-        }
-    } else {
-        const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = accumulator row
+    if (warp < 4) {
+        // =============================== builders ===============================
+        const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = A row
         const int py = m >> 4, px = m & 15;
         const float* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
         float stage[SS_NLD];
-        StemTile c = stem_decode(p, blockIdx.x < p.total ? blockIdx.x : 0);
+        StemTile c = stem_decode(p, (int)blockIdx.x < p.total ? (int)blockIdx.x : 0);
         if ((int)blockIdx.x < p.total) stem_load_window(p, c, m, stage);
-        uint32_t n = 0, ti = 0;
+        uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // everybody has finished reading the previous window
 #pragma unroll
             for (int i = 0; i < SS_NLD; ++i) {
                 const int idx = m + i * 128;
@@ -471,15 +454,14 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
                 if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const StemTile cur = c;
             if (t + (int)gridDim.x < p.total) {                 // next tile's window: in flight while this tile is built
                 c = stem_decode(p, t + gridDim.x);
                 stem_load_window(p, c, m, stage);
             }
+            if (ti > 0) mbar_wait(bar_free, (ti - 1) & 1);      // the previous tile's MMAs have read the patch buffer
             // ---- this pixel's patch, (r, s, c) order: element k = r*21 + s*3 + c sits at sIn[2*py + r][6*px + (k % 21)] ----
-#pragma unroll 1
-            for (int kb = 0; kb < SS_KB; ++kb, ++n) {
-                if (n > 0) mbar_wait(bar_free, (n - 1) & 1);    // the MMAs that read the slot's previous content are done
+#pragma unroll
+            for (int kb = 0; kb < SS_KB; ++kb) {
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
                     uint4 oh, ol;
@@ -492,18 +474,52 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
                         const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
                         sp_split2(a, b, ph[e], pl[e]);
                     }
-                    uint8_t* dst = sA + m * 128 + ((c8 ^ (m & 7)) << 4);
+                    uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
                     *reinterpret_cast<uint4*>(dst) = oh;
-                    *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
+                    *reinterpret_cast<uint4*>(dst + SS_OFF_ALO) = ol;
                 }
-                fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core (async proxy)
-                tc_fence_before();
-                mbar_arrive(bar_a);
             }
-            // ---- epilogue: [hi box | lo box] staged in the slot (the MMAs are done), one TMA store ----
-            mbar_wait(bar_mma, ti & 1);
+            fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_a);
+        }
+    } else if (warp == 4) {
+        // =============================== weights once, then the MMA issuer ===============================
+        if (lane == 0) {
+            mbar_expect_tx(bar_b, SS_KB * SS_B_TILE);
+#pragma unroll
+            for (int kb = 0; kb < SS_KB; ++kb) tma_load_3d(sB + kb * SS_B_TILE, &p.mapB, bar_b, kb * 64, 0, 0);
+        }
+        mbar_wait(bar_b, 0);
+        constexpr uint32_t idesc = make_idesc_f16(64);
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
+            mbar_wait(bar_a, ti & 1);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const uint32_t td = tmem_base + buf * 128;
+#pragma unroll
+            for (int kb = 0; kb < SS_KB; ++kb) {
+                const uint32_t a = smem_u32(sA + kb * TC_A_BYTES), b = smem_u32(sB + kb * SS_B_TILE);
+                umma_f16split_x4(td, td + 64, make_desc_sw128(a), make_desc_sw128(a + SS_OFF_ALO), make_desc_sw128(b),
+                                 make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_free);
+            umma_commit(&tmem_full[buf]);
+        }
+    } else {
+        // =============================== epilogue (warps 5..8) ===============================
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const bool leader = (warp == 5 && lane == 0);
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
+            const uint32_t buf = ti & 1;
+            const StemTile c = stem_decode(p, t);
+            asm volatile("bar.sync 2, 128;" ::: "memory");      // the leader's previous store has read the staging buffer
+            mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int cb = 0; cb < 2; ++cb) {
                 uint32_t v[32], x[32];
@@ -524,23 +540,24 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) sp_split2(fmaxf(o[2 * e], 0.f), fmaxf(o[2 * e + 1], 0.f), ph[e], pl[e]);
                     const int chunk = cb * 4 + j;
-                    uint8_t* dst = sA + m * 128 + ((chunk ^ (m & 7)) << 4);
+                    uint8_t* dst = sStg + m * 128 + ((chunk ^ (m & 7)) << 4);
                     *reinterpret_cast<uint4*>(dst) = oh;
                     *reinterpret_cast<uint4*>(dst + TC_A_BYTES) = ol;
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (m == 0) {
-                tma_store_4d(&p.mapY[cur.img], sA, 0, cur.ox0, cur.oy0, 0);
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (leader) {
+                tma_store_4d(&p.mapY[c.img], sStg, 0, c.ox0, c.oy0, 0);
                 tma_store_commit_and_wait_read();
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the slot and the window buffer are free again
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 128);
+    if (warp == 4) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace rf
@@ -657,7 +674,7 @@ int rf_stem7_split_impl(const float* x, int nimg, const int* hw_host, const void
         attr[dev] = true;
     }
     p.total = tiles;
-    const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+    const int grid = tiles < num_sms() ? tiles : num_sms();
     stem7_split_kernel<<<grid, SS_THREADS, SS_SMEM, as_stream(stream)>>>(p);
     RF_LAUNCHED();
     return 0;
