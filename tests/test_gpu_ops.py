@@ -200,3 +200,31 @@ def test_compose_fine(rf, m21):
     f_nc, _ = WO.compose_fine(f8, coarse, grid, clamp=False)
     g_nc, _, _ = rf.ops.compose_fine(f8.cuda(), None, None, coarse.cuda(), clamp=False, want_match=False)
     close(g_nc.cpu(), f_nc, 5e-6)
+
+
+def test_warp_grid_reference_internal_consistency(rf):
+    """rf_warp_grid under the pin the reference itself offers for kornia 0.1.4 (see tests/test_oracle_golden.py): the identity
+    (and any power-of-two multiple of it) reproduces, bit for bit, the base grid the fine flow is added to on this side
+    (pipeline.base_grid = torch.linspace on the device = what compose_fine regenerates) - the consistency the reference has
+    between kornia's meshgrid and the drivers' own linspace grid, both built by the same CPU linspace - and Homography(X, Y)
+    -> warp_grid carries the four target sample points onto their source points.  (CPU torch.linspace itself is only defined
+    up to an ulp: its vectorised kernel adds lane offsets to a per-vector base, so it depends on the host's SIMD width.)"""
+    from oracle import outil_oracle as OO
+    from oracle import warp_oracle as WO
+    for h, w in ((48, 64), (30, 41), (2, 2), (480, 640)):
+        for scale in (1.0, 4.0):
+            got = rf.ops.warp_grid(scale * torch.eye(3).cuda().view(1, 3, 3), h, w)
+            assert torch.equal(got, rf.pipeline.base_grid(h, w))
+            assert (got.cpu() - WO.base_grid(h, w)).abs().max().item() <= 1.2e-7
+    rs = np.random.RandomState(0)
+    h, w = 33, 47
+    Y = np.array([[-1, -1, 1], [1, -1, 1], [-1, 1, 1], [1, 1, 1]], dtype=np.float32)
+    Hgt = np.eye(3) + rs.uniform(-0.2, 0.2, (3, 3))
+    Hgt[2, :2] = rs.uniform(-0.05, 0.05, 2)
+    X = Y @ Hgt.T
+    X = (X / X[:, 2:]).astype(np.float32)
+    H = rf.outil.Homography(torch.from_numpy(X[None]).cuda(), torch.from_numpy(Y[None]).cuda())
+    np.testing.assert_allclose(H.cpu().numpy(), OO.Homography(X[None], Y[None]), atol=2e-6)
+    g = rf.kornia_geometry.HomographyWarper(h, w).warp_grid(H)[0].cpu().numpy()
+    corners = np.stack([g[0, 0], g[0, w - 1], g[h - 1, 0], g[h - 1, w - 1]])
+    assert np.abs(corners - X[:, :2]).max() < 1e-5

@@ -215,3 +215,27 @@ def test_coarse_align_variant_B():
     assert len(c.match1) == int(g["nbMatch"])
     np.testing.assert_allclose(H, g["H"], atol=1e-5)
     assert np.array_equal(mask, g["inlierMask"]) and mask[0].sum() == 0          # the masked top rows hold no inlier
+
+
+def test_warp_grid_reference_internal_consistency():
+    """The pin the reference itself offers for kornia 0.1.4's ``HomographyWarper.warp_grid`` (not installed, not vendored):
+    (1) the drivers add the fine flow to their OWN ``linspace`` grid (evaluation/evalHpatch/evaluation.py:187-189) and sample
+    the coarse grid with it, which is only consistent if the identity homography reproduces that grid exactly; (2)
+    ``Homography(X, Y)`` fits source = H * target (utils/outil.py:73-81) and its output goes straight into ``warp_grid``
+    (evaluation.py:218), so the warped grid must carry the four target sample points onto their source points."""
+    for h, w in ((48, 64), (30, 41), (2, 2)):
+        ident = WO.warp_grid(np.eye(3, dtype=np.float32)[None], h, w)
+        assert torch.equal(ident, WO.base_grid(h, w))
+        assert torch.equal(WO.warp_grid(4.0 * np.eye(3, dtype=np.float32)[None], h, w), WO.base_grid(h, w))     # the scale of H cancels (a power of two: exactly)
+    rs = np.random.RandomState(0)
+    h, w = 33, 47
+    # target points = the four corner nodes of the grid (x, y, 1); source points = a random projective image of them
+    Y = np.array([[-1, -1, 1], [1, -1, 1], [-1, 1, 1], [1, 1, 1]], dtype=np.float32)
+    Hgt = np.eye(3) + rs.uniform(-0.2, 0.2, (3, 3))
+    Hgt[2, :2] = rs.uniform(-0.05, 0.05, 2)
+    X = (Y @ Hgt.T)
+    X = (X / X[:, 2:]).astype(np.float32)
+    H = OO.Homography(X[None], Y[None])                       # (1,3,3): maps target -> source
+    g = WO.warp_grid(H, h, w)[0].numpy()
+    corners = np.stack([g[0, 0], g[0, w - 1], g[h - 1, 0], g[h - 1, w - 1]])
+    assert np.abs(corners - X[:, :2]).max() < 1e-5
