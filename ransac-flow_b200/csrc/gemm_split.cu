@@ -16,12 +16,12 @@
 //   warp 0    : TMA producer.  Tap streaming (1x1 of any stride, 3x3 / stride 2): A = (64 ch, tw, th, 2) box at the tap's
 //               offset (zero padding by out-of-bounds fill), B = (64 k, 64 rows, 2) box.  HALO (3x3 / stride 1): A = the
 //               (8+2) x (16+2) halo of one 64-channel block once, the nine taps are nine UMMA descriptors into it (see
-//               tc_halo_kernel in gemm_tc.cu), B = nine weight boxes.  Runs ahead across tiles; prefetches the residual
-//               tile of tile i into epilogue staging buffer i & 1.
+//               tc_halo_kernel in gemm_tc.cu), B = nine weight boxes.  Runs ahead across tiles, never waits for an epilogue.
 //   warp 1    : MMA issuer.  Two accumulator PAIRS (main | cross) x 64 columns x 2 buffers = 256 TMEM columns: tile i+1
 //               multiplies while tile i drains.
-//   warps 2-5 : epilogue group 0 (even tiles), warps 6-9: group 1 (odd tiles): TMEM -> main + cross * 2^-11 + bias
-//               (+ residual hi + lo * 2^-11) -> ReLU -> split -> swizzled staging [hi box | lo box] -> one TMA store.
+//   warps 2-5 : epilogue group 0 (even tiles), warps 6-9: group 1 (odd tiles): residual rows global -> registers (issued
+//               before the wait for the accumulators), TMEM -> main + cross * 2^-11 + bias (+ residual hi + lo * 2^-11) ->
+//               ReLU -> split -> swizzled staging [hi box | lo box] -> one TMA store.
 //               `out32`: fp32 rows straight to global memory instead (the 49- / 1-channel outputs of the heads).
 #include <cstdlib>
 
@@ -38,7 +38,6 @@ constexpr int SP_HALO_PLANE = SP_HALO_LD * (SP_HALO_TH + 2) * 128;          // 2
 struct alignas(64) SplitParams {
     CUtensorMap mapA[RF_MAX_IMGS];        // per image: input (Cin, W, H, 2) fp16
     CUtensorMap mapY[RF_MAX_IMGS];        // per image: output (Cout, Wo, Ho, 2), box (64, tw, th, 2)
-    CUtensorMap mapR[RF_MAX_IMGS];        // per image: residual, same geometry
     CUtensorMap mapB;                     // weights (K, Cout, 2), box (64, 64, 2)
     int nimg;
     int tile_start[RF_MAX_IMGS + 1];
@@ -50,6 +49,8 @@ struct alignas(64) SplitParams {
     int tiles_m, tiles_n;
     const float* bias;
     float* y32;                           // out32: fp32 [P][Cout]
+    const __half* res;                    // residual hi plane [P][Cout] (lo plane `res_plane` elements further), nullable
+    long long res_plane;
 };
 
 // BN = 64: the two epilogue groups take alternate tiles.  BN = 128 (tap streaming only): each group takes one 64-channel half of
@@ -145,9 +146,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     uint64_t* emptyB = fullB + NB;
     uint64_t* tmem_full = emptyB + NB;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
-    uint64_t* res_full = tmem_empty + 2;        // [2]
-    uint64_t* stg_free = res_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.tiles_m * p.tiles_n;
     const int kc = p.Cin / BK;
@@ -157,7 +156,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); mbar_init(&res_full[i], 1); mbar_init(&stg_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
@@ -173,21 +172,6 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             uint32_t ia_cnt = 0, ib_cnt = 0, ti = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const SpTile c = sp_decode<HALO, BN>(p, t);
-                if (has_res) {
-                    if (WIDE) {                                          // one residual box per group and tile
-#pragma unroll
-                        for (uint32_t g = 0; g < 2; ++g) {
-                            mbar_wait(&stg_free[g], (ti & 1) ^ 1);       // tile ti-1's store has read this buffer (passes at once for ti = 0)
-                            mbar_expect_tx(&res_full[g], Cfg::STG);
-                            tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0 + 64 * g, c.ox0, c.oy0, 0);
-                        }
-                    } else {
-                        const uint32_t g = ti & 1;
-                        mbar_wait(&stg_free[g], ((ti >> 1) & 1) ^ 1);    // tile ti-2's store has read this buffer (passes at once for ti < 2)
-                        mbar_expect_tx(&res_full[g], Cfg::STG);
-                        tma_load_4d(sStg + g * Cfg::STG, &p.mapR[c.img], &res_full[g], c.n0, c.ox0, c.oy0, 0);
-                    }
-                }
                 for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
                     const int sa = ia_cnt % NA;
                     mbar_wait(&emptyA[sa], ((ia_cnt / NA) & 1) ^ 1);
@@ -255,16 +239,31 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const uint32_t buf = WIDE ? (k & 1) : g;                        // accumulator pair of this tile
             const uint32_t fph = WIDE ? ((k >> 1) & 1) : (k & 1);           // phase of its tmem_full barrier
             const int nbase = c.n0 + (WIDE ? 64 * (int)g : 0);              // first output channel of this group's 64-wide slice
+            const int py = m / c.tw, px = m - py * c.tw;
+            const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
+            const long long pix = p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px);
+            // residual: this thread's pixel row (64 channels, hi and lo plane) straight from global memory into registers, issued
+            // BEFORE the wait for the accumulators so that its latency hides behind the tile's MMAs.  (The first version brought
+            // the residual tile in by TMA from the producer warp, which had to wait for the staging buffer of tile i-2: that
+            // wait stalled the operand loads of tile i behind the epilogue of tile i-2 - the c3 + residual layers ran at 2-3x
+            // their floors.)
+            uint4 rh[8], rl[8];
+            if (has_res) {
+                const __half* rp = p.res + pix * p.Cout + nbase;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = pvalid && (nbase + 8 * j + 8 <= p.Cout);
+                    rh[j] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + 8 * j)) : make_uint4(0, 0, 0, 0);
+                    rl[j] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane + 8 * j)) : make_uint4(0, 0, 0, 0);
+                }
+            }
             // the leader comes here only after the previous store has read the staging buffer
             if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             mbar_wait(&tmem_full[buf], fph);
             tc_fence_after();
-            if (has_res) mbar_wait(&res_full[g], k & 1);
             const uint32_t trow = tmem_base + buf * (2 * BN) + (WIDE ? 64 * g : 0) + ((uint32_t)(q * 32) << 16);
-            const int py = m / c.tw, px = m - py * c.tw;
-            const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
-            float* yrow = p.out32 ? p.y32 + (p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px)) * p.Cout : nullptr;
-#pragma unroll 1
+            float* yrow = p.out32 ? p.y32 + pix * p.Cout : nullptr;
+#pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
                 uint32_t v[32], x[32];
                 tmem_ld32x2(trow + cb * 32, v, trow + BN + cb * 32, x);
@@ -296,9 +295,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                     uint4* hp = reinterpret_cast<uint4*>(stg + m * 128 + ((chunk ^ (m & 7)) << 4));
                     uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hp) + TC_A_BYTES);
                     if (has_res) {
-                        const uint4 rh = *hp, rl = *lp;
-                        const __half2* h = reinterpret_cast<const __half2*>(&rh);
-                        const __half2* l = reinterpret_cast<const __half2*>(&rl);
+                        const __half2* h = reinterpret_cast<const __half2*>(&rh[chunk]);
+                        const __half2* l = reinterpret_cast<const __half2*>(&rl[chunk]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 fh = __half22float2(h[e]), fl = __half22float2(l[e]);
@@ -327,7 +325,6 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 if (leader) {
                     if (nbase < p.Cout) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
                     tma_store_commit_and_wait_read();
-                    if (has_res) mbar_arrive(&stg_free[g]);
                 }
             }
         }
@@ -581,7 +578,6 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     memset(&p, 0, sizeof(p));
     const bool halo = (cp.R == 3 && cp.stride == 1 && cp.pad == 1);
     const char* xb = reinterpret_cast<const char*>(cp.x);
-    const char* rb = reinterpret_cast<const char*>(cp.residual);
     char* yb = reinterpret_cast<char*>(cp.y);
     const unsigned long long in_plane = (unsigned long long)set.in_pix[set.n] * cp.Cin * 2ull;
     const unsigned long long out_plane = (unsigned long long)set.out_pix[set.n] * cp.Cout * 2ull;
@@ -601,9 +597,6 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
         if (!out32) {
             rc = get_map4(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
                           out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
-            if (!rc && cp.residual)
-                rc = get_map4(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
-                              out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
             if (rc) return rc;
         }
     }
@@ -612,7 +605,10 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     // 128-channel tiles for the tap-streaming layers that have them (RF_SPLIT_BN=64 forces the narrow tile everywhere)
     static int bn_env = -1;
     if (bn_env < 0) { const char* e = getenv("RF_SPLIT_BN"); bn_env = e ? atoi(e) : 128; }
-    const int BN = (!halo && cp.Cout >= 128 && bn_env == 128) ? 128 : 64;
+    // measured per layer (profiles/r2_*): wide tiles pay for deep-K layers with >= 2 channel tiles and no residual (ResNet
+    // down-sampling 1x1s, bottleneck c1 of layer 3, the stride-2 3x3s): -7 .. -15 %; the residual layers and 128-channel outputs
+    // are faster with narrow tiles taken alternately by the two epilogue groups
+    const int BN = (!halo && cp.residual == nullptr && cp.Cout >= 256 && bn_env == 128) ? 128 : 64;
     int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, (unsigned)BN, 2, 1, 2);
     if (rc) return rc;
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
@@ -620,6 +616,8 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     p.out32 = out32 ? 1 : 0;
     p.bias = cp.bias;
     p.y32 = out32 ? cp.y : nullptr;
+    p.res = reinterpret_cast<const __half*>(cp.residual);
+    p.res_plane = (long long)set.out_pix[set.n] * cp.Cout;
     p.tiles_m = tiles;
     p.tiles_n = (cp.Cout + BN - 1) / BN;
     const long long total = (long long)p.tiles_m * p.tiles_n;
