@@ -19,9 +19,9 @@
 //               tc_halo_kernel in gemm_tc.cu), B = nine weight boxes.  Runs ahead across tiles, never waits for an epilogue.
 //   warp 1    : MMA issuer.  Two accumulator PAIRS (main | cross) x 64 columns x 2 buffers = 256 TMEM columns: tile i+1
 //               multiplies while tile i drains.
-//   warps 2-5 : epilogue group 0 (even tiles), warps 6-9: group 1 (odd tiles): residual rows global -> registers (issued
-//               before the wait for the accumulators), TMEM -> main + cross * 2^-11 + bias (+ residual hi + lo * 2^-11) ->
-//               ReLU -> split -> swizzled staging [hi box | lo box] -> one TMA store.
+//   warps 2-5 : epilogue group 0 (even tiles), warps 6-9: group 1 (odd tiles): TMEM -> main + cross * 2^-11 + bias
+//               (+ residual hi + lo * 2^-11, TMA-loaded into the group's staging buffer by its own leader) -> ReLU -> split ->
+//               swizzled staging [hi box | lo box] -> one TMA store.
 //               `out32`: fp32 rows straight to global memory instead (the 49- / 1-channel outputs of the heads).
 #include <cstdlib>
 
@@ -38,6 +38,7 @@ constexpr int SP_HALO_PLANE = SP_HALO_LD * (SP_HALO_TH + 2) * 128;          // 2
 struct alignas(64) SplitParams {
     CUtensorMap mapA[RF_MAX_IMGS];        // per image: input (Cin, W, H, 2) fp16
     CUtensorMap mapY[RF_MAX_IMGS];        // per image: output (Cout, Wo, Ho, 2), box (64, tw, th, 2)
+    CUtensorMap mapR[RF_MAX_IMGS];        // per image: residual, same geometry as the output
     CUtensorMap mapB;                     // weights (K, Cout, 2), box (64, 64, 2)
     int nimg;
     int tile_start[RF_MAX_IMGS + 1];
@@ -49,8 +50,6 @@ struct alignas(64) SplitParams {
     int tiles_m, tiles_n;
     const float* bias;
     float* y32;                           // out32: fp32 [P][Cout]
-    const __half* res;                    // residual hi plane [P][Cout] (lo plane `res_plane` elements further), nullable
-    long long res_plane;
 };
 
 // BN = 64: the two epilogue groups take alternate tiles.  BN = 128 (tap streaming only): each group takes one 64-channel half of
@@ -146,7 +145,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     uint64_t* emptyB = fullB + NB;
     uint64_t* tmem_full = emptyB + NB;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_full = tmem_empty + 2;        // [2] the group's residual tile has landed in its staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.tiles_m * p.tiles_n;
     const int kc = p.Cin / BK;
@@ -156,7 +156,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); mbar_init(&res_full[i], 1); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
@@ -234,7 +234,18 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
         uint8_t* stg = sStg + g * Cfg::STG;
         uint32_t k = 0;                                                     // this group's tile counter
-        for (int t = blockIdx.x + (WIDE ? 0 : (int)g * (int)gridDim.x); t < total; t += (WIDE ? 1 : 2) * gridDim.x, ++k) {
+        const int t_first = blockIdx.x + (WIDE ? 0 : (int)g * (int)gridDim.x), t_step = (WIDE ? 1 : 2) * (int)gridDim.x;
+        // Residual tiles come in by TMA into the group's OWN staging buffer, issued by the group's leader: the first one here,
+        // the next one as soon as the store of the current tile has read the buffer out.  (First version: the producer warp
+        // issued them and had to wait for the staging buffer of tile i-2 - that wait stalled the operand loads of tile i behind
+        // the epilogue of tile i-2; second version: each thread loaded its residual row from global memory into registers -
+        // 16 uncoalesced 16-byte loads per thread through an L1 squeezed to ~28 KB by the 220 KB of shared memory: 1.3-1.5x slower.)
+        if (leader && has_res && t_first < total) {
+            const SpTile c0 = sp_decode<HALO, BN>(p, t_first);
+            mbar_expect_tx(&res_full[g], Cfg::STG);
+            tma_load_4d(stg, &p.mapR[c0.img], &res_full[g], c0.n0 + (WIDE ? 64 * (int)g : 0), c0.ox0, c0.oy0, 0);
+        }
+        for (int t = t_first; t < total; t += t_step, ++k) {
             const SpTile c = sp_decode<HALO, BN>(p, t);
             const uint32_t buf = WIDE ? (k & 1) : g;                        // accumulator pair of this tile
             const uint32_t fph = WIDE ? ((k >> 1) & 1) : (k & 1);           // phase of its tmem_full barrier
@@ -242,28 +253,14 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const int py = m / c.tw, px = m - py * c.tw;
             const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
             const long long pix = p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px);
-            // residual: this thread's pixel row (64 channels, hi and lo plane) straight from global memory into registers, issued
-            // BEFORE the wait for the accumulators so that its latency hides behind the tile's MMAs.  (The first version brought
-            // the residual tile in by TMA from the producer warp, which had to wait for the staging buffer of tile i-2: that
-            // wait stalled the operand loads of tile i behind the epilogue of tile i-2 - the c3 + residual layers ran at 2-3x
-            // their floors.)
-            uint4 rh[8], rl[8];
-            if (has_res) {
-                const __half* rp = p.res + pix * p.Cout + nbase;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool ok = pvalid && (nbase + 8 * j + 8 <= p.Cout);
-                    rh[j] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + 8 * j)) : make_uint4(0, 0, 0, 0);
-                    rl[j] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + p.res_plane + 8 * j)) : make_uint4(0, 0, 0, 0);
-                }
-            }
             // the leader comes here only after the previous store has read the staging buffer
             if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             mbar_wait(&tmem_full[buf], fph);
             tc_fence_after();
+            if (has_res) mbar_wait(&res_full[g], k & 1);
             const uint32_t trow = tmem_base + buf * (2 * BN) + (WIDE ? 64 * g : 0) + ((uint32_t)(q * 32) << 16);
             float* yrow = p.out32 ? p.y32 + pix * p.Cout : nullptr;
-#pragma unroll
+#pragma unroll 1
             for (int cb = 0; cb < 2; ++cb) {
                 uint32_t v[32], x[32];
                 tmem_ld32x2(trow + cb * 32, v, trow + BN + cb * 32, x);
@@ -295,8 +292,9 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                     uint4* hp = reinterpret_cast<uint4*>(stg + m * 128 + ((chunk ^ (m & 7)) << 4));
                     uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(hp) + TC_A_BYTES);
                     if (has_res) {
-                        const __half2* h = reinterpret_cast<const __half2*>(&rh[chunk]);
-                        const __half2* l = reinterpret_cast<const __half2*>(&rl[chunk]);
+                        const uint4 rh = *hp, rl = *lp;
+                        const __half2* h = reinterpret_cast<const __half2*>(&rh);
+                        const __half2* l = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const float2 fh = __half22float2(h[e]), fl = __half22float2(l[e]);
@@ -325,6 +323,11 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 if (leader) {
                     if (nbase < p.Cout) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
                     tma_store_commit_and_wait_read();
+                    if (has_res && t + t_step < total) {                    // the group's next residual tile, into the buffer just read out
+                        const SpTile cn = sp_decode<HALO, BN>(p, t + t_step);
+                        mbar_expect_tx(&res_full[g], Cfg::STG);
+                        tma_load_4d(stg, &p.mapR[cn.img], &res_full[g], cn.n0 + (WIDE ? 64 * (int)g : 0), cn.ox0, cn.oy0, 0);
+                    }
                 }
             }
         }
@@ -578,6 +581,7 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     memset(&p, 0, sizeof(p));
     const bool halo = (cp.R == 3 && cp.stride == 1 && cp.pad == 1);
     const char* xb = reinterpret_cast<const char*>(cp.x);
+    const char* rb = reinterpret_cast<const char*>(cp.residual);
     char* yb = reinterpret_cast<char*>(cp.y);
     const unsigned long long in_plane = (unsigned long long)set.in_pix[set.n] * cp.Cin * 2ull;
     const unsigned long long out_plane = (unsigned long long)set.out_pix[set.n] * cp.Cout * 2ull;
@@ -597,6 +601,9 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
         if (!out32) {
             rc = get_map4(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
                           out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
+            if (!rc && cp.residual)
+                rc = get_map4(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
+                              out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
             if (rc) return rc;
         }
     }
@@ -616,8 +623,7 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     p.out32 = out32 ? 1 : 0;
     p.bias = cp.bias;
     p.y32 = out32 ? cp.y : nullptr;
-    p.res = reinterpret_cast<const __half*>(cp.residual);
-    p.res_plane = (long long)set.out_pix[set.n] * cp.Cout;
+
     p.tiles_m = tiles;
     p.tiles_n = (cp.Cout + BN - 1) / BN;
     const long long total = (long long)p.tiles_m * p.tiles_n;
