@@ -55,27 +55,33 @@ struct alignas(64) SplitParams {
 // BN = 64: the two epilogue groups take alternate tiles.  BN = 128 (tap streaming only): each group takes one 64-channel half of
 // EVERY tile - twice the work per operand byte fetched from L2 (the tap-streaming layers are L2-bandwidth bound at BN = 64:
 // 48 KB per K block for 12 MMAs) and N = 128 MMAs, which the shared-memory read port can feed at the full tensor rate.
-template <bool HALO, int BN_>
+// RES2 (tap streaming, BN = 64, layers with a residual): TWO staging buffers per epilogue group, so that the residual tile of
+// the group's next tile is in flight while the current one is combined and stored; paid for with a 2-deep operand ring (these
+// layers have K <= 256: one to four K blocks per tile).
+template <bool HALO, int BN_, bool RES2_ = false>
 struct SplitCfg {
     static constexpr int BN = BN_;
+    static constexpr bool RES2 = RES2_;
     static constexpr int B_PLANE = BN * 128;                                  // 8 / 16 KB
     static constexpr int B_TILE = 2 * B_PLANE;                                // hi + lo planes of one weight tile
     static constexpr int A_LO = HALO ? SP_HALO_PLANE : TC_A_BYTES;            // offset of the lo plane inside an A slot
     static constexpr int A_TX = 2 * A_LO;
     static constexpr int A_SLOT = HALO ? 46 * 1024 : 2 * TC_A_BYTES;          // 1024-byte aligned slots
-    static constexpr int NA = HALO ? 2 : (BN == 128 ? 2 : 3);
-    static constexpr int NB = HALO ? 4 : 3;
+    static constexpr int NA = HALO ? 2 : ((BN == 128 || RES2) ? 2 : 3);
+    static constexpr int NB = HALO ? 4 : (RES2 ? 2 : 3);
+    static constexpr int NSB = RES2 ? 2 : 1;                                  // staging buffers per epilogue group
     static constexpr int TB = HALO ? 9 : 1;                                   // B tiles consumed per A slot
     static constexpr int STG = 2 * TC_A_BYTES;                                // per epilogue group: [hi box | lo box] of 64 channels
     static constexpr int OFF_B = NA * A_SLOT;
     static constexpr int OFF_STG = OFF_B + NB * B_TILE;
-    static constexpr int DATA_BYTES = OFF_STG + 2 * STG;
+    static constexpr int DATA_BYTES = OFF_STG + 2 * NSB * STG;
     static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
     static constexpr int TMEM_COLS = 4 * BN;                                  // 2 buffers x (main | cross)
     static_assert(!(HALO && BN != 64), "halo reuse runs with 64-channel tiles");
+    static_assert(!RES2 || (!HALO && BN == 64), "double-buffered staging: tap streaming, 64-channel tiles");
 };
 static_assert(SplitCfg<true, 64>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false, 64>::SMEM_BYTES <= 227 * 1024 &&
-              SplitCfg<false, 128>::SMEM_BYTES <= 227 * 1024, "shared memory");
+              SplitCfg<false, 128>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false, 64, true>::SMEM_BYTES <= 227 * 1024, "shared memory");
 static_assert(SplitCfg<true, 64>::A_TX <= SplitCfg<true, 64>::A_SLOT, "halo slot");
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -128,10 +134,11 @@ __device__ __forceinline__ void sp_split2(float a, float b, __half2& hi, __half2
     lo = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
 }
 
-template <bool HALO, int BN_>
+template <bool HALO, int BN_, bool RES2 = false>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 tc_split_kernel(const __grid_constant__ SplitParams p) {
-    using Cfg = SplitCfg<HALO, BN_>;
+    using Cfg = SplitCfg<HALO, BN_, RES2>;
+    constexpr int NSB = Cfg::NSB;
     constexpr int BN = Cfg::BN, NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB, BK = TC_BK_F16;
     constexpr bool WIDE = BN == 128;            // both epilogue groups work on every tile (one 64-channel half each)
     extern __shared__ uint8_t smem_raw[];
@@ -145,8 +152,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     uint64_t* emptyB = fullB + NB;
     uint64_t* tmem_full = emptyB + NB;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2] 128 arrivals
-    uint64_t* res_full = tmem_empty + 2;        // [2] the group's residual tile has landed in its staging buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* res_full = tmem_empty + 2;        // [2 groups][2 buffers] the residual tile has landed in that staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.tiles_m * p.tiles_n;
     const int kc = p.Cin / BK;
@@ -156,7 +163,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); mbar_init(&res_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); }
+        for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.mapA[0]); tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
@@ -232,7 +240,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         const int q = warp & 3;                                             // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
         const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
-        uint8_t* stg = sStg + g * Cfg::STG;
+        uint8_t* stg_base = sStg + g * NSB * Cfg::STG;
         uint32_t k = 0;                                                     // this group's tile counter
         const int t_first = blockIdx.x + (WIDE ? 0 : (int)g * (int)gridDim.x), t_step = (WIDE ? 1 : 2) * (int)gridDim.x;
         // Residual tiles come in by TMA into the group's OWN staging buffer, issued by the group's leader: the first one here,
@@ -240,10 +248,12 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         // issued them and had to wait for the staging buffer of tile i-2 - that wait stalled the operand loads of tile i behind
         // the epilogue of tile i-2; second version: each thread loaded its residual row from global memory into registers -
         // 16 uncoalesced 16-byte loads per thread through an L1 squeezed to ~28 KB by the 220 KB of shared memory: 1.3-1.5x slower.)
+        // RES2: two buffers per group - the residual of tile k + 1 is issued while tile k is being combined, a whole group
+        // cycle ahead of its use, and the store of tile k needs no wait before the group moves on.
         if (leader && has_res && t_first < total) {
             const SpTile c0 = sp_decode<HALO, BN>(p, t_first);
-            mbar_expect_tx(&res_full[g], Cfg::STG);
-            tma_load_4d(stg, &p.mapR[c0.img], &res_full[g], c0.n0 + (WIDE ? 64 * (int)g : 0), c0.ox0, c0.oy0, 0);
+            mbar_expect_tx(&res_full[2 * g], Cfg::STG);
+            tma_load_4d(stg_base, &p.mapR[c0.img], &res_full[2 * g], c0.n0 + (WIDE ? 64 * (int)g : 0), c0.ox0, c0.oy0, 0);
         }
         for (int t = t_first; t < total; t += t_step, ++k) {
             const SpTile c = sp_decode<HALO, BN>(p, t);
@@ -255,9 +265,19 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const long long pix = p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px);
             // the leader comes here only after the previous store has read the staging buffer
             if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            const uint32_t sb = RES2 ? (k & 1) : 0;                         // staging buffer of this tile
+            uint8_t* stg = stg_base + sb * Cfg::STG;
             mbar_wait(&tmem_full[buf], fph);
             tc_fence_after();
-            if (has_res) mbar_wait(&res_full[g], k & 1);
+            if (has_res) mbar_wait(&res_full[2 * g + sb], RES2 ? ((k >> 1) & 1) : (k & 1));
+            if (RES2 && leader) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the other buffer's store (tile k - 1) has read it out
+                if (has_res && t + t_step < total) {
+                    const SpTile cn = sp_decode<HALO, BN>(p, t + t_step);
+                    mbar_expect_tx(&res_full[2 * g + (sb ^ 1)], Cfg::STG);
+                    tma_load_4d(stg_base + (sb ^ 1) * Cfg::STG, &p.mapR[cn.img], &res_full[2 * g + (sb ^ 1)], cn.n0, cn.ox0, cn.oy0, 0);
+                }
+            }
             const uint32_t trow = tmem_base + buf * (2 * BN) + (WIDE ? 64 * g : 0) + ((uint32_t)(q * 32) << 16);
             float* yrow = p.out32 ? p.y32 + pix * p.Cout : nullptr;
 #pragma unroll 1
@@ -322,15 +342,20 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (leader) {
                     if (nbase < p.Cout) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
-                    tma_store_commit_and_wait_read();
-                    if (has_res && t + t_step < total) {                    // the group's next residual tile, into the buffer just read out
-                        const SpTile cn = sp_decode<HALO, BN>(p, t + t_step);
-                        mbar_expect_tx(&res_full[g], Cfg::STG);
-                        tma_load_4d(stg, &p.mapR[cn.img], &res_full[g], cn.n0 + (WIDE ? 64 * (int)g : 0), cn.ox0, cn.oy0, 0);
+                    if (RES2) {
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // read out while the group works on its next tile
+                    } else {
+                        tma_store_commit_and_wait_read();
+                        if (has_res && t + t_step < total) {                // the group's next residual tile, into the buffer just read out
+                            const SpTile cn = sp_decode<HALO, BN>(p, t + t_step);
+                            mbar_expect_tx(&res_full[2 * g], Cfg::STG);
+                            tma_load_4d(stg, &p.mapR[cn.img], &res_full[2 * g], cn.n0 + (WIDE ? 64 * (int)g : 0), cn.ox0, cn.oy0, 0);
+                        }
                     }
                 }
             }
         }
+        if (RES2 && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -629,17 +654,21 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     const long long total = (long long)p.tiles_m * p.tiles_n;
     RF_REQUIRE(total < (1ll << 30), "rf_conv2d_nhwc: too many tiles");
     const int grid = total < num_sms() ? (int)total : num_sms();
-    static bool attr[64][3] = {{false}};
+    static bool attr[64][4] = {{false}};
     const int dev = current_device();
-    const int which = halo ? 1 : (BN == 128 ? 2 : 0);
+    static int res2_env = -1;
+    if (res2_env < 0) { const char* e = getenv("RF_SPLIT_RES2"); res2_env = e ? atoi(e) : 1; }
+    const int which = halo ? 1 : (BN == 128 ? 2 : ((cp.residual != nullptr && res2_env) ? 3 : 0));
     if (!attr[dev][which]) {
         if (which == 1) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true, 64>::SMEM_BYTES));
         else if (which == 2) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 128>::SMEM_BYTES));
+        else if (which == 3) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 64, true>::SMEM_BYTES));
         else RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 64>::SMEM_BYTES));
         attr[dev][which] = true;
     }
     if (which == 1) tc_split_kernel<true, 64><<<grid, SP_THREADS, SplitCfg<true, 64>::SMEM_BYTES, st>>>(p);
     else if (which == 2) tc_split_kernel<false, 128><<<grid, SP_THREADS, SplitCfg<false, 128>::SMEM_BYTES, st>>>(p);
+    else if (which == 3) tc_split_kernel<false, 64, true><<<grid, SP_THREADS, SplitCfg<false, 64, true>::SMEM_BYTES, st>>>(p);
     else tc_split_kernel<false, 64><<<grid, SP_THREADS, SplitCfg<false, 64>::SMEM_BYTES, st>>>(p);
     RF_LAUNCHED();
     return 0;
