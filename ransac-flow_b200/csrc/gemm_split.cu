@@ -658,7 +658,10 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     const int dev = current_device();
     static int res2_env = -1;
     if (res2_env < 0) { const char* e = getenv("RF_SPLIT_RES2"); res2_env = e ? atoi(e) : 1; }
-    const int which = halo ? 1 : (BN == 128 ? 2 : ((cp.residual != nullptr && res2_env) ? 3 : 0));
+    // double-buffered staging pays for the HBM-bound residual layers with one or two K blocks per tile (ResNet layer 1 / 2
+    // c3 + residual: 147 -> 121 us, 81 -> 64 us); with four K blocks (layer 3) the 2-deep operand ring costs more than the
+    // residual prefetch gains (45 -> 52 us): measured, profiles/README.md
+    const int which = halo ? 1 : (BN == 128 ? 2 : ((cp.residual != nullptr && cp.K <= 128 && res2_env) ? 3 : 0));
     if (!attr[dev][which]) {
         if (which == 1) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true, 64>::SMEM_BYTES));
         else if (which == 2) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 128>::SMEM_BYTES));
