@@ -409,12 +409,12 @@ def run_b200(args, rank, world, local):
 
     stages = roofline = None
     if cfg in (2, 3):
-        # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, mean of 5 pairs) ----
+        # ---- where a pair's GPU time goes: the device path stage by stage (eager launches, CUDA events, median of 7 pairs) ----
         def stage_breakdown():
             names = ["pyramid+preproc+resnet50_conv4(8 imgs)+l2norm", "corr+mutual_nn", "fine_features(target)", "build_matches+ransac",
                      "warp_grid+PredFlowMask"]
-            acc = np.zeros(len(names))
-            reps, skip = 5, 3                     # the first eager passes of these model objects build TMA maps / layer programs
+            acc = []
+            reps, skip = 7, 3                     # the first eager passes of these model objects build TMA maps / layer programs
             for rep in range(reps + skip):
                 s_, t_ = resident[rep % len(resident)]
                 evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
@@ -445,9 +445,10 @@ def run_b200(args, rank, world, local):
                 torch.cuda.synchronize()
                 if rep < skip:
                     continue
-                acc += np.array([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
-                                 evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
-            return {n: round(float(v / reps), 4) for n, v in zip(names, acc)}
+                acc.append([evs[0].elapsed_time(marks["pre"]), marks["pre"].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
+                            evs[3].elapsed_time(evs[4]), evs[4].elapsed_time(evs[5])])
+            med = np.median(np.array(acc), axis=0)    # median: an eager pass now and then pays a cudaMalloc / host hiccup
+            return {n: round(float(v), 4) for n, v in zip(names, med)}
         stages = stage_breakdown()
 
         # ---- roofline of the kernel BASELINE names (corr + mutual-NN), timed alone with CUDA events ----

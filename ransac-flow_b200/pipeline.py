@@ -58,8 +58,20 @@ def PredFlowMask_device(IsTensor, featt, flowCoarse, size, network, with_match21
             corr12 = ops.corr_neigh(ft, fs, k, ld, tc)
             corr21 = ops.corr_neigh(fs, ft, k, ld, tc)
             both = Ragged(torch.cat([corr12.data, corr21.data], dim=0), corr12.hw + corr21.hw)
-        flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
-        mboth = network["netMatch"].forward_ragged(both)                    # (2,1,h8,w8): match12, match21 in one batch
+        # the two heads are independent: the flow head (one image: 152 tiles in its widest layer, i.e. one full wave + 4 tiles on 148
+        # SMs) runs on the side stream and fills the tails of the matchability head's kernels (two images) and vice versa
+        main, side = torch.cuda.current_stream(), _side_stream()
+        if _HEADS_TWO_STREAMS and side != main:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
+            corr12.data.record_stream(side)
+            mboth = network["netMatch"].forward_ragged(both)                # (2,1,h8,w8): match12, match21 in one batch
+            main.wait_stream(side)
+            flowDown8.record_stream(main)
+        else:
+            flowDown8 = network["netFlowCoarse"].forward_ragged(corr12)
+            mboth = network["netMatch"].forward_ragged(both)                # (2,1,h8,w8): match12, match21 in one batch
         flow12, match, _ = ops.compose_fine(flowDown8, mboth[0:1], mboth[1:2] if with_match21 else None, flowCoarse,
                                             clamp=True, align_corners=align_corners)
         return flow12, match, flowDown8, mboth
@@ -80,6 +92,7 @@ def PredFlowMask(IsTensor, featt, flowCoarse, grid, network, with_match21=False,
 
 _pinned = {}
 _side = {}
+_HEADS_TWO_STREAMS = os.environ.get("RF_HEADS_TWO_STREAMS", "1") != "0"
 
 
 def _side_stream():

@@ -101,10 +101,11 @@ groups = {}
 for i, (name, P, fl, by) in enumerate(layers):
     th, tt = by / HBM * 1e6, 3 * fl / TF * 1e6
     kname, us = times[i] if i < len(times) else ("", float("nan"))
-    variant = "halo" if "<(bool)1" in kname or "ILb1" in kname else ("tap BN128" if "128" in kname else ("tap BN64" if kname else ""))
+    targs = kname[kname.find("<") + 1:kname.find(">")].replace("(bool)", "").replace("(int)", "").replace(" ", "").split(",") if "<" in kname else []
+    variant = "" if len(targs) < 2 else ("halo" if targs[0] in ("1", "true") else "tap BN%s%s" % (targs[1], " RES2" if len(targs) > 2 and targs[2] in ("1", "true") else ""))
     fl_us = max(th, tt)
     print("%-46s %8d %7.2f %8.1f %8.1f %9.1f %9.1f %6.2f  %s" % (name, P, fl / 1e9, by / 1e6, th, tt, us, us / fl_us if us == us else float("nan"), variant))
-    g = groups.setdefault(name.split(" ")[0] + (" " + name.split(" ")[1] if name.startswith(("flow", "match")) else ""), [0.0, 0.0, 0.0, 0.0])
+    g = groups.setdefault(" ".join(name.split(" ")[:2]) if name.startswith(("flow", "match", "FE(warped")) else name.split(" ")[0], [0.0, 0.0, 0.0, 0.0])
     g[0] += fl
     g[1] += by
     g[2] += fl_us
