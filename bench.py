@@ -403,6 +403,11 @@ def run_b200(args, rank, world, local):
     ms_e2e, _, out, allr, gather_ms = timed(True, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
     assert allr.shape[0] == args.steps * P * world
+    if os.environ.get("RF_BENCH_REPEAT_RESIDENT") and rank == 0 and world == 1:      # experiment: order dependence of the two timed regions
+        ms2 = timed(False, args.steps, 2)[0]
+        ms3 = timed(True, args.steps, 2)[0]
+        print("repeat: resident %.1f pairs/s (first %.1f), host %.1f pairs/s (first %.1f)" % (
+            P * args.steps / (ms2 * 1e-3), P * args.steps / (ms_dev * 1e-3), P * args.steps / (ms3 * 1e-3), P * args.steps / (ms_e2e * 1e-3)), file=sys.stderr)
     if rank != 0:
         return                                       # the per-kernel sections below are rank 0's (no collective inside)
     nH_mean = float(np.mean([len(o["H"]) for o in [out]]))

@@ -364,13 +364,13 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
 
 // ------------------------------------------------------------------------------------------------------------
 // ResNet-50 stem, fused, split operands: conv 7x7 / stride 2 / pad 3 on the 3-channel fp32 image + folded BN + ReLU ->
-// split NHWC, without an im2col matrix in HBM.  PERSISTENT and warp specialised, one CTA per SM, 288 threads:
-//   warps 0-3 : builders.  Stage the 37 x 21 x 3 input window of the tile in shared memory (the NEXT tile's window is
+// split NHWC, without an im2col matrix in HBM.  PERSISTENT and warp specialised, one CTA per SM, 416 threads:
+//   warps 0-7 : builders (two threads per output pixel, half a patch each).  Stage the 37 x 21 x 3 input window of the tile in shared memory (the NEXT tile's window is
 //               already in flight in registers), then build the tile's 147-long (r, s, c) patches as hi / lo planes
 //               straight in the 128-byte-swizzled K-major layout (3 + 3 K blocks of 64), fence.proxy.async, arrive;
-//   warp 4    : loads the split weights ONCE per CTA (48 KB), then per tile nine MMA groups into accumulator pair
+//   warp 8    : loads the split weights ONCE per CTA (48 KB), then per tile nine MMA groups into accumulator pair
 //               (tile & 1); one commit hands the patch buffer back to the builders, one publishes the accumulators;
-//   warps 5-8 : epilogue.  TMEM -> + bias, ReLU, split -> [hi box | lo box] staging -> one TMA store of both planes,
+//   warps 9-12: epilogue.  TMEM -> + bias, ReLU, split -> [hi box | lo box] staging -> one TMA store of both planes,
 //               overlapped with the builders' next tile.
 // History (config 2, 7132 tiles): one tile per CTA, everything serial, 155 KB: 358 us; persistent with a single reused K-block
 // slot and two CTAs per SM: 408 us (three build -> MMA -> commit round trips per tile); this version: see profiles/.
@@ -386,8 +386,9 @@ constexpr int SS_OFF_STG = SS_OFF_B + SS_KB * SS_B_TILE;                  // 144
 constexpr int SS_OFF_IN = SS_OFF_STG + 2 * TC_A_BYTES;                    // 176 KB
 constexpr int SS_OFF_BAR = SS_OFF_IN + SS_IN_H * SS_IN_LD * 4;
 constexpr int SS_SMEM = SS_OFF_BAR + 128 + 1024;
-constexpr int SS_THREADS = 288;
-constexpr int SS_NLD = (SS_IN_H * SS_IN_W + 127) / 128;                   // window floats per builder thread
+constexpr int SS_BUILD = 256;                                             // builder threads: two per output pixel (half a patch each)
+constexpr int SS_THREADS = SS_BUILD + 32 + 128;                           // + MMA warp + 4 epilogue warps
+constexpr int SS_NLD = (SS_IN_H * SS_IN_W + SS_BUILD - 1) / SS_BUILD;      // window floats per builder thread
 static_assert(SS_SMEM <= 227 * 1024, "stem shared memory");
 
 struct alignas(64) StemSplitParams {
@@ -415,17 +416,42 @@ __device__ __forceinline__ StemTile stem_decode(const StemSplitParams& p, int t)
     c.oy0 = tyi * SS_TH;
     return c;
 }
-// the (zero padded) 21 x 111 input window of a tile, 128 threads x SS_NLD floats
+// the (zero padded) 21 x 111 input window of a tile, SS_BUILD threads x SS_NLD floats
 __device__ __forceinline__ void stem_load_window(const StemSplitParams& p, const StemTile& c, int m, float (&stage)[SS_NLD]) {
     const int H = p.H[c.img], WC = p.W[c.img] * SS_C;
     const float* src = p.x + p.in_pix[c.img] * SS_C;
     const int iy0 = c.oy0 * 2 - 3, col0 = (c.ox0 * 2 - 3) * SS_C;
 #pragma unroll
     for (int i = 0; i < SS_NLD; ++i) {
-        const int idx = m + i * 128;
+        const int idx = m + i * SS_BUILD;
         const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
         const int iy = iy0 + r, col = col0 + j;
         stage[i] = (idx < SS_IN_H * SS_IN_W && iy >= 0 && iy < H && col >= 0 && col < WC) ? __ldg(src + (long long)iy * WC + col) : 0.f;
+    }
+}
+
+// half a patch: the 16-byte chunks 4 * HALF .. 4 * HALF + 3 of each of the three K blocks of pixel m, hi and lo planes
+template <int HALF>
+__device__ __forceinline__ void stem_build_half(const float* __restrict__ base, uint8_t* sA, int m) {
+#pragma unroll
+    for (int kb = 0; kb < SS_KB; ++kb) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c8 = HALF * 4 + cc;
+            uint4 oh, ol;
+            __half2* ph = reinterpret_cast<__half2*>(&oh);
+            __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
+                const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
+                const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
+                sp_split2(a, b, ph[e], pl[e]);
+            }
+            uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = oh;
+            *reinterpret_cast<uint4*>(dst + SS_OFF_ALO) = ol;
+        }
     }
 }
 
@@ -447,12 +473,13 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
 
     if (threadIdx.x == 0) {
         mbar_init(bar_b, 1);
-        mbar_init(bar_a, 128);
+        mbar_init(bar_a, SS_BUILD);
         mbar_init(bar_free, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
         fence_barrier_init();
     }
-    if (warp == 4) {
+    constexpr int WMMA = SS_BUILD / 32;                         // the MMA warp sits right behind the builders
+    if (warp == WMMA) {
         if (lane == 0) { tma_prefetch_desc(&p.mapB); tma_prefetch_desc(&p.mapY[0]); }
         tmem_alloc(tmem_slot, 256);
     }
@@ -461,53 +488,38 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < WMMA) {
         // =============================== builders ===============================
-        const int m = threadIdx.x;                              // 0..127: output pixel inside the tile = A row
+        const int bt = threadIdx.x;                             // 0..255
+        const int m = bt & 127, half = bt >> 7;                 // output pixel inside the tile = A row; which half of each K block
         const int py = m >> 4, px = m & 15;
         const float* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
         float stage[SS_NLD];
         StemTile c = stem_decode(p, (int)blockIdx.x < p.total ? (int)blockIdx.x : 0);
-        if ((int)blockIdx.x < p.total) stem_load_window(p, c, m, stage);
+        if ((int)blockIdx.x < p.total) stem_load_window(p, c, bt, stage);
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // everybody has finished reading the previous window
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // everybody has finished reading the previous window
 #pragma unroll
             for (int i = 0; i < SS_NLD; ++i) {
-                const int idx = m + i * 128;
+                const int idx = bt + i * SS_BUILD;
                 const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
                 if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (t + (int)gridDim.x < p.total) {                 // next tile's window: in flight while this tile is built
                 c = stem_decode(p, t + gridDim.x);
-                stem_load_window(p, c, m, stage);
+                stem_load_window(p, c, bt, stage);
             }
             if (ti > 0) mbar_wait(bar_free, (ti - 1) & 1);      // the previous tile's MMAs have read the patch buffer
             // ---- this pixel's patch, (r, s, c) order: element k = r*21 + s*3 + c sits at sIn[2*py + r][6*px + (k % 21)] ----
-#pragma unroll
-            for (int kb = 0; kb < SS_KB; ++kb) {
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    uint4 oh, ol;
-                    __half2* ph = reinterpret_cast<__half2*>(&oh);
-                    __half2* pl = reinterpret_cast<__half2*>(&ol);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
-                        const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
-                        const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
-                        sp_split2(a, b, ph[e], pl[e]);
-                    }
-                    uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = oh;
-                    *reinterpret_cast<uint4*>(dst + SS_OFF_ALO) = ol;
-                }
-            }
+            // (thread `half` of the pixel builds the 16-byte chunks 4 * half .. 4 * half + 3 of each K block; warp-uniform branch, so
+            // that every (k / 21, k % 21) stays a compile-time constant)
+            if (half == 0) stem_build_half<0>(base, sA, m); else stem_build_half<1>(base, sA, m);
             fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(bar_a);
         }
-    } else if (warp == 4) {
+    } else if (warp == WMMA) {
         // =============================== weights once, then the MMA issuer ===============================
         if (lane == 0) {
             mbar_expect_tx(bar_b, SS_KB * SS_B_TILE);
@@ -536,7 +548,7 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
         // =============================== epilogue (warps 5..8) ===============================
         const int q = warp & 3;                                 // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const bool leader = (warp == 5 && lane == 0);
+        const bool leader = (warp == WMMA + 1 && lane == 0);
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1;
@@ -582,7 +594,7 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (warp == WMMA) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace rf
