@@ -175,6 +175,13 @@ class GraphedAligner:
         self.max_graphs = max_graphs    # datasets with many image sizes (HPatches, MegaDepth, YFCC): LRU-bounded graph memory
         self.replayed_kernels = 0       # library kernels executed through graph replays (they bypass rf_launch_count)
 
+    def _device(self, s_in, t_in):
+        """The device work of one pair, queued on the current stream: (packed results, flow12 | None, (H, W), flowDown8 shape)."""
+        return _single_device(self.coarse, self.net, s_in, t_in, self.m21)
+
+    def _unpack(self, host, flow12, size, f8shape):
+        return _unpack_single(host, flow12, size, f8shape)
+
     def _programs(self):
         """Every LayerProgram whose cached activation buffers a captured graph of this aligner points into."""
         progs = [p for p in (self.coarse.net.program, self.coarse.net._program_f16, self.coarse.net._program_split) if p is not None]
@@ -206,13 +213,13 @@ class GraphedAligner:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(self.warmup):                       # eager runs: func attributes, TMA maps, caches, buffers
-                _single_device(self.coarse, self.net, s_in, t_in, self.m21)
+                self._device(s_in, t_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(g):
-            packed, flow12, size, f8shape = _single_device(self.coarse, self.net, s_in, t_in, self.m21)
+            packed, flow12, size, f8shape = self._device(s_in, t_in)
         # the compiled program entries (activation buffers) this graph's kernels point into: every entry whose image-set
         # signature the warm-up / capture of THIS input size touched
         touched = {(id(p), k) for p in self._programs() for k in p._compiled if k in p.__dict__.get("_touched", ())}
@@ -260,11 +267,93 @@ class GraphedAligner:
         buffer, overwritten by the next replay with these input sizes)."""
         c, done = ticket
         done.synchronize()
-        return _unpack_single(c["host"].numpy().copy(), c["flow12"].clone() if copy else c["flow12"], c["size"], c["f8shape"])
+        f12 = c["flow12"]
+        return self._unpack(c["host"].numpy().copy(), (f12.clone() if copy else f12) if f12 is not None else None, c["size"], c["f8shape"])
 
     def __call__(self, Is, It, copy=True):
         """Is, It: uint8 (H, W, 3) torch tensors (CUDA, or pinned host for an asynchronous H2D) or numpy arrays."""
         return self.fetch(self.enqueue(Is, It), copy)
+
+
+def _multi_device(coarseModel, network, Is, It, maxCoarse, maskRegionTh, with_match21, samples=None):
+    """The multi-hypothesis loop of evaluation/evalCorr/evaluation.py:211-243 with NO host control at all: every one of the
+    ``maxCoarse + 1`` iterations is queued unconditionally; what the reference decides on the host - stop at the first failed
+    RANSAC (:215-216), stop at the first hypothesis whose new-region matchability mean is below ``maskRegionTh`` (:226), update
+    the mask (:236) - becomes a device-side ``alive`` flag that gates the mask update, and the host drops the hypotheses
+    after the first dead one when it unpacks.  Accepted hypotheses are computed from exactly the state the reference's loop
+    would have had; dead ones are wasted work (none when every hypothesis is accepted, the common case at maxCoarse = 10).
+    One packed result tensor: per hypothesis [alive, status, nbMatch, nbInlier, H(9), flowDown8, matchDown8] - the tensors
+    the drivers save (evaluation.py:244-260); the full-resolution maps stay on the device and are not returned."""
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    box = {}
+
+    def start_target_features():
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            box["featt"] = fine_features(network["netFeatCoarse"], coarseModel.ItTensor)
+    coarseModel.setPair(Is, It, after_preproc=start_target_features)
+    Itw, Ith = coarseModel.target_size
+    dev = coarseModel.ItTensor.device
+    Mask = torch.zeros((Ith, Itw), device=dev)
+    alive = torch.ones((), device=dev, dtype=torch.bool)
+    recs, featt, f8shape = [], None, None
+    for k in range(maxCoarse + 1):
+        fgMask = (Mask > 0.5).float()                                    # It_bg = 1 everywhere: (Mask + (1 - It_bg)) > 0.5
+        Hd, nb, mask, status, cnt = coarseModel.getCoarse_device(fgMask if k > 0 else None, None if samples is None else samples[k])
+        flowCoarse = ops.warp_grid(Hd.view(1, 3, 3), Ith, Itw)
+        if featt is None:
+            main.wait_stream(side)
+            featt = box["featt"]
+            featt.data.record_stream(main)
+        flow12, match, f8, mboth = PredFlowMask_device(coarseModel.IsTensor, featt, flowCoarse, (Ith, Itw), network, with_match21)
+        newreg = (match[0, 0] * (1 - fgMask)).mean()
+        ok = (status[0] == 0) & ((newreg > maskRegionTh) if k > 0 else torch.ones((), device=dev, dtype=torch.bool))
+        alive = alive & ok
+        matchFine = match[0, 0] if k == 0 else match[0, 0] * (1 - fgMask)
+        Mask = torch.where(alive, ((Mask + matchFine) >= 1.0).float(), Mask)
+        recs.append(torch.cat([alive.float().reshape(1), status.float(), cnt.float(), nb.float(), Hd, f8.reshape(-1), mboth.reshape(-1)]))
+        f8shape = tuple(f8.shape)
+    return torch.cat(recs), None, (Ith, Itw), f8shape
+
+
+def _unpack_multi(host, size, f8shape, nhyp):
+    host = host.reshape(nhyp, -1)
+    if host[0, 1] == 2 or any(host[i, 1] == 2 and host[:i, 0].all() for i in range(nhyp)):
+        raise TypeError("'NoneType' object is not subscriptable")          # utils/outil.py:162
+    n = 0
+    while n < nhyp and host[n, 0] > 0.5:
+        n += 1
+    if n == 0:
+        return dict(H=np.zeros((0,)), flowDown8=np.zeros((0,)), matchDown8=np.zeros((0,)), flow12=[], match=[], nbMatch=[], nbInlier=[])
+    n8 = int(np.prod(f8shape))
+    return dict(H=host[:n, 4:13].reshape(n, 3, 3).astype(np.float32),
+                flowDown8=host[:n, 13:13 + n8].reshape((n,) + tuple(f8shape[1:])),
+                matchDown8=host[:n, 13 + n8:13 + 2 * n8].reshape(n, 2, f8shape[2], f8shape[3]),
+                flow12=[], match=[], nbMatch=[int(v) for v in host[:n, 2]], nbInlier=[int(v) for v in host[:n, 3]])
+
+
+def align_pair_multi(coarseModel, network, Is, It, maxCoarse=10, maskRegionTh=0.01, with_match21=True, samples=None):
+    """``align_pair_device`` without any host round trip inside the loop (see ``_multi_device``): one pinned D2H at the end.
+    Returns H / flowDown8 / matchDown8 / nbMatch / nbInlier of the accepted hypotheses (what the drivers save)."""
+    packed, _, size, f8shape = _multi_device(coarseModel, network, Is, It, maxCoarse, maskRegionTh, with_match21, samples)
+    return _unpack_multi(_to_host(packed).copy(), size, f8shape, maxCoarse + 1)
+
+
+class GraphedMultiAligner(GraphedAligner):
+    """The whole multi-hypothesis pair (``align_pair_multi``: trunk, matching, ``maxCoarse + 1`` x (RANSAC, warp, fine flow,
+    acceptance test, mask update)) as ONE CUDA graph per input size: ~0.6 k kernels per pair at maxCoarse = 10 with no host
+    work between them.  BASELINE config 4 (evalCorr / evalYFCC semantics) is measured through it."""
+
+    def __init__(self, coarseModel, network, maxCoarse=10, maskRegionTh=0.01, with_match21=True, warmup=2, max_graphs=4):
+        super().__init__(coarseModel, network, with_match21=with_match21, warmup=warmup, max_graphs=max_graphs)
+        self.maxCoarse, self.maskRegionTh = maxCoarse, maskRegionTh
+
+    def _device(self, s_in, t_in):
+        return _multi_device(self.coarse, self.net, s_in, t_in, self.maxCoarse, self.maskRegionTh, self.m21)
+
+    def _unpack(self, host, flow12, size, f8shape):
+        return _unpack_multi(host, size, f8shape, self.maxCoarse + 1)
 
 
 class ConcurrentAligner:
@@ -275,8 +364,10 @@ class ConcurrentAligner:
     their activation buffers per module, so lanes cannot share modules).  Results are per pair and identical to what a
     single GraphedAligner returns for it."""
 
-    def __init__(self, make_models, lanes=2, with_match21=False):
-        self.lanes = [GraphedAligner(*make_models(), with_match21=with_match21) for _ in range(lanes)]
+    def __init__(self, make_models, lanes=2, with_match21=False, make_aligner=None):
+        """``make_aligner(coarseModel, network)`` (optional): the per-lane aligner, e.g. a ``GraphedMultiAligner``."""
+        mk = make_aligner or (lambda c, n: GraphedAligner(c, n, with_match21=with_match21))
+        self.lanes = [mk(*make_models()) for _ in range(lanes)]
         self.streams = [torch.cuda.Stream() for _ in range(lanes)]
 
     @property

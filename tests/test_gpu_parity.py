@@ -224,3 +224,39 @@ def test_device_path_draws_the_reference_sample_stream(rf, engine):
         assert np.array_equal(g["H"], b["H"]) and np.array_equal(g["flowDown8"], b["flowDown8"])
     g2 = ga(s, t)                                     # no reseed: the generator moved on, fresh samples
     assert g2["H"].shape == (1, 3, 3)
+
+
+@pytest.mark.parametrize("engine", ["fp32", "f16x3"], indirect=True)
+@pytest.mark.parametrize("sat", [False, True])
+def test_hostless_multi_hypothesis_loop_equals_the_steered_loops(rf, engine, sat):
+    """align_pair_multi / GraphedMultiAligner (all maxCoarse + 1 iterations queued unconditionally, acceptance and mask update
+    gated by a device-side flag, ONE CUDA graph per pair) return what the host-steered loops return - and therefore what the
+    oracle's loop returns - under the same seed, and against the oracle with injected sample tables."""
+    onet = _SAT.setdefault("net", saturating_net()) if sat else None
+    o = oracle_pair(12, 96, 128, 96, 3, maxCoarse=3, m21=True, net=onet)
+    ref = o["ref"]
+    net = product_net(rf, onet) if sat else networks(rf)
+    c = rf.CoarseAlignA(3, 1000, 0.05, "Homography", 96, 2, False, 2, True, False, resnet_state_dict=o["rsd"], verbose=False)
+    samples = o["samples"] + [o["samples"][-1]] * 4
+    out = rf.pipeline.align_pair_multi(c, net, o["Is"], o["It"], maxCoarse=3, with_match21=True, samples=samples)
+    nH = len(ref["H"])
+    assert out["H"].shape == ref["H"].shape and nH >= 2
+    np.testing.assert_allclose(out["H"], ref["H"], atol=1e-5)
+    assert np.abs(out["flowDown8"] - ref["flowDown8"]).max() < FLOW_TOL and np.abs(out["matchDown8"] - ref["matchDown8"]).max() < FLOW_TOL
+    # own sample stream: eager hostless loop == host-steered device loop == replayed graph, bit for bit
+    src, tgt, _ = synth.make_pair(12, 96, 128)
+    s, t = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+    c.device_preproc = True
+    torch.manual_seed(5)
+    a = rf.pipeline.align_pair_device(c, net, s, t, maxCoarse=3, with_match21=True)
+    torch.manual_seed(5)
+    b = rf.pipeline.align_pair_multi(c, net, s, t, maxCoarse=3, with_match21=True)
+    assert len(b["H"]) == len(a["H"]) >= 1 and np.array_equal(a["H"], b["H"])
+    assert np.array_equal(a["flowDown8"], b["flowDown8"]) and np.array_equal(a["matchDown8"], b["matchDown8"]) and a["nbMatch"] == b["nbMatch"]
+    ga = rf.pipeline.GraphedMultiAligner(c, net, maxCoarse=3, with_match21=True)
+    ga.prepare(s, t)
+    for _ in range(2):
+        torch.manual_seed(5)
+        g = ga(s, t)
+        assert np.array_equal(g["H"], b["H"]) and np.array_equal(g["flowDown8"], b["flowDown8"]) and np.array_equal(g["matchDown8"], b["matchDown8"])
+    assert ga.graphs[next(iter(ga.graphs))]["n_kernels"] > 150
