@@ -90,11 +90,11 @@ def ncu_facts(precision, v2):
     """What the committed `ncu --set full` capture of the correlation kernel says (profiles/*.json, one launch at config 2):
     DRAM bytes read + written, duration and tensor-pipe activity of the dominant launch.  {} when there is no capture."""
     try:
-        pf = {1: "r1_corr_ncu.json", 2: "r1_corr_pipe_ncu.json" if v2 else "r1_corr_f16_ncu.json"}[int(precision)]
+        pf = {1: "r1_corr_ncu.json", 2: "r2_ncu_full_kernels.json" if v2 else "r1_corr_f16_ncu.json"}[int(precision)]
         prof = json.load(open(os.path.join(ROOT, "profiles", pf)))
         l = [l for l in prof["launches"] if "tc_kernel" in l["kernel"] or "tc_corr_pipe" in l["kernel"]][0]
         dur = l["gpu__time_duration.sum"]
-        us = float(dur["value"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(dur["unit"], 1.0)
+        us = float(dur["value"]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}.get(dur["unit"], 1.0)
         return {"file": "profiles/" + pf, "traffic": l["dram_traffic_bytes"], "kernel_us": us,
                 "tensor_pct": float(l["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"])}
     except Exception:  # noqa: BLE001
@@ -527,6 +527,17 @@ def run_b200(args, rank, world, local):
             except Exception as e:  # noqa: BLE001
                 parity = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    if rank == 0 and roofline is not None:
+        # the whole pair against the chip: 655 GFLOP of convolutions + correlation per pair, x3 MMAs on the split
+        # engine; ~8.4 GB of algorithmic HBM traffic per pair at 4 B per activation element (profiles/r2_split_floor_analysis.txt)
+        pps = P * args.steps / (ms_dev * 1e-3)                      # this GPU's pairs/s
+        mma = 3.0 if args.engine == "f16x3" else 1.0
+        gb = 8.4 if args.engine in ("f16x3", "fp32", "tf32") else 4.3
+        pk = peaks()
+        roofline["whole_pair"] = {"algorithmic_gflop_per_pair": 655.0 + 32.1, "algorithmic_tflops": (655.0 + 32.1) * pps / 1e3,
+                                  "tensor_frac_algorithmic": (655.0 + 32.1) * pps / 1e3 / pk["bf16_tflops"],
+                                  "tensor_frac_executed": mma * (655.0 + 32.1) * pps / 1e3 / pk["bf16_tflops"],
+                                  "algorithmic_hbm_gb_per_pair": gb, "hbm_frac": gb * pps / pk["hbm_gbs"]}
     if rank == 0:
         hw8 = (H_img // 8) * (W_img // 8)
         d2h = int(H_img * W_img * 4 + 4 * hw8 * 4 + 9 * 4 + 64) if cfg in (2, 3) else (int(11 * (13 + 4 * hw8) * 4) if (cfg == 4 and graphed) else None)

@@ -182,7 +182,7 @@ def test_bench_roofline_record_is_complete():
     assert abs(r["algorithmic_gflop"] - 2 * 13065 * 1200 * 1024 / 1e9) < 1e-9 and abs(r["algorithmic_mb"] - 58.44) < 0.01
     assert abs(r["achieved"] - 32.108544 / 0.112) < 1e-6 and abs(r["executed_tensor_frac"] - 3 * r["frac"]) < 1e-12
     assert r["traffic"] == bench.ncu_facts(2, True)["traffic"] and 55e6 < r["traffic"] < 70e6          # ~ the algorithmic bytes
-    assert r["ncu_capture"] == "profiles/r1_corr_pipe_ncu.json" and 0.5 < r["executed_tensor_frac_kernel_ncu"] < 1.0
+    assert r["ncu_capture"] == "profiles/r2_ncu_full_kernels.json" and 0.5 < r["executed_tensor_frac_kernel_ncu"] < 1.0
     assert bench.roofline_record(0, False, 1.0, 0.04, 10, pk)["executed_tensor_frac"] is None and bench.ncu_facts(0, False) == {}
     assert abs(bench.roofline_record(1, False, 0.24, 0.04, 10, pk)["executed_tensor_frac"] - 6 * (32.108544 / 0.24) / 1703.4) < 1e-9
 
