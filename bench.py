@@ -402,6 +402,10 @@ def run_b200(args, rank, world, local):
 
     # set-up, untimed and before the W warm-up steps of the contract: a B200 needs ~1.5 s of this load before its clocks / power
     # state settle (measured: the first of two identical timed regions is 4 % slower than the second, whichever input path)
+    # (the clock sampler starts first: nvidia-smi's own start-up perturbs the GPU for about a second)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     if graphed:
         t_pre = time.perf_counter()
         i_pre = 0
@@ -409,9 +413,6 @@ def run_b200(args, rank, world, local):
             step(i_pre, False)
             i_pre += 1
         torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms_dev, launches, out, _, _ = timed(False, args.steps, args.warmup)
     ms_e2e, _, out, allr, gather_ms = timed(True, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
