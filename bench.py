@@ -54,14 +54,38 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line).  Sampled in-process through
+    NVML - the library nvidia-smi itself reads - every 100 ms: spawning `nvidia-smi -lms 100` next to the bench perturbed the
+    first timed region (every other 32-pair step took 143 instead of 123 ms while nvidia-smi was starting up on the 8-GPU
+    box); the subprocess form is kept as the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop_flag, self.thread, self.max_mhz = None, None, False, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                                  # CUDA_VISIBLE_DEVICES may renumber the GPUs: resolve through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -69,21 +93,40 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append([mhz] + [bool(r & b) for b in bits])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            reasons = [nm for j, nm in enumerate(self.NAMES) if any(r[1 + j] for r in self.rows)]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML in-process, 100 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower().startswith("active") for r in self.rows)]
+        reasons = [n for j, n in enumerate(self.NAMES) if any(len(r) >= 7 and r[3 + j].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def ncu_facts(precision, v2):
@@ -380,8 +423,10 @@ def run_b200(args, rank, world, local):
         l0 = rf._lib.launch_count() + replayed()
         e0.record()
         recs = []
+        tstamps = [time.perf_counter()]
         for i in range(K):
             outs = step(i, from_host)
+            tstamps.append(time.perf_counter())
             for k, out in enumerate(outs):
                 recs.append(shard.pack_record(rank + world * (i * P + k), out["H"][0] if len(out["H"]) else None,
                                               status=0 if len(out["H"]) else 1))
@@ -393,6 +438,8 @@ def run_b200(args, rank, world, local):
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
+        if os.environ.get("RF_BENCH_STEP_TIMES") and rank == 0:
+            print("step ms (host clock, from_host=%s): %s; gather %.1f" % (from_host, " ".join("%.1f" % (1e3 * (b - a)) for a, b in zip(tstamps, tstamps[1:])), gather_ms), file=sys.stderr)
         launches = rf._lib.launch_count() + replayed() - l0
         if world > 1:
             tmax = torch.tensor([ms], device=dev)
