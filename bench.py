@@ -447,8 +447,10 @@ def run_b200(args, rank, world, local):
             ms = float(tmax.item())
         return ms, launches, outs[-1], allr, gather_ms
 
-    # set-up, untimed and before the W warm-up steps of the contract: a B200 needs ~1.5 s of this load before its clocks / power
-    # state settle (measured: the first of two identical timed regions is 4 % slower than the second, whichever input path)
+    # set-up, untimed and before the W warm-up steps of the contract: under this load the B200 runs into its software power cap and
+    # needs ~5 s before the power controller settles - until then every other 32-pair step takes 139 instead of 123 ms (measured
+    # with per-step host timestamps: the first of two identical timed regions was 4-5 % slower than the second, whichever input
+    # path came first and whether the clocks were sampled by nvidia-smi or in-process).  A long-running job sees the settled state.
     # (the clock sampler starts first: nvidia-smi's own start-up perturbs the GPU for about a second)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -456,7 +458,7 @@ def run_b200(args, rank, world, local):
     if graphed:
         t_pre = time.perf_counter()
         i_pre = 0
-        while time.perf_counter() - t_pre < float(os.environ.get("RF_PREWARM_SECONDS", "2.0")):
+        while time.perf_counter() - t_pre < float(os.environ.get("RF_PREWARM_SECONDS", "6.0")):
             step(i_pre, False)
             i_pre += 1
         torch.cuda.synchronize()
