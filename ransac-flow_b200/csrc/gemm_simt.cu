@@ -514,7 +514,7 @@ using namespace rf;
 // tensor-core engines live in gemm_tc.cu
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
                       unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2,
-                      const void* const* presplit = nullptr);
+                      const void* const* presplit = nullptr, void* const* tail = nullptr);
 int rf_corr_v2_mode();
 size_t rf_corr_tc_workspace(int NA, int NB, int C);
 int rf_conv2d_tc(const ImgSet& set, const ConvParams& p, const void* w_tc, cudaStream_t st, bool f16, bool out32);
@@ -581,12 +581,17 @@ extern "C" int rf_corr_mutual_nn_presplit(const void* A_hi, const void* A_lo, in
     cudaStream_t st = as_stream(stream);
     unsigned long long* rowbest = reinterpret_cast<unsigned long long*>(ws);
     unsigned long long* colbest = rowbest + NA;
-    RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB) * sizeof(unsigned long long), st));
+    RF_CUDA(cudaMemsetAsync(ws, 0, ((size_t)NA + NB + 1) * sizeof(unsigned long long), st));       // keys + the tail's ticket counter
     if (NA == 0 || NB == 0) {
         RF_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), st));
         return 0;
     }
     const void* planes[4] = {A_hi, A_lo, B_hi, B_lo};
+    const char* e = getenv("RF_CORR_TAIL");          // 1 (default): mutual test + compaction in the correlation kernel's last CTA (2 graph nodes)
+    if ((e ? atoi(e) : 1) && NA <= 49152) {
+        void* tail[4] = {idx1_out, idx2_out, count_out, colbest + NB};
+        return rf_corr_argmax_tc(nullptr, NA, nullptr, NB, C, rowbest, colbest, nullptr, st, 2, true, planes, tail);
+    }
     int rc = rf_corr_argmax_tc(nullptr, NA, nullptr, NB, C, rowbest, colbest, nullptr, st, 2, true, planes);
     if (rc) return rc;
     return launch_mutual_compact(rowbest, colbest, NA, NB, (long long*)idx1_out, (long long*)idx2_out, count_out, st);

@@ -49,6 +49,11 @@ struct alignas(64) TcParams {
     float* y;
     unsigned long long* rowbest;          // MODE_CORR
     unsigned long long* colbest;
+    // tc_corr_pipe_kernel, optional fused tail: the last CTA to finish runs the mutual test + order-preserving compaction
+    unsigned int* done_counter;           // zeroed by the caller with the keys
+    long long* tail_idx1;                 // nullptr: no tail
+    long long* tail_idx2;
+    int* tail_count;
     int NA, NB;
 };
 
@@ -1203,8 +1208,56 @@ tc_corr_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n
         }
     }
     tc_fence_before();
+    if (p.tail_idx1 != nullptr) __threadfence();                // this thread's arg-max atomics are performed before the ticket below
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (p.tail_idx1 == nullptr) return;
+    // ---- fused tail: utils/outil.py:38-43 (mutual test, S*S > 0, nonzero() order) by the LAST CTA to finish, on the idle ring.
+    // Same algorithm as mutual_cols_compact_kernel (gemm_simt.cu), six warps instead of 32: identical index lists.
+    __shared__ unsigned int s_last;
+    __shared__ int s_cnt[TC_THREADS / 32];
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int* sRow = reinterpret_cast<int*>(smem);                   // 0 = unmatched row, j + 1 = matched with column j
+    const int tid = threadIdx.x, NA = p.NA, NB = p.NB;
+    constexpr int NW = TC_THREADS / 32;
+    for (int i = tid; i < NA; i += TC_THREADS) sRow[i] = 0;
+    __syncthreads();
+    for (int j = tid; j < NB; j += TC_THREADS) {
+        const unsigned long long ck = __ldcg(p.colbest + j);
+        if (ck == 0ull) continue;
+        const uint32_t i = key_index(ck);
+        if (i >= (uint32_t)NA) continue;
+        const unsigned long long rk = __ldcg(p.rowbest + i);
+        const float v = key_value(rk);
+        if (rk != 0ull && key_index(rk) == (uint32_t)j && (__fmul_rn(v, v) > 0.f)) sRow[i] = j + 1;
+    }
+    __syncthreads();
+    const int chunk = (((NA + 31) / 32) + NW - 1) / NW * 32;    // rows per warp, a multiple of 32
+    const int begin = warp * chunk;
+    int cnt = 0;
+    for (int b = 0; b < chunk; b += 32) {
+        const int i = begin + b + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, i < NA && sRow[i] != 0));
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int off = 0, total_m = 0;
+    for (int w = 0; w < NW; ++w) { const int v = s_cnt[w]; off += (w < warp) ? v : 0; total_m += v; }
+    for (int b = 0; b < chunk; b += 32) {
+        const int i = begin + b + lane;
+        const int f = (i < NA) ? sRow[i] : 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, f != 0);
+        if (f) {
+            const int o = off + __popc(bal & ((1u << lane) - 1u));
+            p.tail_idx1[o] = i;
+            p.tail_idx2[o] = (long long)(f - 1);
+        }
+        off += __popc(bal);
+    }
+    if (tid == 0) *p.tail_count = total_m;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1778,9 +1831,11 @@ static int launch_corr_pipe(const TcParams& p, int tiles_m, int tiles_n, cudaStr
 // v2 (precision 2 only): the caller has NOT zeroed rowbest / colbest (contiguous, NA + NB keys): the split launch does it
 // presplit (precision 2, v2 only; nullable): {A hi, A lo, B hi, B lo} fp16 planes written by the producer of the features
 // (rf_l2norm_split_nhwc): no split launch; the caller has zeroed the keys.
+// tail (nullable; v2 only): {idx1, idx2, count, done_counter} - the persistent kernel's last CTA also runs the mutual test and
+// the compaction (NA <= 49152: the row table lives in the idle operand ring); done_counter is zeroed by the caller.
 int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, int C,
                       unsigned long long* rowbest, unsigned long long* colbest, void* ws, cudaStream_t st, int precision, bool v2,
-                      const void* const* presplit) {
+                      const void* const* presplit, void* const* tail) {
     const bool f16 = precision == 2;
     RF_REQUIRE(presplit == nullptr || (v2 && f16), "rf_corr_mutual_nn: pre-split operands go with the persistent fp16-split kernel");
     RF_REQUIRE(!v2 || f16, "rf_corr_mutual_nn: the persistent correlation kernel is the fp16-split one (precision 2)");
@@ -1834,6 +1889,13 @@ int rf_corr_argmax_tc(const float* featA, int NA, const float* featB, int NB, in
     if (rc) return rc;
     p.R = 1; p.S = 1; p.pad = 0; p.stride = 1; p.Cin = C; p.Cout = NB;
     p.rowbest = rowbest; p.colbest = colbest; p.NA = NA; p.NB = NB;
+    if (tail != nullptr) {
+        RF_REQUIRE(v2 && (size_t)NA * sizeof(int) <= (size_t)CorrPipeCfg::OFF_T, "rf_corr_mutual_nn: fused compaction needs the persistent kernel and NA <= 49152");
+        p.tail_idx1 = static_cast<long long*>(tail[0]);
+        p.tail_idx2 = static_cast<long long*>(tail[1]);
+        p.tail_count = static_cast<int*>(tail[2]);
+        p.done_counter = static_cast<unsigned int*>(tail[3]);
+    }
     if (v2) return launch_corr_pipe(p, p.tiles_x[0], (NB + 127) / 128, st);
     if (f16) return launch_tc<128, MODE_CORR, false, true>(p, p.tiles_x[0], (NB + 127) / 128, st);
     if (wide) return launch_tc<256, MODE_CORR, false>(p, p.tiles_x[0], (NB + 255) / 256, st);

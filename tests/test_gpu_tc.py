@@ -208,9 +208,9 @@ def test_corr_persistent_kernel_identical_to_one_tile_kernel(rf, monkeypatch, C,
 @pytest.mark.parametrize("C,NA,NB,seed", [(1024, 13065, 1200, 0), (1024, 2107, 300, 1), (64, 129, 127, 2), (256, 1, 1, 4), (1024, 300, 1200, 5),
                                            (1024, 25747, 8250, 7)])
 def test_corr_presplit_operands_and_column_compaction_identical(rf, monkeypatch, C, NA, NB, seed):
-    """rf_corr_mutual_nn_presplit (operand planes written by rf_l2norm_split_nhwc, key memset, persistent kernel, column-driven
-    compaction) == rf_corr_mutual_nn at precision 2 (split launch + row-driven compaction): identical index lists, with
-    either compaction kernel (RF_COMPACT_COLS)."""
+    """rf_corr_mutual_nn_presplit (operand planes written by rf_l2norm_split_nhwc, key memset, persistent kernel whose last CTA
+    runs the mutual test + compaction) == rf_corr_mutual_nn at precision 2 (split launch + separate compaction): identical
+    index lists, also with the separate column-driven / row-driven compaction kernels (RF_CORR_TAIL, RF_COMPACT_COLS)."""
     g = torch.Generator().manual_seed(seed)
     raw = torch.cat([torch.randn(NA + NB, C, generator=g).abs()]).cuda()
     raw[NA:NA + min(NA, NB) // 2] = raw[torch.randperm(NA, generator=g)[:min(NA, NB) // 2].cuda()] + 0.05 * raw[NA:NA + min(NA, NB) // 2]
@@ -220,11 +220,13 @@ def test_corr_presplit_operands_and_column_compaction_identical(rf, monkeypatch,
     rows = rf.ops.from_split(planes)                              # the fp32 values those planes stand for
     ref = rf.ops.corr_mutual_nn(rows[:NA].contiguous(), rows[NA:].contiguous(), 2)
     nref = int(ref[2].item())
-    for cols in ("1", "0"):
+    for tail, cols in (("1", "1"), ("0", "1"), ("0", "0")):        # fused tail in the correlation kernel / column-driven / row-driven kernel
+        monkeypatch.setenv("RF_CORR_TAIL", tail)
         monkeypatch.setenv("RF_COMPACT_COLS", cols)
-        got = rf.ops.corr_mutual_nn_presplit(planes[0, :NA], planes[1, :NA], planes[0, NA:], planes[1, NA:])
-        n = int(got[2].item())
-        assert n == nref and torch.equal(got[0][:n], ref[0][:n]) and torch.equal(got[1][:n], ref[1][:n]), cols
+        for _ in range(2):                                        # twice: the ticket counter is re-zeroed per call
+            got = rf.ops.corr_mutual_nn_presplit(planes[0, :NA], planes[1, :NA], planes[0, NA:], planes[1, NA:])
+            n = int(got[2].item())
+            assert n == nref and torch.equal(got[0][:n], ref[0][:n]) and torch.equal(got[1][:n], ref[1][:n]), (tail, cols)
         again = rf.ops.corr_mutual_nn(rows[:NA].contiguous(), rows[NA:].contiguous(), 2)
         assert int(again[2].item()) == nref and torch.equal(again[0][:n], ref[0][:n])
     assert nref >= 1 and (NB <= 2 or not bool((ref[1][:nref] == 1).any()))
