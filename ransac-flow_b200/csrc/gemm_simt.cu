@@ -587,8 +587,11 @@ extern "C" int rf_corr_mutual_nn_presplit(const void* A_hi, const void* A_lo, in
         return 0;
     }
     const void* planes[4] = {A_hi, A_lo, B_hi, B_lo};
-    const char* e = getenv("RF_CORR_TAIL");          // 1 (default): mutual test + compaction in the correlation kernel's last CTA (2 graph nodes)
-    if ((e ? atoi(e) : 1) && NA <= 49152) {
+    // RF_CORR_TAIL=1: mutual test + compaction in the correlation kernel's last CTA (2 graph nodes instead of 3).  Measured
+    // SLOWER at config 2 (92.3 vs 86.5 us per call: 192 threads of one CTA do serially what the 1024-thread kernel does
+    // while nothing else is left to overlap with), so the separate column-driven kernel stays the default.
+    const char* e = getenv("RF_CORR_TAIL");
+    if ((e ? atoi(e) : 0) && NA <= 49152) {
         void* tail[4] = {idx1_out, idx2_out, count_out, colbest + NB};
         return rf_corr_argmax_tc(nullptr, NA, nullptr, NB, C, rowbest, colbest, nullptr, st, 2, true, planes, tail);
     }
