@@ -448,10 +448,11 @@ def run_b200(args, rank, world, local):
         return ms, launches, outs[-1], allr, gather_ms
 
     # set-up, untimed and before the W warm-up steps of the contract: a couple of seconds of the real load (clocks, power state,
-    # allocator).  Observation left unexplained (profiles/README.md): in the FIRST timed region of a process every other 32-pair
-    # step takes ~139 instead of ~123 ms, with 2 s or 6 s of pre-warm and whether the clocks are sampled by nvidia-smi or through
-    # NVML in-process; a second resident-input region later in the same process runs at the host-input region's speed.  `value`
-    # (first region) is therefore ~4 % conservative against `e2e` (second region).
+    # allocator).  Observation (profiles/README.md): with device-resident inputs every other 32-pair step takes ~139 instead of
+    # ~123 ms (per-step host timestamps), whatever the pre-warm (2 s, 6 s, a discarded dry-run region) and however the clocks are
+    # sampled, while the pinned-host-input region of the same process is flat: the resident path copies each pair device-to-device
+    # into the graph's static input buffers on the lane's stream, the host path uses the copy engines.  `value` is therefore ~4 %
+    # conservative against `e2e`.
     # (the clock sampler starts first: nvidia-smi's own start-up perturbs the GPU for about a second)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -463,8 +464,6 @@ def run_b200(args, rank, world, local):
             step(i_pre, False)
             i_pre += 1
         torch.cuda.synchronize()
-        if os.environ.get("RF_BENCH_DRYRUN_REGION", "1") != "0":
-            timed(False, max(2, args.steps // 2), 1)         # a discarded pass through the measurement path itself (events, records, gather)
     ms_dev, launches, out, _, _ = timed(False, args.steps, args.warmup)
     ms_e2e, _, out, allr, gather_ms = timed(True, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None
