@@ -397,9 +397,8 @@ def run_b200(args, rank, world, local):
         """One step = P pairs: returns the list of per-pair results."""
         src = host if from_host else resident                                       # pinned host (H2D inside) or HBM-resident
         outs = []
-        if multi is not None:
-            for r in range(P // lanes):                                             # lanes graphs side by side, one D2H each
-                outs += multi([src[(i * P + r * lanes + k) % len(src)] for k in range(lanes)], copy=False)
+        if multi is not None:                                                       # lanes graphs side by side, each lane refilled as it completes
+            outs = multi.run([src[(i * P + r) % len(src)] for r in range(P)], copy=False)
         elif aligner is not None:
             for r in range(P):
                 outs.append(aligner(*src[(i * P + r) % len(src)], copy=False))      # one CUDA-graph launch + one pinned D2H

@@ -420,6 +420,29 @@ class ConcurrentAligner:
     def __call__(self, pairs, copy=True):
         return self.fetch(self.enqueue(pairs), copy)
 
+    def run(self, pairs, copy=True):
+        """Any number of pairs through the lanes WITHOUT a barrier between rounds: lane k is refilled as soon as its previous
+        pair has been fetched, so the lanes drift apart instead of starting every round in lock-step (their tails and launch
+        gaps then overlap each other's work).  Results in the order of ``pairs``.  With ``copy=False`` a result's ``flow12`` is
+        valid only until its lane is refilled."""
+        main = torch.cuda.current_stream()
+        L = len(self.lanes)
+        for s in self.streams:
+            s.wait_stream(main)
+        tickets, owner, out = [None] * L, [None] * L, [None] * len(pairs)
+        for i, (Is, It) in enumerate(pairs):
+            k = i % L
+            if tickets[k] is not None:
+                out[owner[k]] = self.lanes[k].fetch(tickets[k], copy)
+            with torch.cuda.stream(self.streams[k]):
+                tickets[k], owner[k] = self.lanes[k].enqueue(Is, It), i
+        for k in range(L):
+            if tickets[k] is not None:
+                out[owner[k]] = self.lanes[k].fetch(tickets[k], copy)
+        for s in self.streams:
+            main.wait_stream(s)
+        return out
+
 
 def align_pair(coarseModel, network, Is, It, maxCoarse=0, maskRegionTh=0.01, with_match21=False, It_bg=None):
     """One pair through the evaluation loop (evaluation/evalHpatch/evaluation.py:172-243).

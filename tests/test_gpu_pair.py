@@ -318,6 +318,10 @@ def test_concurrent_aligner_equals_graphed_aligner(rf):
         outs = multi(pairs[:2]) + multi(pairs[2:])
         outs2 = multi(pairs[:2]) + multi(pairs[2:3])          # buffers are reused; a short batch is fine
         assert len(outs) == 4 and len(outs2) == 3
+        outs3 = multi.run(pairs + pairs[:3])                  # 7 pairs through 2 lanes without round barriers, results in input order
+        assert len(outs3) == 7
+        for o, r in zip(outs3, ref + ref[:3]):
+            assert o["nbMatch"] == r["nbMatch"] and o["flowDown8"].shape == r["flowDown8"].shape
         for o, r in list(zip(outs, ref)) + list(zip(outs2, ref[:3])):
             assert o["nbMatch"] == r["nbMatch"] and o["nbMatch"] >= 4
             assert len(o["H"]) == len(r["H"])
@@ -327,7 +331,7 @@ def test_concurrent_aligner_equals_graphed_aligner(rf):
                 assert o["match"][0].shape == r["match"][0].shape
             print("pair: matches %d, inliers single %d / concurrent %d" % (o["nbMatch"], r["nbInlier"], o["nbInlier"]))
         g0 = multi.lanes[0].graphs[next(iter(multi.lanes[0].graphs))]
-        assert multi.replayed_kernels == 7 * g0["n_kernels"] and g0["n_kernels"] > 50
+        assert multi.replayed_kernels == 14 * g0["n_kernels"] and g0["n_kernels"] > 50
     finally:
         rf.model.set_engine("fp32")
         rf.outil.corr_precision = 0
