@@ -35,8 +35,8 @@ def conv(name, hw, cin, cout, k, s, p, res=False, in_b=4, out_b=4):
     return o
 
 
-def fe(tag):
-    x = conv(tag + " stem (im2col 27->64) 64->64 1x1", [(480, 640)], 64, 64, 1, 1, 0)
+def fe(tag, n_img=2):
+    x = conv(tag + " stem (im2col 27->64) 64->64 1x1", [(480, 640)] * n_img, 64, 64, 1, 1, 0)
     x = out_hw(x, 4, 2, 1)
     cin = 64
     for layer, planes, stride in (("l1", 64, 1), ("l2", 128, 2), ("l3", 256, 2)):
@@ -73,9 +73,8 @@ def head(tag, n_img, cout_last):
     conv(tag + " conv4 128->%d (fp32 out)" % cout_last, x, 128, cout_last, 3, 1, 1)
 
 
-fe("FE(target)")
 trunk()
-fe("FE(warped source)")
+fe("FE[source,target]")          # the sync-free path runs the FeatureExtractor once, on [warped source, target] as one batch
 head("flow head", 1, 49)
 head("match head", 2, 1)
 
@@ -105,7 +104,7 @@ for i, (name, P, fl, by) in enumerate(layers):
     variant = "" if len(targs) < 2 else ("halo" if targs[0] in ("1", "true") else "tap BN%s%s" % (targs[1], " RES2" if len(targs) > 2 and targs[2] in ("1", "true") else ""))
     fl_us = max(th, tt)
     print("%-46s %8d %7.2f %8.1f %8.1f %9.1f %9.1f %6.2f  %s" % (name, P, fl / 1e9, by / 1e6, th, tt, us, us / fl_us if us == us else float("nan"), variant))
-    g = groups.setdefault(" ".join(name.split(" ")[:2]) if name.startswith(("flow", "match", "FE(warped")) else name.split(" ")[0], [0.0, 0.0, 0.0, 0.0])
+    g = groups.setdefault(" ".join(name.split(" ")[:2]) if name.startswith(("flow", "match")) else name.split(" ")[0], [0.0, 0.0, 0.0, 0.0])
     g[0] += fl
     g[1] += by
     g[2] += fl_us
