@@ -306,7 +306,7 @@ def parity_report(rf, torch, ref, coarse, net, pair, engine):
         "engine": engine, "pair": "pair 0 of the workload, shared raw sample table %% match count, oracle = oracle/pair_oracle.py (CPU fp32)",
         "matches_oracle": len(exp), "matches_b200": len(got), "match_symdiff": len(got ^ exp),
         "max_abs_score_dev": dev, "symdiff_worst_margin": max(margins, default=0.0),
-        "symdiff_all_proven_ties": bool(all(m <= 2 * dev + 1e-6 for m in margins)),
+        "symdiff_all_proven_ties": bool(all(m <= 2 * dev + 3e-6 for m in margins)),      # 3e-6: the fp16-split correlation kernel's own arithmetic
         "stage_ransac_on_oracle_matches": {"status": int(status.item()), "nb_inlier_equal": bool(int(nb.item()) == int(ref["nbInlier"])),
                                            "inlier_mask_equal": bool(np.array_equal(mask.cpu().numpy().astype(bool), ref["isInlier"])),
                                            "max_abs_H": float(np.abs(Hd.cpu().numpy().reshape(3, 3) - ref["H"][0]).max())},

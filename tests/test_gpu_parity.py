@@ -3,7 +3,8 @@ with NO conditional asserts:
 
   (a) match set: every pair in the symmetric difference of the product's and the oracle's mutual-NN lists must be a PROVEN
       arg-max tie - its margin in the oracle's own fp32 score matrix is below twice the largest score deviation the engine's
-      features can cause (measured on the spot, and itself bounded for the fp32-grade engines);
+      features can cause (measured on the spot, and itself bounded for the fp32-grade engines) plus the correlation kernel's
+      own arithmetic error;
   (b) coarse stage in isolation: the ORACLE's match list + sample table -> H, inlier count and inlier mask bit-exact;
   (c) fine stage in isolation: the ORACLE's H -> flowDown8, matchDown8 and flow12 on ALL pixels within north_star's 1e-3;
   (d) end to end with the oracle's samples: identical when the match sets coincide (checked whenever they do).
@@ -71,9 +72,11 @@ def tie_report(score, ref_pairs, got_pairs):
 
 
 @pytest.mark.parametrize("engine", ["fp32", "f16x3", "f16", "tf32"], indirect=True)
-@pytest.mark.parametrize("h,w,minSize,nbScale", [(96, 128, 96, 3), (480, 640, 480, 7)])
-def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
-    o = oracle_pair(11, h, w, minSize, nbScale)
+@pytest.mark.parametrize("h,w,minSize,nbScale,seed", [(96, 128, 96, 3, 11), (480, 640, 480, 7, 11), (480, 640, 480, 7, 23), (480, 640, 480, 7, 1)])
+def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale, seed):
+    if seed != 11 and engine not in STRICT:
+        pytest.skip("the reduced-precision fast modes are characterised on one pair per size")
+    o = oracle_pair(seed, h, w, minSize, nbScale)
     oc, ref = o["oc"], o["ref"]
     net = networks(rf)
     c = rf.CoarseAlignA(nbScale, 1000, 0.05, "Homography", minSize, 2, False, 2, True, False, resnet_state_dict=o["rsd"], verbose=False)
@@ -93,8 +96,12 @@ def test_whole_pair_vs_oracle(rf, engine, h, w, minSize, nbScale):
           % (engine, h, w, len(ref_pairs), len(got_pairs), len(ties), dev, worst))
     if engine in STRICT:
         assert dev < 2e-5, "features are not fp32-grade"
+        # a flipped arg-max implies margin <= 2 x (score deviation caused by the features) + 2 x (the correlation kernel's own
+        # arithmetic error: exact FMA at precision 0; <= 1.2e-6 at K = 1024 for the fp16-split tensor-core kernel, whose fp32
+        # accumulation truncates - tests/test_gpu_split.py measures that error)
+        slack = 1e-6 if PREC[engine] == 0 else 3e-6
         for pair, margin in ties:
-            assert margin <= 2 * dev + 1e-6, "pair %s differs from the oracle and is not an arg-max tie (margin %.3g, score noise %.3g)" % (pair, margin, dev)
+            assert margin <= 2 * dev + slack, "pair %s differs from the oracle and is not an arg-max tie (margin %.3g, score noise %.3g)" % (pair, margin, dev)
         assert len(ties) <= max(2, len(ref_pairs) // 50)
 
     # ---- (b) coarse stage in isolation: the oracle's matches and samples -> bit-exact RANSAC ----------------------------
