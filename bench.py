@@ -258,15 +258,20 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = args.steps / dt
     if args.dump_parity and cfg in (2, 3):
+        from oracle import outil_oracle as OO
         oc.raw_samples = raw_sample_table()
-        s0, t0_ = pairs[0]
-        ref = PO.align_pair(oc, net, Image.fromarray(s0), Image.fromarray(t0_), maxCoarse=0)
-        featt = oc.featt.contiguous().view(oc.featt.shape[1], -1).numpy()
-        score = oc.featsMultiScale.numpy().T @ featt
-        _, nbInl, isInl, _ = __import__("oracle.outil_oracle", fromlist=["x"]).RANSAC_from_samples(oc.match1, oc.match2, oc.last_samples, 0.05)
-        np.savez(args.dump_parity, index1=oc.index1, index2=oc.index2, score=score, match1=oc.match1, match2=oc.match2,
-                 samples=oc.last_samples, H=ref["H"], nbInlier=np.int64(nbInl), isInlier=np.asarray(isInl, dtype=bool),
-                 flowDown8=ref["flowDown8"], matchDown8=ref["matchDown8"], flow12=ref["flow12"][0].numpy(), match=ref["match"][0])
+        dump = {}
+        for pi in (0, 1):                                         # pairs 0 and 1 of the workload
+            s0, t0_ = pairs[pi]
+            ref = PO.align_pair(oc, net, Image.fromarray(s0), Image.fromarray(t0_), maxCoarse=0)
+            featt = oc.featt.contiguous().view(oc.featt.shape[1], -1).numpy()
+            score = oc.featsMultiScale.numpy().T @ featt
+            _, nbInl, isInl, _ = OO.RANSAC_from_samples(oc.match1, oc.match2, oc.last_samples, 0.05)
+            for key, arr in dict(index1=oc.index1, index2=oc.index2, score=score, match1=oc.match1, match2=oc.match2, samples=oc.last_samples,
+                             H=ref["H"], nbInlier=np.int64(nbInl), isInlier=np.asarray(isInl, dtype=bool), flowDown8=ref["flowDown8"],
+                                 matchDown8=ref["matchDown8"], flow12=ref["flow12"][0].numpy(), match=ref["match"][0]).items():
+                dump["%s_%d" % (key, pi)] = arr
+        np.savez(args.dump_parity, **dump)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,9 +281,9 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def parity_report(rf, torch, ref, coarse, net, pair, engine):
-    """How far the timed engine is from the CPU oracle on pair 0 (outside the timed region).  `ref` = the arrays the
-    cpu_baseline child wrote.  (a) match set and tie proofs, (b) the oracle's matches + samples through the RANSAC kernel,
+def parity_report(rf, torch, ref, coarse, net, pair, engine, label="pair 0"):
+    """How far the timed engine is from the CPU oracle on one pair of the workload (outside the timed region).  `ref` = the
+    arrays the cpu_baseline child wrote for that pair.  (a) match set and tie proofs, (b) the oracle's matches + samples through the RANSAC kernel,
     (c) the oracle's H through the fine stage, (d) end to end with the shared sample table."""
     import PIL.Image as Image
     raw = raw_sample_table()
@@ -303,7 +308,7 @@ def parity_report(rf, torch, ref, coarse, net, pair, engine):
     f12, match, f8, mb = rf.pipeline.PredFlowMask_device(coarse.IsTensor, featt, fc, (Ith, Itw), net)
     same = len(got ^ exp) == 0
     rec = {
-        "engine": engine, "pair": "pair 0 of the workload, shared raw sample table %% match count, oracle = oracle/pair_oracle.py (CPU fp32)",
+        "engine": engine, "pair": label + " of the workload, shared raw sample table % match count, oracle = oracle/pair_oracle.py (CPU fp32)",
         "matches_oracle": len(exp), "matches_b200": len(got), "match_symdiff": len(got ^ exp),
         "max_abs_score_dev": dev, "symdiff_worst_margin": max(margins, default=0.0),
         "symdiff_all_proven_ties": bool(all(m <= 2 * dev + 3e-6 for m in margins)),      # 3e-6: the fp16-split correlation kernel's own arithmetic
@@ -574,7 +579,11 @@ def run_b200(args, rank, world, local):
                    "sample": "CPU oracle did not finish in 420 s (%s)" % type(e).__name__}
         if cfg in (2, 3) and os.path.exists(dump):
             try:
-                parity = parity_report(rf, torch, dict(np.load(dump)), coarse, net, resident[0], args.engine)
+                allref = dict(np.load(dump))
+                sub = lambda pi: {k[:-2]: v for k, v in allref.items() if k.endswith("_%d" % pi)}
+                parity = parity_report(rf, torch, sub(0), coarse, net, resident[0], args.engine, "pair 0")
+                parity["pair1"] = parity_report(rf, torch, sub(1), coarse, net, resident[1], args.engine, "pair 1")
+                parity["within_north_star"] = bool(parity["within_north_star"] and parity["pair1"]["within_north_star"])
             except Exception as e:  # noqa: BLE001
                 parity = {"error": "%s: %s" % (type(e).__name__, e)}
 
