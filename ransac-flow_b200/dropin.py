@@ -52,12 +52,23 @@ def install(variant="A"):
     return mod
 
 
+def select_engine(name=None):
+    """The conv / correlation engine the mirrored modules run on: ``$RF_ENGINE`` or 'f16x3' - the fp32-grade tensor-core engine
+    (fp16 hi / lo split operands), whose results reproduce the reference's fp32 arg-max; 'fp32' = exact-FMA SIMT kernels."""
+    from . import model, outil
+    name = name or os.environ.get("RF_ENGINE", "f16x3")
+    model.set_engine(name)
+    outil.corr_precision = {"fp32": 0, "tf32": 1}.get(name, 2)
+    return name
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])
     install(variant_for(script))
+    select_engine()
     sys.argv = [script] + argv[1:]
     os.chdir(os.path.dirname(script))
     sys.path.insert(0, os.path.dirname(script))

@@ -151,10 +151,13 @@ def test_dropin_runs_a_reference_style_driver_end_to_end(rf, tmp_path, monkeypat
     monkeypatch.setenv("RF_RESNET50_WEIGHTS", str(tmp_path / "resnet50.pth"))
     saved = {k: sys.modules.get(k) for k in ("coarseAlignFeatMatch", "outil", "model", "kornia", "kornia.geometry")}
     argv, cwd, path = list(sys.argv), os.getcwd(), list(sys.path)
+    monkeypatch.delenv("RF_ENGINE", raising=False)             # the launcher's default engine: f16x3 (fp32-grade tensor cores)
     try:
         dropin.main([str(drv_dir / "driver.py"), "--img1", str(tmp_path / "a.png"), "--img2", str(tmp_path / "b.png"),
                      "--resumePth", str(tmp_path / "ckpt.pth"), "--outdir", out])
     finally:
+        assert rf.model.get_engine() == rf.ops.ENGINE_SPLIT
+        dropin.select_engine("fp32")
         sys.argv, sys.path[:] = argv, path
         os.chdir(cwd)
         for k, v in saved.items():
