@@ -141,6 +141,14 @@ int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
                    const float* w, const float* w_tc, const float* bias, const float* residual,
                    int Cout, int R, int S, int stride, int pad, int relu, int engine,
                    float* y, void* stream);
+/* Engine 4 only: a 1x1 convolution over TWO inputs whose channels are concatenated along K,
+ *   y = act(W[:, :Cin1] x1 + W[:, Cin1:] x2[::stride2, ::stride2] + bias),
+ * i.e. a ResNet bottleneck's conv3 + bn3 and its down-sampling branch (downsample.0 + downsample.1 of torchvision's Bottleneck,
+ * which quick_start/coarseAlignFeatMatch.py:31-38 runs up to layer3) + the residual add + ReLU as ONE GEMM: the branch's output
+ * never goes to HBM.  x1 / x2 / y split tensors; hw1 = sizes of x1 and y, hw2 = sizes of x2 ((h2 - 1) / stride2 + 1 == h1);
+ * w_split = [2][Cout][Cin1 + Cin2] fp16; Cin1 % 64 == Cin2 % 64 == 0, Cout % 8 == 0, stride2 1 or 2. */
+int rf_conv1x1_dual_split(const void* x1, const void* x2, int nimg, const int* hw1_host, const int* hw2_host, int Cin1, int Cin2,
+                          int stride2, const void* w_split, const float* bias, int Cout, int relu, void* y, void* stream);
 /* A whole network in one call: `layers_host[n]` executed in order over a ragged batch.  Buffers are numbered
  * "slots" (`slots_host[i]` = device pointer, caller-allocated); slot `layers[0].src` holds the input images
  * (`hw_host` = their sizes) and every layer's output sizes follow from its input's.  This is what the Python
@@ -154,6 +162,7 @@ int rf_conv2d_nhwc(const float* x, int nimg, const int* hw_host, int Cin,
 #define RF_OP_STEM7 5     /* engines 2 / 4 only: ResNet-50 stem fused (7x7 / stride 2 / pad 3 on the 3-channel fp32 image + bias + ReLU ->
                              fp16 / split, 64 channels) without the im2col matrix; w_f16 = [64][192] ([2][64][192] for engine 4) in
                              (r, s, c) order, zero padded */
+#define RF_OP_CONV_DUAL 6  /* engine 4 only: rf_conv1x1_dual_split; src = x1 (Cin channels), src2 = x2 (Cin2 channels, stride2), w_f16 = [2][Cout][Cin + Cin2] */
 #define RF_MAX_SLOTS 32
 typedef struct rf_layer {
     int op;
@@ -164,6 +173,7 @@ typedef struct rf_layer {
     const float* bias;              /* [Cout] or NULL */
     const void* w_f16;              /* engine 2: [Cout][k*k*Cin] fp16; engine 4: [2][Cout][k*k*Cin] fp16 hi / lo planes (NULL otherwise) */
     int flags;                      /* engines 2 / 4: RF_LAYER_* */
+    int src2, Cin2, stride2;        /* RF_OP_CONV_DUAL: second input slot, its channels and sampling stride (ignored otherwise) */
 } rf_layer_t;
 #define RF_LAYER_OUT_F32 1          /* conv: fp16 operands, fp32 output (RF_ENGINE_F16_OUT32; engine 4: RF_ENGINE_SPLIT_OUT32) */
 #define RF_LAYER_TF32 2             /* conv: fp32 input and output on the TF32 engine (e.g. a 49-channel head after an OUT_F32 layer) */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "rf_prediction": (i32, [vp, vp, i32, vp, i32, vp, vp]),
     "rf_build_matches": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "rf_conv2d_nhwc": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "rf_conv1x1_dual_split": (i32, [vp, vp, i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]),
     "rf_maxpool2d_nhwc": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp]),
     "rf_blur_downsample_nhwc": (i32, [vp, i32, vp, i32, i32, vp, vp]),
     "rf_l2norm_nhwc": (i32, [vp, i64, i32, vp, vp, vp]),

@@ -52,7 +52,8 @@ class ResNet50Conv4:
         self._program_split = None                # split activations ('f16x3' engine), built on first use
         self.out_channels = self.program.chan[-1]
 
-    def _build(self, kalign):
+    def _build(self, kalign, fuse_downsample=False):
+        """``fuse_downsample`` (split engine): a block's conv3 and its down-sampling 1x1 run as one dual-input GEMM."""
         sd, dev = self._sd, self.device
         P = LayerProgram(3, device=dev)
         if kalign == 64 and os.environ.get("RF_STEM_FUSED", "1") != "0":
@@ -67,9 +68,14 @@ class ResNet50Conv4:
                 out = P.conv(x, FoldedConv(sd[p + ".conv1.weight"], _BN(sd, p + ".bn1"), 1, pad=0, device=dev), relu=True)
                 out = P.conv(out, FoldedConv(sd[p + ".conv2.weight"], _BN(sd, p + ".bn2"), s, pad=1, device=dev), relu=True)
                 r = x
+                c3 = FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0, device=dev)
                 if (p + ".downsample.0.weight") in sd:
-                    r = P.conv(x, FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0, device=dev), relu=False)
-                x = P.conv(out, FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0, device=dev), relu=True, res=r)
+                    ds = FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), s, pad=0, device=dev)
+                    if fuse_downsample:
+                        x = P.conv_dual(out, x, FoldedConv.concat_k(c3, ds), s, relu=True)
+                        continue
+                    r = P.conv(x, ds, relu=False)
+                x = P.conv(out, c3, relu=True, res=r)
         return P
 
     def __call__(self, x):
@@ -79,7 +85,8 @@ class ResNet50Conv4:
         eng = rfmodel.get_engine()
         if eng == ops.ENGINE_SPLIT:
             if self._program_split is None:
-                self._program_split = self._build(64)    # same topology as the fp16 program; the weights are read as hi / lo planes
+                # the fp16 program's topology with the weights read as hi / lo planes; conv3 + down-sampling branch fused
+                self._program_split = self._build(64, fuse_downsample=os.environ.get("RF_FUSE_DOWNSAMPLE", "1") != "0")
             out, ohw = self._program_split.run(x, eng)
         elif eng == ops.ENGINE_F16:
             if self._program_f16 is None:

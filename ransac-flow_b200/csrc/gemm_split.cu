@@ -31,7 +31,7 @@
 namespace rf {
 
 constexpr int SP_BN = 64;
-constexpr int SP_THREADS = 320;
+constexpr int sp_threads(int epw) { return 64 + 2 * 32 * epw; }          // producer warp + MMA warp + two epilogue groups of `epw` warps
 constexpr int SP_HALO_TW = 8, SP_HALO_TH = 16, SP_HALO_LD = SP_HALO_TW + 2;
 constexpr int SP_HALO_PLANE = SP_HALO_LD * (SP_HALO_TH + 2) * 128;          // 23040 B: one plane of a halo block
 
@@ -48,6 +48,8 @@ struct alignas(64) SplitParams {
     long long out_pix[RF_MAX_IMGS + 1];
     int R, S, pad, stride, Cin, Cout, relu, has_res, out32;
     int tiles_m, tiles_n;
+    int kc1, stride2;                     // dual-input 1x1: K blocks [0, kc1) come from mapA, the rest from mapR (second input, its own stride)
+    int dbg;                              // timing experiments only (RF_SPLIT_DBG): 1 no B loads, 2 no MMAs, 4 no A loads, 8 no epilogue math / store
     const float* bias;
     float* y32;                           // out32: fp32 [P][Cout]
 };
@@ -126,18 +128,24 @@ __device__ __forceinline__ SpTile sp_decode(const SplitParams& p, int t) {
 }
 
 // split one fp32 value pair into (hi, lo * 2^11) half2 pairs, saturating like the fp16 engine
+// (cvt.rn.satfinite: one instruction per pair converts, packs and clamps to +-65504; an overflowing value gets hi = lo = 65504)
+__device__ __forceinline__ __half2 sp_pack_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // first source -> upper half
+    return *reinterpret_cast<__half2*>(&r);
+}
 __device__ __forceinline__ void sp_split2(float a, float b, __half2& hi, __half2& lo) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    hi = __floats2half2_rn(a, b);
+    hi = sp_pack_sat(a, b);
     const float2 f = __half22float2(hi);
-    lo = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
+    lo = sp_pack_sat((a - f.x) * 2048.f, (b - f.y) * 2048.f);
 }
 
-template <bool HALO, int BN_, bool RES2 = false>
-__global__ void __launch_bounds__(SP_THREADS, 1)
+template <bool HALO, int BN_, bool RES2 = false, int EPW = 8>
+__global__ void __launch_bounds__(sp_threads(EPW), 1)
 tc_split_kernel(const __grid_constant__ SplitParams p) {
     using Cfg = SplitCfg<HALO, BN_, RES2>;
+    static_assert(EPW == 4 || EPW == 8, "epilogue warps per group");
+    constexpr int GT = 32 * EPW;                // threads of one epilogue group
     constexpr int NSB = Cfg::NSB;
     constexpr int BN = Cfg::BN, NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB, BK = TC_BK_F16;
     constexpr bool WIDE = BN == 128;            // both epilogue groups work on every tile (one 64-channel half each)
@@ -163,7 +171,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 256 : 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], WIDE ? 2 * GT : GT); }
         for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
         fence_barrier_init();
     }
@@ -183,20 +191,28 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 for (int ia = 0; ia < NAI; ++ia, ++ia_cnt) {
                     const int sa = ia_cnt % NA;
                     mbar_wait(&emptyA[sa], ((ia_cnt / NA) & 1) ^ 1);
-                    mbar_expect_tx(&fullA[sa], Cfg::A_TX);
                     int tap = 0, cc = ia;
-                    if (HALO) {
+                    if (p.dbg & 4) {
+                        if (!HALO) { tap = ia / kc; cc = ia - tap * kc; }
+                        mbar_arrive(&fullA[sa]);
+                    } else if (HALO) {
+                        mbar_expect_tx(&fullA[sa], Cfg::A_TX);
                         tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], ia * BK, c.ox0 - 1, c.oy0 - 1, 0);
                     } else {
+                        mbar_expect_tx(&fullA[sa], Cfg::A_TX);
                         tap = ia / kc;
                         cc = ia - tap * kc;
                         const int r = tap / p.S, sx = tap - r * p.S;
-                        tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], cc * BK, c.ox0 * p.stride + sx - p.pad,
-                                    c.oy0 * p.stride + r - p.pad, 0);
+                        if (cc < p.kc1)
+                            tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapA[c.img], &fullA[sa], cc * BK, c.ox0 * p.stride + sx - p.pad,
+                                        c.oy0 * p.stride + r - p.pad, 0);
+                        else                                                // second input of a dual 1x1 (the fused down-sampling branch)
+                            tma_load_4d(sA + sa * Cfg::A_SLOT, &p.mapR[c.img], &fullA[sa], (cc - p.kc1) * BK, c.ox0 * p.stride2, c.oy0 * p.stride2, 0);
                     }
                     for (int jb = 0; jb < TB; ++jb, ++ib_cnt) {
                         const int sb = ib_cnt % NB;
                         mbar_wait(&emptyB[sb], ((ib_cnt / NB) & 1) ^ 1);
+                        if (p.dbg & 1) { mbar_arrive(&fullB[sb]); continue; }
                         mbar_expect_tx(&fullB[sb], Cfg::B_TILE);
                         const int btap = HALO ? jb : tap;
                         tma_load_3d(sB + sb * Cfg::B_TILE, &p.mapB, &fullB[sb], btap * p.Cin + cc * BK, c.n0, 0);
@@ -227,7 +243,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                     if (HALO) { const int r = jb / 3, sx = jb - r * 3; aaddr += (uint32_t)((r * SP_HALO_LD + sx) * 128); }
                     const uint64_t ahi = HALO ? sp_desc_halo(aaddr) : make_desc_sw128(aaddr);
                     const uint64_t alo = HALO ? sp_desc_halo(aaddr + Cfg::A_LO) : make_desc_sw128(aaddr + Cfg::A_LO);
-                    umma_f16split_x4(td, tx, ahi, alo, make_desc_sw128(bb), make_desc_sw128(bb + Cfg::B_PLANE), idesc, (ia | jb) != 0 ? 1u : 0u);
+                    if (!(p.dbg & 2))
+                        umma_f16split_x4(td, tx, ahi, alo, make_desc_sw128(bb), make_desc_sw128(bb + Cfg::B_PLANE), idesc, (ia | jb) != 0 ? 1u : 0u);
                     umma_commit(&emptyB[sb]);
                 }
                 umma_commit(&emptyA[sa]);
@@ -236,13 +253,23 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
         }
     } else {
         // =============================== epilogue groups ===============================
-        const uint32_t g = (uint32_t)(warp - 2) >> 2;                       // 0: warps 2-5, 1: warps 6-9
+        // A group is EPW warps.  EPW = 4: one warp per TMEM lane quarter, 64 columns each; EPW = 8: two warps per quarter, 32
+        // columns each - the epilogue is ~11 fp32 instructions per output element (combine, bias, residual hi + lo, ReLU, split)
+        // in dependent chains, and with K <= 256 it, not the MMAs or HBM, sets the tile rate (ncu: 2.5 warps per scheduler,
+        // 6.2 cycles between issues); sixteen epilogue warps halve the drain time of an accumulator pair.
+        const uint32_t g = (uint32_t)(warp - 2) / EPW;                      // group 0 / 1
+        const int idx = (warp - 2) % EPW;
         const int q = warp & 3;                                             // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+        const bool leader = idx == 0 && lane == 0;
+        constexpr int NCB = EPW == 8 ? 1 : 2;                               // 32-column blocks per thread
+        const int cb0 = EPW == 8 ? (idx >> 2) : 0;
         uint8_t* stg_base = sStg + g * NSB * Cfg::STG;
         uint32_t k = 0;                                                     // this group's tile counter
         const int t_first = blockIdx.x + (WIDE ? 0 : (int)g * (int)gridDim.x), t_step = (WIDE ? 1 : 2) * (int)gridDim.x;
+        auto group_sync = [&]() {
+            if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory"); else asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory");
+        };
         // Residual tiles come in by TMA into the group's OWN staging buffer, issued by the group's leader: the first one here,
         // the next one as soon as the store of the current tile has read the buffer out.  (First version: the producer warp
         // issued them and had to wait for the staging buffer of tile i-2 - that wait stalled the operand loads of tile i behind
@@ -255,6 +282,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             mbar_expect_tx(&res_full[2 * g], Cfg::STG);
             tma_load_4d(stg_base, &p.mapR[c0.img], &res_full[2 * g], c0.n0 + (WIDE ? 64 * (int)g : 0), c0.ox0, c0.oy0, 0);
         }
+        const bool bias_vec = p.bias != nullptr && (p.Cout & 3) == 0;
         for (int t = t_first; t < total; t += t_step, ++k) {
             const SpTile c = sp_decode<HALO, BN>(p, t);
             const uint32_t buf = WIDE ? (k & 1) : g;                        // accumulator pair of this tile
@@ -263,16 +291,18 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const int py = m / c.tw, px = m - py * c.tw;
             const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
             const long long pix = p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px);
-            // the leader comes here only after the previous store has read the staging buffer
-            if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            // the leader comes here only after the previous store has read the staging buffer (two buffers, no residual: the
+            // store of tile k - 2 used this tile's buffer; the one of tile k - 1 may still be reading the other)
+            if (RES2 && !has_res && leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            group_sync();
             const uint32_t sb = RES2 ? (k & 1) : 0;                         // staging buffer of this tile
             uint8_t* stg = stg_base + sb * Cfg::STG;
             mbar_wait(&tmem_full[buf], fph);
             tc_fence_after();
             if (has_res) mbar_wait(&res_full[2 * g + sb], RES2 ? ((k >> 1) & 1) : (k & 1));
-            if (RES2 && leader) {
+            if (RES2 && has_res && leader) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the other buffer's store (tile k - 1) has read it out
-                if (has_res && t + t_step < total) {
+                if (t + t_step < total) {
                     const SpTile cn = sp_decode<HALO, BN>(p, t + t_step);
                     mbar_expect_tx(&res_full[2 * g + (sb ^ 1)], Cfg::STG);
                     tma_load_4d(stg_base + (sb ^ 1) * Cfg::STG, &p.mapR[cn.img], &res_full[2 * g + (sb ^ 1)], cn.n0, cn.ox0, cn.oy0, 0);
@@ -281,7 +311,8 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const uint32_t trow = tmem_base + buf * (2 * BN) + (WIDE ? 64 * g : 0) + ((uint32_t)(q * 32) << 16);
             float* yrow = p.out32 ? p.y32 + pix * p.Cout : nullptr;
 #pragma unroll 1
-            for (int cb = 0; cb < 2; ++cb) {
+            for (int cbi = 0; cbi < ((p.dbg & 8) ? 0 : NCB); ++cbi) {
+                const int cb = cb0 + cbi;
                 uint32_t v[32], x[32];
                 tmem_ld32x2(trow + cb * 32, v, trow + BN + cb * 32, x);
                 const int n = nbase + cb * 32;
@@ -291,7 +322,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(x[8 * j + e]), 0.00048828125f, __uint_as_float(v[8 * j + e]));
                     if (p.bias != nullptr) {
-                        if (n + 8 * j + 8 <= p.Cout && (p.Cout & 3) == 0) {
+                        if (bias_vec && n + 8 * j + 8 <= p.Cout) {
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * j));
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * j + 4));
                             o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
@@ -336,12 +367,12 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);                                  // accumulator pair drained (128 arrivals per group)
+            mbar_arrive(&tmem_empty[buf]);                                  // accumulator pair drained (GT arrivals per group)
             if (!p.out32) {
                 fence_proxy_async();
-                if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                group_sync();
                 if (leader) {
-                    if (nbase < p.Cout) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
+                    if (nbase < p.Cout && !(p.dbg & 8)) tma_store_4d(&p.mapY[c.img], stg, nbase, c.ox0, c.oy0, 0);
                     if (RES2) {
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // read out while the group works on its next tile
                     } else {
@@ -607,7 +638,18 @@ bool rf_conv2d_split_supported(const ConvParams& p) {
 
 // x / residual / y: split tensors ([2][P][C] fp16, planes `P * C` elements apart); w_split: [2][Cout][K] fp16; out32: y is
 // fp32 [P][Cout] (no residual).
+// dual: a second input (x2, its own per-image sizes hw2, Cin2 channels, sampled with stride2) whose channels continue the K axis
+// of a 1x1 convolution: y = act(W[:, :Cin] x + W[:, Cin:] x2[::stride2] + bias) - a bottleneck's conv3 and its down-sampling
+// branch in one GEMM (the branch's output never goes to HBM and comes back as a residual).
+struct SplitDual { const void* x2; const int* hw2; int Cin2, stride2; };
+
+static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const void* w_split, cudaStream_t st, bool out32, const SplitDual* dual);
+
 int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split, cudaStream_t st, bool out32) {
+    return rf_conv2d_split_impl(set, cp, w_split, st, out32, nullptr);
+}
+
+static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const void* w_split, cudaStream_t st, bool out32, const SplitDual* dual) {
     RF_REQUIRE(w_split != nullptr, "rf_conv2d_nhwc: engine 4 needs the split weights ([2][Cout][R*S*Cin] fp16)");
     RF_REQUIRE(rf_conv2d_split_supported(cp), "rf_conv2d_nhwc: engine 4 needs stride 1 or 2, 1x1 or 3x3, Cin % 64 == 0");
     RF_REQUIRE(out32 || (cp.Cout % 8) == 0, "rf_conv2d_nhwc: engine 4 needs Cout % 8 == 0 for split outputs");
@@ -622,6 +664,18 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     char* yb = reinterpret_cast<char*>(cp.y);
     const unsigned long long in_plane = (unsigned long long)set.in_pix[set.n] * cp.Cin * 2ull;
     const unsigned long long out_plane = (unsigned long long)set.out_pix[set.n] * cp.Cout * 2ull;
+    long long in2_pix[RF_MAX_IMGS + 1] = {0};
+    if (dual) {
+        RF_REQUIRE(!halo && cp.R == 1 && cp.stride == 1 && cp.pad == 0 && cp.residual == nullptr && !out32 && dual->x2 != nullptr &&
+                   (dual->Cin2 % TC_BK_F16) == 0 && (dual->stride2 == 1 || dual->stride2 == 2) && ((uintptr_t)dual->x2 % 16) == 0,
+                   "rf_conv1x1_dual_split: 1x1 / stride 1 on the first input, no residual, Cin2 % 64 == 0, stride2 1 or 2");
+        for (int i = 0; i < set.n; ++i) {
+            RF_REQUIRE((dual->hw2[2 * i] - 1) / dual->stride2 + 1 == set.Ho[i] && (dual->hw2[2 * i + 1] - 1) / dual->stride2 + 1 == set.Wo[i],
+                       "rf_conv1x1_dual_split: the second input, sampled with stride2, must have the first input's size");
+            in2_pix[i + 1] = in2_pix[i] + (long long)dual->hw2[2 * i] * dual->hw2[2 * i + 1];
+        }
+    }
+    const unsigned long long in2_plane = dual ? (unsigned long long)in2_pix[set.n] * dual->Cin2 * 2ull : 0ull;
     p.nimg = set.n;
     int tiles = 0;
     for (int i = 0; i < set.n; ++i) {
@@ -638,6 +692,12 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
         if (!out32) {
             rc = get_map4(&p.mapY[i], yb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
                           out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
+            if (!rc && dual) {
+                const long long off2 = in2_pix[i];
+                rc = get_map4(&p.mapR[i], static_cast<const char*>(dual->x2) + off2 * dual->Cin2 * 2, (unsigned long long)dual->Cin2,
+                              (unsigned long long)dual->hw2[2 * i + 1], (unsigned long long)dual->hw2[2 * i], 2, in2_plane, TC_BK_F16, (unsigned)tw,
+                              (unsigned)th, 2, (unsigned)dual->stride2, 2);
+            }
             if (!rc && cp.residual)
                 rc = get_map4(&p.mapR[i], rb + set.out_pix[i] * cp.Cout * 2, (unsigned long long)cp.Cout, (unsigned long long)set.Wo[i], (unsigned long long)set.Ho[i], 2,
                               out_plane, TC_BK_F16, (unsigned)tw, (unsigned)th, 2, 1, 2);
@@ -652,41 +712,79 @@ int rf_conv2d_split(const ImgSet& set, const ConvParams& cp, const void* w_split
     // measured per layer (profiles/r2_*): wide tiles pay for deep-K layers with >= 2 channel tiles and no residual (ResNet
     // down-sampling 1x1s, bottleneck c1 of layer 3, the stride-2 3x3s): -7 .. -15 %; the residual layers and 128-channel outputs
     // are faster with narrow tiles taken alternately by the two epilogue groups
-    const int BN = (!halo && cp.residual == nullptr && cp.Cout >= 256 && bn_env == 128) ? 128 : 64;
+    static int shallow_env = -1;
+    if (shallow_env < 0) { const char* e = getenv("RF_SPLIT_SHALLOW"); shallow_env = e ? atoi(e) : 1; }
+    // one or two K blocks per tile and no residual: the epilogue sets the tile rate, and the double-buffered-staging variant
+    // (64-channel tiles, store read-out off the critical path) beats the wide tile (ResNet layer1 down-sampling 1x1: 79 -> 75 us)
+    const bool shallow = !halo && cp.R == 1 && cp.K <= 128 && shallow_env != 0;
+    const int BN = (!halo && !shallow && cp.residual == nullptr && cp.Cout >= 256 && bn_env == 128) ? 128 : 64;
     int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, (unsigned)BN, 2, 1, 2);
     if (rc) return rc;
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
+    p.kc1 = cp.Cin / TC_BK_F16;
+    p.stride2 = 1;
+    if (dual) { p.Cin = cp.Cin + dual->Cin2; p.stride2 = dual->stride2; }      // the kernel's K axis: both inputs
     p.has_res = cp.residual != nullptr ? 1 : 0;
     p.out32 = out32 ? 1 : 0;
     p.bias = cp.bias;
     p.y32 = out32 ? cp.y : nullptr;
+    static int dbg_env = -1;
+    if (dbg_env < 0) { const char* e = getenv("RF_SPLIT_DBG"); dbg_env = e ? atoi(e) : 0; }
+    p.dbg = dbg_env;
 
     p.tiles_m = tiles;
     p.tiles_n = (cp.Cout + BN - 1) / BN;
     const long long total = (long long)p.tiles_m * p.tiles_n;
     RF_REQUIRE(total < (1ll << 30), "rf_conv2d_nhwc: too many tiles");
     const int grid = total < num_sms() ? (int)total : num_sms();
-    static bool attr[64][4] = {{false}};
-    const int dev = current_device();
-    static int res2_env = -1;
+    static int res2_env = -1, epw_env = -1;
     if (res2_env < 0) { const char* e = getenv("RF_SPLIT_RES2"); res2_env = e ? atoi(e) : 1; }
+    if (epw_env < 0) { const char* e = getenv("RF_SPLIT_EPW"); epw_env = (e && atoi(e) == 4) ? 4 : 8; }
     // double-buffered staging pays for the HBM-bound residual layers with one or two K blocks per tile (ResNet layer 1 / 2
     // c3 + residual: 147 -> 121 us, 81 -> 64 us); with four K blocks (layer 3) the 2-deep operand ring costs more than the
     // residual prefetch gains (45 -> 52 us): measured, profiles/README.md
-    const int which = halo ? 1 : (BN == 128 ? 2 : ((cp.residual != nullptr && cp.K <= 128 && res2_env) ? 3 : 0));
-    if (!attr[dev][which]) {
-        if (which == 1) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<true, 64>::SMEM_BYTES));
-        else if (which == 2) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 128>::SMEM_BYTES));
-        else if (which == 3) RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 64, true>::SMEM_BYTES));
-        else RF_CUDA(cudaFuncSetAttribute(tc_split_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SplitCfg<false, 64>::SMEM_BYTES));
-        attr[dev][which] = true;
+    const int which = halo ? 1 : (BN == 128 ? 2 : ((((cp.residual != nullptr && cp.K <= 128) || shallow) && res2_env) ? 3 : 0));
+    const int dev = current_device();
+    static bool attr[64][8] = {{false}};
+    auto launch = [&](auto kernel, int smem, int threads, int slot) -> int {
+        if (!attr[dev][slot]) {
+            RF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr[dev][slot] = true;
+        }
+        kernel<<<grid, threads, smem, st>>>(p);
+        return 0;
+    };
+    int lrc;
+    if (epw_env == 8) {
+        if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 8>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(8), 0);
+        else if (which == 2) lrc = launch(tc_split_kernel<false, 128, false, 8>, SplitCfg<false, 128>::SMEM_BYTES, sp_threads(8), 1);
+        else if (which == 3) lrc = launch(tc_split_kernel<false, 64, true, 8>, SplitCfg<false, 64, true>::SMEM_BYTES, sp_threads(8), 2);
+        else lrc = launch(tc_split_kernel<false, 64, false, 8>, SplitCfg<false, 64>::SMEM_BYTES, sp_threads(8), 3);
+    } else {
+        if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 4>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(4), 4);
+        else if (which == 2) lrc = launch(tc_split_kernel<false, 128, false, 4>, SplitCfg<false, 128>::SMEM_BYTES, sp_threads(4), 5);
+        else if (which == 3) lrc = launch(tc_split_kernel<false, 64, true, 4>, SplitCfg<false, 64, true>::SMEM_BYTES, sp_threads(4), 6);
+        else lrc = launch(tc_split_kernel<false, 64, false, 4>, SplitCfg<false, 64>::SMEM_BYTES, sp_threads(4), 7);
     }
-    if (which == 1) tc_split_kernel<true, 64><<<grid, SP_THREADS, SplitCfg<true, 64>::SMEM_BYTES, st>>>(p);
-    else if (which == 2) tc_split_kernel<false, 128><<<grid, SP_THREADS, SplitCfg<false, 128>::SMEM_BYTES, st>>>(p);
-    else if (which == 3) tc_split_kernel<false, 64, true><<<grid, SP_THREADS, SplitCfg<false, 64, true>::SMEM_BYTES, st>>>(p);
-    else tc_split_kernel<false, 64><<<grid, SP_THREADS, SplitCfg<false, 64>::SMEM_BYTES, st>>>(p);
+    if (lrc) return lrc;
     RF_LAUNCHED();
     return 0;
+}
+
+extern "C" int rf_conv1x1_dual_split(const void* x1, const void* x2, int nimg, const int* hw1_host, const int* hw2_host, int Cin1, int Cin2,
+                                     int stride2, const void* w_split, const float* bias, int Cout, int relu, void* y, void* stream) {
+    RF_REQUIRE(x1 != nullptr && x2 != nullptr && y != nullptr && hw1_host != nullptr && hw2_host != nullptr, "rf_conv1x1_dual_split: null pointer");
+    RF_REQUIRE(Cin1 >= 1 && Cin2 >= 1 && Cout >= 1, "rf_conv1x1_dual_split: bad channel counts");
+    ImgSet set;
+    RF_REQUIRE(make_imgset(set, nimg, hw1_host, 1, 1, 0) == 0, "rf_conv1x1_dual_split: bad image set");
+    ConvParams p;
+    p.x = static_cast<const float*>(x1); p.w = nullptr; p.bias = bias; p.residual = nullptr; p.y = static_cast<float*>(y);
+    p.Cin = Cin1; p.Cout = Cout; p.R = 1; p.S = 1; p.stride = 1; p.pad = 0; p.relu = relu;
+    p.round_out = 0;
+    p.Mtot = set.out_pix[nimg];
+    p.K = Cin1 + Cin2;
+    SplitDual dual{x2, hw2_host, Cin2, stride2};
+    return rf_conv2d_split_impl(set, p, w_split, as_stream(stream), false, &dual);
 }
 
 // engine 4: fused ResNet-50 stem.  x fp32 [sum HW][3], w_split [2][64][192] fp16 ((r, s, c) order, zero padded), bias fp32 [64],

@@ -43,6 +43,10 @@ extern "C" int rf_run_layers(const rf_layer_t* L, int n, void* const* slots, int
                 const float* res = l.res >= 0 ? static_cast<const float*>(slots[l.res]) : nullptr;
                 rc = rf_conv2d_nhwc(x, nimg, shw, l.Cin, l.w, static_cast<const float*>(l.w_f16), l.bias, res, l.Cout, k, k, stride, pad, l.relu,
                                     (l.flags & RF_LAYER_OUT_F32) ? RF_ENGINE_SPLIT_OUT32 : RF_ENGINE_SPLIT, y, stream);
+            } else if (l.op == RF_OP_CONV_DUAL) {
+                RF_REQUIRE(l.src2 >= 0 && l.src2 < RF_MAX_SLOTS && known[l.src2] && l.dst != l.src2 && l.res < 0 && k == 1 && stride == 1 && pad == 0,
+                           "rf_run_layers: RF_OP_CONV_DUAL needs a written second input slot, k = 1, stride 1, pad 0, no residual");
+                rc = rf_conv1x1_dual_split(x, slots[l.src2], nimg, shw, hw[l.src2], l.Cin, l.Cin2, l.stride2, l.w_f16, l.bias, l.Cout, l.relu, y, stream);
             } else if (l.op == RF_OP_MAXPOOL) {
                 rc = rf_maxpool_split_impl(x, nimg, shw, l.Cin, k, stride, pad, y, stream);
             } else if (l.op == RF_OP_BLUR) {

@@ -88,6 +88,21 @@ class FoldedConv:
         self.cout, self.cin, self.k, self.stride = cout, cin, k, stride
         self.pad = (k // 2) if pad is None else pad
 
+    @classmethod
+    def concat_k(cls, fa, fb):
+        """Two folded 1x1 convolutions with the same output channels as ONE whose K axis is [fa's inputs | fb's inputs] and whose
+        bias is the sum: y = fa(x1) + fb(x2) (LayerProgram.conv_dual; fb's stride is applied by the kernel to its input)."""
+        assert fa.k == 1 and fb.k == 1 and fa.cout == fb.cout and fa.pad == 0 and fb.pad == 0
+        f = cls.__new__(cls)
+        f._wt = torch.cat([fa._wt, fb._wt], dim=1).contiguous()
+        f._dev, f._w_f16 = fa._dev, None
+        f.w = torch.cat([fa.w, fb.w], dim=0).contiguous()
+        f.w_tc = torch.cat([fa.w_tc, fb.w_tc], dim=1).contiguous()
+        ba = fa.bias if fa.bias is not None else torch.zeros(fa.cout, device=fa._dev)
+        f.bias = (ba + fb.bias) if fb.bias is not None else ba
+        f.cout, f.cin, f.cin2, f.k, f.stride, f.pad = fa.cout, fa.cin, fb.cin, 1, 1, 0
+        return f
+
     @property
     def w_split(self):
         """[2][Cout][R*S*Cin] fp16: hi = fp16(w), lo = fp16((w - hi) * 2^11) - the engine-4 operand; built on first use."""

@@ -106,6 +106,19 @@ def conv2d(x, w_packed, bias, Cout, k, stride, pad, relu, residual=None, engine=
     return Ragged(y, ohw)
 
 
+def conv1x1_dual_split(x1, x2, stride2, w_split, bias, relu):
+    """Split engine: y = act(W[:, :C1] x1 + W[:, C1:] x2[::stride2, ::stride2] + bias) in one GEMM (x1, x2, y split ragged
+    tensors; w_split [2][Cout][C1 + C2] fp16) - a bottleneck's conv3 fused with its down-sampling branch."""
+    need_cuda(x1.data, x2.data, w_split, bias)
+    assert x1.split and x2.split and x1.data.is_contiguous() and x2.data.is_contiguous() and x1.n == x2.n
+    assert w_split.dim() == 3 and w_split.dtype == torch.float16 and w_split.shape[2] == x1.C + x2.C and w_split.is_contiguous()
+    cout = w_split.shape[1]
+    y = torch.empty((2, sum(h * w for h, w in x1.hw), cout), device=x1.data.device, dtype=torch.float16)
+    check(lib.rf_conv1x1_dual_split(ptr(x1.data), ptr(x2.data), x1.n, x1._c, x2._c, x1.C, x2.C, int(stride2), ptr(w_split), ptr(bias),
+                                    cout, int(relu), ptr(y), stream()))
+    return Ragged(y, x1.hw)
+
+
 def maxpool2d(x, k, stride, pad):
     need_cuda(x.data)
     ohw = _out_hw(x.hw, k, stride, pad)

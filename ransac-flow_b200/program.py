@@ -11,7 +11,7 @@ import torch
 
 from ._lib import check, lib, need_cuda, stream
 
-RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR, RF_OP_STEM7 = 0, 1, 2, 3, 4, 5
+RF_OP_CONV, RF_OP_MAXPOOL, RF_OP_BLUR, RF_OP_IM2COL, RF_OP_POOLBLUR, RF_OP_STEM7, RF_OP_CONV_DUAL = 0, 1, 2, 3, 4, 5, 6
 RF_MAX_SLOTS = 32
 RF_LAYER_OUT_F32, RF_LAYER_TF32 = 1, 2
 
@@ -19,7 +19,8 @@ RF_LAYER_OUT_F32, RF_LAYER_TF32 = 1, 2
 class rf_layer_t(C.Structure):
     _fields_ = [("op", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
                 ("Cin", C.c_int), ("Cout", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("relu", C.c_int),
-                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("w_f16", C.c_void_p), ("flags", C.c_int)]
+                ("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("w_f16", C.c_void_p), ("flags", C.c_int),
+                ("src2", C.c_int), ("Cin2", C.c_int), ("stride2", C.c_int)]
 
 
 lib.rf_run_layers.restype = C.c_int
@@ -35,6 +36,7 @@ class LayerProgram:
         self.chan = [cin]
         self._keep = []          # folded weights (keeps the device tensors alive)
         self.flags = {}          # op index -> RF_LAYER_* (fp16 engine only)
+        self.dual = {}           # op index -> (second input tensor, its channels, its stride)   (RF_OP_CONV_DUAL, split engine only)
         self._compiled = {}
 
     # -- topology --------------------------------------------------------------------------------
@@ -46,6 +48,17 @@ class LayerProgram:
         self.ops.append((RF_OP_CONV, src, -1 if res is None else res, fc.cin, fc.cout, fc.k, fc.stride, fc.pad, int(relu), fc))
         self._keep.append(fc)
         self.chan.append(fc.cout)
+        return len(self.chan) - 1
+
+    def conv_dual(self, src, src2, fc, stride2, relu):
+        """Split engine only: 1x1 conv over [src | src2 sampled with stride2] (``fc`` = FoldedConv.concat_k(conv3, downsample)):
+        a bottleneck's conv3 + its down-sampling branch + the add + ReLU in one GEMM."""
+        assert fc.k == 1 and self.chan[src] == fc.cin and self.chan[src2] == fc.cin2, (self.chan[src], self.chan[src2], fc.cin, fc.cin2)
+        self.dual[len(self.ops)] = (src2, fc.cin2, stride2)
+        self.ops.append((RF_OP_CONV_DUAL, src, -1, fc.cin, fc.cout, 1, 1, 0, int(relu), fc))
+        self._keep.append(fc)
+        self.chan.append(fc.cout)
+        self.split_only = True
         return len(self.chan) - 1
 
     def maxpool(self, src, k, stride, pad):
@@ -111,6 +124,8 @@ class LayerProgram:
             last_use[o[1]] = i
             if o[2] >= 0:
                 last_use[o[2]] = i
+            if i in self.dual:
+                last_use[self.dual[i][0]] = i
         last_use[n_t - 1] = len(self.ops)                       # the output outlives the program
         # pixel counts per tensor
         hws = [list(hw)]
@@ -154,7 +169,10 @@ class LayerProgram:
                 L.w_f16 = fc.w_f16.data_ptr() if f16 else (fc.w_split.data_ptr() if split else None)
                 L.flags = self.flags.get(i, 0) if (f16 or split) else 0
                 L.bias = fc.bias.data_ptr() if fc.bias is not None else None
-            for t in {o[1], o[2]}:
+            L.src2 = -1
+            if i in self.dual:
+                L.src2, L.Cin2, L.stride2 = slot_of[self.dual[i][0]], self.dual[i][1], self.dual[i][2]
+            for t in {o[1], o[2], self.dual[i][0] if i in self.dual else -1}:
                 if t > 0 and last_use[t] == i:
                     free.append(slot_of[t])
         assert len(slot_elems) <= RF_MAX_SLOTS
@@ -172,6 +190,7 @@ class LayerProgram:
         need_cuda(x.data)
         f16, split = int(engine) == 2, int(engine) == 4
         assert f16 or split or not getattr(self, "f16_only", False), "this program uses tensor-core-engine-only layers"
+        assert split or not getattr(self, "split_only", False), "this program uses split-engine-only layers (conv_dual)"
         key = (tuple(x.hw), str(x.data.device), int(engine) if (f16 or split) else 0)
         if key not in self._compiled:
             # compiled entries own the activation buffers; captured CUDA graphs hold raw pointers into them, so entries are

@@ -75,6 +75,63 @@ def test_conv2d_split(rf, cin, cout, k, sizes, relu, res, stride):
     assert worst <= SPLIT_TOL, worst
 
 
+@pytest.mark.parametrize("c1,c2,cout,stride2,sizes", [
+    (64, 64, 256, 1, [(60, 80), (13, 17), (1, 1)]), (128, 256, 512, 2, [(31, 41), (30, 40), (7, 5)]), (256, 512, 1024, 2, [(15, 20), (8, 11)]),
+    (64, 128, 64, 2, [(9, 9)])])
+@pytest.mark.parametrize("relu", [True, False])
+def test_conv1x1_dual_split(rf, c1, c2, cout, stride2, sizes, relu):
+    """conv3 + down-sampling branch as one GEMM over two inputs == the two convolutions added, in fp64 on the split operands."""
+    g = torch.Generator().manual_seed(c1 + 3 * c2 + cout + stride2)
+    x2s = [torch.randn(1, c2, h, w, generator=g) for h, w in sizes]                                    # the block's input
+    x1s = [torch.randn(1, c1, (h - 1) // stride2 + 1, (w - 1) // stride2 + 1, generator=g) for h, w in sizes]   # conv2's output
+    w1 = torch.randn(cout, c1, generator=g) / np.sqrt(c1)
+    w2 = torch.randn(cout, c2, generator=g) / np.sqrt(c2)
+    bias = torch.randn(cout, generator=g)
+    s1, s2 = sragged(rf, x1s), sragged(rf, x2s)
+    ws = rf.ops.to_split(torch.cat([w1, w2], dim=1).contiguous().cuda())
+    wq = rf.ops.from_split(ws).double().cpu()
+    y = rf.ops.conv1x1_dual_split(s1, s2, stride2, ws, bias.cuda(), relu)
+    torch.cuda.synchronize()
+    assert y.split and y.hw == s1.hw
+    worst = 0.0
+    for i in range(len(sizes)):
+        a = simage(rf, s1, i).double().cpu()
+        b = simage(rf, s2, i).double().cpu()[:, :, ::stride2, ::stride2]
+        ref = F.conv2d(a, wq[:, :c1, None, None]) + F.conv2d(b, wq[:, c1:, None, None]) + bias.double().view(1, -1, 1, 1)
+        ref = F.relu(ref) if relu else ref
+        got = simage(rf, y, i).double().cpu()
+        assert tuple(got.shape) == tuple(ref.shape)
+        worst = max(worst, (got - ref).abs().max().item() / max(1.0, ref.abs().max().item()))
+    assert worst <= SPLIT_TOL, worst
+
+
+def test_dual_rejects_mismatched_sizes(rf):
+    g = torch.Generator().manual_seed(0)
+    s1 = sragged(rf, [torch.randn(1, 64, 8, 8, generator=g)])
+    s2 = sragged(rf, [torch.randn(1, 64, 8, 8, generator=g)])
+    ws = rf.ops.to_split(torch.randn(64, 128, generator=g).cuda())
+    with pytest.raises(rf._lib.RFError):     # stride 2 on an 8 x 8 second input gives 4 x 4, not the first input's 8 x 8
+        rf.ops.conv1x1_dual_split(s1, s2, 2, ws, None, True)
+
+
+def test_resnet50_split_fused_downsample_matches_unfused(rf):
+    """The trunk with conv3 + down-sampling fused == the plain topology to split precision (one fp32 accumulation instead of
+    two rounded-to-22-bit halves added: differences of a few 1e-7 of the feature scale)."""
+    from ransac_flow_b200.coarseAlignFeatMatch import ResNet50Conv4
+    net = ResNet50Conv4(synth.resnet50_conv4_state(0), device="cuda")
+    g = torch.Generator().manual_seed(5)
+    x = ragged(rf, [torch.rand(1, 3, 96, 128, generator=g), torch.rand(1, 3, 70, 50, generator=g)])
+    outs = []
+    for fuse in (True, False):
+        P = net._build(64, fuse_downsample=fuse)
+        out, ohw = P.run(x, rf.ops.ENGINE_SPLIT)
+        outs.append(rf.ops.from_split(out.clone()))
+        assert sum(1 for o in P.ops if o[0] == 6) == (3 if fuse else 0)
+    torch.cuda.synchronize()
+    scale = outs[1].abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-5 * max(1.0, scale), ((outs[0] - outs[1]).abs().max().item(), scale)
+
+
 @pytest.mark.parametrize("cin,cout,sizes", [(128, 49, [(60, 80)]), (128, 1, [(6, 8), (6, 8)]), (64, 49, [(12, 16)])])
 def test_conv2d_split_fp32_output(rf, cin, cout, sizes):
     """Engine 5: split operands, plain fp32 rows out (the 49- / 1-channel last layers of the heads)."""

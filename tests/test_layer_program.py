@@ -14,6 +14,7 @@ def _programs(rf):
     net = ResNet50Conv4(synth.resnet50_conv4_state(0), device="cpu")
     yield "resnet50 fp32", net.program, False, 3
     yield "resnet50 f16", net._build(64), True, 3
+    yield "resnet50 split (conv3 + down-sampling fused)", net._build(64, fuse_downsample=True), "split", 3
     fe = rf.model.FeatureExtractor()
     fe.load_state_dict(synth.feature_extractor_state(0))
     fe.eval()
@@ -35,7 +36,9 @@ def test_slot_assignment_never_aliases_live_tensors(rf, hw):
             hw_in = [(h // 8, w // 8) for h, w in hw]
         else:
             hw_in = hw
-        c = P._compile(hw_in, torch.device("cpu"), f16)
+        split = f16 == "split"
+        f16 = f16 is True
+        c = P._compile(hw_in, torch.device("cpu"), f16, split)
         n_ops = len(P.ops)
         layers = c["layers"]
         # symbolic tensor -> slot, replayed in execution order with liveness from the topology
@@ -44,6 +47,8 @@ def test_slot_assignment_never_aliases_live_tensors(rf, hw):
             last_use[o[1]] = i
             if o[2] >= 0:
                 last_use[o[2]] = i
+            if i in P.dual:
+                last_use[P.dual[i][0]] = i                       # the second input of a dual 1x1
         last_use[n_ops] = n_ops                                  # the output outlives the program
         slot_of = {0: 0}
         for i, o in enumerate(P.ops):
@@ -51,6 +56,10 @@ def test_slot_assignment_never_aliases_live_tensors(rf, hw):
             assert L.src == slot_of[o[1]] and (L.res == -1) == (o[2] < 0), name
             if o[2] >= 0:
                 assert L.res == slot_of[o[2]], name
+            if i in P.dual:
+                assert (L.op, L.src2, L.Cin2, L.stride2) == (6, slot_of[P.dual[i][0]], P.chan[P.dual[i][0]], P.dual[i][2]), name
+            else:
+                assert L.src2 == -1, name
             live = {t for t, s in slot_of.items() if last_use.get(t, -1) >= i}
             for t in live:                                       # the destination must not overwrite anything still needed
                 assert slot_of[t] != L.dst, (name, i, t)
@@ -64,8 +73,10 @@ def test_slot_assignment_never_aliases_live_tensors(rf, hw):
             px = sum(h * w for h, w in _hw_of(P, hw_in, t))
             esz = _esize(P, t, f16)
             assert c["bufs"][s].numel() >= px * P.chan[t] * esz, (name, t)
-        assert c["out_dtype"] == (torch.float16 if (f16 and "Net" not in name) else torch.float32), name
+        assert c["out_dtype"] == (torch.float16 if ((f16 or split) and "Net" not in name) else torch.float32), name
         assert c["in_dtype"] == (torch.float16 if (f16 and "Net" in name) else torch.float32), name
+        if split:                                                # three fused blocks: 3 layers fewer than the plain topology
+            assert sum(1 for o in P.ops if o[0] == 6) == 3 and n_ops == 41
 
 
 def _hw_of(P, hw, t):
