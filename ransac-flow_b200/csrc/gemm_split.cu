@@ -714,9 +714,10 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     // are faster with narrow tiles taken alternately by the two epilogue groups
     static int shallow_env = -1;
     if (shallow_env < 0) { const char* e = getenv("RF_SPLIT_SHALLOW"); shallow_env = e ? atoi(e) : 1; }
-    // one or two K blocks per tile and no residual: the epilogue sets the tile rate, and the double-buffered-staging variant
+    // ONE K block per tile and no residual (two K blocks - the fused conv3 + down-sampling of layer1 - need both operand slots of
+    // that variant for one tile, which serialises load latency and MMAs: 116 us against 85 us with the wide tile): the epilogue sets the tile rate, and the double-buffered-staging variant
     // (64-channel tiles, store read-out off the critical path) beats the wide tile (ResNet layer1 down-sampling 1x1: 79 -> 75 us)
-    const bool shallow = !halo && cp.R == 1 && cp.K <= 128 && shallow_env != 0;
+    const bool shallow = !halo && cp.R == 1 && cp.K <= 64 && shallow_env != 0;
     const int BN = (!halo && !shallow && cp.residual == nullptr && cp.Cout >= 256 && bn_env == 128) ? 128 : 64;
     int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, (unsigned)BN, 2, 1, 2);
     if (rc) return rc;
