@@ -70,7 +70,7 @@ struct SplitCfg {
     static constexpr int A_TX = 2 * A_LO;
     static constexpr int A_SLOT = HALO ? 46 * 1024 : 2 * TC_A_BYTES;          // 1024-byte aligned slots
     static constexpr int NA = HALO ? 2 : ((BN == 128 || RES2) ? 2 : 3);
-    static constexpr int NB = HALO ? 4 : (RES2 ? 2 : 3);
+    static constexpr int NB = HALO ? (BN == 128 ? 2 : 4) : (RES2 ? 2 : 3);
     static constexpr int NSB = RES2 ? 2 : 1;                                  // staging buffers per epilogue group
     static constexpr int TB = HALO ? 9 : 1;                                   // B tiles consumed per A slot
     static constexpr int STG = 2 * TC_A_BYTES;                                // per epilogue group: [hi box | lo box] of 64 channels
@@ -79,9 +79,9 @@ struct SplitCfg {
     static constexpr int DATA_BYTES = OFF_STG + 2 * NSB * STG;
     static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512;
     static constexpr int TMEM_COLS = 4 * BN;                                  // 2 buffers x (main | cross)
-    static_assert(!(HALO && BN != 64), "halo reuse runs with 64-channel tiles");
     static_assert(!RES2 || (!HALO && BN == 64), "double-buffered staging: tap streaming, 64-channel tiles");
 };
+static_assert(SplitCfg<true, 128>::SMEM_BYTES <= 227 * 1024, "shared memory");
 static_assert(SplitCfg<true, 64>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false, 64>::SMEM_BYTES <= 227 * 1024 &&
               SplitCfg<false, 128>::SMEM_BYTES <= 227 * 1024 && SplitCfg<false, 64, true>::SMEM_BYTES <= 227 * 1024, "shared memory");
 static_assert(SplitCfg<true, 64>::A_TX <= SplitCfg<true, 64>::A_SLOT, "halo slot");
@@ -718,7 +718,16 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     // that variant for one tile, which serialises load latency and MMAs: 116 us against 85 us with the wide tile): the epilogue sets the tile rate, and the double-buffered-staging variant
     // (64-channel tiles, store read-out off the critical path) beats the wide tile (ResNet layer1 down-sampling 1x1: 79 -> 75 us)
     const bool shallow = !halo && cp.R == 1 && cp.K <= 64 && shallow_env != 0;
-    const int BN = (!halo && !shallow && cp.residual == nullptr && cp.Cout >= 256 && bn_env == 128) ? 128 : 64;
+    static int halo_bn_env = -1;
+    if (halo_bn_env < 0) { const char* e = getenv("RF_SPLIT_HALO_BN"); halo_bn_env = e ? atoi(e) : 128; }
+    // halo reuse with 128-channel tiles (N = 128 MMAs: less issue overhead per MAC, half the halo-block traffic; two-deep weight ring)
+    const bool halo_wide = halo && halo_bn_env == 128 && cp.Cout >= 128 && (cp.Cout % 128) == 0;
+    static int bn_min_env = -1, res_bn_env = -1;
+    if (bn_min_env < 0) { const char* e = getenv("RF_SPLIT_BN_MIN"); bn_min_env = e ? atoi(e) : 256; }
+    if (res_bn_env < 0) { const char* e = getenv("RF_SPLIT_RES_BN"); res_bn_env = e ? atoi(e) : 64; }
+    const bool tap_wide = !halo && !shallow && bn_env == 128 && (cp.Cout % 128) == 0 &&
+                          (cp.residual == nullptr ? cp.Cout >= bn_min_env : (res_bn_env == 128 && cp.K > 128));
+    const int BN = (halo_wide || tap_wide) ? 128 : 64;
     int rc = get_map(&p.mapB, w_split, (unsigned long long)cp.K, (unsigned long long)cp.Cout, 2, TC_BK_F16, (unsigned)BN, 2, 1, 2);
     if (rc) return rc;
     p.R = cp.R; p.S = cp.S; p.pad = cp.pad; p.stride = cp.stride; p.Cin = cp.Cin; p.Cout = cp.Cout; p.relu = cp.relu;
@@ -744,9 +753,9 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     // double-buffered staging pays for the HBM-bound residual layers with one or two K blocks per tile (ResNet layer 1 / 2
     // c3 + residual: 147 -> 121 us, 81 -> 64 us); with four K blocks (layer 3) the 2-deep operand ring costs more than the
     // residual prefetch gains (45 -> 52 us): measured, profiles/README.md
-    const int which = halo ? 1 : (BN == 128 ? 2 : ((((cp.residual != nullptr && cp.K <= 128) || shallow) && res2_env) ? 3 : 0));
+    const int which = halo ? (halo_wide ? 4 : 1) : (BN == 128 ? 2 : ((((cp.residual != nullptr && cp.K <= 128) || shallow) && res2_env) ? 3 : 0));
     const int dev = current_device();
-    static bool attr[64][8] = {{false}};
+    static bool attr[64][10] = {{false}};
     auto launch = [&](auto kernel, int smem, int threads, int slot) -> int {
         if (!attr[dev][slot]) {
             RF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -757,12 +766,14 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     };
     int lrc;
     if (epw_env == 8) {
-        if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 8>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(8), 0);
+        if (which == 4) lrc = launch(tc_split_kernel<true, 128, false, 8>, SplitCfg<true, 128>::SMEM_BYTES, sp_threads(8), 8);
+        else if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 8>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(8), 0);
         else if (which == 2) lrc = launch(tc_split_kernel<false, 128, false, 8>, SplitCfg<false, 128>::SMEM_BYTES, sp_threads(8), 1);
         else if (which == 3) lrc = launch(tc_split_kernel<false, 64, true, 8>, SplitCfg<false, 64, true>::SMEM_BYTES, sp_threads(8), 2);
         else lrc = launch(tc_split_kernel<false, 64, false, 8>, SplitCfg<false, 64>::SMEM_BYTES, sp_threads(8), 3);
     } else {
-        if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 4>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(4), 4);
+        if (which == 4) lrc = launch(tc_split_kernel<true, 128, false, 4>, SplitCfg<true, 128>::SMEM_BYTES, sp_threads(4), 9);
+        else if (which == 1) lrc = launch(tc_split_kernel<true, 64, false, 4>, SplitCfg<true, 64>::SMEM_BYTES, sp_threads(4), 4);
         else if (which == 2) lrc = launch(tc_split_kernel<false, 128, false, 4>, SplitCfg<false, 128>::SMEM_BYTES, sp_threads(4), 5);
         else if (which == 3) lrc = launch(tc_split_kernel<false, 64, true, 4>, SplitCfg<false, 64, true>::SMEM_BYTES, sp_threads(4), 6);
         else lrc = launch(tc_split_kernel<false, 64, false, 4>, SplitCfg<false, 64>::SMEM_BYTES, sp_threads(4), 7);
