@@ -589,7 +589,8 @@ def run_b200(args, rank, world, local):
 
     if rank == 0 and roofline is not None:
         # the whole pair against the chip: 655 GFLOP of convolutions + correlation per pair, x3 MMAs on the split
-        # engine; ~8.4 GB of algorithmic HBM traffic per pair at 4 B per activation element (profiles/r2_split_floor_analysis.txt)
+        # engine; ~8.4 GB of algorithmic HBM traffic per pair at 4 B per activation element, every layer reading its inputs and writing
+        # its output once (the fused conv3 + down-sampling GEMMs of the split engine move 1.1 GB less: profiles/r2_split_floor_analysis.txt)
         pps = P * args.steps / (ms_dev * 1e-3)                      # this GPU's pairs/s
         mma = 3.0 if args.engine == "f16x3" else 1.0
         gb = 8.4 if args.engine in ("f16x3", "fp32", "tf32") else 4.3

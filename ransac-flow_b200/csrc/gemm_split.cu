@@ -724,7 +724,7 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     const bool halo_wide = halo && halo_bn_env == 128 && cp.Cout >= 128 && (cp.Cout % 128) == 0;
     static int bn_min_env = -1, res_bn_env = -1;
     if (bn_min_env < 0) { const char* e = getenv("RF_SPLIT_BN_MIN"); bn_min_env = e ? atoi(e) : 256; }
-    if (res_bn_env < 0) { const char* e = getenv("RF_SPLIT_RES_BN"); res_bn_env = e ? atoi(e) : 64; }
+    if (res_bn_env < 0) { const char* e = getenv("RF_SPLIT_RES_BN"); res_bn_env = e ? atoi(e) : 128; }
     const bool tap_wide = !halo && !shallow && bn_env == 128 && (cp.Cout % 128) == 0 &&
                           (cp.residual == nullptr ? cp.Cout >= bn_min_env : (res_bn_env == 128 && cp.K > 128));
     const int BN = (halo_wide || tap_wide) ? 128 : 64;

@@ -19,4 +19,8 @@ full() {
 }
 full corr "tc_corr_pipe" 0 1
 full stem "stem7_split" 0 1
+# tc_split_kernel launches of a pair, in order: layer1 = 0..8 (5 = block 1 conv3 + residual, double-buffered staging),
+# layer3 block 1 = 24 (c1), 25 (3x3 halo reuse, 128-channel tiles), 26 (conv3 + residual, wide tile)
+full res2 "tc_split_kernel" 5 1
+full halo128 "tc_split_kernel" 25 2
 wc -l $OUT/r2_launches_f16x3.csv $OUT/r2_metrics_f16x3.csv; du -sh $OUT

@@ -60,8 +60,13 @@ def trunk():
             y = conv("trunk %s.%d c1 1x1 %d->%d" % (layer, b, cin, planes), x, cin, planes, 1, 1, 0)
             y = conv("trunk %s.%d c2 3x3/%d" % (layer, b, s), y, planes, planes, 3, s, 1)
             if b == 0:
-                conv("trunk %s.%d ds 1x1/%d %d->%d" % (layer, b, s, cin, planes * 4), x, cin, planes * 4, 1, s, 0)
-            x = conv("trunk %s.%d c3+res 1x1 %d->%d" % (layer, b, planes, planes * 4), y, planes, planes * 4, 1, 1, 0, res=True)
+                # conv3 + the down-sampling 1x1 (stride s on the block's input) as ONE dual-input GEMM: reads y and the sampled x, writes once
+                P = px(y)
+                layers.append(("trunk %s.%d c3 + ds/%d fused %d|%d->%d" % (layer, b, s, planes, cin, planes * 4), P, 2.0 * P * planes * 4 * (planes + cin),
+                               P * (planes + cin) * 4 + P * planes * 4 * 4 + planes * 4 * (planes + cin) * 4))
+                x = y
+            else:
+                x = conv("trunk %s.%d c3+res 1x1 %d->%d" % (layer, b, planes, planes * 4), y, planes, planes * 4, 1, 1, 0, res=True)
             cin = planes * 4
 
 
@@ -101,7 +106,7 @@ for i, (name, P, fl, by) in enumerate(layers):
     th, tt = by / HBM * 1e6, 3 * fl / TF * 1e6
     kname, us = times[i] if i < len(times) else ("", float("nan"))
     targs = kname[kname.find("<") + 1:kname.find(">")].replace("(bool)", "").replace("(int)", "").replace(" ", "").split(",") if "<" in kname else []
-    variant = "" if len(targs) < 2 else ("halo" if targs[0] in ("1", "true") else "tap BN%s%s" % (targs[1], " RES2" if len(targs) > 2 and targs[2] in ("1", "true") else ""))
+    variant = "" if len(targs) < 2 else ("%s BN%s%s" % ("halo" if targs[0] in ("1", "true") else "tap", targs[1], " 2xstaging" if len(targs) > 2 and targs[2] in ("1", "true") else ""))
     fl_us = max(th, tt)
     print("%-46s %8d %7.2f %8.1f %8.1f %9.1f %9.1f %6.2f  %s" % (name, P, fl / 1e9, by / 1e6, th, tt, us, us / fl_us if us == us else float("nan"), variant))
     g = groups.setdefault(" ".join(name.split(" ")[:2]) if name.startswith(("flow", "match")) else name.split(" ")[0], [0.0, 0.0, 0.0, 0.0])
