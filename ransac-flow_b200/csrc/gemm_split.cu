@@ -49,7 +49,7 @@ struct alignas(64) SplitParams {
     int R, S, pad, stride, Cin, Cout, relu, has_res, out32;
     int tiles_m, tiles_n;
     int kc1, stride2;                     // dual-input 1x1: K blocks [0, kc1) come from mapA, the rest from mapR (second input, its own stride)
-    int dbg;                              // timing experiments only (RF_SPLIT_DBG): 1 no B loads, 2 no MMAs, 4 no A loads, 8 no epilogue math / store
+    int dbg;                              // timing experiments only (RF_SPLIT_DBG): 1 no B loads, 2 no MMAs, 4 no A loads, 8 no epilogue math / store, 16 three MMAs per K step instead of two
     const float* bias;
     float* y32;                           // out32: fp32 [P][Cout]
 };
@@ -243,8 +243,12 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
                     if (HALO) { const int r = jb / 3, sx = jb - r * 3; aaddr += (uint32_t)((r * SP_HALO_LD + sx) * 128); }
                     const uint64_t ahi = HALO ? sp_desc_halo(aaddr) : make_desc_sw128(aaddr);
                     const uint64_t alo = HALO ? sp_desc_halo(aaddr + Cfg::A_LO) : make_desc_sw128(aaddr + Cfg::A_LO);
-                    if (!(p.dbg & 2))
+                    if (p.dbg & 2) {
+                    } else if (p.dbg & 16) {         // three N-wide MMAs per step (the first version; kept for A/B timing)
                         umma_f16split_x4(td, tx, ahi, alo, make_desc_sw128(bb), make_desc_sw128(bb + Cfg::B_PLANE), idesc, (ia | jb) != 0 ? 1u : 0u);
+                    } else {                         // [B hi | B lo] as one 2N-wide instruction + A lo x B hi
+                        umma_f16split2_x4(td, BN, ahi, alo, make_desc_sw128(bb), make_idesc_f16(2 * BN), idesc, (ia | jb) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&emptyB[sb]);
                 }
                 umma_commit(&emptyA[sa]);

@@ -1147,8 +1147,12 @@ tc_corr_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
                 const uint32_t sb = sa + 2 * TC_A_BYTES;
-                umma_f16split_x4(td, tx, make_desc_sw128(sa), make_desc_sw128(sa + TC_A_BYTES), make_desc_sw128(sb),
-                                 make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
+                if (p.stages == 3)      // RF_CORR_MMA3=1: three N = 128 instructions per K step (the first version; A/B timing)
+                    umma_f16split_x4(td, tx, make_desc_sw128(sa), make_desc_sw128(sa + TC_A_BYTES), make_desc_sw128(sb),
+                                     make_desc_sw128(sb + Cfg::B_BYTES), idesc, it != 0 ? 1u : 0u);
+                else                    // [B hi | B lo] are adjacent in the stage, [main | cross] in TMEM: one N = 256 instruction + A lo x B hi
+                    umma_f16split2_x4(td, BN, make_desc_sw128(sa), make_desc_sw128(sa + TC_A_BYTES), make_desc_sw128(sb),
+                                      make_idesc_f16(2 * BN), idesc, it != 0 ? 1u : 0u);
                 umma_commit(&empty[st]);
             }
             umma_commit(&tmem_full[buf]);
@@ -1823,7 +1827,11 @@ static int launch_corr_pipe(const TcParams& p, int tiles_m, int tiles_n, cudaStr
     }
     const long long total = (long long)tiles_m * tiles_n;
     const int grid = total < num_sms() ? (int)total : num_sms();
-    tc_corr_pipe_kernel<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles_m, tiles_n);
+    static int mma3 = -1;
+    if (mma3 < 0) { const char* e = getenv("RF_CORR_MMA3"); mma3 = (e && atoi(e) != 0) ? 1 : 0; }
+    TcParams q = p;
+    q.stages = mma3 ? 3 : 0;              // this kernel's ring depth is fixed; the field selects the MMA sequence
+    tc_corr_pipe_kernel<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(q, tiles_m, tiles_n);
     RF_LAUNCHED();
     return 0;
 }

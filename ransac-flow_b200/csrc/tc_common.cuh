@@ -174,6 +174,34 @@ __device__ __forceinline__ void umma_f16split_x4(uint32_t tmem_d, uint32_t tmem_
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %6, t;\n\t}"
         ::"r"(tmem_d), "r"(tmem_x), "l"(ahi), "l"(alo), "l"(bhi), "l"(blo), "r"(idesc), "r"(acc_first) : "memory");
 }
+// The same products with TWO MMAs per K = 16 step instead of three, for operand tiles whose hi and lo B planes are adjacent in
+// shared memory ([N rows hi][N rows lo], N * 128 bytes each) and whose main and cross accumulators are adjacent in TMEM
+// ([tmem_d, tmem_d + N) main, [tmem_d + N, tmem_d + 2N) cross):
+//   A hi x [B hi | B lo]  as ONE N' = 2N instruction  -> main += hi*hi, cross += hi*lo
+//   A lo x  B hi                                      -> cross += lo*hi
+// A tcgen05.mma costs ~36 cycles + 0.62 cycles per column on B200 whatever its width (measured: N = 64 / 128 / 256 ->
+// 75 / 131 / 194 cycles), so wider instructions are cheaper per MAC: 3 x 131 -> 194 + 131 cycles at N = 128.
+__device__ __forceinline__ void umma_f16split2_x4(uint32_t tmem_d, uint32_t n, uint64_t ahi, uint64_t alo, uint64_t bhi,
+                                                  uint32_t idesc_wide, uint32_t idesc, uint32_t acc_first) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b64 ah, al, bh;\n\t.reg .b32 tx;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "add.u32 tx, %0, %1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [tx], %3, %4, %7, t;\n\t"
+        "add.u64 ah, %2, 2;\n\tadd.u64 al, %3, 2;\n\tadd.u64 bh, %4, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [tx], al, bh, %7, t;\n\t"
+        "add.u64 ah, %2, 4;\n\tadd.u64 al, %3, 4;\n\tadd.u64 bh, %4, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [tx], al, bh, %7, t;\n\t"
+        "add.u64 ah, %2, 6;\n\tadd.u64 al, %3, 6;\n\tadd.u64 bh, %4, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah, bh, %5, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [tx], al, bh, %7, t;\n\t}"
+        ::"r"(tmem_d), "r"(n), "l"(ahi), "l"(alo), "l"(bhi), "r"(idesc_wide), "r"(acc_first), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
