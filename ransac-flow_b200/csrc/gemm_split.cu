@@ -150,7 +150,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
     constexpr int BN = Cfg::BN, NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB, BK = TC_BK_F16;
     constexpr bool WIDE = BN == 128;            // both epilogue groups work on every tile (one 64-channel half each)
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = smem;
     uint8_t* sB = smem + Cfg::OFF_B;
     uint8_t* sStg = smem + Cfg::OFF_STG;
@@ -422,7 +422,8 @@ constexpr int SS_OFF_IN = SS_OFF_STG + 2 * TC_A_BYTES;                    // 176
 constexpr int SS_OFF_BAR = SS_OFF_IN + SS_IN_H * SS_IN_LD * 4;
 constexpr int SS_SMEM = SS_OFF_BAR + 128 + 1024;
 constexpr int SS_BUILD = 256;                                             // builder threads: two per output pixel (half a patch each)
-constexpr int SS_THREADS = SS_BUILD + 32 + 128;                           // + MMA warp + 4 epilogue warps
+constexpr int SS_EPI = 256;                                               // epilogue threads: two warps per TMEM lane quarter, 32 columns each
+constexpr int SS_THREADS = SS_BUILD + 32 + SS_EPI;                        // + MMA warp + 8 epilogue warps
 constexpr int SS_NLD = (SS_IN_H * SS_IN_W + SS_BUILD - 1) / SS_BUILD;      // window floats per builder thread
 static_assert(SS_SMEM <= 227 * 1024, "stem shared memory");
 
@@ -465,23 +466,32 @@ __device__ __forceinline__ void stem_load_window(const StemSplitParams& p, const
     }
 }
 
+// one staged window element: (hi, lo * 2^11) fp16 pair packed in 32 bits (hi in the low half).  The window is split ONCE when it is
+// staged (2 331 values per tile); the patches (24 576 values per tile, every input pixel sits in ~12 of them) are then pure
+// byte shuffles: 2 LDS + 2 PRMT per element pair instead of 2 LDS + ~12 conversions / subtractions / multiplications.
+__device__ __forceinline__ uint32_t stem_pack_split(float v) {
+    __half2 hi, lo;
+    sp_split2(v, 0.f, hi, lo);
+    return (*reinterpret_cast<uint32_t*>(&hi) & 0xFFFFu) | (*reinterpret_cast<uint32_t*>(&lo) << 16);
+}
+
 // half a patch: the 16-byte chunks 4 * HALF .. 4 * HALF + 3 of each of the three K blocks of pixel m, hi and lo planes
-template <int HALF>
-__device__ __forceinline__ void stem_build_half(const float* __restrict__ base, uint8_t* sA, int m) {
-#pragma unroll
-    for (int kb = 0; kb < SS_KB; ++kb) {
+template <int HALF, int kb>
+__device__ __forceinline__ void stem_build_half(const uint32_t* __restrict__ base, uint8_t* sA, int m) {
+    {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int c8 = HALF * 4 + cc;
             uint4 oh, ol;
-            __half2* ph = reinterpret_cast<__half2*>(&oh);
-            __half2* pl = reinterpret_cast<__half2*>(&ol);
+            uint32_t* ph = reinterpret_cast<uint32_t*>(&oh);
+            uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int k0 = kb * 64 + c8 * 8 + 2 * e, k1 = k0 + 1;
-                const float a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0.f;
-                const float b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0.f;
-                sp_split2(a, b, ph[e], pl[e]);
+                const uint32_t a = k0 < SS_KK ? base[(k0 / 21) * SS_IN_LD + (k0 % 21)] : 0u;
+                const uint32_t b = k1 < SS_KK ? base[(k1 / 21) * SS_IN_LD + (k1 % 21)] : 0u;
+                ph[e] = __byte_perm(a, b, 0x5410);          // (hi(a), hi(b))
+                pl[e] = __byte_perm(a, b, 0x7632);          // (lo(a), lo(b))
             }
             uint8_t* dst = sA + kb * TC_A_BYTES + m * 128 + ((c8 ^ (m & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = oh;
@@ -493,24 +503,23 @@ __device__ __forceinline__ void stem_build_half(const float* __restrict__ base, 
 __global__ void __launch_bounds__(SS_THREADS, 1)
 stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = smem;
     uint8_t* sB = smem + SS_OFF_B;
     uint8_t* sStg = smem + SS_OFF_STG;
-    float* sIn = reinterpret_cast<float*>(smem + SS_OFF_IN);
+    uint32_t* sIn = reinterpret_cast<uint32_t*>(smem + SS_OFF_IN);      // the staged window as packed (hi, lo) pairs
     uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + SS_OFF_BAR);
-    uint64_t* bar_a = bar_b + 1;          // 128 arrivals: the tile's patches are in shared memory
-    uint64_t* bar_free = bar_a + 1;       // commit: the MMAs reading the patches are done
-    uint64_t* tmem_full = bar_free + 1;   // [2] commit: accumulator pair complete
+    uint64_t* bar_a = bar_b + 1;          // [3] SS_BUILD arrivals: K block kb of the tile's patches is in shared memory
+    uint64_t* bar_free = bar_a + SS_KB;   // [3] commit: the MMAs reading K block kb are done
+    uint64_t* tmem_full = bar_free + SS_KB;   // [2] commit: accumulator pair complete
     uint64_t* tmem_empty = tmem_full + 2; // [2] 128 arrivals: the epilogue has drained it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_b, 1);
-        mbar_init(bar_a, SS_BUILD);
-        mbar_init(bar_free, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+        for (int i = 0; i < SS_KB; ++i) { mbar_init(&bar_a[i], SS_BUILD); mbar_init(&bar_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], SS_EPI); }
         fence_barrier_init();
     }
     constexpr int WMMA = SS_BUILD / 32;                         // the MMA warp sits right behind the builders
@@ -528,7 +537,7 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
         const int bt = threadIdx.x;                             // 0..255
         const int m = bt & 127, half = bt >> 7;                 // output pixel inside the tile = A row; which half of each K block
         const int py = m >> 4, px = m & 15;
-        const float* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
+        const uint32_t* base = sIn + (2 * py) * SS_IN_LD + 6 * px;
         float stage[SS_NLD];
         StemTile c = stem_decode(p, (int)blockIdx.x < p.total ? (int)blockIdx.x : 0);
         if ((int)blockIdx.x < p.total) stem_load_window(p, c, bt, stage);
@@ -539,20 +548,28 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
             for (int i = 0; i < SS_NLD; ++i) {
                 const int idx = bt + i * SS_BUILD;
                 const int r = idx / SS_IN_W, j = idx - r * SS_IN_W;
-                if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stage[i];
+                if (idx < SS_IN_H * SS_IN_W) sIn[r * SS_IN_LD + j] = stem_pack_split(stage[i]);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (t + (int)gridDim.x < p.total) {                 // next tile's window: in flight while this tile is built
                 c = stem_decode(p, t + gridDim.x);
                 stem_load_window(p, c, bt, stage);
             }
-            if (ti > 0) mbar_wait(bar_free, (ti - 1) & 1);      // the previous tile's MMAs have read the patch buffer
+            // the three K blocks of the patch buffer are a ring between the builders and the MMA warp: block kb of this tile is
+            // built as soon as the previous tile's MMAs on block kb are done, while its blocks kb + 1.. are still being multiplied
+            // (one barrier pair for the whole buffer serialised build and MMAs: 2.3 k + 2.7 k cycles per tile)
             // ---- this pixel's patch, (r, s, c) order: element k = r*21 + s*3 + c sits at sIn[2*py + r][6*px + (k % 21)] ----
             // (thread `half` of the pixel builds the 16-byte chunks 4 * half .. 4 * half + 3 of each K block; warp-uniform branch, so
             // that every (k / 21, k % 21) stays a compile-time constant)
-            if (half == 0) stem_build_half<0>(base, sA, m); else stem_build_half<1>(base, sA, m);
-            fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(bar_a);
+#define RF_STEM_BLOCK(KB)                                                                                              \
+            if (ti > 0) mbar_wait(&bar_free[KB], (ti - 1) & 1);                                                          \
+            if (half == 0) stem_build_half<0, KB>(base, sA, m); else stem_build_half<1, KB>(base, sA, m);                \
+            fence_proxy_async();            /* generic-proxy writes -> visible to the tensor core (async proxy) */      \
+            mbar_arrive(&bar_a[KB]);
+            RF_STEM_BLOCK(0)
+            RF_STEM_BLOCK(1)
+            RF_STEM_BLOCK(2)
+#undef RF_STEM_BLOCK
         }
     } else if (warp == WMMA) {
         // =============================== weights once, then the MMA issuer ===============================
@@ -567,33 +584,37 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
         for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1;
             mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);
-            mbar_wait(bar_a, ti & 1);
             tc_fence_after();
             const uint32_t td = tmem_base + buf * 128;
 #pragma unroll
             for (int kb = 0; kb < SS_KB; ++kb) {
+                mbar_wait(&bar_a[kb], ti & 1);
+                tc_fence_after();
                 const uint32_t a = smem_u32(sA + kb * TC_A_BYTES), b = smem_u32(sB + kb * SS_B_TILE);
-                umma_f16split_x4(td, td + 64, make_desc_sw128(a), make_desc_sw128(a + SS_OFF_ALO), make_desc_sw128(b),
-                                 make_desc_sw128(b + 64 * 128), idesc, kb != 0 ? 1u : 0u);
+                // [B hi | B lo] are adjacent (SS_B_TILE), main | cross accumulators too: two MMAs per K step
+                umma_f16split2_x4(td, 64, make_desc_sw128(a), make_desc_sw128(a + SS_OFF_ALO), make_desc_sw128(b), make_idesc_f16(128), idesc,
+                                  kb != 0 ? 1u : 0u);
+                umma_commit(&bar_free[kb]);
             }
-            umma_commit(bar_free);
             umma_commit(&tmem_full[buf]);
         }
     } else {
-        // =============================== epilogue (warps 5..8) ===============================
+        // =============================== epilogue (8 warps) ===============================
+        // one 4-warp group drained an accumulator pair in ~5 k cycles - the tile rate of the whole kernel (the builders and the
+        // MMAs need ~2.5 k each); two warps per lane quarter, 32 of the 64 columns each
         const int q = warp & 3;                                 // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
+        const int cb = (warp - (WMMA + 1)) >> 2;                // this warp's 32-column block
         const bool leader = (warp == WMMA + 1 && lane == 0);
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++ti) {
             const uint32_t buf = ti & 1;
             const StemTile c = stem_decode(p, t);
-            asm volatile("bar.sync 2, 128;" ::: "memory");      // the leader's previous store has read the staging buffer
+            asm volatile("bar.sync 2, %0;" ::"n"(SS_EPI) : "memory");      // the leader's previous store has read the staging buffer
             mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int cb = 0; cb < 2; ++cb) {
+            {
                 uint32_t v[32], x[32];
                 tmem_ld32x2(trow + cb * 32, v, trow + 64 + cb * 32, x);
 #pragma unroll
@@ -620,7 +641,7 @@ stem7_split_kernel(const __grid_constant__ StemSplitParams p) {
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);
             fence_proxy_async();
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(SS_EPI) : "memory");
             if (leader) {
                 tma_store_4d(&p.mapY[c.img], sStg, 0, c.ox0, c.oy0, 0);
                 tma_store_commit_and_wait_read();

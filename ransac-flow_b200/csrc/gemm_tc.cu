@@ -246,7 +246,7 @@ tc_kernel(const __grid_constant__ TcParams p) {
     const bool res_pf = F16 && MODE == MODE_CONV && p.res_pf;
     constexpr int RES_BYTES = (BN / 64) * TC_A_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* res_stg = smem + NST * Cfg::STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(res_stg + (res_pf ? RES_BYTES : 0));
     uint64_t* empty = full + STAGES;
@@ -445,7 +445,7 @@ tc_halo_kernel(const __grid_constant__ TcParams p, int desc_mode) {
     constexpr int NA = Cfg::NA, NB = Cfg::NB;
     constexpr int BK = tc_bk<F16>();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = smem;
     uint8_t* sB = smem + NA * HALO_A_SLOT;
     uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
@@ -590,7 +590,7 @@ tc_persist_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) 
     using Cfg = PCfg<BN, HALO>;
     constexpr int NA = Cfg::NA, NB = Cfg::NB, TB = Cfg::TB;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = smem;
     uint8_t* sB = smem + Cfg::OFF_B;
     uint8_t* sStg = smem + Cfg::OFF_STG;
@@ -775,7 +775,7 @@ tc_resb_kernel(const __grid_constant__ TcParams p, int tiles_m) {
     constexpr int BN = Cfg::BN, NA = Cfg::NA;
     constexpr int BK = tc_bk<F16>();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sB = smem;
     uint8_t* sA = smem + Cfg::OFF_A;
     uint8_t* sStg = smem + Cfg::OFF_STG;
@@ -937,7 +937,7 @@ tc_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n) {
     using Cfg = PipeCfg<BN>;
     constexpr int NS = Cfg::NS, NBOX = BN / 64, BK = TC_BK_F16;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sStg = smem + Cfg::OFF_STG;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
     uint64_t* empty = full + NS;
@@ -1086,7 +1086,7 @@ tc_corr_pipe_kernel(const __grid_constant__ TcParams p, int tiles_m, int tiles_n
     using Cfg = CorrPipeCfg;
     constexpr int NS = Cfg::NS, BN = Cfg::BN, BK = TC_BK_F16, LD = Cfg::LD;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     float* sT = reinterpret_cast<float*>(smem + Cfg::OFF_T);
     unsigned long long* sP = reinterpret_cast<unsigned long long*>(smem + Cfg::OFF_P);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
@@ -1300,7 +1300,7 @@ struct alignas(64) StemParams {
 __global__ void __launch_bounds__(STEM_THREADS, 2)
 stem7_f16_kernel(const __grid_constant__ StemParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     uint8_t* sA = smem;
     uint8_t* sB = smem + STEM_OFF_B;
     float* sIn = reinterpret_cast<float*>(smem + STEM_OFF_IN);
