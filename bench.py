@@ -434,7 +434,10 @@ def run_b200(args, rank, world, local):
             for k, out in enumerate(outs):
                 recs.append(shard.pack_record(rank + world * (i * P + k), out["H"][0] if len(out["H"]) else None,
                                               status=0 if len(out["H"]) else 1))
-        g0 = time.perf_counter()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()                                                          # ranks drift apart (each GPU sits at its own power-capped
+        g0 = time.perf_counter()                                                    # clock): the gather's own time, not the wait for the slowest
         allr = shard.gather_records(recs, K * P * world, world, dev)                # the one collective: per-pair records
         e1.record()
         torch.cuda.synchronize()
@@ -648,10 +651,17 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # stdout carries exactly ONE line, the JSON record: whatever the libraries print meanwhile (NCCL writes its version / INFO lines
+    # to file descriptor 1 when NCCL_DEBUG asks for them) goes to stderr
+    sys.stdout.flush()
+    fd_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(fd_out, "w")
     if world > 1:
         from ransac_flow_b200 import shard
         rank, world, local = shard.init_from_env("nccl")
     run_b200(args, rank, world, local)
+    sys.stdout.flush()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
