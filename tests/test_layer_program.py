@@ -105,3 +105,30 @@ def test_fp16_handover_flags(rf):
     Pf = fe._fold_build(True)
     assert all(Pf.flags.get(i, 0) == 0 for i in range(len(Pf.ops))) and Pf.chan[-1] == 256
     assert np.prod([o[6] for o in Pf.ops if o[0] in (0, 4) and o[6] > 1]) == 8      # total stride of the main path
+
+
+def test_concat_k_folds_conv3_and_downsample_into_one_weight_matrix(rf):
+    """FoldedConv.concat_k (host logic of the fused bottleneck tail): [W3 | Wd] with the summed folded-BN biases reproduces
+    bn3(conv3(h)) + bn_d(conv_d(x[::s])) - checked here with plain torch on the CPU."""
+    import torch.nn.functional as F
+    from ransac_flow_b200.coarseAlignFeatMatch import _BN
+    sd = synth.resnet50_conv4_state(0)
+    p = "layer2.0"
+    c3 = rf.model.FoldedConv(sd[p + ".conv3.weight"], _BN(sd, p + ".bn3"), 1, pad=0, device="cpu")
+    ds = rf.model.FoldedConv(sd[p + ".downsample.0.weight"], _BN(sd, p + ".downsample.1"), 2, pad=0, device="cpu")
+    f = rf.model.FoldedConv.concat_k(c3, ds)
+    assert (f.cin, f.cin2, f.cout, f.k, f.pad) == (128, 256, 512, 1, 0) and f.w_split.shape == (2, 512, 384)
+    g = torch.Generator().manual_seed(0)
+    h, x = torch.randn(1, 128, 5, 7, generator=g), torch.randn(1, 256, 10, 13, generator=g)
+
+    def bn(y, name):
+        b = _BN(sd, name)
+        return F.batch_norm(y, b.running_mean, b.running_var, b.weight, b.bias, False, 0.0, b.eps)
+
+    ref = bn(F.conv2d(h, sd[p + ".conv3.weight"]), p + ".bn3") + bn(F.conv2d(x, sd[p + ".downsample.0.weight"], stride=2), p + ".downsample.1")
+    cat = torch.cat([h, x[:, :, ::2, ::2]], dim=1)                       # the kernel's K axis: conv2's output | the sampled block input
+    got = torch.einsum("ok,nkhw->nohw", f._wt, cat) + f.bias.view(1, -1, 1, 1)
+    assert (got - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    # the split planes carry the same matrix to 22 bits
+    w22 = f.w_split[0].float() + f.w_split[1].float() / 2048.0
+    assert (w22 - f._wt).abs().max().item() <= 2.0 ** -21 * f._wt.abs().max().item()
