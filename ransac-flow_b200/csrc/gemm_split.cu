@@ -43,7 +43,10 @@ struct alignas(64) SplitParams {
     int nimg;
     int tile_start[RF_MAX_IMGS + 1];
     int tiles_x[RF_MAX_IMGS];
+    float inv_tiles_x[RF_MAX_IMGS];       // 1 / tiles_x, 1 / tiles_n: tile decoding without integer divisions (sp_fast_div)
+    float inv_tiles_n;
     int tw[RF_MAX_IMGS];
+    int tw_shift[RF_MAX_IMGS];            // log2(tw): tiles are tw x (128 / tw) pixels, tw a power of two
     int Ho[RF_MAX_IMGS], Wo[RF_MAX_IMGS];
     long long out_pix[RF_MAX_IMGS + 1];
     int R, S, pad, stride, Cin, Cout, relu, has_res, out32;
@@ -107,20 +110,34 @@ __device__ __forceinline__ uint64_t sp_desc_halo(uint32_t saddr) {
     return d;
 }
 
-struct SpTile { int img, ox0, oy0, tw, n0; };
+static_assert(sizeof(SplitParams) <= 32764, "kernel parameter space (CUDA 12.1+ large kernel parameters)");
+
+struct SpTile { int img, ox0, oy0, tw, n0, tw_shift; };
+
+// a / d for 0 <= a < 2^24 with inv = 1.0f / d: the float quotient is within one of the exact one, one correction step makes it exact
+// (an integer division is ~25 instructions; the tile decode runs once per tile in every warp of the kernel)
+__device__ __forceinline__ int sp_fast_div(int a, int d, float inv) {
+    int q = __float2int_rz(__int2float_rn(a) * inv);
+    const int r = a - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
 
 template <bool HALO, int BN = SP_BN>
 __device__ __forceinline__ SpTile sp_decode(const SplitParams& p, int t) {
     SpTile c;
-    const int mt = t / p.tiles_n, nt = t - mt * p.tiles_n;      // channel tiles fastest: co-running CTAs share the pixel tile
+    const int mt = sp_fast_div(t, p.tiles_n, p.inv_tiles_n), nt = t - mt * p.tiles_n;      // channel tiles fastest: co-running CTAs share the pixel tile
     int img = 0;
 #pragma unroll
     for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && mt >= p.tile_start[j]) ? 1 : 0;
     const int tloc = mt - p.tile_start[img];
     c.img = img;
     c.tw = HALO ? SP_HALO_TW : p.tw[img];
-    const int th = 128 / c.tw;
-    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    c.tw_shift = HALO ? 3 : p.tw_shift[img];
+    const int th = 128 >> c.tw_shift;
+    const int tyi = sp_fast_div(tloc, p.tiles_x[img], p.inv_tiles_x[img]), txi = tloc - tyi * p.tiles_x[img];
     c.ox0 = txi * c.tw;
     c.oy0 = tyi * th;
     c.n0 = nt * BN;
@@ -292,7 +309,7 @@ tc_split_kernel(const __grid_constant__ SplitParams p) {
             const uint32_t buf = WIDE ? (k & 1) : g;                        // accumulator pair of this tile
             const uint32_t fph = WIDE ? ((k >> 1) & 1) : (k & 1);           // phase of its tmem_full barrier
             const int nbase = c.n0 + (WIDE ? 64 * (int)g : 0);              // first output channel of this group's 64-wide slice
-            const int py = m / c.tw, px = m - py * c.tw;
+            const int py = m >> c.tw_shift, px = m - (py << c.tw_shift);
             const bool pvalid = (c.oy0 + py < p.Ho[c.img]) && (c.ox0 + px < p.Wo[c.img]);
             const long long pix = p.out_pix[c.img] + (long long)(c.oy0 + py) * p.Wo[c.img] + (c.ox0 + px);
             // the leader comes here only after the previous store has read the staging buffer (two buffers, no residual: the
@@ -433,6 +450,7 @@ struct alignas(64) StemSplitParams {
     int nimg, total;
     int tile_start[RF_MAX_IMGS + 1];
     int tiles_x[RF_MAX_IMGS];
+    float inv_tiles_x[RF_MAX_IMGS];
     int H[RF_MAX_IMGS], W[RF_MAX_IMGS];
     long long in_pix[RF_MAX_IMGS];
     const float* x;
@@ -446,7 +464,7 @@ __device__ __forceinline__ StemTile stem_decode(const StemSplitParams& p, int t)
 #pragma unroll
     for (int j = 1; j < RF_MAX_IMGS; ++j) img += (j < p.nimg && t >= p.tile_start[j]) ? 1 : 0;
     const int tloc = t - p.tile_start[img];
-    const int tyi = tloc / p.tiles_x[img], txi = tloc - tyi * p.tiles_x[img];
+    const int tyi = sp_fast_div(tloc, p.tiles_x[img], p.inv_tiles_x[img]), txi = tloc - tyi * p.tiles_x[img];
     c.img = img;
     c.ox0 = txi * SS_TW;
     c.oy0 = tyi * SS_TH;
@@ -706,7 +724,11 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
     for (int i = 0; i < set.n; ++i) {
         const int tw = halo ? SP_HALO_TW : pick_tw(set.Ho[i], set.Wo[i]), th = 128 / tw;
         p.tw[i] = tw;
+        p.tw_shift[i] = 0;
+        while ((1 << p.tw_shift[i]) < tw) ++p.tw_shift[i];
+        RF_REQUIRE((1 << p.tw_shift[i]) == tw, "rf_conv2d_nhwc: tile width must be a power of two");
         p.tiles_x[i] = (set.Wo[i] + tw - 1) / tw;
+        p.inv_tiles_x[i] = 1.0f / (float)p.tiles_x[i];
         p.tile_start[i] = tiles;
         tiles += p.tiles_x[i] * ((set.Ho[i] + th - 1) / th);
         p.Ho[i] = set.Ho[i]; p.Wo[i] = set.Wo[i];
@@ -769,8 +791,9 @@ static int rf_conv2d_split_impl(const ImgSet& set, const ConvParams& cp, const v
 
     p.tiles_m = tiles;
     p.tiles_n = (cp.Cout + BN - 1) / BN;
+    p.inv_tiles_n = 1.0f / (float)p.tiles_n;
     const long long total = (long long)p.tiles_m * p.tiles_n;
-    RF_REQUIRE(total < (1ll << 30), "rf_conv2d_nhwc: too many tiles");
+    RF_REQUIRE(total < (1ll << 24), "rf_conv2d_nhwc: too many tiles");          // sp_fast_div is exact below 2^24
     const int grid = total < num_sms() ? (int)total : num_sms();
     static int res2_env = -1, epw_env = -1;
     if (res2_env < 0) { const char* e = getenv("RF_SPLIT_RES2"); res2_env = e ? atoi(e) : 1; }
@@ -838,6 +861,7 @@ int rf_stem7_split_impl(const float* x, int nimg, const int* hw_host, const void
     int tiles = 0;
     for (int i = 0; i < nimg; ++i) {
         p.tiles_x[i] = (set.Wo[i] + SS_TW - 1) / SS_TW;
+        p.inv_tiles_x[i] = 1.0f / (float)p.tiles_x[i];
         p.tile_start[i] = tiles;
         tiles += p.tiles_x[i] * ((set.Ho[i] + SS_TH - 1) / SS_TH);
         p.H[i] = set.H[i]; p.W[i] = set.W[i];
